@@ -1,0 +1,67 @@
+// C-ABI plumbing: version, thread-local error string, GEMM dispatch.
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace spa3d {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+}  // namespace spa3d
+
+extern "C" {
+
+int spa3d_version(void) { return 100; }
+
+const char* spa3d_last_error(void) { return spa3d::g_err; }
+
+int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
+               const float* bias, int act, const void* residual, int64_t ldr, int r_dtype,
+               void* C, int64_t ldc, int c_dtype, int64_t M, int N, int K, int impl,
+               void* stream) {
+  using namespace spa3d;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  if (M == 0) return 0;
+  bool tc_ok = (a_dtype == SPA3D_BF16) && gemm_tcgen05_applicable(A, lda, Wt, ldw, M, N, K);
+  if (impl == SPA3D_GEMM_TCGEN05) {
+    SPA3D_REQUIRE(tc_ok, "gemm: tcgen05 path not applicable (dtype=%d lda=%lld ldw=%lld K=%d)",
+                  a_dtype, (long long)lda, (long long)ldw, K);
+  }
+  if (impl != SPA3D_GEMM_SIMT && tc_ok) {
+    return gemm_tcgen05(A, lda, Wt, ldw, bias, act, residual, ldr, r_dtype, C, ldc, c_dtype, M, N,
+                        K, st);
+  }
+  // SIMT fp32-accumulate path: B(k,n) = Wt[n*ldw + k]
+  return gemm_simt(A, lda, 1, a_dtype, Wt, 1, ldw, a_dtype, bias, act, residual, ldr, r_dtype, C,
+                   ldc, c_dtype, M, N, K, 0, st);
+}
+
+int spa3d_gemm_strided(const void* A, int64_t sam, int64_t sak, int a_dtype, const void* B,
+                       int64_t sbk, int64_t sbn, int b_dtype, void* C, int64_t ldc, int c_dtype,
+                       int64_t M, int N, int64_t K, int accumulate, void* stream) {
+  using namespace spa3d;
+  SPA3D_REQUIRE(!accumulate || c_dtype == SPA3D_F32, "gemm_strided: accumulate needs f32 C");
+  if (M == 0 || N == 0) return 0;
+  return gemm_simt(A, sam, sak, a_dtype, B, sbk, sbn, b_dtype, nullptr, 0, nullptr, 0, 0, C, ldc,
+                   c_dtype, M, N, K, accumulate, (cudaStream_t)stream);
+}
+
+}  // extern "C"

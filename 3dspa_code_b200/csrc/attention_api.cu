@@ -1,0 +1,52 @@
+// C-ABI entry points for the attention cores; dispatch between the tensor-core kernel
+// (bf16, short sequences held in one tile) and the fp32 SIMT kernel.
+#include "common.cuh"
+
+namespace spa3d {
+int attention_fwd_simt(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                       int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
+                       float* lse_out, int64_t batch, int heads, int Lq, int Lk, int Dh,
+                       cudaStream_t st);
+int attention_bwd_simt(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                       int64_t ldv, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
+                       void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                       int dtype, const uint8_t* key_mask, const float* lse, float* delta_ws,
+                       int64_t batch, int heads, int Lq, int Lk, int Dh, cudaStream_t st);
+bool attention_fwd_mma_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq, int64_t ldk,
+                                  int64_t ldv, int64_t ldo);
+int attention_fwd_mma(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                      int64_t ldv, void* o, int64_t ldo, const uint8_t* key_mask, float* lse_out,
+                      int64_t batch, int heads, int Lq, int Lk, int Dh, cudaStream_t st);
+}  // namespace spa3d
+
+extern "C" {
+
+int spa3d_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                        int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
+                        float* lse_out, int64_t batch, int heads, int Lq, int Lk, int Dh,
+                        void* stream) {
+  using namespace spa3d;
+  if (batch == 0 || Lq == 0) return 0;
+  SPA3D_REQUIRE(Lk > 0, "attention: Lk must be > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (attention_fwd_mma_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, ldo))
+    return attention_fwd_mma(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse_out, batch, heads, Lq, Lk,
+                             Dh, st);
+  return attention_fwd_simt(q, ldq, k, ldk, v, ldv, o, ldo, dtype, key_mask, lse_out, batch, heads,
+                            Lq, Lk, Dh, st);
+}
+
+int spa3d_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                        int64_t ldv, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
+                        void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                        int dtype, const uint8_t* key_mask, const float* lse, float* delta_ws,
+                        int64_t batch, int heads, int Lq, int Lk, int Dh, void* stream) {
+  using namespace spa3d;
+  if (batch == 0 || Lq == 0) return 0;
+  SPA3D_REQUIRE(lse != nullptr && delta_ws != nullptr, "attention_bwd: lse/delta_ws required");
+  return attention_bwd_simt(q, ldq, k, ldk, v, ldv, o, ldo, d_o, lddo, dq, lddq, dk, lddk, dv, lddv,
+                            dtype, key_mask, lse, delta_ws, batch, heads, Lq, Lk, Dh,
+                            (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Shared helpers for the 3DSPA B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cfloat>
+#include <cstdio>
+
+#include "../../include/spa3d_b200.h"
+
+namespace spa3d {
+
+// ---- error plumbing (thread-local message, int status; never throws across the C ABI) ----
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define SPA3D_REQUIRE(cond, ...)      \
+  do {                                \
+    if (!(cond)) {                    \
+      spa3d::set_error(__VA_ARGS__);  \
+      return 1;                       \
+    }                                 \
+  } while (0)
+
+// ---- dtype helpers ----
+using bf16 = __nv_bfloat16;
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__device__ __forceinline__ void stf(T* p, float v);
+template <>
+__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// dispatch a generic lambda on a dtype code: f(T{}) with T in {float, bf16}
+#define SPA3D_DISPATCH(code, T, ...)                               \
+  do {                                                             \
+    if ((code) == SPA3D_F32) {                                     \
+      using T = float;                                             \
+      __VA_ARGS__;                                                 \
+    } else if ((code) == SPA3D_BF16) {                             \
+      using T = spa3d::bf16;                                       \
+      __VA_ARGS__;                                                 \
+    } else {                                                       \
+      spa3d::set_error("bad dtype code %d", (int)(code));          \
+      return 1;                                                    \
+    }                                                              \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// flax nn.gelu(approximate=True)
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k = 0.7978845608028654f;  // sqrt(2/pi)
+  float u = k * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k = 0.7978845608028654f;
+  float x2 = x * x;
+  float u = k * (x + 0.044715f * x * x2);
+  float t = tanhf(u);
+  float du = k * (1.0f + 3.0f * 0.044715f * x2);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+
+constexpr float kNormEps = 1e-6f;  // flax LayerNorm / RMSNorm epsilon
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// internal entry points implemented in the other translation units
+int gemm_simt(const void* A, int64_t sam, int64_t sak, int a_dtype, const void* B, int64_t sbk,
+              int64_t sbn, int b_dtype, const float* bias, int act, const void* residual,
+              int64_t ldr, int r_dtype, void* C, int64_t ldc, int c_dtype, int64_t M, int N,
+              int64_t K, int accumulate, cudaStream_t st);
+int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias,
+                 int act, const void* residual, int64_t ldr, int r_dtype, void* C, int64_t ldc,
+                 int c_dtype, int64_t M, int N, int K, cudaStream_t st);
+bool gemm_tcgen05_applicable(const void* A, int64_t lda, const void* Wt, int64_t ldw, int64_t M,
+                             int N, int K);
+
+}  // namespace spa3d

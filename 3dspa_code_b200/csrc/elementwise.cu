@@ -1,0 +1,722 @@
+// Bandwidth-bound kernels of the 3DSPA hot path: Fourier features, norms, masks, quantiser,
+// decoder token assembly, output split, loss, optimiser.  Each function cites the reference
+// lines it replaces in include/spa3d_b200.h.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace spa3d {
+
+// ------------------------------------------------------------------------------------------
+// SinusoidalEmbedding (track_autoencoder.py:18-38)
+// ------------------------------------------------------------------------------------------
+struct FourierScales {
+  float s[64];
+};
+
+template <typename TO, bool EXACT>
+__global__ void fourier_kernel(const float* __restrict__ x, int64_t ldx, TO* __restrict__ out,
+                               int64_t ldo, int64_t rows, int C, int Ctot, int F, float scale_factor,
+                               int append_time, int out_group, FourierScales sc) {
+  // one thread per (row, coord, freq): writes the sin and the cos(=sin(.+pi/2)) feature
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = rows * Ctot * F;
+  if (idx >= total) return;
+  int f = (int)(idx % F);
+  int c = (int)((idx / F) % Ctot);
+  int64_t r = idx / ((int64_t)F * Ctot);
+  float v;
+  if (c < C) {
+    v = x[r * ldx + c];
+  } else if (append_time > 0 && c == C) {
+    // fr_id = arange(T)/T in float32 (track_autoencoder_3d.py:126)
+    v = __fdiv_rn((float)(r % append_time), (float)append_time);
+  } else {
+    v = 0.f;  // query_frame // 150.0 == 0 (track_autoencoder_3d.py:268-269)
+  }
+  v = __fdiv_rn(v, scale_factor);
+  float a0 = __fmul_rn(v, sc.s[f]);
+  float a1 = __fadd_rn(a0, 1.57079632679489661923f);  // float32(0.5*pi)
+  float s0, s1;
+  if (EXACT) {
+    s0 = (float)sin((double)a0);
+    s1 = (float)sin((double)a1);
+  } else {
+    s0 = sinf(a0);
+    s1 = sinf(a1);
+  }
+  int64_t ro = out_group > 0 ? r + r / out_group + 1 : r;
+  TO* o = out + ro * ldo + (int64_t)c * 2 * F;
+  stf<TO>(o + f, s0);
+  stf<TO>(o + F + f, s1);
+}
+
+template <typename TS, typename TD>
+__global__ void convert_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst,
+                               int64_t ldd, int64_t rows, int cols, int out_group) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int64_t r = idx / cols;
+  int c = (int)(idx % cols);
+  int64_t ro = out_group > 0 ? r + r / out_group + 1 : r;
+  stf<TD>(dst + ro * ldd + c, ldf<TS>(src + r * lds + c));
+}
+
+template <typename TD>
+__global__ void set_rows_kernel(TD* __restrict__ dst, int64_t ld, int64_t row_stride,
+                                const float* __restrict__ vec, int64_t rows, int cols) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int64_t r = idx / cols;
+  int c = (int)(idx % cols);
+  stf<TD>(dst + r * row_stride * ld + c, vec[c]);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (scale only, eps 1e-6, fast variance) - one warp per row
+// ------------------------------------------------------------------------------------------
+template <typename TX, typename TY>
+__global__ void layernorm_fwd_kernel(const TX* __restrict__ x, int64_t ldx,
+                                     const float* __restrict__ scale, TY* __restrict__ y,
+                                     int64_t ldy, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, int64_t rows, int d) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int lane = threadIdx.x & 31;
+  const TX* xr = x + row * ldx;
+  float s = 0.f, ss = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    float v = ldf<TX>(xr + i);
+    s += v;
+    ss += v * v;
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  float mean = s / d;
+  float var = fmaxf(ss / d - mean * mean, 0.f);
+  float rstd = rsqrtf(var + kNormEps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  TY* yr = y + row * ldy;
+  for (int i = lane; i < d; i += 32) {
+    float v = ldf<TX>(xr + i);
+    stf<TY>(yr + i, (v - mean) * rstd * scale[i]);
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*scale;  dscale += dy*xhat
+template <typename TX, typename TDY, typename TDX>
+__global__ void layernorm_bwd_kernel(const TX* __restrict__ x, int64_t ldx,
+                                     const float* __restrict__ scale,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const TDY* __restrict__ dy, int64_t lddy, TDX* __restrict__ dx,
+                                     int64_t lddx, int dx_accumulate,
+                                     float* __restrict__ dscale_partial, int64_t rows, int d) {
+  // grid-stride over rows, one warp per row; per-block partial dscale accumulated in smem
+  extern __shared__ float s_ds[];  // [d]
+  for (int i = threadIdx.x; i < d; i += blockDim.x) s_ds[i] = 0.f;
+  __syncthreads();
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
+    const TX* xr = x + row * ldx;
+    const TDY* dyr = dy + row * lddy;
+    float mu = mean[row], rs = rstd[row];
+    float sg = 0.f, sgx = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      float xh = (ldf<TX>(xr + i) - mu) * rs;
+      float dyv = ldf<TDY>(dyr + i);
+      float g = dyv * scale[i];
+      sg += g;
+      sgx += g * xh;
+      atomicAdd(&s_ds[i], dyv * xh);
+    }
+    sg = warp_sum(sg) / d;
+    sgx = warp_sum(sgx) / d;
+    TDX* dxr = dx + row * lddx;
+    for (int i = lane; i < d; i += 32) {
+      float xh = (ldf<TX>(xr + i) - mu) * rs;
+      float g = ldf<TDY>(dyr + i) * scale[i];
+      float v = rs * (g - sg - xh * sgx);
+      if (dx_accumulate) v += ldf<TDX>(dxr + i);
+      stf<TDX>(dxr + i, v);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * d + i] = s_ds[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// per-head RMSNorm (attention.py:166-167), in place; one warp per (row, head)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void head_rmsnorm_fwd_kernel(T* __restrict__ buf, int64_t ld, const float* __restrict__ scale,
+                                        float out_mul, float* __restrict__ rstd_out, int64_t rows,
+                                        int heads, int Dh) {
+  int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= rows * heads) return;
+  int lane = threadIdx.x & 31;
+  int64_t r = wid / heads;
+  int h = (int)(wid % heads);
+  T* p = buf + r * ld + (int64_t)h * Dh;
+  float ss = 0.f;
+  for (int i = lane; i < Dh; i += 32) {
+    float v = ldf<T>(p + i);
+    ss += v * v;
+  }
+  ss = warp_sum(ss);
+  float rstd = rsqrtf(ss / Dh + kNormEps);
+  if (lane == 0 && rstd_out) rstd_out[wid] = rstd;
+  for (int i = lane; i < Dh; i += 32) stf<T>(p + i, ldf<T>(p + i) * rstd * scale[i] * out_mul);
+}
+
+// y = x*rstd*scale*mul.  Given dy: g = dy*scale*mul; dx = rstd*(g - xhat*mean(g*xhat)), xhat = x*rstd.
+// xhat is recovered from the saved output: xhat = y/(scale*mul) (scale==0 => that channel's
+// output carries no information and its g is 0 as well).
+template <typename TY, typename TD>
+__global__ void head_rmsnorm_bwd_kernel(const TY* __restrict__ y, int64_t ldy,
+                                        const float* __restrict__ scale, float out_mul,
+                                        const float* __restrict__ rstd, TD* __restrict__ d_io,
+                                        int64_t ldd, float* __restrict__ dscale_partial,
+                                        int64_t rows, int heads, int Dh) {
+  extern __shared__ float s_ds[];  // [Dh]
+  for (int i = threadIdx.x; i < Dh; i += blockDim.x) s_ds[i] = 0.f;
+  __syncthreads();
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  int64_t total = rows * heads;
+  for (int64_t wid = (int64_t)blockIdx.x * nwarp + warp; wid < total; wid += (int64_t)gridDim.x * nwarp) {
+    int64_t r = wid / heads;
+    int h = (int)(wid % heads);
+    const TY* yp = y + r * ldy + (int64_t)h * Dh;
+    TD* dp = d_io + r * ldd + (int64_t)h * Dh;
+    float rs = rstd[wid];
+    float sgx = 0.f;
+    for (int i = lane; i < Dh; i += 32) {
+      float sm = scale[i] * out_mul;
+      float xh = sm != 0.f ? ldf<TY>(yp + i) / sm : 0.f;
+      float dyv = ldf<TD>(dp + i);
+      sgx += dyv * sm * xh;
+      atomicAdd(&s_ds[i], dyv * xh * out_mul);
+    }
+    sgx = warp_sum(sgx) / Dh;
+    for (int i = lane; i < Dh; i += 32) {
+      float sm = scale[i] * out_mul;
+      float xh = sm != 0.f ? ldf<TY>(yp + i) / sm : 0.f;
+      float g = ldf<TD>(dp + i) * sm;
+      stf<TD>(dp + i, rs * (g - xh * sgx));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Dh; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * Dh + i] = s_ds[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// key mask (R1), quantiser, decoder tokens, output split, loss
+// ------------------------------------------------------------------------------------------
+__global__ void key_mask_kernel(const float* __restrict__ visible, const int32_t* __restrict__ boundary,
+                                uint8_t* __restrict__ mask, int B, int N, int T, int ro) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int L = T + ro;
+  int64_t total = (int64_t)B * N * L;
+  if (idx >= total) return;
+  int j = (int)(idx % L);
+  int64_t bn = idx / L;
+  int b = (int)(bn / N);
+  uint8_t m;
+  if (ro && j == 0) {
+    m = 1;
+  } else {
+    int t = j - ro;
+    m = (visible[bn * T + t] != 0.f) && (t < boundary[b]);
+  }
+  mask[idx] = m;
+}
+
+__global__ void quantize_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                float* __restrict__ y, uint8_t* __restrict__ pass, int64_t n,
+                                int discretize) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = x[i];
+  if (pass) pass[i] = (v >= -1.f && v <= 1.f);
+  v = fminf(fmaxf(v, -1.f), 1.f);
+  if (discretize) {
+    float d = __fdiv_rn(rintf(__fmul_rn(v, 128.f)), 128.f);
+    d = __fsub_rn(__fadd_rn(d, __fdiv_rn(noise[i], 128.f)), 1.0f / 256.0f);
+    // straight-through: latents - stop_gradient(latents - disc)
+    v = __fsub_rn(v, __fsub_rn(v, d));
+  }
+  y[i] = v;
+}
+
+template <typename TL, typename TQ, typename TT>
+__global__ void decoder_tokens_fwd_kernel(const TL* __restrict__ lat, const TQ* __restrict__ qe,
+                                          const int32_t* __restrict__ qframe, TT* __restrict__ tok,
+                                          int B, int Q, int L, int C) {
+  // one block per (b, q, token); threads over channels
+  int64_t row = blockIdx.x;  // (b*Q + q)*(L+1) + tkn
+  int tkn = (int)(row % (L + 1));
+  int64_t bq = row / (L + 1);
+  int b = (int)(bq / Q);
+  int D = C + 128;
+  TT* o = tok + row * D;
+  if (tkn == 0) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) stf<TT>(o + c, ldf<TQ>(qe + bq * D + c));
+    return;
+  }
+  const TL* l = lat + ((int64_t)b * L + (tkn - 1)) * C;
+  int off = qframe[bq] * 5;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float v;
+    if (c < C) {
+      v = ldf<TL>(l + c);
+    } else {
+      int src = c - C + off;
+      v = (src >= 0 && src < C) ? ldf<TL>(l + src) : 0.f;
+    }
+    stf<TT>(o + c, v);
+  }
+}
+
+// d_lat[b,n,c] = sum_q d_tok[b,q,1+n,c] + sum_q [0 <= c-5t_q < 128] d_tok[b,q,1+n,C + c-5t_q]
+template <typename TT>
+__global__ void decoder_tokens_bwd_kernel(const TT* __restrict__ d_tok, const int32_t* __restrict__ qframe,
+                                          float* __restrict__ d_lat, float* __restrict__ d_qe, int B,
+                                          int Q, int L, int C) {
+  int D = C + 128;
+  int64_t bn = blockIdx.x;  // b*L + n   (blocks [0, B*L)) then query rows [B*L, B*L + B*Q)
+  if (bn >= (int64_t)B * L) {
+    int64_t bq = bn - (int64_t)B * L;
+    const TT* src = d_tok + bq * (L + 1) * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) d_qe[bq * D + c] = ldf<TT>(src + c);
+    return;
+  }
+  int b = (int)(bn / L), n = (int)(bn % L);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int q = 0; q < Q; ++q) {
+      int64_t bq = (int64_t)b * Q + q;
+      const TT* src = d_tok + (bq * (L + 1) + 1 + n) * D;
+      acc += ldf<TT>(src + c);
+      int w = c - qframe[bq] * 5;
+      if (w >= 0 && w < 128) acc += ldf<TT>(src + C + w);
+    }
+    d_lat[bn * C + c] = acc;
+  }
+}
+
+__global__ void split_outputs_kernel(const float* __restrict__ ho, float* __restrict__ tracks,
+                                     float* __restrict__ vis, float* __restrict__ cert, int64_t rows,
+                                     int T, int coords) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * T) return;
+  int64_t r = idx / T;
+  int t = (int)(idx % T);
+  const float* h = ho + r * 4 * T;
+  for (int c = 0; c < coords; ++c) tracks[idx * coords + c] = h[c * T + t];
+  vis[idx] = h[coords * T + t];
+  if (cert) cert[idx] = (coords == 3) ? 0.f : h[3 * T + t];
+}
+
+__device__ __forceinline__ float log_sigmoid(float x) {
+  // stable: min(x,0) - log1p(exp(-|x|))
+  return fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
+}
+
+__global__ void loss_fwd_kernel(const float* __restrict__ ho, const float* __restrict__ tt,
+                                const float* __restrict__ tv, float* __restrict__ sums, int64_t rows,
+                                int T) {
+  float pos = 0.f, bce = 0.f, nv = 0.f;
+  int64_t total = rows * T;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx / T;
+    int t = (int)(idx % T);
+    const float* h = ho + r * 4 * T;
+    float v = tv[idx];
+    float e = fabsf(h[t] - tt[idx * 3]) + fabsf(h[T + t] - tt[idx * 3 + 1]) + fabsf(h[2 * T + t] - tt[idx * 3 + 2]);
+    pos += e * v;
+    float l = h[3 * T + t];
+    bce += -v * log_sigmoid(l) - (1.f - v) * log_sigmoid(-l);
+    nv += v;
+  }
+  __shared__ float sh[3][32];
+  pos = warp_sum(pos); bce = warp_sum(bce); nv = warp_sum(nv);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][w] = pos; sh[1][w] = bce; sh[2][w] = nv; }
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    pos = lane < nw ? sh[0][lane] : 0.f;
+    bce = lane < nw ? sh[1][lane] : 0.f;
+    nv = lane < nw ? sh[2][lane] : 0.f;
+    pos = warp_sum(pos); bce = warp_sum(bce); nv = warp_sum(nv);
+    if (lane == 0) { atomicAdd(sums, pos); atomicAdd(sums + 1, bce); atomicAdd(sums + 2, nv); }
+  }
+}
+
+__global__ void loss_bwd_kernel(const float* __restrict__ ho, const float* __restrict__ tt,
+                                const float* __restrict__ tv, float* __restrict__ dho, float l1w,
+                                float bcew, float inv_denom, int64_t rows, int T) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * T) return;
+  int64_t r = idx / T;
+  int t = (int)(idx % T);
+  const float* h = ho + r * 4 * T;
+  float* d = dho + r * 4 * T;
+  float v = tv[idx];
+  float s = l1w * inv_denom * v;
+  for (int c = 0; c < 3; ++c) {
+    float diff = h[c * T + t] - tt[idx * 3 + c];
+    d[c * T + t] = diff > 0.f ? s : (diff < 0.f ? -s : 0.f);
+  }
+  float l = h[3 * T + t];
+  float sig = 1.f / (1.f + expf(-l));
+  d[3 * T + t] = bcew * inv_denom * (sig - v);
+}
+
+template <typename TP, typename TDY, typename TDX>
+__global__ void gelu_bwd_kernel(const TP* __restrict__ pre, int64_t ldp, const TDY* __restrict__ dy,
+                                int64_t lddy, TDX* __restrict__ dx, int64_t lddx, int64_t rows, int cols) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int64_t r = idx / cols;
+  int c = (int)(idx % cols);
+  stf<TDX>(dx + r * lddx + c, ldf<TDY>(dy + r * lddy + c) * gelu_tanh_grad(ldf<TP>(pre + r * ldp + c)));
+}
+
+// column sums: block handles 32 columns x a slab of rows; atomics across slabs
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ out,
+                              int64_t rows, int cols, int64_t rows_per_block) {
+  __shared__ float sh[8][33];
+  int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  int ry = threadIdx.x >> 5;  // 0..7
+  int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc = 0.f;
+  if (c < cols)
+    for (int64_t r = r0 + ry; r < r1; r += 8) acc += ldf<T>(x + r * ldx + c);
+  sh[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x & 31];
+    atomicAdd(out + c, s);
+  }
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += alpha * x[i];
+}
+
+__global__ void zero_kernel(float* __restrict__ p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = g[i];
+    acc += v * v;
+  }
+  __shared__ float sh[32];
+  acc = warp_sum(acc);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh[w] = acc;
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    acc = lane < nw ? sh[lane] : 0.f;
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(out, acc);
+  }
+}
+
+// optax.chain(clip_by_global_norm(c), adamw(lr, wd)) - train.py:239-243
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, int64_t n, const float* __restrict__ sumsq,
+                             float clip_norm, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gn = sqrtf(*sumsq);
+  float sc = gn < clip_norm ? 1.f : clip_norm / gn;
+  float gi = g[i] * sc;
+  float mi = b1 * m[i] + (1.f - b1) * gi;
+  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  float mh = mi / bc1, vh = vi / bc2;
+  float pi = p[i];
+  p[i] = pi - lr * (mh / (sqrtf(vh) + eps) + wd * pi);
+}
+
+template <typename TT, typename TO>
+__global__ void masked_mean_kernel(const TT* __restrict__ tok, int64_t ldt, const float* __restrict__ vis,
+                                   TO* __restrict__ out, int64_t ldo, int T, int W) {
+  int64_t s = blockIdx.x;
+  __shared__ float cnt_s;
+  if (threadIdx.x < 32) {
+    float c = 0.f;
+    for (int t = threadIdx.x; t < T; t += 32) c += vis[s * T + t] != 0.f ? 1.f : 0.f;
+    c = warp_sum(c);
+    if (threadIdx.x == 0) cnt_s = fmaxf(c, 1.f);
+  }
+  __syncthreads();
+  float cnt = cnt_s;
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t)
+      if (vis[s * T + t] != 0.f) acc += ldf<TT>(tok + (s * T + t) * ldt + c);
+    stf<TO>(out + s * ldo + c, acc / cnt);
+  }
+}
+
+template <typename TX, typename TY>
+__global__ void gelu_fwd_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y, int64_t ldy,
+                                int64_t rows, int cols) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int64_t r = idx / cols;
+  int c = (int)(idx % cols);
+  stf<TY>(y + r * ldy + c, gelu_tanh(ldf<TX>(x + r * ldx + c)));
+}
+
+static inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace spa3d
+
+using namespace spa3d;
+
+extern "C" {
+
+int spa3d_fourier_features(const float* x, int64_t ldx, void* out, int64_t ldo, int out_dtype,
+                           int64_t rows, int C, int num_freq, float scale_factor, int append_time,
+                           int tail_zero, int exact, int out_row_group, void* stream) {
+  SPA3D_REQUIRE(num_freq > 0 && num_freq <= 64, "fourier: num_freq must be in 1..64");
+  if (rows == 0) return 0;
+  FourierScales sc;
+  for (int i = 0; i < num_freq; ++i) sc.s[i] = (float)pow(2.0, (double)i / 3.0);
+  int Ctot = C + (append_time > 0 ? 1 : 0) + (tail_zero ? 1 : 0);
+  int64_t total = rows * Ctot * num_freq;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(out_dtype, TO, {
+    if (exact)
+      fourier_kernel<TO, true><<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, (TO*)out, ldo, rows, C, Ctot, num_freq, scale_factor, append_time, out_row_group, sc);
+    else
+      fourier_kernel<TO, false><<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, (TO*)out, ldo, rows, C, Ctot, num_freq, scale_factor, append_time, out_row_group, sc);
+  });
+  return check_launch("fourier_features");
+}
+
+int spa3d_set_rows(void* dst, int64_t ld, int dst_dtype, int64_t row_stride, const float* vec,
+                   int64_t rows, int cols, void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(dst_dtype, TD, {
+    set_rows_kernel<TD><<<blocks_for(rows * cols, 256), 256, 0, st>>>((TD*)dst, ld, row_stride, vec, rows, cols);
+  });
+  return check_launch("set_rows");
+}
+
+int spa3d_convert(const void* src, int64_t lds, int src_dtype, void* dst, int64_t ldd, int dst_dtype,
+                  int64_t rows, int cols, int out_row_group, void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(src_dtype, TS, SPA3D_DISPATCH(dst_dtype, TD, {
+    convert_kernel<TS, TD><<<blocks_for(rows * cols, 256), 256, 0, st>>>((const TS*)src, lds, (TD*)dst, ldd, rows, cols, out_row_group);
+  }));
+  return check_launch("convert");
+}
+
+int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* scale, void* y,
+                        int64_t ldy, int y_dtype, float* mean_out, float* rstd_out, int64_t rows,
+                        int d, void* stream) {
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(x_dtype, TX, SPA3D_DISPATCH(y_dtype, TY, {
+    layernorm_fwd_kernel<TX, TY><<<blocks_for(rows, 8), 256, 0, st>>>((const TX*)x, ldx, scale, (TY*)y, ldy, mean_out, rstd_out, rows, d);
+  }));
+  return check_launch("layernorm_fwd");
+}
+
+int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
+                        const float* mean, const float* rstd, const void* dy, int64_t lddy,
+                        int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int dx_accumulate,
+                        float* dscale_partial, int num_partials, int64_t rows, int d, void* stream) {
+  SPA3D_REQUIRE(num_partials > 0, "layernorm_bwd: num_partials must be > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(x_dtype, TX, SPA3D_DISPATCH(dy_dtype, TDY, SPA3D_DISPATCH(dx_dtype, TDX, {
+    layernorm_bwd_kernel<TX, TDY, TDX><<<num_partials, 256, d * sizeof(float), st>>>(
+        (const TX*)x, ldx, scale, mean, rstd, (const TDY*)dy, lddy, (TDX*)dx, lddx, dx_accumulate, dscale_partial, rows, d);
+  })));
+  return check_launch("layernorm_bwd");
+}
+
+int spa3d_head_rmsnorm_fwd(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
+                           float* rstd_out, int64_t rows, int heads, int Dh, void* stream) {
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(dtype, T, {
+    head_rmsnorm_fwd_kernel<T><<<blocks_for(rows * heads, 8), 256, 0, st>>>((T*)buf, ld, scale, out_mul, rstd_out, rows, heads, Dh);
+  });
+  return check_launch("head_rmsnorm_fwd");
+}
+
+int spa3d_head_rmsnorm_bwd(const void* y, int64_t ldy, int y_dtype, const float* scale, float out_mul,
+                           const float* rstd, void* dy_inout, int64_t ldd, int d_dtype,
+                           float* dscale_partial, int num_partials, int64_t rows, int heads, int Dh,
+                           void* stream) {
+  SPA3D_REQUIRE(num_partials > 0, "head_rmsnorm_bwd: num_partials must be > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(y_dtype, TY, SPA3D_DISPATCH(d_dtype, TD, {
+    head_rmsnorm_bwd_kernel<TY, TD><<<num_partials, 256, Dh * sizeof(float), st>>>(
+        (const TY*)y, ldy, scale, out_mul, rstd, (TD*)dy_inout, ldd, dscale_partial, rows, heads, Dh);
+  }));
+  return check_launch("head_rmsnorm_bwd");
+}
+
+int spa3d_masked_mean_fwd(const void* tok, int64_t ldt, int tok_dtype, const float* visible, void* out,
+                          int64_t ldo, int out_dtype, int64_t S, int T, int W, void* stream) {
+  if (S == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(tok_dtype, TT, SPA3D_DISPATCH(out_dtype, TO, {
+    masked_mean_kernel<TT, TO><<<(unsigned)S, 128, 0, st>>>((const TT*)tok, ldt, visible, (TO*)out, ldo, T, W);
+  }));
+  return check_launch("masked_mean_fwd");
+}
+
+int spa3d_gelu_fwd(const void* x, int64_t ldx, int x_dtype, void* y, int64_t ldy, int y_dtype,
+                   int64_t rows, int cols, void* stream) {
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(x_dtype, TX, SPA3D_DISPATCH(y_dtype, TY, {
+    gelu_fwd_kernel<TX, TY><<<blocks_for(rows * cols, 256), 256, 0, st>>>((const TX*)x, ldx, (TY*)y, ldy, rows, cols);
+  }));
+  return check_launch("gelu_fwd");
+}
+
+int spa3d_build_key_mask(const float* visible, const int32_t* boundary_frame, uint8_t* mask, int B,
+                         int N, int T, int has_readout, void* stream) {
+  int64_t total = (int64_t)B * N * (T + (has_readout ? 1 : 0));
+  if (total == 0) return 0;
+  key_mask_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(visible, boundary_frame, mask, B, N, T, has_readout ? 1 : 0);
+  return check_launch("build_key_mask");
+}
+
+int spa3d_quantize_fwd(const float* x, const float* noise, float* y, uint8_t* pass_mask, int64_t n,
+                       int discretize, void* stream) {
+  SPA3D_REQUIRE(!discretize || noise, "quantize: discretize needs a noise tensor");
+  if (n == 0) return 0;
+  quantize_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, noise, y, pass_mask, n, discretize);
+  return check_launch("quantize_fwd");
+}
+
+int spa3d_decoder_tokens_fwd(const void* lat, int lat_dtype, const void* query_emb, int qe_dtype,
+                             const int32_t* query_frame, void* tokens, int tok_dtype, int B, int Q,
+                             int L, int C, void* stream) {
+  int64_t rows = (int64_t)B * Q * (L + 1);
+  if (rows == 0) return 0;
+  SPA3D_REQUIRE(C >= 128, "decoder_tokens: latent width %d < 128", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(lat_dtype, TL, SPA3D_DISPATCH(qe_dtype, TQ, SPA3D_DISPATCH(tok_dtype, TT, {
+    decoder_tokens_fwd_kernel<TL, TQ, TT><<<(unsigned)rows, 256, 0, st>>>((const TL*)lat, (const TQ*)query_emb, query_frame, (TT*)tokens, B, Q, L, C);
+  })));
+  return check_launch("decoder_tokens_fwd");
+}
+
+int spa3d_decoder_tokens_bwd(const void* d_tokens, int tok_dtype, const int32_t* query_frame,
+                             float* d_lat, float* d_query_emb, int B, int Q, int L, int C,
+                             void* stream) {
+  int64_t blocks = (int64_t)B * L + (int64_t)B * Q;
+  if (blocks == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(tok_dtype, TT, {
+    decoder_tokens_bwd_kernel<TT><<<(unsigned)blocks, 256, 0, st>>>((const TT*)d_tokens, query_frame, d_lat, d_query_emb, B, Q, L, C);
+  });
+  return check_launch("decoder_tokens_bwd");
+}
+
+int spa3d_split_outputs(const float* head_out, float* tracks, float* visible_logits, int64_t rows,
+                        int T, int coords, float* certain_logits, void* stream) {
+  if (rows == 0) return 0;
+  SPA3D_REQUIRE(coords == 2 || coords == 3, "split_outputs: coords must be 2 or 3");
+  split_outputs_kernel<<<blocks_for(rows * T, 256), 256, 0, (cudaStream_t)stream>>>(head_out, tracks, visible_logits, certain_logits, rows, T, coords);
+  return check_launch("split_outputs");
+}
+
+int spa3d_loss_fwd(const float* head_out, const float* target_tracks, const float* target_vis,
+                   float* sums, int64_t rows, int T, void* stream) {
+  if (rows == 0) return 0;
+  int64_t total = rows * T;
+  unsigned nb = blocks_for(total, 256);
+  unsigned cap = (unsigned)num_sms() * 8;
+  if (nb > cap) nb = cap;
+  loss_fwd_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(head_out, target_tracks, target_vis, sums, rows, T);
+  return check_launch("loss_fwd");
+}
+
+int spa3d_loss_bwd(const float* head_out, const float* target_tracks, const float* target_vis,
+                   float* d_head_out, float l1_w, float bce_w, float inv_denom, int64_t rows, int T,
+                   void* stream) {
+  if (rows == 0) return 0;
+  loss_bwd_kernel<<<blocks_for(rows * T, 256), 256, 0, (cudaStream_t)stream>>>(head_out, target_tracks, target_vis, d_head_out, l1_w, bce_w, inv_denom, rows, T);
+  return check_launch("loss_bwd");
+}
+
+int spa3d_gelu_bwd(const void* pre, int64_t ldp, int p_dtype, const void* dy, int64_t lddy,
+                   int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int64_t rows, int cols,
+                   void* stream) {
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_DISPATCH(p_dtype, TP, SPA3D_DISPATCH(dy_dtype, TDY, SPA3D_DISPATCH(dx_dtype, TDX, {
+    gelu_bwd_kernel<TP, TDY, TDX><<<blocks_for(rows * cols, 256), 256, 0, st>>>((const TP*)pre, ldp, (const TDY*)dy, lddy, (TDX*)dx, lddx, rows, cols);
+  })));
+  return check_launch("gelu_bwd");
+}
+
+int spa3d_colsum(const void* x, int64_t ldx, int dtype, float* out, int accumulate, int64_t rows,
+                 int cols, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) zero_kernel<<<blocks_for(cols, 256), 256, 0, st>>>(out, cols);
+  if (rows == 0) return check_launch("colsum");
+  int64_t slabs = (rows + 1023) / 1024;
+  if (slabs > 4096) slabs = 4096;
+  int64_t rpb = (rows + slabs - 1) / slabs;
+  dim3 grid((cols + 31) / 32, (unsigned)slabs);
+  SPA3D_DISPATCH(dtype, T, {
+    colsum_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, out, rows, cols, rpb);
+  });
+  return check_launch("colsum");
+}
+
+int spa3d_axpy(float* y, const float* x, float alpha, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  axpy_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y, x, alpha, n);
+  return check_launch("axpy");
+}
+
+int spa3d_sumsq(const float* g, int64_t n, float* sumsq, void* stream) {
+  if (n == 0) return 0;
+  unsigned nb = blocks_for(n, 1024);
+  unsigned cap = (unsigned)num_sms() * 8;
+  if (nb > cap) nb = cap;
+  sumsq_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(g, n, sumsq);
+  return check_launch("sumsq");
+}
+
+int spa3d_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
+                     float clip_norm, float lr, float b1, float b2, float eps, float wd, int step,
+                     void* stream) {
+  if (n == 0) return 0;
+  float bc1 = (float)(1.0 - pow((double)b1, (double)step)), bc2 = (float)(1.0 - pow((double)b2, (double)step));
+  adamw_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sumsq, clip_norm, lr, b1, b2, eps, wd, bc1, bc2);
+  return check_launch("adamw_step");
+}
+
+}  // extern "C"

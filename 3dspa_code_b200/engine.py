@@ -1,0 +1,263 @@
+"""Forward pass of the 3D semantic point-track autoencoder on the B200 kernels.
+
+Mirrors TrackAutoEncoder3D.encode / get_decoder_context / decode
+(/root/reference/track_autoencoder_3d.py:123-307) and the transformer blocks of attention.py,
+as a straight-line sequence of C-ABI kernel launches (ops.py).  Also runs TRAJAN 2D
+(track_autoencoder.py:205-345) through the same kernels.
+
+Precision modes
+  "bf16"  activations/weights bf16 into tcgen05 GEMMs and mma attention, fp32 accumulate,
+          fp32 residual stream and outputs            (north_star tolerance 2e-2)
+  "fp32"  everything float32 on the SIMT kernels        (north_star tolerance 1e-4)
+
+Data layout in HBM: every activation is a row-major [tokens, width] matrix; a "sequence" is a
+run of consecutive rows (T+1 = 151 rows per support track, 129 per query, 128 latents per clip).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops, params as P
+
+
+@dataclass
+class DeviceWeights:
+    """Packed parameters resident on the GPU: fp32 masters + compute-dtype shadows."""
+
+    meta: dict
+    f32: Dict[str, torch.Tensor]   # packed layout, float32 (norm scales, biases, masters)
+    c: Dict[str, torch.Tensor]     # matrices in the compute dtype ([out, in], K contiguous)
+    cdt: torch.dtype
+    embed_bias: torch.Tensor = None
+
+    @staticmethod
+    def from_tree(tree, precision="bf16", device="cuda"):
+        meta = P.tree_meta(tree)
+        packed = P.pack(tree)
+        cdt = torch.bfloat16 if precision == "bf16" else torch.float32
+        f32 = {k: torch.from_numpy(v).to(device) for k, v in packed.items()}
+        w = DeviceWeights(meta, f32, {}, cdt)
+        w.refresh()
+        return w
+
+    def refresh(self):
+        """(Re)derive compute-dtype shadows from the fp32 masters (after an optimiser step)."""
+        for k, v in self.f32.items():
+            if v.dim() == 2 and (k.endswith("_t") or k.endswith(".Wt")):
+                if self.cdt == torch.float32:
+                    self.c[k] = v
+                else:
+                    dst = self.c.get(k)
+                    if dst is None:
+                        dst = torch.empty_like(v, dtype=self.cdt)
+                        self.c[k] = dst
+                    ops.convert(v, dst)
+        eb = self.f32["embed.b_track"].clone()
+        for k in ("embed.b_dino", "embed.b_depth"):
+            if k in self.f32:
+                ops.axpy(eb, self.f32[k], 1.0)
+        self.embed_bias = eb
+
+
+def _as_dev(x, dtype, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype, non_blocking=True)
+
+
+class Engine:
+    """Inference-time executor (no autograd).  Training uses autograd_fns.TrainEngine."""
+
+    def __init__(self, cfg, weights: DeviceWeights, exact_sin: Optional[bool] = None):
+        self.cfg = cfg
+        self.w = weights
+        self.cdt = weights.cdt
+        self.exact = (weights.cdt == torch.float32) if exact_sin is None else exact_sin
+        self.dev = weights.f32["latents_init"].device
+
+    # ---- transformer blocks (attention.py:11-185) ---------------------------------------------
+    def _attn_core(self, pre, q, k, v, batch, Lq, Lk, m, key_mask=None):
+        """per-head RMSNorm on q,k (+ q/sqrt(Dh)), then softmax(qk^T)v."""
+        H, Dh = m["heads"], m["Dh"]
+        ops.head_rmsnorm_fwd(q, self.w.f32[pre + "norm_query"], 1.0 / math.sqrt(Dh), H, Dh)
+        ops.head_rmsnorm_fwd(k, self.w.f32[pre + "norm_key"], 1.0, H, Dh)
+        o = torch.empty(q.shape[0], H * Dh, device=self.dev, dtype=self.cdt)
+        ops.attention_fwd(q, k, v, o, batch, H, Lq, Lk, Dh, key_mask)
+        return o
+
+    def transformer(self, short, x, batch, L, key_mask=None, kv=None, Lkv=0, out_rows="all"):
+        """ImprovedTransformer (attention.py:22-53) on x [batch*L, d] (fp32 residual stream).
+
+        kv: optional [batch*Lkv, d_kv] cross-attention inputs (compute dtype, un-normed).
+        out_rows: "all" -> final LayerNorm of every token; "first" -> only token 0 of every sequence
+        (the read-out token, track_autoencoder_3d.py:187,286).
+        """
+        m = self.w.meta[short]
+        A = m["heads"] * m["Dh"]
+        w, f = self.w.c, self.w.f32
+        for i in range(m["layers"]):
+            pre = f"{short}.{i}."
+            xn = ops.layernorm_fwd(x, f[pre + "norm_q"], self.cdt)
+            qkv = ops.gemm(xn, w[pre + "self.Wqkv_t"])
+            o = self._attn_core(pre + "self.", qkv[:, :A], qkv[:, A : 2 * A], qkv[:, 2 * A :], batch, L, L, m, key_mask)
+            a = ops.gemm(o, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x, out_dtype=torch.float32)
+            del qkv, o
+            if kv is not None:
+                qc = ops.gemm(xn, w[pre + "cross.Wq_t"])
+                kvp = ops.gemm(kv, w[pre + "cross.Wkv_t"])
+                oc = self._attn_core(pre + "cross.", qc, kvp[:, :A], kvp[:, A:], batch, L, Lkv, m, None)
+                a = ops.gemm(oc, w[pre + "cross.Wo_t"], f[pre + "cross.bo"], residual=a, out_dtype=torch.float32)
+                del qc, kvp, oc
+            an = ops.layernorm_fwd(a, f[pre + "norm_attn"], self.cdt)
+            h = ops.gemm(an, w[pre + "W1_t"], f[pre + "b1"], act=ops.ACT_GELU)
+            x = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=a, out_dtype=torch.float32)
+            del xn, an, h, a
+        d = m["d"]
+        if out_rows == "first":
+            return ops.layernorm_fwd(x, f[f"{short}.norm_encoder"], self.cdt, rows=batch, ldx=L * d, d=d)
+        return ops.layernorm_fwd(x, f[f"{short}.norm_encoder"], self.cdt)
+
+    # ---- encoder ---------------------------------------------------------------------------------
+    def embed_tracks(self, tracks, dino, depth, readout):
+        """embed_track_pos_visible (+ read-out slot): returns the fp32 token matrix
+        [B*N*(T+ro), W] (track_autoencoder_3d.py:123-165)."""
+        cfg, meta = self.cfg, self.w.meta
+        B, N, T, C = tracks.shape
+        ro = 1 if readout else 0
+        rows = B * N * T
+        K = meta["fourier_in"] + (meta["dino_dim"] if dino is not None else 0) + (meta["depth_dim"] if depth is not None else 0)
+        wt = self.w.c["embed.Wt"]
+        bias = self.w.embed_bias
+        if K != wt.shape[1]:
+            # a feature the checkpoint has a projection for was not supplied (:140,145): use the
+            # matching column block of the concatenated kernel and only the biases in play
+            cols = list(range(meta["fourier_in"]))
+            off = meta["fourier_in"]
+            bias = self.w.f32["embed.b_track"].clone()
+            if meta["has_dino"]:
+                if dino is not None:
+                    cols += list(range(off, off + meta["dino_dim"]))
+                    ops.axpy(bias, self.w.f32["embed.b_dino"])
+                off += meta["dino_dim"]
+            if meta["has_depth"] and depth is not None:
+                cols += list(range(off, off + meta["depth_dim"]))
+                ops.axpy(bias, self.w.f32["embed.b_depth"])
+            wt = wt[:, cols].contiguous()
+        grp = T if ro else 0
+        a = torch.empty(B * N * (T + ro), K, device=self.dev, dtype=self.cdt)
+        if ro:
+            a.view(B * N, T + 1, K)[:, 0].zero_()
+        ops.fourier_features(tracks.view(rows, C), a, cfg.num_frequencies, cfg.track_scale_factor, append_time=T,
+                             exact=self.exact, out_row_group=grp)
+        off = meta["fourier_in"]
+        if dino is not None:
+            ops.convert(dino.view(rows, -1), a[:, off : off + meta["dino_dim"]], out_row_group=grp)
+            off += meta["dino_dim"]
+        if depth is not None:
+            ops.convert(depth.view(rows, -1), a[:, off : off + meta["depth_dim"]], out_row_group=grp)
+        x = ops.gemm(a, wt, bias, out_dtype=torch.float32)
+        if ro:
+            ops.set_rows(x, T + 1, self.w.f32["readout_token"].view(-1), B * N)
+        return x
+
+    def encode(self, inputs):
+        """encode (track_autoencoder_3d.py:190-204 / track_autoencoder.py:234-246) -> [B,128,latent] f32."""
+        meta = self.w.meta
+        dev = self.dev
+        tracks = _as_dev(inputs["support_tracks"], torch.float32, dev)
+        visible = _as_dev(inputs["support_tracks_visible"], torch.float32, dev)
+        boundary = _as_dev(inputs["boundary_frame"], torch.int32, dev)
+        B, N, T, _ = tracks.shape
+        three_d = meta["coords"] == 3
+        dino = depth = None
+        if three_d and self.cfg.use_dino and meta["has_dino"] and inputs.get("dino_features") is not None:
+            dino = _as_dev(inputs["dino_features"], torch.float32, dev)
+        if three_d and self.cfg.use_depth and meta["has_depth"] and inputs.get("depth_features") is not None:
+            depth = _as_dev(inputs["depth_features"], torch.float32, dev)
+        x = self.embed_tracks(tracks, dino, depth, readout=three_d)
+        key_mask = ops.build_key_mask(visible, boundary, has_readout=three_d)
+        L = T + (1 if three_d else 0)
+        if three_d:
+            st = self.transformer("itt", x, B * N, L, key_mask, out_rows="first")  # [B*N, W]
+        else:
+            tok = self.transformer("itt", x, B * N, L, key_mask)  # [B*N*T, W]
+            st = self._masked_mean(tok, visible, B * N, T)
+        del x
+        nl, E = meta["latent_tokens"], meta["E"]
+        lat = self.w.f32["latents_init"].unsqueeze(0).expand(B, nl, E).reshape(B * nl, E).contiguous()
+        lat = self.transformer("t2l", lat, B, nl, kv=st, Lkv=N)
+        z = ops.gemm(lat, self.w.c["compressor.Wt"], self.w.f32["compressor.b"], out_dtype=torch.float32)
+        return z.view(B, nl, meta["latent_dim"])
+
+    def _masked_mean(self, tok, visible, seqs, T):
+        """TRAJAN pooling (track_autoencoder.py:230-232): sum(tok*vis)/max(1,sum vis)."""
+        return ops.masked_mean_fwd(tok, visible.reshape(seqs, T).contiguous(), seqs, T, self.cdt)
+
+    # ---- decoder ---------------------------------------------------------------------------------
+    def get_decoder_context(self, inputs):
+        """get_decoder_context (track_autoencoder_3d.py:206-233): Fourier features of the query
+        xyz (always the exact sine: they are re-embedded at 1290x gain) and int32 query frames."""
+        cfg, dev = self.cfg, self.dev
+        coords = self.w.meta["coords"]
+        if "query_points" in inputs and inputs["query_points"] is not None:
+            qp = _as_dev(inputs["query_points"], torch.float32, dev)
+            B, Q, _ = qp.shape
+            xyz = qp[..., 1:].reshape(B * Q, coords).contiguous()
+            qframe = torch.round(qp[..., 0]).to(torch.int32).contiguous()  # half-to-even, like jnp.round
+        else:
+            B = inputs["support_tracks"].shape[0]
+            gc = torch.arange(32, dtype=torch.float32) / 32.0 + 1.0 / 64.0
+            qx, qy = torch.meshgrid(gc, gc, indexing="xy")
+            comps = [qx, qy] + ([torch.zeros_like(qx)] if coords == 3 else [])
+            grid = torch.stack(comps, dim=-1).reshape(-1, coords)
+            Q = grid.shape[0]
+            xyz = grid.unsqueeze(0).expand(B, Q, coords).reshape(B * Q, coords).contiguous().to(dev)
+            qframe = torch.zeros(B, Q, dtype=torch.int32, device=dev)
+        dq = torch.empty(B * Q, coords * 2 * cfg.num_frequencies, device=dev, dtype=torch.float32)
+        ops.fourier_features(xyz, dq, cfg.num_frequencies, cfg.track_scale_factor, exact=True)
+        return DecoderContext(dq.view(B, Q, -1), qframe, inputs.get("boundary_frame"))
+
+    def decode(self, latents, ctx, noise=None, discretize=True):
+        """decode (track_autoencoder_3d.py:248-307) -> head output [B*Q, 4T] f32."""
+        cfg, meta, dev = self.cfg, self.w.meta, self.dev
+        w, f = self.w.c, self.w.f32
+        latents = _as_dev(latents, torch.float32, dev)
+        B, nl, ld_ = latents.shape
+        if discretize:
+            if noise is None:
+                raise ValueError(
+                    "discretize=True needs the explicit `noise` tensor U[0,1) of shape [B,%d,%d]: the reference draws it "
+                    "from jax.random.uniform(PRNGKey(0)), which cannot be reproduced without JAX (DESIGN.md)" % (nl, ld_)
+                )
+            noise = _as_dev(noise, torch.float32, dev)
+        zq = ops.quantize_fwd(latents.reshape(B * nl, ld_), noise.reshape(B * nl, ld_) if discretize else None, discretize)
+        zc = zq if self.cdt == torch.float32 else ops.convert(zq, torch.empty_like(zq, dtype=self.cdt))
+        x = ops.gemm(zc, w["decompressor.Wt"], f["decompressor.b"], out_dtype=torch.float32)
+        C = meta["D"] - 128
+        lat = self.transformer("dec", x, B, nl)  # [B*nl, C] cdt
+        Q = ctx.query_frame.shape[1]
+        dq = ctx.decoder_query.reshape(B * Q, -1)
+        qfeat = torch.empty(B * Q, meta["query_in"], device=dev, dtype=self.cdt)
+        # query_frame // time_scale_factor (:268-269) is 0 for every in-range frame: tail_zero
+        if int(ctx.query_frame.max().item()) >= cfg.time_scale_factor or int(ctx.query_frame.min().item()) < 0:
+            raise ValueError("query frames outside [0, time_scale_factor) are not supported")
+        ops.fourier_features(dq, qfeat, cfg.num_frequencies, cfg.track_scale_factor, tail_zero=True, exact=self.exact)
+        qe = ops.gemm(qfeat, w["query_encoder.Wt"], f["query_encoder.b"], out_dtype=torch.float32)
+        tokens = torch.empty(B * Q * (nl + 1), meta["D"], device=dev, dtype=torch.float32)
+        ops.decoder_tokens_fwd(lat, qe, ctx.query_frame, tokens, B, Q, nl, C)
+        out = self.transformer("tra", tokens, B * Q, nl + 1, out_rows="first")  # [B*Q, D]
+        return ops.gemm(out, w["track_predictor.Wt"], f["track_predictor.b"], out_dtype=torch.float32)
+
+
+@dataclass
+class DecoderContext:
+    """TrackAutoEncoderDecoderContext (track_autoencoder.py:108-114)."""
+
+    decoder_query: torch.Tensor
+    query_frame: torch.Tensor
+    boundary_frame: object

@@ -1,0 +1,267 @@
+"""Tensor-level wrappers over the C ABI (include/spa3d_b200.h).
+
+PyTorch is used here only as plumbing: device memory (caching allocator), streams and dtypes.
+Every function passes raw device pointers, sizes and the current CUDA stream to
+lib3dspa_b200.so; nothing here computes on the host or falls back to torch kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+_TD = {F32: torch.float32, BF16: torch.bfloat16}
+
+launch_count = 0  # number of kernel-launching C-ABI calls issued (bench.py reports it)
+
+
+def dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype} (float32 / bfloat16 only)") from None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError("spa3d ops need CUDA tensors (there is no CPU path)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _ld(t):
+    if t.dim() < 2:
+        return t.shape[-1] if t.dim() == 1 else 1
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise ValueError("last dimension must be contiguous")
+    return t.stride(-2)
+
+
+def _call(name, *args):
+    global launch_count
+    launch_count += 1
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+def version():
+    return _lib.lib().spa3d_version()
+
+
+# ---- K0 ------------------------------------------------------------------------------------
+def lift_sample(tracks_2d, depth=None, dino=None, video_hw=None, intrinsics=None, out_dtype=torch.float32,
+                depth_feature_dim=256, want_xyz=True, want_dino=True, want_depth=True):
+    """tracks_2d [N,T,2] f32, depth [T,H,W,(1)] f32, dino [T,Hp,Wp,D] f32 -> (xyz, dino_feat, depth_feat)."""
+    N, T = tracks_2d.shape[:2]
+    dev = tracks_2d.device
+    H = W = Hp = Wp = D = 0
+    xyz = dfeat = zfeat = None
+    if depth is not None:
+        H, W = depth.shape[1:3]
+        if want_xyz:
+            xyz = torch.empty(N, T, 3, device=dev, dtype=torch.float32)
+        if want_depth:
+            zfeat = torch.empty(N, T, depth_feature_dim, device=dev, dtype=out_dtype)
+    if dino is not None and want_dino:
+        Hp, Wp, D = dino.shape[1:4]
+        dfeat = torch.empty(N, T, D, device=dev, dtype=out_dtype)
+    vh, vw = video_hw if video_hw is not None else (H, W)
+    intr = None
+    if intrinsics is not None:
+        intr = (ctypes.c_float * 4)(*[float(v) for v in intrinsics])
+    _call("spa3d_lift_sample", _p(tracks_2d), _p(depth), _p(dino), _p(xyz), _p(dfeat), _p(zfeat), _DT[out_dtype],
+          N, T, H, W, Hp, Wp, D, depth_feature_dim, vh, vw, ctypes.cast(intr, ctypes.c_void_p) if intr else None, _stream())
+    return xyz, dfeat, zfeat
+
+
+# ---- elementwise ---------------------------------------------------------------------------
+def fourier_features(x, out, num_freq=32, scale_factor=1.0, append_time=0, tail_zero=False, exact=True, out_row_group=0):
+    rows, C = x.shape
+    _call("spa3d_fourier_features", _p(x), _ld(x), _p(out), _ld(out), dt(out), rows, C, num_freq, float(scale_factor),
+          int(append_time), int(tail_zero), int(exact), int(out_row_group), _stream())
+    return out
+
+
+def convert(src, dst, out_row_group=0):
+    rows, cols = src.shape
+    _call("spa3d_convert", _p(src), _ld(src), dt(src), _p(dst), _ld(dst), dt(dst), rows, cols, int(out_row_group), _stream())
+    return dst
+
+
+def set_rows(dst, row_stride, vec, rows):
+    _call("spa3d_set_rows", _p(dst), _ld(dst), dt(dst), int(row_stride), _p(vec), int(rows), vec.numel(), _stream())
+    return dst
+
+
+def gemm(a, wt, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=None, impl=GEMM_AUTO):
+    """out[M,N] = act(a[M,K] @ wt[N,K]^T + bias) + residual."""
+    M, K = a.shape
+    N = wt.shape[0]
+    assert wt.shape[1] == K and wt.dtype == a.dtype, (a.shape, wt.shape, a.dtype, wt.dtype)
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype or a.dtype)
+    _call("spa3d_gemm", _p(a), _ld(a), _p(wt), _ld(wt), dt(a), _p(bias), int(act), _p(residual),
+          _ld(residual) if residual is not None else 0, dt(residual) if residual is not None else F32,
+          _p(out), _ld(out), dt(out), M, N, K, int(impl), _stream())
+    return out
+
+
+def gemm_strided(a, sam, sak, b, sbk, sbn, out, M, N, K, accumulate=False):
+    _call("spa3d_gemm_strided", _p(a), int(sam), int(sak), dt(a), _p(b), int(sbk), int(sbn), dt(b), _p(out), _ld(out),
+          dt(out), int(M), int(N), int(K), int(accumulate), _stream())
+    return out
+
+
+def layernorm_fwd(x, scale, out_dtype, rows=None, ldx=None, d=None, stats=False, out=None):
+    rows = x.shape[0] if rows is None else rows
+    d = x.shape[-1] if d is None else d
+    ldx = _ld(x) if ldx is None else ldx
+    if out is None:
+        out = torch.empty(rows, d, device=x.device, dtype=out_dtype)
+    mean = rstd = None
+    if stats:
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _call("spa3d_layernorm_fwd", _p(x), int(ldx), dt(x), _p(scale), _p(out), _ld(out), dt(out), _p(mean), _p(rstd), int(rows), int(d), _stream())
+    return (out, mean, rstd) if stats else out
+
+
+def layernorm_bwd(x, scale, mean, rstd, dy, dx, rows=None, ldx=None, lddx=None, d=None, accumulate=False, num_partials=296):
+    rows = x.shape[0] if rows is None else rows
+    d = x.shape[-1] if d is None else d
+    ldx = _ld(x) if ldx is None else ldx
+    lddx = _ld(dx) if lddx is None else lddx
+    partial = torch.empty(num_partials, d, device=x.device, dtype=torch.float32)
+    _call("spa3d_layernorm_bwd", _p(x), int(ldx), dt(x), _p(scale), _p(mean), _p(rstd), _p(dy), _ld(dy), dt(dy), _p(dx), int(lddx),
+          dt(dx), int(accumulate), _p(partial), num_partials, int(rows), int(d), _stream())
+    dscale = torch.empty(d, device=x.device, dtype=torch.float32)
+    colsum(partial, dscale)
+    return dscale
+
+
+def head_rmsnorm_fwd(buf, scale, out_mul, heads, Dh, save_rstd=False):
+    rows = buf.shape[0]
+    rstd = torch.empty(rows, heads, device=buf.device, dtype=torch.float32) if save_rstd else None
+    _call("spa3d_head_rmsnorm_fwd", _p(buf), _ld(buf), dt(buf), _p(scale), float(out_mul), _p(rstd), rows, heads, Dh, _stream())
+    return rstd
+
+
+def head_rmsnorm_bwd(y, scale, out_mul, rstd, d_io, heads, Dh, num_partials=296):
+    rows = y.shape[0]
+    partial = torch.empty(num_partials, Dh, device=y.device, dtype=torch.float32)
+    _call("spa3d_head_rmsnorm_bwd", _p(y), _ld(y), dt(y), _p(scale), float(out_mul), _p(rstd), _p(d_io), _ld(d_io), dt(d_io),
+          _p(partial), num_partials, rows, heads, Dh, _stream())
+    dscale = torch.empty(Dh, device=y.device, dtype=torch.float32)
+    colsum(partial, dscale)
+    return dscale
+
+
+def attention_fwd(q, k, v, out, batch, heads, Lq, Lk, Dh, key_mask=None, save_stats=False):
+    stats = torch.empty(batch, heads, Lq, 2, device=q.device, dtype=torch.float32) if save_stats else None
+    _call("spa3d_attention_fwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(out), _ld(out), dt(q), _p(key_mask), _p(stats),
+          int(batch), heads, Lq, Lk, Dh, _stream())
+    return stats
+
+
+def attention_bwd(q, k, v, o, d_o, dq, dk, dv, stats, batch, heads, Lq, Lk, Dh, key_mask=None):
+    delta = torch.empty(batch * heads * Lq, device=q.device, dtype=torch.float32)
+    _call("spa3d_attention_bwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), _ld(o), _p(d_o), _ld(d_o), _p(dq), _ld(dq),
+          _p(dk), _ld(dk), _p(dv), _ld(dv), dt(q), _p(key_mask), _p(stats), _p(delta), int(batch), heads, Lq, Lk, Dh, _stream())
+
+
+def masked_mean_fwd(tok, visible, S, T, out_dtype):
+    W = tok.shape[1]
+    out = torch.empty(S, W, device=tok.device, dtype=out_dtype)
+    _call("spa3d_masked_mean_fwd", _p(tok), _ld(tok), dt(tok), _p(visible), _p(out), _ld(out), dt(out), int(S), int(T), W, _stream())
+    return out
+
+
+def gelu_fwd(x, y):
+    rows, cols = x.shape
+    _call("spa3d_gelu_fwd", _p(x), _ld(x), dt(x), _p(y), _ld(y), dt(y), rows, cols, _stream())
+    return y
+
+
+def build_key_mask(visible, boundary_frame, has_readout=True):
+    B, N, T = visible.shape[:3]
+    mask = torch.empty(B, N, T + (1 if has_readout else 0), device=visible.device, dtype=torch.uint8)
+    _call("spa3d_build_key_mask", _p(visible), _p(boundary_frame), _p(mask), B, N, T, int(has_readout), _stream())
+    return mask
+
+
+def quantize_fwd(x, noise, discretize=True, save_mask=False):
+    y = torch.empty_like(x)
+    mask = torch.empty(x.shape, device=x.device, dtype=torch.uint8) if save_mask else None
+    _call("spa3d_quantize_fwd", _p(x), _p(noise), _p(y), _p(mask), x.numel(), int(discretize), _stream())
+    return (y, mask) if save_mask else y
+
+
+def decoder_tokens_fwd(lat, query_emb, query_frame, tokens, B, Q, L, C):
+    _call("spa3d_decoder_tokens_fwd", _p(lat), dt(lat), _p(query_emb), dt(query_emb), _p(query_frame), _p(tokens), dt(tokens), B, Q, L, C, _stream())
+    return tokens
+
+
+def decoder_tokens_bwd(d_tokens, query_frame, d_lat, d_qe, B, Q, L, C):
+    _call("spa3d_decoder_tokens_bwd", _p(d_tokens), dt(d_tokens), _p(query_frame), _p(d_lat), _p(d_qe), B, Q, L, C, _stream())
+
+
+def split_outputs(head_out, T, coords=3):
+    rows = head_out.shape[0]
+    tracks = torch.empty(rows, T, coords, device=head_out.device, dtype=torch.float32)
+    vis = torch.empty(rows, T, 1, device=head_out.device, dtype=torch.float32)
+    cert = torch.empty(rows, T, 1, device=head_out.device, dtype=torch.float32)
+    _call("spa3d_split_outputs", _p(head_out), _p(tracks), _p(vis), rows, T, coords, _p(cert), _stream())
+    return tracks, vis, cert
+
+
+def loss_fwd(head_out, target_tracks, target_vis, sums, T):
+    _call("spa3d_loss_fwd", _p(head_out), _p(target_tracks), _p(target_vis), _p(sums), head_out.shape[0], T, _stream())
+    return sums
+
+
+def loss_bwd(head_out, target_tracks, target_vis, l1_w, bce_w, inv_denom, T):
+    d = torch.empty_like(head_out)
+    _call("spa3d_loss_bwd", _p(head_out), _p(target_tracks), _p(target_vis), _p(d), float(l1_w), float(bce_w), float(inv_denom), head_out.shape[0], T, _stream())
+    return d
+
+
+def gelu_bwd(pre, dy, dx):
+    rows, cols = pre.shape
+    _call("spa3d_gelu_bwd", _p(pre), _ld(pre), dt(pre), _p(dy), _ld(dy), dt(dy), _p(dx), _ld(dx), dt(dx), rows, cols, _stream())
+    return dx
+
+
+def colsum(x, out, accumulate=False):
+    rows, cols = x.shape
+    _call("spa3d_colsum", _p(x), _ld(x), dt(x), _p(out), int(accumulate), rows, cols, _stream())
+    return out
+
+
+def axpy(y, x, alpha=1.0):
+    _call("spa3d_axpy", _p(y), _p(x), float(alpha), y.numel(), _stream())
+    return y
+
+
+def sumsq(g, out):
+    _call("spa3d_sumsq", _p(g), g.numel(), _p(out), _stream())
+
+
+def adamw_step(p, g, m, v, sumsq_t, clip_norm, lr, b1, b2, eps, wd, step):
+    _call("spa3d_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(sumsq_t), float(clip_norm), float(lr), float(b1), float(b2),
+          float(eps), float(wd), int(step), _stream())
+
+
+def inv_sqrt(d):
+    return 1.0 / math.sqrt(d)

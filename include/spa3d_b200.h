@@ -1,0 +1,216 @@
+/*
+ * spa3d_b200.h - C ABI of lib3dspa_b200.so: the B200 (sm_100a) kernels behind the 3DSPA hot path.
+ *
+ * The reference (TheProParadox/3dspa_code) is pure JAX/Flax: it has no plugin / FFI layer.  The
+ * boundary it offers is the Flax module call `TrackAutoEncoder3D.apply({'params': p}, batch)`
+ * (track_autoencoder_3d.py:309-357) whose body XLA lowers to device kernels.  Each entry point
+ * below replaces one group of those XLA-emitted ops and is shaped the
+ * way an XLA FFI custom call (or a torch custom op) binds a kernel: caller-owned device buffers
+ * as plain pointers, integer sizes / leading dimensions, scalar attributes, an explicit
+ * cudaStream_t, and an int status (0 = ok).  The library never allocates, frees or synchronises
+ * and holds no mutable global state; every call is re-entrant.  See INTEGRATION.md for the
+ * XLA-FFI and torch custom-op bindings.
+ *
+ * Conventions
+ *   - all matrices are row-major; `ld*` = elements between consecutive rows.
+ *   - dtype codes: SPA3D_F32 = 0, SPA3D_BF16 = 1.
+ *   - "tokens" = rows of the flattened [sequences x length, width] activation matrix.
+ *   - stream is a cudaStream_t passed as void*.
+ *   - on failure the call returns non-zero; spa3d_last_error() gives a thread-local message.
+ */
+#ifndef SPA3D_B200_H_
+#define SPA3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPA3D_F32 0
+#define SPA3D_BF16 1
+
+#define SPA3D_ACT_NONE 0
+#define SPA3D_ACT_GELU_TANH 1 /* flax nn.gelu(approximate=True), attention.py:106 */
+
+#define SPA3D_GEMM_AUTO 0   /* tcgen05 when operands are bf16 and shapes allow, else SIMT fp32 */
+#define SPA3D_GEMM_SIMT 1   /* fp32 FMA path (the "fp32-accumulate" accurate mode)           */
+#define SPA3D_GEMM_TCGEN05 2 /* force the tcgen05/TMEM/TMA kernel; error if not applicable   */
+
+int spa3d_version(void);
+const char* spa3d_last_error(void);
+
+/* ---- K0: feature lifting (inference.py:287-447) ------------------------------------------
+ * One pass over N x T track points: bilinear depth sample + pinhole unprojection
+ * (lift_2d_to_3d, :287-336), bilinear DINO patch sample (:339-395) and the 256-channel depth
+ * feature (:398-447: ch0=d, ch1=d/10, ch2=d_t-d_{t-1}, rest 0).  float32 arithmetic in the
+ * reference's operation order (bit-exact with the NumPy code for float32 inputs).
+ *   tracks_2d [N,T,2] f32 (pixels)   depth [T,H,W] f32   dino [T,Hp,Wp,D] f32
+ *   xyz [N,T,3] f32   dino_out [N,T,D] (f32|bf16)   depth_out [N,T,Cd] (f32|bf16)
+ * Any of depth/dino/xyz/dino_out/depth_out may be NULL to skip that output.
+ * intrinsics = {fx, fy, cx, cy} as float (host values). */
+int spa3d_lift_sample(const float* tracks_2d, const float* depth, const float* dino,
+                      float* xyz, void* dino_out, void* depth_out, int out_dtype,
+                      int N, int T, int H, int W, int Hp, int Wp, int D, int Cd,
+                      int video_H, int video_W, const float* intrinsics, void* stream);
+
+/* ---- a1: SinusoidalEmbedding (track_autoencoder.py:18-38) --------------------------------
+ * out[r, c*2F + f] = sin(x[r,c]/scale * 2^(f/3)),  out[r, c*2F + F + f] = sin(... + pi/2).
+ * x [rows, C] f32 (ldx).  If append_time > 0 an extra coordinate (r % append_time)/append_time
+ * is appended (the fr_id of track_autoencoder_3d.py:126-131).  If tail_zero != 0 one more
+ * coordinate equal to 0 is appended (the query_frame // 150.0 feature, :268-269, defect D6).
+ * exact != 0: correctly-rounded float32 sine (double-precision evaluation).
+ * out [*, ldo] (f32|bf16), written at column offset 0.  out_row_group > 0 leaves room for one
+ * extra leading row per group of that many input rows: output row = r + r/out_row_group + 1
+ * (the read-out token slot of track_autoencoder_3d.py:161-165). */
+int spa3d_fourier_features(const float* x, int64_t ldx, void* out, int64_t ldo, int out_dtype,
+                           int64_t rows, int C, int num_freq, float scale_factor,
+                           int append_time, int tail_zero, int exact, int out_row_group,
+                           void* stream);
+
+/* Row-wise dtype conversion / strided copy: dst[r', 0:cols] = (dst_dtype) src[r, 0:cols],
+ * r' = r (+ r/out_row_group + 1 when out_row_group > 0). */
+int spa3d_convert(const void* src, int64_t lds, int src_dtype, void* dst, int64_t ldd,
+                  int dst_dtype, int64_t rows, int cols, int out_row_group, void* stream);
+
+/* dst[i*row_stride, 0:cols] = vec[0:cols] for i < rows  (writes the learned read-out token,
+ * ParamStateInit, track_autoencoder.py:41-53, into slot 0 of every sequence). */
+int spa3d_set_rows(void* dst, int64_t ld, int dst_dtype, int64_t row_stride, const float* vec,
+                   int64_t rows, int cols, void* stream);
+
+/* ---- K2/K4/K5/K9/K11: dense contractions ---------------------------------------------------
+ * C = epilogue(A[M,K] . W + bias) (+ residual), the Flax Dense / DenseGeneral of
+ * attention.py:106-107,154-183 and track_autoencoder_3d.py:73-115.
+ *   A      [M,K]  lda, a_dtype
+ *   Wt     [N,K]  ldw, a_dtype  - the Flax kernel [K,N] TRANSPOSED (K contiguous)
+ *   bias   [N] f32 or NULL;  act applied after bias;  residual [M,N] ldr, r_dtype or NULL,
+ *          added after the activation;  C [M,N] ldc, c_dtype.
+ * impl selects the kernel (SPA3D_GEMM_*).  The tcgen05 kernel needs bf16 A/Wt, K % 8 == 0 and
+ * 16-byte aligned rows. */
+int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
+               const float* bias, int act, const void* residual, int64_t ldr, int r_dtype,
+               void* C, int64_t ldc, int c_dtype, int64_t M, int N, int K, int impl,
+               void* stream);
+
+/* General strided fp32-accumulate GEMM used by the backward pass:
+ *   C[m,n] (+)= sum_k A(m,k) * B(k,n),  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].
+ * accumulate != 0 adds into C (C must be f32 then). */
+int spa3d_gemm_strided(const void* A, int64_t sam, int64_t sak, int a_dtype,
+                       const void* B, int64_t sbk, int64_t sbn, int b_dtype,
+                       void* C, int64_t ldc, int c_dtype, int64_t M, int N, int64_t K,
+                       int accumulate, void* stream);
+
+/* ---- LayerNorm(use_bias=False) (attention.py:49,76,103; flax eps 1e-6, fast variance) ------
+ * y[r,:] = (x[r,:]-mean)*rsqrt(var+1e-6)*scale.  x [rows,d] ldx x_dtype; y ldy y_dtype.
+ * mean_out / rstd_out ([rows] f32) may be NULL.  row_stride_tokens > 1 normalises only rows
+ * r*row_stride_tokens (used to read token 0 of every sequence, track_autoencoder_3d.py:187,286). */
+int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
+                        void* y, int64_t ldy, int y_dtype, float* mean_out, float* rstd_out,
+                        int64_t rows, int d, void* stream);
+int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
+                        const float* mean, const float* rstd, const void* dy, int64_t lddy,
+                        int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int dx_accumulate,
+                        float* dscale_partial, int num_partials, int64_t rows, int d,
+                        void* stream);
+
+/* ---- per-head RMSNorm of q and k (attention.py:166-167) + q/sqrt(Dh) (flax attention) ------
+ * In place on a packed projection buffer: for every row and head h < heads,
+ *   buf[r, h*Dh : (h+1)*Dh] = x * rsqrt(mean(x^2)+1e-6) * scale[:] * out_mul.
+ * rstd_out [rows, heads] f32 may be NULL (saved for backward). */
+int spa3d_head_rmsnorm_fwd(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
+                           float* rstd_out, int64_t rows, int heads, int Dh, void* stream);
+int spa3d_head_rmsnorm_bwd(const void* y, int64_t ldy, int y_dtype, const float* scale,
+                           float out_mul, const float* rstd, void* dy_inout, int64_t ldd,
+                           int d_dtype, float* dscale_partial, int num_partials, int64_t rows,
+                           int heads, int Dh, void* stream);
+
+/* ---- K3/K6: softmax(q k^T [+ key mask]) v  (flax nn.dot_product_attention, attention.py:175)
+ * Batched over `batch` independent sequences and `heads` heads.
+ *   q [batch*Lq, *] ldq : head h at columns [h*Dh, (h+1)*Dh)   (already RMS-normed and /sqrt(Dh))
+ *   k, v [batch*Lk, *] ldk/ldv, same column convention;  o [batch*Lq, heads*Dh] ldo.
+ *   key_mask [batch, Lk] uint8 or NULL: 0 => logit replaced by -FLT_MAX (finfo.min semantics,
+ *   an all-masked row yields uniform weights).
+ *   lse_out [batch, heads, Lq, 2] f32 or NULL: softmax statistics saved for the backward,
+ *   (row max, 1/row sum) - kept separate so all-masked rows (max = -FLT_MAX) stay exact.
+ * dtype applies to q,k,v,o.  Lq==Lk<=256 with a mask is the per-track temporal self-attention
+ * (track_autoencoder_3d.py:182-184); Lq=128, Lk=N is the latents<-tracks cross-attention (:201). */
+int spa3d_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                        int64_t ldv, void* o, int64_t ldo, int dtype, const uint8_t* key_mask,
+                        float* lse_out, int64_t batch, int heads, int Lq, int Lk, int Dh,
+                        void* stream);
+int spa3d_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                        int64_t ldv, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
+                        void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                        int dtype, const uint8_t* key_mask, const float* lse, float* delta_ws,
+                        int64_t batch, int heads, int Lq, int Lk, int Dh, void* stream);
+/* delta_ws: caller-provided scratch, [batch*heads*Lq] f32. */
+
+/* ---- R1 key mask (track_autoencoder_3d.py:167-184, repaired) -------------------------------
+ * mask[b,n,0] = 1 (if has_readout); mask[b,n,j] = visible[b,n,t]!=0 && t < boundary[b]. */
+int spa3d_build_key_mask(const float* visible, const int32_t* boundary_frame, uint8_t* mask,
+                         int B, int N, int T, int has_readout, void* stream);
+
+/* ---- TRAJAN pooling (track_autoencoder.py:230-232) -----------------------------------------
+ * out[s,:] = sum_t tok[s,t,:]*(vis[s,t]!=0) / max(1, sum_t (vis[s,t]!=0)).  tok [S*T, W]. */
+int spa3d_masked_mean_fwd(const void* tok, int64_t ldt, int tok_dtype, const float* visible,
+                          void* out, int64_t ldo, int out_dtype, int64_t S, int T, int W,
+                          void* stream);
+
+/* elementwise tanh-GELU: y = gelu(x) (used by the training path, which keeps the pre-activation) */
+int spa3d_gelu_fwd(const void* x, int64_t ldx, int x_dtype, void* y, int64_t ldy, int y_dtype,
+                   int64_t rows, int cols, void* stream);
+
+/* ---- K7: clip / quantise / noise with straight-through gradient (:251-260) -----------------
+ * y = clip(x,-1,1); if discretize: y = round_half_even(y*128)/128 + noise/128 - 1/256.
+ * pass_mask (uint8, may be NULL) records |x|<=1 for the straight-through backward. */
+int spa3d_quantize_fwd(const float* x, const float* noise, float* y, uint8_t* pass_mask,
+                       int64_t n, int discretize, void* stream);
+
+/* ---- K10: decoder token assembly (track_autoencoder_3d.py:276-284, append_time_feat :235-246)
+ * tokens[b,q,0,:]   = query_emb[b,q,:]                      (D = C + 128 channels)
+ * tokens[b,q,1+n,:] = [ lat[b,n,0:C] , lat[b,n,5*t:5*t+128] ]   t = query_frame[b,q]
+ * (window entries beyond C are 0, as in the reference's eye() einsum).
+ * lat [B,L,C] lat_dtype; query_emb [B*Q, D]; tokens [B*Q*(L+1), D] tok_dtype. */
+int spa3d_decoder_tokens_fwd(const void* lat, int lat_dtype, const void* query_emb, int qe_dtype,
+                             const int32_t* query_frame, void* tokens, int tok_dtype, int B, int Q,
+                             int L, int C, void* stream);
+/* d_lat[b,n,c] = sum_q ( d_tok[b,q,1+n,c] + window contributions ); d_qe = d_tok[b,q,0,:]. */
+int spa3d_decoder_tokens_bwd(const void* d_tokens, int tok_dtype, const int32_t* query_frame,
+                             float* d_lat, float* d_query_emb, int B, int Q, int L, int C,
+                             void* stream);
+
+/* ---- K11: output split + loss (track_autoencoder_3d.py:289-301, train.py:96-129) -----------
+ * head_out [rows, 4*T] f32 (x|y|z|vis blocks) -> tracks [rows,T,3], visible_logits [rows,T]. */
+int spa3d_split_outputs(const float* head_out, float* tracks, float* visible_logits,
+                        int64_t rows, int T, int coords, float* certain_logits, void* stream);
+/* sums[0] += sum |pred-tgt|*vis, sums[1] += sum BCE(logit,vis), sums[2] += sum vis.
+ * (sums must be zeroed by the caller; the three scalars of compute_loss_3d follow on host or
+ * after an all-reduce of sums across ranks.) */
+int spa3d_loss_fwd(const float* head_out, const float* target_tracks, const float* target_vis,
+                   float* sums, int64_t rows, int T, void* stream);
+/* d_head_out for total = l1_w*pos + bce_w*vis with the GLOBAL normaliser inv_denom. */
+int spa3d_loss_bwd(const float* head_out, const float* target_tracks, const float* target_vis,
+                   float* d_head_out, float l1_w, float bce_w, float inv_denom, int64_t rows,
+                   int T, void* stream);
+
+/* ---- elementwise helpers for the backward pass ---------------------------------------------
+ * gelu_bwd: dx = dy * gelu'(pre)   (pre = pre-activation);  colsum: out[n] (+)= sum_r x[r,n]. */
+int spa3d_gelu_bwd(const void* pre, int64_t ldp, int p_dtype, const void* dy, int64_t lddy,
+                   int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int64_t rows, int cols,
+                   void* stream);
+int spa3d_colsum(const void* x, int64_t ldx, int dtype, float* out, int accumulate,
+                 int64_t rows, int cols, void* stream);
+/* y = a + b elementwise over n floats (y may alias a). */
+int spa3d_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
+
+/* ---- a16: optimiser (train.py:41-57,239-243; optax adamw + clip_by_global_norm) ------------
+ * sumsq[0] += sum g^2 ;  then adamw with clip factor computed on device from sumsq. */
+int spa3d_sumsq(const float* g, int64_t n, float* sumsq, void* stream);
+int spa3d_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
+                     float clip_norm, float lr, float b1, float b2, float eps, float wd,
+                     int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPA3D_B200_H_ */

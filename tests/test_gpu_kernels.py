@@ -1,0 +1,380 @@
+"""Per-kernel parity on a B200: every C-ABI entry point against the oracle / plain torch fp64.
+
+Integer / index / float32-op-order work is compared bit-exactly; floating-point kernels with the
+tolerance written next to each assert.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lifting as olift
+from oracle import model as om
+from tests.helpers import product, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def spa():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return product()
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.asarray(a)) if not isinstance(a, torch.Tensor) else a
+    t = t.cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+# ---- K0 ------------------------------------------------------------------------------------
+def _lift_case(spa, g, prefix=""):
+    k = lambda n: g[prefix + n]
+    depth, dino, tracks = k("depth"), k("dino"), k("tracks")
+    intr = k("intrinsics")
+    intr = None if np.isnan(intr).any() else tuple(float(v) for v in intr)
+    T, H, W = depth.shape[:3]
+    L = spa.lifting
+    np.testing.assert_array_equal(L.lift_2d_to_3d(tracks, depth, intr), k("xyz"))
+    np.testing.assert_array_equal(L.sample_dino_features_for_tracks(dino, tracks, (T, H, W, 3)), k("dino_feat"))
+    np.testing.assert_array_equal(L.sample_depth_features_for_tracks(depth, tracks), k("depth_feat"))
+    xyz, df, zf = L.lift_and_sample(tracks, depth, dino, (T, H, W, 3), intr)
+    np.testing.assert_array_equal(xyz.cpu().numpy(), k("xyz"))
+    np.testing.assert_array_equal(df.cpu().numpy(), k("dino_feat"))
+    np.testing.assert_array_equal(zf.cpu().numpy(), k("depth_feat"))
+
+
+def test_lift_sample_golden_bit_exact(spa, golden_dir):
+    """CUDA gather vs fixtures produced by the reference's own NumPy loops (inference.py:287-447)."""
+    _lift_case(spa, np.load(os.path.join(golden_dir, "lifting_small.npz")))
+    g = np.load(os.path.join(golden_dir, "lifting_edges.npz"))
+    for case in ("integer", "far_out", "one_px", "intrinsics"):
+        _lift_case(spa, g, case + "/")
+
+
+def test_lift_sample_config4_shape_vs_oracle(spa):
+    """Larger case (oracle finishes in seconds): 512 tracks x 20 frames on a 518x518 video."""
+    rs = np.random.RandomState(0)
+    N, T, H, W = 512, 20, 518, 518
+    depth = rs.uniform(0.5, 10, (T, H, W, 1)).astype(np.float32)
+    dino = rs.standard_normal((T, 37, 37, 768)).astype(np.float32)
+    tr = np.stack([rs.uniform(-20, W + 20, (N, T)), rs.uniform(-20, H + 20, (N, T))], -1).astype(np.float32)
+    xyz, df, zf = spa.lifting.lift_and_sample(tr, depth, dino, (T, H, W, 3))
+    np.testing.assert_array_equal(xyz.cpu().numpy(), olift.lift_2d_to_3d(tr, depth))
+    np.testing.assert_array_equal(df.cpu().numpy(), olift.sample_dino_features_for_tracks(dino, tr, (T, H, W, 3)))
+    np.testing.assert_array_equal(zf.cpu().numpy(), olift.sample_depth_features_for_tracks(depth, tr))
+    # bf16 output variant (fast path): equals the rounded f32 result
+    _, dfb, _ = spa.lifting.lift_and_sample(tr, depth, dino, (T, H, W, 3), out_dtype=torch.bfloat16)
+    assert torch.equal(dfb, df.to(torch.bfloat16))
+
+
+# ---- Fourier features ---------------------------------------------------------------------
+def test_fourier_exact_matches_oracle(spa):
+    rs = np.random.RandomState(1)
+    x = rs.uniform(-1, 1, (1000, 3)).astype(np.float32)
+    out = torch.empty(1000, 192, device="cuda")
+    spa.ops.fourier_features(dev(x), out, 32, 1.0, exact=True)
+    ref = om.sinusoidal_embedding(torch.from_numpy(x), 32)
+    diff = (out.cpu() - ref).abs()
+    # correctly-rounded sine on both sides: at most isolated 1-ulp differences from the two libms
+    assert float(diff.max()) <= 1.2e-7 and float((diff > 0).float().mean()) < 1e-3
+    # time coordinate + read-out row layout + tail zero
+    T = 7
+    xt = rs.uniform(-1, 1, (3 * T, 3)).astype(np.float32)
+    out = torch.zeros(3 * (T + 1), 256, device="cuda")
+    spa.ops.fourier_features(dev(xt), out, 32, 1.0, append_time=T, exact=True, out_row_group=T)
+    fr = (torch.arange(T, dtype=torch.float32) / T).repeat(3)[:, None]
+    ref = om.sinusoidal_embedding(torch.cat([torch.from_numpy(xt), fr], 1), 32)
+    got = out.view(3, T + 1, 256)
+    assert torch.all(got[:, 0] == 0)
+    assert float((got[:, 1:].reshape(3 * T, 256).cpu() - ref).abs().max()) <= 1.2e-7
+    out = torch.empty(5, 4 * 64, device="cuda")
+    spa.ops.fourier_features(dev(x[:5]), out, 32, 1.0, tail_zero=True, exact=True)
+    assert torch.all(out[:, 192:224] == 0) and torch.all(out[:, 224:] == 1)
+    # fast sine (bf16 path) stays within float32 sinf accuracy
+    outf = torch.empty(1000, 192, device="cuda")
+    spa.ops.fourier_features(dev(x), outf, 32, 1.0, exact=False)
+    assert float((outf.cpu() - om.sinusoidal_embedding(torch.from_numpy(x), 32)).abs().max()) < 1e-6
+
+
+# ---- GEMMs -----------------------------------------------------------------------------------
+def _gemm_ref(a, wt, bias, act, res):
+    y = a.double() @ wt.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    if act:
+        y = om.gelu_tanh(y)
+    if res is not None:
+        y = y + res.double()
+    return y
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+def test_gemm_shapes(spa, impl):
+    ops = spa.ops
+    torch.manual_seed(0)
+    dtype = torch.float32 if impl == "simt" else torch.bfloat16
+    code = ops.GEMM_SIMT if impl == "simt" else ops.GEMM_TCGEN05
+    shapes = [(1, 64, 96), (127, 96, 256), (128, 128, 384), (129, 192, 64), (1000, 256, 1280), (333, 600, 1280),
+              (2048 + 77, 384, 768), (515, 2304, 384), (300, 1536, 384), (256, 1280, 12352), (700, 1152, 96),
+              (150, 88, 200), (64, 512, 1152)]
+    for (M, N, K) in shapes:
+        a = torch.randn(M, K, device="cuda").to(dtype)
+        wt = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(dtype)
+        bias = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda")
+        for variant in range(4):
+            b = bias if variant in (1, 2, 3) else None
+            act = ops.ACT_GELU if variant == 2 else ops.ACT_NONE
+            r = res if variant == 3 else None
+            odt = torch.float32 if variant in (0, 3) else dtype
+            y = ops.gemm(a, wt, b, act, r, out_dtype=odt, impl=code)
+            ref = _gemm_ref(a, wt, b, act, r)
+            tol = 2e-5 if odt == torch.float32 else 6e-3  # fp32 accumulate of identical operands / bf16 store
+            assert rel_err(y, ref) < tol, (impl, M, N, K, variant, rel_err(y, ref))
+
+
+def test_gemm_auto_dispatch_and_views(spa):
+    """bf16 operands with strided views (a column block of a wider matrix) take the tcgen05 path."""
+    ops = spa.ops
+    torch.manual_seed(1)
+    big = torch.randn(500, 3 * 768, device="cuda").to(torch.bfloat16)
+    a = big[:, 768:1536]
+    wt = (torch.randn(384, 768, device="cuda") / 28).to(torch.bfloat16)
+    y = ops.gemm(a, wt, out_dtype=torch.float32)
+    assert rel_err(y, a.double() @ wt.double().t()) < 2e-5
+
+
+def test_gemm_strided_backward_layouts(spa):
+    ops = spa.ops
+    torch.manual_seed(2)
+    M, N, K = 300, 70, 130
+    x = torch.randn(M, K, device="cuda")
+    dy = torch.randn(M, N, device="cuda")
+    # dW^T[N,K] = dY^T X : A(n,m) = dy[m,n] (sam=1, sak=N), B(m,k) = x[m,k]
+    dwt = torch.zeros(N, K, device="cuda")
+    ops.gemm_strided(dy, 1, N, x, K, 1, dwt, N, K, M)
+    assert rel_err(dwt, dy.double().t() @ x.double()) < 1e-5
+    ops.gemm_strided(dy, 1, N, x, K, 1, dwt, N, K, M, accumulate=True)
+    assert rel_err(dwt, 2 * (dy.double().t() @ x.double())) < 1e-5
+
+
+# ---- norms -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [48, 384, 1280])
+def test_layernorm_fwd_bwd(spa, d):
+    ops = spa.ops
+    torch.manual_seed(3)
+    rows = 777
+    x = (torch.randn(rows, d, device="cuda") * 2 + 0.5).requires_grad_(True)
+    scale = (1 + 0.2 * torch.randn(d, device="cuda")).requires_grad_(True)
+    y, mean, rstd = ops.layernorm_fwd(x.detach(), scale.detach(), torch.float32, stats=True)
+    ref = om.layer_norm(x.double(), scale.double())
+    assert rel_err(y, ref) < 1e-5
+    dy = torch.randn(rows, d, device="cuda")
+    ref.backward(dy.double())
+    dx = torch.empty_like(dy)
+    dscale = ops.layernorm_bwd(x.detach(), scale.detach(), mean, rstd, dy, dx)
+    assert rel_err(dx, x.grad) < 1e-4 and rel_err(dscale, scale.grad) < 1e-4
+    # bf16 output and "first token of each sequence" addressing
+    yb = ops.layernorm_fwd(x.detach(), scale.detach(), torch.bfloat16, rows=rows // 7, ldx=7 * d, d=d)
+    assert rel_err(yb, ref[::7]) < 6e-3
+
+
+def test_head_rmsnorm_fwd_bwd(spa):
+    ops = spa.ops
+    torch.manual_seed(4)
+    rows, H, Dh = 500, 8, 96
+    buf = torch.randn(rows, 3 * H * Dh, device="cuda")
+    scale = (1 + 0.2 * torch.randn(Dh, device="cuda")).requires_grad_(True)
+    x = buf[:, : H * Dh].clone().requires_grad_(True)
+    ref = om.rms_norm(x.double().view(rows, H, Dh), scale.double()) / math.sqrt(Dh)
+    q = buf[:, : H * Dh]
+    rstd = ops.head_rmsnorm_fwd(q, scale.detach(), 1 / math.sqrt(Dh), H, Dh, save_rstd=True)
+    assert rel_err(q, ref.reshape(rows, -1)) < 1e-5
+    dy = torch.randn(rows, H * Dh, device="cuda")
+    ref.backward(dy.double().view(rows, H, Dh))
+    d_io = dy.clone()
+    dscale = ops.head_rmsnorm_bwd(q, scale.detach(), 1 / math.sqrt(Dh), rstd, d_io, H, Dh)
+    assert rel_err(d_io, x.grad) < 1e-4 and rel_err(dscale, scale.grad) < 1e-4
+
+
+# ---- attention ---------------------------------------------------------------------------------
+def _attn_ref(q, k, v, mask, batch, H, Lq, Lk, Dh):
+    q4 = q.double().view(batch, Lq, H, Dh)
+    k4 = k.double().view(batch, Lk, H, Dh)
+    v4 = v.double().view(batch, Lk, H, Dh)
+    w = torch.einsum("bqhd,bkhd->bhqk", q4, k4)
+    if mask is not None:
+        w = torch.where(mask.view(batch, 1, 1, Lk) != 0, w, torch.full_like(w, torch.finfo(torch.float32).min))
+    w = torch.softmax(w, dim=-1)
+    return torch.einsum("bhqk,bkhd->bqhd", w, v4).reshape(batch * Lq, H * Dh)
+
+
+@pytest.mark.parametrize("dtype,Lq,Lk,Dh", [
+    (torch.float32, 151, 151, 96), (torch.float32, 128, 300, 96), (torch.float32, 13, 13, 64),
+    (torch.bfloat16, 151, 151, 96), (torch.bfloat16, 129, 129, 96), (torch.bfloat16, 128, 128, 64),
+    (torch.bfloat16, 16, 16, 96), (torch.bfloat16, 37, 37, 64), (torch.bfloat16, 128, 2048, 96),
+])
+def test_attention_fwd(spa, dtype, Lq, Lk, Dh):
+    ops = spa.ops
+    torch.manual_seed(5)
+    batch, H = 5, 8
+    A = H * Dh
+    qkv = torch.randn(batch * max(Lq, Lk), 3 * A, device="cuda")
+    q = (qkv[: batch * Lq, :A] / math.sqrt(Dh)).to(dtype)
+    k = qkv[: batch * Lk, A : 2 * A].to(dtype)
+    v = qkv[: batch * Lk, 2 * A :].to(dtype)
+    mask = None
+    if Lq == Lk:
+        mask = (torch.rand(batch, Lk, device="cuda") < 0.8).to(torch.uint8)
+        mask[:, 0] = 1
+        mask[1] = 0  # one sequence entirely masked -> uniform weights (finfo.min semantics)
+    o = torch.empty(batch * Lq, A, device="cuda", dtype=dtype)
+    ops.attention_fwd(q, k, v, o, batch, H, Lq, Lk, Dh, mask)
+    ref = _attn_ref(q, k, v, mask, batch, H, Lq, Lk, Dh)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(o, ref) < tol, rel_err(o, ref)
+
+
+@pytest.mark.parametrize("dtype,Lq,Lk", [(torch.float32, 40, 40), (torch.float32, 16, 70), (torch.bfloat16, 151, 151)])
+def test_attention_bwd(spa, dtype, Lq, Lk):
+    ops = spa.ops
+    torch.manual_seed(6)
+    batch, H, Dh = 3, 4, 96
+    A = H * Dh
+    q = (torch.randn(batch * Lq, A, device="cuda") / math.sqrt(Dh)).to(dtype)
+    k = torch.randn(batch * Lk, A, device="cuda").to(dtype)
+    v = torch.randn(batch * Lk, A, device="cuda").to(dtype)
+    mask = None
+    if Lq == Lk:
+        mask = (torch.rand(batch, Lk, device="cuda") < 0.7).to(torch.uint8)
+        mask[:, 0] = 1
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qd, kd, vd, mask, batch, H, Lq, Lk, Dh)
+    d_o = torch.randn(batch * Lq, A, device="cuda").to(dtype)
+    ref.backward(d_o.double())
+    o = torch.empty(batch * Lq, A, device="cuda", dtype=dtype)
+    stats = ops.attention_fwd(q, k, v, o, batch, H, Lq, Lk, Dh, mask, save_stats=True)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ops.attention_bwd(q, k, v, o, d_o, dq, dk, dv, stats, batch, H, Lq, Lk, Dh, mask)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    for got, want in ((dq, qd.grad), (dk, kd.grad), (dv, vd.grad)):
+        assert rel_err(got, want) < tol, rel_err(got, want)
+
+
+# ---- small kernels --------------------------------------------------------------------------------
+def test_key_mask_matches_oracle(spa):
+    rs = np.random.RandomState(7)
+    B, N, T = 3, 5, 11
+    vis = (rs.uniform(size=(B, N, T, 1)) < 0.7).astype(np.float32)
+    bd = np.array([T, T - 4, 0], np.int32)
+    m = spa.ops.build_key_mask(dev(vis), dev(bd), True)
+    ref = om.key_mask_3d(torch.from_numpy(vis), torch.from_numpy(bd))
+    assert torch.equal(m.cpu().bool(), ref)
+    m2 = spa.ops.build_key_mask(dev(vis), dev(bd), False)
+    assert torch.equal(m2.cpu().bool(), ref[..., 1:])
+
+
+def test_quantize_bit_exact(spa):
+    rs = np.random.RandomState(8)
+    x = (rs.standard_normal((4, 128, 96)) * 0.8).astype(np.float32)
+    x.reshape(-1)[:6] = [0.5 / 128, 1.5 / 128, 2.5 / 128, -0.5 / 128, 1.0, -1.0]  # ties + clip edges
+    noise = rs.uniform(size=x.shape).astype(np.float32)
+    y, mask = spa.ops.quantize_fwd(dev(x), dev(noise), True, save_mask=True)
+    ref = om.quantize_latents(torch.from_numpy(x), torch.from_numpy(noise), True)
+    assert torch.equal(y.cpu(), ref)
+    assert torch.equal(mask.cpu().bool(), torch.from_numpy((x >= -1) & (x <= 1)))
+    y2 = spa.ops.quantize_fwd(dev(x), None, False)
+    assert torch.equal(y2.cpu(), torch.clamp(torch.from_numpy(x), -1, 1))
+
+
+def test_decoder_tokens_fwd_bwd(spa):
+    ops = spa.ops
+    torch.manual_seed(9)
+    B, Q, L, C = 2, 5, 7, 200
+    D = C + 128
+    lat = torch.randn(B, L, C, device="cuda")
+    qe = torch.randn(B * Q, D, device="cuda")
+    qf = torch.tensor([[0, 3, 14, 20, 39], [1, 2, 40, 0, 7]], dtype=torch.int32, device="cuda")  # 5*40+127 > C: zero fill
+    tok = torch.empty(B * Q * (L + 1), D, device="cuda")
+    ops.decoder_tokens_fwd(lat, qe, qf, tok, B, Q, L, C)
+    latq = lat[:, None].expand(B, Q, L, C).cpu()
+    ref = torch.cat([qe.view(B, Q, 1, D).cpu(), om.append_time_feat(latq, qf.cpu())], dim=2)
+    assert torch.equal(tok.view(B, Q, L + 1, D).cpu(), ref)
+    g = torch.randn_like(tok)
+    d_lat = torch.empty(B, L, C, device="cuda")
+    d_qe = torch.empty(B * Q, D, device="cuda")
+    ops.decoder_tokens_bwd(g, qf, d_lat, d_qe, B, Q, L, C)
+    lat_r = lat.cpu().double().requires_grad_(True)
+    qe_r = qe.cpu().double().requires_grad_(True)
+    ref2 = torch.cat([qe_r.view(B, Q, 1, D), om.append_time_feat(lat_r[:, None].expand(B, Q, L, C), qf.cpu())], dim=2)
+    ref2.backward(g.view(B, Q, L + 1, D).cpu().double())
+    assert rel_err(d_lat, lat_r.grad) < 1e-5 and rel_err(d_qe, qe_r.grad) < 1e-6
+
+
+def test_split_and_loss(spa):
+    ops = spa.ops
+    torch.manual_seed(10)
+    rows, T = 37, 12
+    ho = torch.randn(rows, 4 * T, device="cuda")
+    tracks, vis, cert = ops.split_outputs(ho, T, 3)
+    h = ho.cpu()
+    assert torch.equal(tracks.cpu(), torch.stack([h[:, :T], h[:, T : 2 * T], h[:, 2 * T : 3 * T]], -1))
+    assert torch.equal(vis.cpu()[..., 0], h[:, 3 * T :]) and not cert.any()
+    tt = torch.randn(rows, T, 3, device="cuda")
+    tv = (torch.rand(rows, T, 1, device="cuda") < 0.6).float()
+    sums = torch.zeros(3, device="cuda")
+    ops.loss_fwd(ho, tt, tv, sums, T)
+    hod = h.double().requires_grad_(True)
+    pred = om.Results(torch.stack([hod[:, :T], hod[:, T : 2 * T], hod[:, 2 * T : 3 * T]], -1)[None],
+                      hod[:, 3 * T :, None][None], None)
+    ref = om.compute_loss_3d(pred, {"query_tracks": tt.cpu().double()[None], "query_tracks_visible": tv.cpu().double()[None]})
+    nv = float(sums[2])
+    assert nv == float(tv.sum())
+    assert abs(float(sums[0]) / max(nv, 1) - float(ref["position_loss"])) < 1e-5 * float(ref["position_loss"])
+    assert abs(float(sums[1]) / max(nv, 1) - float(ref["visible_loss"])) < 1e-5 * float(ref["visible_loss"])
+    ref["total_loss"].backward()
+    d = ops.loss_bwd(ho, tt, tv, 5000.0, 1e-8, 1.0 / max(nv, 1), T)
+    assert rel_err(d, hod.grad) < 1e-5
+
+
+def test_gelu_colsum_adamw(spa):
+    ops = spa.ops
+    torch.manual_seed(11)
+    pre = torch.randn(300, 200, device="cuda").requires_grad_(True)
+    dy = torch.randn(300, 200, device="cuda")
+    om.gelu_tanh(pre.double()).backward(dy.double())
+    dx = torch.empty_like(dy)
+    ops.gelu_bwd(pre.detach(), dy, dx)
+    assert rel_err(dx, pre.grad) < 1e-5
+    y = ops.gelu_fwd(pre.detach(), torch.empty_like(dy))
+    assert rel_err(y, om.gelu_tanh(pre.detach().double())) < 1e-6
+    out = torch.empty(200, device="cuda")
+    ops.colsum(dy, out)
+    assert rel_err(out, dy.double().sum(0)) < 1e-5
+    # AdamW + global-norm clip vs the oracle restatement of optax (train.py:239-243)
+    p = torch.randn(5000, device="cuda")
+    g = torch.randn(5000, device="cuda") * 0.05
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    pr, mr, vr = [p.cpu().clone()], [torch.zeros(5000)], [torch.zeros(5000)]
+    for step in (1, 2, 3):
+        ss = torch.zeros(1, device="cuda")
+        ops.sumsq(g, ss)
+        ops.adamw_step(p, g, m, v, ss, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
+        om.adamw_step(pr, [g.cpu().clone()], mr, vr, step, 1e-3)
+    assert rel_err(p, pr[0]) < 1e-5
+
+
+def test_masked_mean(spa):
+    torch.manual_seed(12)
+    S, T, W = 9, 14, 50
+    tok = torch.randn(S * T, W, device="cuda")
+    vis = (torch.rand(S, T, device="cuda") < 0.5).float()
+    vis[2] = 0
+    out = spa.ops.masked_mean_fwd(tok, vis, S, T, torch.float32)
+    ref = (tok.view(S, T, W) * vis[..., None]).sum(1) / torch.clamp(vis.sum(1, keepdim=True), min=1.0)
+    assert rel_err(out, ref) < 1e-5
