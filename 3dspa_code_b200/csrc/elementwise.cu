@@ -622,7 +622,6 @@ int spa3d_decoder_tokens_fwd(const void* lat, int lat_dtype, const void* query_e
                              int L, int C, void* stream) {
   int64_t rows = (int64_t)B * Q * (L + 1);
   if (rows == 0) return 0;
-  SPA3D_REQUIRE(C >= 128, "decoder_tokens: latent width %d < 128", C);
   cudaStream_t st = (cudaStream_t)stream;
   SPA3D_DISPATCH(lat_dtype, TL, SPA3D_DISPATCH(qe_dtype, TQ, SPA3D_DISPATCH(tok_dtype, TT, {
     decoder_tokens_fwd_kernel<TL, TQ, TT><<<(unsigned)rows, 256, 0, st>>>((const TL*)lat, (const TQ*)query_emb, query_frame, (TT*)tokens, B, Q, L, C);

@@ -40,8 +40,8 @@ def make_inputs(cfg, B=2, N=10, Q=6, T=None, seed=0, dino=True, depth=True, vis_
 
 def rel_err(a, b):
     """Per-tensor max|a-b| / max|b| (the metric DESIGN.md fixes for the north_star tolerances)."""
-    a = torch.as_tensor(np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a)).double()
-    b = torch.as_tensor(np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b)).double()
+    a = a.detach().cpu().double() if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a)).double()
+    b = b.detach().cpu().double() if isinstance(b, torch.Tensor) else torch.as_tensor(np.asarray(b)).double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
