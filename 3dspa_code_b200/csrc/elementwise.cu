@@ -250,6 +250,12 @@ __global__ void quantize_kernel(const float* __restrict__ x, const float* __rest
   y[i] = v;
 }
 
+__global__ void quantize_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ pass,
+                                    float* __restrict__ dx, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = pass[i] ? dy[i] : 0.f;
+}
+
 template <typename TL, typename TQ, typename TT>
 __global__ void decoder_tokens_fwd_kernel(const TL* __restrict__ lat, const TQ* __restrict__ qe,
                                           const int32_t* __restrict__ qframe, TT* __restrict__ tok,
@@ -615,6 +621,12 @@ int spa3d_quantize_fwd(const float* x, const float* noise, float* y, uint8_t* pa
   if (n == 0) return 0;
   quantize_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, noise, y, pass_mask, n, discretize);
   return check_launch("quantize_fwd");
+}
+
+int spa3d_quantize_bwd(const float* dy, const uint8_t* pass_mask, float* dx, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  quantize_bwd_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, pass_mask, dx, n);
+  return check_launch("quantize_bwd");
 }
 
 int spa3d_decoder_tokens_fwd(const void* lat, int lat_dtype, const void* query_emb, int qe_dtype,

@@ -208,6 +208,12 @@ def quantize_fwd(x, noise, discretize=True, save_mask=False):
     return (y, mask) if save_mask else y
 
 
+def quantize_bwd(dy, pass_mask):
+    dx = torch.empty_like(dy)
+    _call("spa3d_quantize_bwd", _p(dy), _p(pass_mask), _p(dx), dy.numel(), _stream())
+    return dx
+
+
 def decoder_tokens_fwd(lat, query_emb, query_frame, tokens, B, Q, L, C):
     _call("spa3d_decoder_tokens_fwd", _p(lat), dt(lat), _p(query_emb), dt(query_emb), _p(query_frame), _p(tokens), dt(tokens), B, Q, L, C, _stream())
     return tokens

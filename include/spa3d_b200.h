@@ -166,6 +166,10 @@ int spa3d_gelu_fwd(const void* x, int64_t ldx, int x_dtype, void* y, int64_t ldy
 int spa3d_quantize_fwd(const float* x, const float* noise, float* y, uint8_t* pass_mask,
                        int64_t n, int discretize, void* stream);
 
+/* straight-through backward of the quantiser: dx = dy where |x| <= 1 (pass_mask), else 0. */
+int spa3d_quantize_bwd(const float* dy, const uint8_t* pass_mask, float* dx, int64_t n,
+                       void* stream);
+
 /* ---- K10: decoder token assembly (track_autoencoder_3d.py:276-284, append_time_feat :235-246)
  * tokens[b,q,0,:]   = query_emb[b,q,:]                      (D = C + 128 channels)
  * tokens[b,q,1+n,:] = [ lat[b,n,0:C] , lat[b,n,5*t:5*t+128] ]   t = query_frame[b,q]
