@@ -505,7 +505,7 @@ class Trainer:
         ss = torch.zeros(1, device=dev)
         ops.sumsq(st.grad, ss)
         self.step_idx += 1
-        ops.adamw_step(st.flat, st.grad, st.m, st.v, st.flat.numel(), ss, self.clip, lr, 0.9, 0.999, 1e-8, self.wd, self.step_idx)
+        ops.adamw_step(st.flat, st.grad, st.m, st.v, ss, self.clip, lr, 0.9, 0.999, 1e-8, self.wd, self.step_idx)
         st.refresh()
         s_host = sums.cpu()
         pos, bce = float(s_host[0]) / denom, float(s_host[1]) / denom

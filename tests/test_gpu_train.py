@@ -40,27 +40,58 @@ def oracle_grads(c, tree, inp, noise, dtype=torch.float64):
     return loss, {k: v.grad for k, v in om.flatten(p).items()}
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("bf16", 6e-2)])
-def test_gradients_match_oracle_autograd(spa, precision, tol):
+def test_gradients_match_oracle_autograd_fp32(spa):
+    """Real loss (train.py:96-129), fp32 path: every parameter leaf vs autograd through the oracle."""
     te = importlib.import_module("3dspa_code_b200.train_engine")
     c, model, tree, inp, noise = _setup(spa)
     loss_ref, gref = oracle_grads(c, tree, inp, noise)
-    store = te.ParamStore(tree, precision)
+    store = te.ParamStore(tree, "fp32")
     eng = te.TrainEngine(model, store)
     denom = max(float(inp["query_tracks_visible"].sum()), 1.0)
     sums = eng.loss_and_backward(inp, noise, denom)
     pos, bce = float(sums[0]) / denom, float(sums[1]) / denom
-    ltol = 1e-4 if precision == "fp32" else 3e-2
-    assert abs(pos - float(loss_ref["position_loss"])) < ltol * float(loss_ref["position_loss"])
-    assert abs(bce - float(loss_ref["visible_loss"])) < ltol * float(loss_ref["visible_loss"])
+    assert abs(pos - float(loss_ref["position_loss"])) < 1e-4 * float(loss_ref["position_loss"])
+    assert abs(bce - float(loss_ref["visible_loss"])) < 1e-4 * float(loss_ref["visible_loss"])
     got = spa.params.flatten(store.grad_tree())
     assert got.keys() == gref.keys()
-    worst = {}
-    for k, g in gref.items():
-        e = rel_err(got[k], g)
-        worst[k] = e
-    bad = {k: v for k, v in worst.items() if v > tol}
+    bad = {k: rel_err(got[k], g) for k, g in gref.items() if rel_err(got[k], g) > 2e-3}
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+
+
+def _cos(a, b):
+    a = torch.as_tensor(np.asarray(a)).double().reshape(-1)
+    b = b.detach().double().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_backward_kernels_linear_functional(spa, precision):
+    """Backward chain in isolation: d(sum(head_out * R))/dparams for a fixed random R.  (The L1 loss
+    gradient is sign(pred - target): a bf16-sized forward error flips isolated signs, which says
+    nothing about the backward kernels, so the bf16 path is checked with a smooth functional.)"""
+    te = importlib.import_module("3dspa_code_b200.train_engine")
+    c, model, tree, inp, noise = _setup(spa, seed=11)
+    B, Q, T = inp["query_points"].shape[0], inp["query_points"].shape[1], c.num_output_frames
+    R = torch.randn(B * Q, 4 * T, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    p = om.to_torch(tree, torch.float64, requires_grad=True)
+    ci = om.cast_inputs(inp, torch.float64)
+    res = om.forward_3d(p, c, ci, torch.as_tensor(noise).double(), False)
+    head = torch.cat([res.tracks[..., 0], res.tracks[..., 1], res.tracks[..., 2], res.visible_logits[..., 0]], dim=-1)
+    (head.reshape(B * Q, 4 * T) * R).sum().backward()
+    gref = {k: v.grad for k, v in om.flatten(p).items()}
+    store = te.ParamStore(tree, precision)
+    eng = te.TrainEngine(model, store)
+    with torch.enable_grad():
+        out = eng.forward_train(inp, noise, discretize=False)
+    out.backward(R.float().cuda())
+    got = spa.params.flatten(store.grad_tree())
+    if precision == "fp32":
+        bad = {k: rel_err(got[k], g) for k, g in gref.items() if rel_err(got[k], g) > 1e-3}
+    else:
+        # bf16: ~0.4 % rounding per op over a ~40-op chain; judge direction and size of every leaf
+        bad = {k: (_cos(got[k], g), rel_err(got[k], g)) for k, g in gref.items()
+               if _cos(got[k], g) < 0.985 or rel_err(got[k], g) > 0.2}
+    assert not bad, sorted(bad.items(), key=lambda kv: str(kv[1]))[:8]
 
 
 def test_microbatching_equals_full_batch(spa):
@@ -79,37 +110,33 @@ def test_microbatching_equals_full_batch(spa):
 
 
 def test_train_step_matches_oracle_adamw(spa):
+    """clip_by_global_norm(1.0) -> adamw(lr(t), wd=0.01) with the warm-up/cosine schedule
+    (train.py:41-57,239-243): the device update, fed its own gradients, equals the oracle's optax
+    restatement; losses and learning rates match the oracle forward."""
     te = importlib.import_module("3dspa_code_b200.train_engine")
     c, model, tree, inp, noise = _setup(spa, seed=7)
     trainer = te.Trainer(model, tree, precision="fp32", base_lr=1e-3, warmup_steps=2, micro_batch=1)
-    # oracle: two steps of clip + AdamW with the schedule of train.py:41-57
-    p = om.to_torch(tree, torch.float64)
-    flat = om.flatten(p)
-    keys = list(flat)
-    params = [flat[k] for k in keys]
+    keys = sorted(om.flatten(tree))
+    params = [torch.as_tensor(np.asarray(om.flatten(tree)[k])).double() for k in keys]
     m = [torch.zeros_like(t) for t in params]
     v = [torch.zeros_like(t) for t in params]
-    ci = om.cast_inputs(inp, torch.float64)
-    logs = []
-    for step in range(2):
-        for t in params:
-            t.requires_grad_(True)
-            t.grad = None
-        res = om.forward_3d(p, c, ci, torch.as_tensor(noise).double(), True)
-        loss = om.compute_loss_3d(res, ci)
-        loss["total_loss"].backward()
-        grads = [t.grad.clone() for t in params]
+    for step in range(3):
+        before = {k: t.clone() for k, t in zip(keys, params)}
+        p = {k: t.clone() for k, t in zip(keys, params)}
+        res = om.forward_3d(spa.params.unflatten(p), c, om.cast_inputs(inp, torch.float64), torch.as_tensor(noise).double(), True)
+        loss = om.compute_loss_3d(res, om.cast_inputs(inp, torch.float64))
+        log = trainer.train_step(inp, noise)
         lr = om.learning_rate(step, 1e-3, 2, 1000000)
-        with torch.no_grad():
-            for t in params:
-                t.requires_grad_(False)
-            om.adamw_step(params, grads, m, v, step + 1, lr)
-        logs.append(trainer.train_step(inp, noise))
-        assert abs(logs[-1]["learning_rate"] - lr) < 1e-12
-        assert abs(logs[-1]["total_loss"] - float(loss["total_loss"])) < 1e-3 * abs(float(loss["total_loss"]))
-    got = spa.params.flatten(trainer.store.tree())
-    # step 0 has lr = 0 (warm-up from 0): only the second step moves the weights
-    worst = max(rel_err(got[k], flat[k]) for k in keys)
-    assert worst < 2e-4, worst
+        assert abs(log["learning_rate"] - lr) < 1e-12
+        assert abs(log["total_loss"] - float(loss["total_loss"])) < 1e-3 * abs(float(loss["total_loss"]))
+        g = spa.params.flatten(trainer.store.grad_tree())
+        grads = [torch.as_tensor(np.asarray(g[k])).double() for k in keys]
+        gn = om.adamw_step(params, grads, m, v, step + 1, lr)
+        assert abs(log["grad_norm"] - float(gn)) < 1e-4 * float(gn)
+        got = spa.params.flatten(trainer.store.tree())
+        worst = max(rel_err(got[k], t) for k, t in zip(keys, params))
+        assert worst < 1e-5, (step, worst)
+        if step == 0:  # lr(0) = 0: the warm-up starts from zero, weights must not move
+            assert all(np.array_equal(got[k], before[k].float().numpy()) for k in keys)
     moved = max(float(np.abs(got[k] - np.asarray(om.flatten(tree)[k])).max()) for k in keys)
     assert moved > 1e-5
