@@ -47,11 +47,43 @@ int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dt
   }
   if (impl != SPA3D_GEMM_SIMT && tc_ok) {
     return gemm_tcgen05(A, lda, Wt, ldw, bias, act, residual, ldr, r_dtype, C, ldc, c_dtype, M, N,
-                        K, st);
+                        K, nullptr, st);
   }
   // SIMT fp32-accumulate path: B(k,n) = Wt[n*ldw + k]
   return gemm_simt(A, lda, 1, a_dtype, Wt, 1, ldw, a_dtype, bias, act, residual, ldr, r_dtype, C,
                    ldc, c_dtype, M, N, K, 0, st);
+}
+
+int spa3d_gemm_rmsnorm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dtype, void* C,
+                       int64_t ldc, int c_dtype, int64_t M, int N, int K, int Dh, int q_cols,
+                       int k_cols, const float* scale_q, const float* scale_k, float q_mul,
+                       float* rstd_out, int impl, void* stream) {
+  using namespace spa3d;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0 && Dh > 0, "gemm_rmsnorm: bad shape");
+  SPA3D_REQUIRE(q_cols % Dh == 0 && k_cols % Dh == 0 && q_cols + k_cols <= N, "gemm_rmsnorm: bad head split");
+  if (M == 0) return 0;
+  bool tc_ok = (a_dtype == SPA3D_BF16) && gemm_tcgen05_applicable(A, lda, Wt, ldw, M, N, K) &&
+               gemm_tcgen05_rms_applicable(N, Dh, q_cols, k_cols);
+  if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_rmsnorm: tcgen05 path not applicable");
+  if (impl != SPA3D_GEMM_SIMT && tc_ok) {
+    RmsEpilogue rms{Dh, q_cols, k_cols, scale_q, scale_k, q_mul, rstd_out};
+    return gemm_tcgen05(A, lda, Wt, ldw, nullptr, 0, nullptr, 0, 0, C, ldc, c_dtype, M, N, K, &rms, st);
+  }
+  // unfused: contraction, then the in-place normalisation pass over the q and k column blocks
+  int rc = spa3d_gemm(A, lda, Wt, ldw, a_dtype, nullptr, 0, nullptr, 0, 0, C, ldc, c_dtype, M, N, K,
+                      impl == SPA3D_GEMM_SIMT ? SPA3D_GEMM_SIMT : SPA3D_GEMM_AUTO, stream);
+  if (rc) return rc;
+  const int nh = (q_cols + k_cols) / Dh;
+  const size_t esz = c_dtype == SPA3D_F32 ? 4 : 2;
+  if (q_cols) {
+    rc = head_rmsnorm_fwd_impl(C, ldc, c_dtype, scale_q, q_mul, rstd_out, nh, M, q_cols / Dh, Dh, st);
+    if (rc) return rc;
+  }
+  if (k_cols)
+    rc = head_rmsnorm_fwd_impl((char*)C + (size_t)q_cols * esz, ldc, c_dtype, scale_k, 1.f,
+                               rstd_out ? rstd_out + q_cols / Dh : nullptr, nh, M, k_cols / Dh, Dh, st);
+  return rc;
 }
 
 int spa3d_gemm_strided(const void* A, int64_t sam, int64_t sak, int a_dtype, const void* B,

@@ -99,9 +99,20 @@ int gemm_simt(const void* A, int64_t sam, int64_t sak, int a_dtype, const void* 
               int64_t sbn, int b_dtype, const float* bias, int act, const void* residual,
               int64_t ldr, int r_dtype, void* C, int64_t ldc, int c_dtype, int64_t M, int N,
               int64_t K, int accumulate, cudaStream_t st);
+struct RmsEpilogue {  // fused per-head RMSNorm of the leading q_cols / k_cols output columns
+  int dh, q_cols, k_cols;
+  const float* scale_q;
+  const float* scale_k;
+  float q_mul;
+  float* rstd_out;  // [M, (q_cols+k_cols)/dh] or null
+};
 int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias,
                  int act, const void* residual, int64_t ldr, int r_dtype, void* C, int64_t ldc,
-                 int c_dtype, int64_t M, int N, int K, cudaStream_t st);
+                 int c_dtype, int64_t M, int N, int K, const RmsEpilogue* rms, cudaStream_t st);
+bool gemm_tcgen05_rms_applicable(int N, int dh, int q_cols, int k_cols);
+int head_rmsnorm_fwd_impl(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
+                          float* rstd_out, int64_t rstd_ld, int64_t rows, int heads, int Dh,
+                          cudaStream_t st);
 bool gemm_tcgen05_applicable(const void* A, int64_t lda, const void* Wt, int64_t ldw, int64_t M,
                              int N, int K);
 

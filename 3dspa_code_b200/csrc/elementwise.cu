@@ -152,8 +152,8 @@ __global__ void layernorm_bwd_kernel(const TX* __restrict__ x, int64_t ldx,
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void head_rmsnorm_fwd_kernel(T* __restrict__ buf, int64_t ld, const float* __restrict__ scale,
-                                        float out_mul, float* __restrict__ rstd_out, int64_t rows,
-                                        int heads, int Dh) {
+                                        float out_mul, float* __restrict__ rstd_out, int64_t rstd_ld,
+                                        int64_t rows, int heads, int Dh) {
   int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= rows * heads) return;
   int lane = threadIdx.x & 31;
@@ -167,7 +167,7 @@ __global__ void head_rmsnorm_fwd_kernel(T* __restrict__ buf, int64_t ld, const f
   }
   ss = warp_sum(ss);
   float rstd = rsqrtf(ss / Dh + kNormEps);
-  if (lane == 0 && rstd_out) rstd_out[wid] = rstd;
+  if (lane == 0 && rstd_out) rstd_out[r * rstd_ld + h] = rstd;
   for (int i = lane; i < Dh; i += 32) stf<T>(p + i, ldf<T>(p + i) * rstd * scale[i] * out_mul);
 }
 
@@ -177,9 +177,10 @@ __global__ void head_rmsnorm_fwd_kernel(T* __restrict__ buf, int64_t ld, const f
 template <typename TY, typename TD>
 __global__ void head_rmsnorm_bwd_kernel(const TY* __restrict__ y, int64_t ldy,
                                         const float* __restrict__ scale, float out_mul,
-                                        const float* __restrict__ rstd, TD* __restrict__ d_io,
-                                        int64_t ldd, float* __restrict__ dscale_partial,
-                                        int64_t rows, int heads, int Dh) {
+                                        const float* __restrict__ rstd, int64_t rstd_ld,
+                                        TD* __restrict__ d_io, int64_t ldd,
+                                        float* __restrict__ dscale_partial, int64_t rows, int heads,
+                                        int Dh) {
   extern __shared__ float s_ds[];  // [Dh]
   for (int i = threadIdx.x; i < Dh; i += blockDim.x) s_ds[i] = 0.f;
   __syncthreads();
@@ -190,7 +191,7 @@ __global__ void head_rmsnorm_bwd_kernel(const TY* __restrict__ y, int64_t ldy,
     int h = (int)(wid % heads);
     const TY* yp = y + r * ldy + (int64_t)h * Dh;
     TD* dp = d_io + r * ldd + (int64_t)h * Dh;
-    float rs = rstd[wid];
+    float rs = rstd[r * rstd_ld + h];
     float sgx = 0.f;
     for (int i = lane; i < Dh; i += 32) {
       float sm = scale[i] * out_mul;
@@ -495,6 +496,16 @@ __global__ void gelu_fwd_kernel(const TX* __restrict__ x, int64_t ldx, TY* __res
 
 static inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+int head_rmsnorm_fwd_impl(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
+                          float* rstd_out, int64_t rstd_ld, int64_t rows, int heads, int Dh,
+                          cudaStream_t st) {
+  if (rows == 0 || heads == 0) return 0;
+  SPA3D_DISPATCH(dtype, T, {
+    head_rmsnorm_fwd_kernel<T><<<blocks_for(rows * heads, 8), 256, 0, st>>>((T*)buf, ld, scale, out_mul, rstd_out, rstd_ld, rows, heads, Dh);
+  });
+  return check_launch("head_rmsnorm_fwd");
+}
+
 }  // namespace spa3d
 
 using namespace spa3d;
@@ -565,24 +576,21 @@ int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* sc
 }
 
 int spa3d_head_rmsnorm_fwd(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
-                           float* rstd_out, int64_t rows, int heads, int Dh, void* stream) {
-  if (rows == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  SPA3D_DISPATCH(dtype, T, {
-    head_rmsnorm_fwd_kernel<T><<<blocks_for(rows * heads, 8), 256, 0, st>>>((T*)buf, ld, scale, out_mul, rstd_out, rows, heads, Dh);
-  });
-  return check_launch("head_rmsnorm_fwd");
+                           float* rstd_out, int64_t rstd_ld, int64_t rows, int heads, int Dh,
+                           void* stream) {
+  return spa3d::head_rmsnorm_fwd_impl(buf, ld, dtype, scale, out_mul, rstd_out, rstd_ld, rows, heads, Dh,
+                                      (cudaStream_t)stream);
 }
 
 int spa3d_head_rmsnorm_bwd(const void* y, int64_t ldy, int y_dtype, const float* scale, float out_mul,
-                           const float* rstd, void* dy_inout, int64_t ldd, int d_dtype,
+                           const float* rstd, int64_t rstd_ld, void* dy_inout, int64_t ldd, int d_dtype,
                            float* dscale_partial, int num_partials, int64_t rows, int heads, int Dh,
                            void* stream) {
   SPA3D_REQUIRE(num_partials > 0, "head_rmsnorm_bwd: num_partials must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
   SPA3D_DISPATCH(y_dtype, TY, SPA3D_DISPATCH(d_dtype, TD, {
     head_rmsnorm_bwd_kernel<TY, TD><<<num_partials, 256, Dh * sizeof(float), st>>>(
-        (const TY*)y, ldy, scale, out_mul, rstd, (TD*)dy_inout, ldd, dscale_partial, rows, heads, Dh);
+        (const TY*)y, ldy, scale, out_mul, rstd, rstd_ld, (TD*)dy_inout, ldd, dscale_partial, rows, heads, Dh);
   }));
   return check_launch("head_rmsnorm_bwd");
 }

@@ -81,43 +81,55 @@ class Engine:
         self.dev = weights.f32["latents_init"].device
 
     # ---- transformer blocks (attention.py:11-185) ---------------------------------------------
-    def _attn_core(self, pre, q, k, v, batch, Lq, Lk, m, key_mask=None):
-        """per-head RMSNorm on q,k (+ q/sqrt(Dh)), then softmax(qk^T)v."""
-        H, Dh = m["heads"], m["Dh"]
-        ops.head_rmsnorm_fwd(q, self.w.f32[pre + "norm_query"], 1.0 / math.sqrt(Dh), H, Dh)
-        ops.head_rmsnorm_fwd(k, self.w.f32[pre + "norm_key"], 1.0, H, Dh)
-        o = torch.empty(q.shape[0], H * Dh, device=self.dev, dtype=self.cdt)
-        ops.attention_fwd(q, k, v, o, batch, H, Lq, Lk, Dh, key_mask)
-        return o
-
     def transformer(self, short, x, batch, L, key_mask=None, kv=None, Lkv=0, out_rows="all"):
         """ImprovedTransformer (attention.py:22-53) on x [batch*L, d] (fp32 residual stream).
 
         kv: optional [batch*Lkv, d_kv] cross-attention inputs (compute dtype, un-normed).
         out_rows: "all" -> final LayerNorm of every token; "first" -> only token 0 of every sequence
-        (the read-out token, track_autoencoder_3d.py:187,286).
+        (the read-out token, track_autoencoder_3d.py:187,286).  With "first" nothing downstream
+        reads tokens 1.. of the last layer, so that layer computes keys/values for every token but
+        queries, output projection, MLP and final norm only for token 0 (dead-code elimination;
+        bench.py reports executed FLOPs from the launches, not from the model formula).
         """
         m = self.w.meta[short]
-        A = m["heads"] * m["Dh"]
+        H, Dh = m["heads"], m["Dh"]
+        A = H * Dh
+        d = m["d"]
         w, f = self.w.c, self.w.f32
         for i in range(m["layers"]):
             pre = f"{short}.{i}."
+            prune = out_rows == "first" and i == m["layers"] - 1 and kv is None and L > 1
             xn = ops.layernorm_fwd(x, f[pre + "norm_q"], self.cdt)
-            qkv = ops.gemm(xn, w[pre + "self.Wqkv_t"])
-            o = self._attn_core(pre + "self.", qkv[:, :A], qkv[:, A : 2 * A], qkv[:, 2 * A :], batch, L, L, m, key_mask)
+            sq, sk = f[pre + "self.norm_query"], f[pre + "self.norm_key"]
+            if prune:
+                wqkv = w[pre + "self.Wqkv_t"]
+                kvp = ops.gemm_rmsnorm(xn, wqkv[A:], Dh, 0, A, sq, sk)                      # keys, values: all tokens
+                q0 = ops.gemm_rmsnorm(xn.view(batch, L * d)[:, :d], wqkv[:A], Dh, A, 0, sq, sk)  # queries: token 0
+                o = torch.empty(batch, A, device=self.dev, dtype=self.cdt)
+                ops.attention_fwd(q0, kvp[:, :A], kvp[:, A:], o, batch, H, 1, L, Dh, key_mask)
+                x = ops.gemm(o, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x.view(batch, L * d)[:, :d], out_dtype=torch.float32)
+                del kvp, q0, o
+                an = ops.layernorm_fwd(x, f[pre + "norm_attn"], self.cdt)
+                h = ops.gemm(an, w[pre + "W1_t"], f[pre + "b1"], act=ops.ACT_GELU)
+                x = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=x, out_dtype=torch.float32)
+                return ops.layernorm_fwd(x, f[f"{short}.norm_encoder"], self.cdt)
+            qkv = ops.gemm_rmsnorm(xn, w[pre + "self.Wqkv_t"], Dh, A, A, sq, sk)
+            o = torch.empty(x.shape[0], A, device=self.dev, dtype=self.cdt)
+            ops.attention_fwd(qkv[:, :A], qkv[:, A : 2 * A], qkv[:, 2 * A :], o, batch, H, L, L, Dh, key_mask)
             a = ops.gemm(o, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x, out_dtype=torch.float32)
             del qkv, o
             if kv is not None:
-                qc = ops.gemm(xn, w[pre + "cross.Wq_t"])
-                kvp = ops.gemm(kv, w[pre + "cross.Wkv_t"])
-                oc = self._attn_core(pre + "cross.", qc, kvp[:, :A], kvp[:, A:], batch, L, Lkv, m, None)
+                cq, ck = f[pre + "cross.norm_query"], f[pre + "cross.norm_key"]
+                qc = ops.gemm_rmsnorm(xn, w[pre + "cross.Wq_t"], Dh, A, 0, cq, ck)
+                kvp = ops.gemm_rmsnorm(kv, w[pre + "cross.Wkv_t"], Dh, 0, A, cq, ck)
+                oc = torch.empty(x.shape[0], A, device=self.dev, dtype=self.cdt)
+                ops.attention_fwd(qc, kvp[:, :A], kvp[:, A:], oc, batch, H, L, Lkv, Dh, None)
                 a = ops.gemm(oc, w[pre + "cross.Wo_t"], f[pre + "cross.bo"], residual=a, out_dtype=torch.float32)
                 del qc, kvp, oc
             an = ops.layernorm_fwd(a, f[pre + "norm_attn"], self.cdt)
             h = ops.gemm(an, w[pre + "W1_t"], f[pre + "b1"], act=ops.ACT_GELU)
             x = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=a, out_dtype=torch.float32)
             del xn, an, h, a
-        d = m["d"]
         if out_rows == "first":
             return ops.layernorm_fwd(x, f[f"{short}.norm_encoder"], self.cdt, rows=batch, ldx=L * d, d=d)
         return ops.layernorm_fwd(x, f[f"{short}.norm_encoder"], self.cdt)

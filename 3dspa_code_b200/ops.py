@@ -154,14 +154,27 @@ def layernorm_bwd(x, scale, mean, rstd, dy, dx, rows=None, ldx=None, lddx=None, 
 def head_rmsnorm_fwd(buf, scale, out_mul, heads, Dh, save_rstd=False):
     rows = buf.shape[0]
     rstd = torch.empty(rows, heads, device=buf.device, dtype=torch.float32) if save_rstd else None
-    _call("spa3d_head_rmsnorm_fwd", _p(buf), _ld(buf), dt(buf), _p(scale), float(out_mul), _p(rstd), rows, heads, Dh, _stream())
+    _call("spa3d_head_rmsnorm_fwd", _p(buf), _ld(buf), dt(buf), _p(scale), float(out_mul), _p(rstd), heads, rows, heads, Dh, _stream())
     return rstd
 
 
+def gemm_rmsnorm(a, wt, Dh, q_cols, k_cols, scale_q, scale_k, save_rstd=False, impl=GEMM_AUTO):
+    """QKV projection with fused per-head RMSNorm (q also multiplied by 1/sqrt(Dh))."""
+    M, K = a.shape
+    N = wt.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=a.dtype)
+    nh = (q_cols + k_cols) // Dh
+    rstd = torch.empty(M, nh, device=a.device, dtype=torch.float32) if save_rstd else None
+    _call("spa3d_gemm_rmsnorm", _p(a), _ld(a), _p(wt), _ld(wt), dt(a), _p(out), _ld(out), dt(out), M, N, K, Dh, q_cols, k_cols,
+          _p(scale_q), _p(scale_k), 1.0 / math.sqrt(Dh), _p(rstd), int(impl), _stream())
+    return (out, rstd) if save_rstd else out
+
+
 def head_rmsnorm_bwd(y, scale, out_mul, rstd, d_io, heads, Dh, num_partials=296):
+    """rstd: a [rows, >=heads] view (row stride = rstd.stride(0))."""
     rows = y.shape[0]
     partial = torch.empty(num_partials, Dh, device=y.device, dtype=torch.float32)
-    _call("spa3d_head_rmsnorm_bwd", _p(y), _ld(y), dt(y), _p(scale), float(out_mul), _p(rstd), _p(d_io), _ld(d_io), dt(d_io),
+    _call("spa3d_head_rmsnorm_bwd", _p(y), _ld(y), dt(y), _p(scale), float(out_mul), _p(rstd), rstd.stride(0), _p(d_io), _ld(d_io), dt(d_io),
           _p(partial), num_partials, rows, heads, Dh, _stream())
     dscale = torch.empty(Dh, device=y.device, dtype=torch.float32)
     colsum(partial, dscale)

@@ -123,18 +123,16 @@ class AttnBlockFn(torch.autograd.Function):
         H, Dh = m["heads"], m["Dh"]
         A = H * Dh
         xn, mean, rstd = ops.layernorm_fwd(x, f[pre + "norm_q"], cdt, stats=True)
-        qkv = ops.gemm(xn, w[pre + "self.Wqkv_t"])
-        rq = ops.head_rmsnorm_fwd(qkv[:, :A], f[pre + "self.norm_query"], 1.0 / math.sqrt(Dh), H, Dh, save_rstd=True)
-        rk = ops.head_rmsnorm_fwd(qkv[:, A : 2 * A], f[pre + "self.norm_key"], 1.0, H, Dh, save_rstd=True)
+        qkv, rqk = ops.gemm_rmsnorm(xn, w[pre + "self.Wqkv_t"], Dh, A, A, f[pre + "self.norm_query"], f[pre + "self.norm_key"], save_rstd=True)
+        rq, rk = rqk[:, :H], rqk[:, H:]
         o = torch.empty(x.shape[0], A, device=x.device, dtype=cdt)
         stats = ops.attention_fwd(qkv[:, :A], qkv[:, A : 2 * A], qkv[:, 2 * A :], o, batch, H, L, L, Dh, key_mask, save_stats=True)
         a = ops.gemm(o, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x, out_dtype=torch.float32)
         ctx.saved = dict(x=x, mean=mean, rstd=rstd, xn=xn, qkv=qkv, rq=rq, rk=rk, o=o, stats=stats)
         if kv is not None:
-            qc = ops.gemm(xn, w[pre + "cross.Wq_t"])
-            kvp = ops.gemm(kv, w[pre + "cross.Wkv_t"])
-            rqc = ops.head_rmsnorm_fwd(qc, f[pre + "cross.norm_query"], 1.0 / math.sqrt(Dh), H, Dh, save_rstd=True)
-            rkc = ops.head_rmsnorm_fwd(kvp[:, :A], f[pre + "cross.norm_key"], 1.0, H, Dh, save_rstd=True)
+            cq, ck = f[pre + "cross.norm_query"], f[pre + "cross.norm_key"]
+            qc, rqc = ops.gemm_rmsnorm(xn, w[pre + "cross.Wq_t"], Dh, A, 0, cq, ck, save_rstd=True)
+            kvp, rkc = ops.gemm_rmsnorm(kv, w[pre + "cross.Wkv_t"], Dh, 0, A, cq, ck, save_rstd=True)
             oc = torch.empty(x.shape[0], A, device=x.device, dtype=cdt)
             stc = ops.attention_fwd(qc, kvp[:, :A], kvp[:, A:], oc, batch, H, L, Lkv, Dh, None, save_stats=True)
             a = ops.gemm(oc, w[pre + "cross.Wo_t"], f[pre + "cross.bo"], residual=a, out_dtype=torch.float32)

@@ -116,13 +116,25 @@ int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* sc
 /* ---- per-head RMSNorm of q and k (attention.py:166-167) + q/sqrt(Dh) (flax attention) ------
  * In place on a packed projection buffer: for every row and head h < heads,
  *   buf[r, h*Dh : (h+1)*Dh] = x * rsqrt(mean(x^2)+1e-6) * scale[:] * out_mul.
- * rstd_out [rows, heads] f32 may be NULL (saved for backward). */
+ * rstd_out[r*rstd_ld + h] f32 may be NULL (saved for backward). */
 int spa3d_head_rmsnorm_fwd(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
-                           float* rstd_out, int64_t rows, int heads, int Dh, void* stream);
+                           float* rstd_out, int64_t rstd_ld, int64_t rows, int heads, int Dh,
+                           void* stream);
 int spa3d_head_rmsnorm_bwd(const void* y, int64_t ldy, int y_dtype, const float* scale,
-                           float out_mul, const float* rstd, void* dy_inout, int64_t ldd,
-                           int d_dtype, float* dscale_partial, int num_partials, int64_t rows,
-                           int heads, int Dh, void* stream);
+                           float out_mul, const float* rstd, int64_t rstd_ld, void* dy_inout,
+                           int64_t ldd, int d_dtype, float* dscale_partial, int num_partials,
+                           int64_t rows, int heads, int Dh, void* stream);
+
+/* QKV projection with the per-head RMSNorm fused into the GEMM epilogue (attention.py:154-173):
+ *   C = A . Wt^T; columns [0,q_cols) normalised per head with scale_q and multiplied by q_mul
+ *   (= 1/sqrt(Dh), flax dot_product_attention), columns [q_cols, q_cols+k_cols) with scale_k, the
+ *   remaining (value) columns stored as is.  rstd_out [M, (q_cols+k_cols)/Dh] f32 or NULL.
+ *   Self-attention: N=3A, q_cols=k_cols=A.  Cross-attention: q projection (q_cols=A, k_cols=0) and
+ *   key/value projection (q_cols=0, k_cols=A, N=2A). */
+int spa3d_gemm_rmsnorm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
+                       void* C, int64_t ldc, int c_dtype, int64_t M, int N, int K, int Dh,
+                       int q_cols, int k_cols, const float* scale_q, const float* scale_k,
+                       float q_mul, float* rstd_out, int impl, void* stream);
 
 /* ---- K3/K6: softmax(q k^T [+ key mask]) v  (flax nn.dot_product_attention, attention.py:175)
  * Batched over `batch` independent sequences and `heads` heads.

@@ -378,3 +378,45 @@ def test_masked_mean(spa):
     out = spa.ops.masked_mean_fwd(tok, vis, S, T, torch.float32)
     ref = (tok.view(S, T, W) * vis[..., None]).sum(1) / torch.clamp(vis.sum(1, keepdim=True), min=1.0)
     assert rel_err(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("impl,Dh", [("tcgen05", 96), ("tcgen05", 64), ("tcgen05", 32), ("simt", 96)])
+def test_gemm_fused_head_rmsnorm(spa, impl, Dh):
+    """QKV projection with the per-head RMSNorm in the GEMM epilogue (attention.py:154-173)."""
+    ops = spa.ops
+    torch.manual_seed(13)
+    H = 8 if Dh != 32 else 2
+    A, d, M = H * Dh, 384, 1000 + 77
+    dtype = torch.bfloat16 if impl == "tcgen05" else torch.float32
+    code = ops.GEMM_TCGEN05 if impl == "tcgen05" else ops.GEMM_SIMT
+    x = torch.randn(M, d, device="cuda").to(dtype)
+    wt = (torch.randn(3 * A, d, device="cuda") / math.sqrt(d)).to(dtype)
+    sq = 1 + 0.2 * torch.randn(Dh, device="cuda")
+    sk = 1 + 0.2 * torch.randn(Dh, device="cuda")
+    raw = x.double() @ wt.double().t()
+    q = om.rms_norm(raw[:, :A].view(M, H, Dh), sq.double()).reshape(M, A) / math.sqrt(Dh)
+    k = om.rms_norm(raw[:, A : 2 * A].view(M, H, Dh), sk.double()).reshape(M, A)
+    ref = torch.cat([q, k, raw[:, 2 * A :]], dim=1)
+    tol = 2e-5 if impl == "simt" else 6e-3
+    out, rstd = ops.gemm_rmsnorm(x, wt, Dh, A, A, sq, sk, save_rstd=True, impl=code)
+    assert rel_err(out[:, :A], ref[:, :A]) < tol and rel_err(out[:, A : 2 * A], ref[:, A : 2 * A]) < tol
+    assert rel_err(out[:, 2 * A :], ref[:, 2 * A :]) < tol
+    rref = torch.rsqrt((raw[:, : 2 * A].view(M, 2 * H, Dh) ** 2).mean(-1) + 1e-6)
+    assert rel_err(rstd, rref) < 1e-4
+    # cross-attention splits: queries only / keys+values only, on a strided "token 0" view of A
+    kv = ops.gemm_rmsnorm(x, wt[A:], Dh, 0, A, sq, sk, impl=code)
+    assert rel_err(kv[:, :A], ref[:, A : 2 * A]) < tol and rel_err(kv[:, A:], ref[:, 2 * A :]) < tol
+    rows = M // 7
+    q0 = ops.gemm_rmsnorm(x[: rows * 7].view(rows, 7 * d)[:, :d], wt[:A], Dh, A, 0, sq, sk, impl=code)
+    assert rel_err(q0, ref[: rows * 7 : 7, :A]) < tol
+
+
+def test_gemm_cluster_multicast_matches_single(spa, monkeypatch):
+    """CL=2 weight-tile multicast (default) vs many M-tile counts incl. odd tails."""
+    ops = spa.ops
+    torch.manual_seed(14)
+    for M in (129, 256, 257, 128 * 7 + 5, 128 * 300 + 1):
+        a = torch.randn(M, 384, device="cuda").to(torch.bfloat16)
+        wt = (torch.randn(768, 384, device="cuda") / 20).to(torch.bfloat16)
+        y = ops.gemm(a, wt, out_dtype=torch.float32, impl=ops.GEMM_TCGEN05)
+        assert rel_err(y, a.double() @ wt.double().t()) < 2e-5, M
