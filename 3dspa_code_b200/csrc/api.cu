@@ -40,7 +40,9 @@ int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dt
   cudaStream_t st = (cudaStream_t)stream;
   SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
   if (M == 0) return 0;
-  bool tc_ok = (a_dtype == SPA3D_BF16) && gemm_tcgen05_applicable(A, lda, Wt, ldw, M, N, K);
+  // the tcgen05 epilogue evaluates GELU with the hardware tanh (2^-11): fine for bf16 outputs only
+  bool tc_ok = (a_dtype == SPA3D_BF16) && gemm_tcgen05_applicable(A, lda, Wt, ldw, M, N, K) &&
+               !(act == SPA3D_ACT_GELU_TANH && c_dtype == SPA3D_F32);
   if (impl == SPA3D_GEMM_TCGEN05) {
     SPA3D_REQUIRE(tc_ok, "gemm: tcgen05 path not applicable (dtype=%d lda=%lld ldw=%lld K=%d)",
                   a_dtype, (long long)lda, (long long)ldw, K);
@@ -64,7 +66,7 @@ int spa3d_gemm_rmsnorm(const void* A, int64_t lda, const void* Wt, int64_t ldw, 
   SPA3D_REQUIRE(q_cols % Dh == 0 && k_cols % Dh == 0 && q_cols + k_cols <= N, "gemm_rmsnorm: bad head split");
   if (M == 0) return 0;
   bool tc_ok = (a_dtype == SPA3D_BF16) && gemm_tcgen05_applicable(A, lda, Wt, ldw, M, N, K) &&
-               gemm_tcgen05_rms_applicable(N, Dh, q_cols, k_cols);
+               gemm_tcgen05_rms_applicable(N, Dh, q_cols, k_cols, c_dtype);
   if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_rmsnorm: tcgen05 path not applicable");
   if (impl != SPA3D_GEMM_SIMT && tc_ok) {
     RmsEpilogue rms{Dh, q_cols, k_cols, scale_q, scale_k, q_mul, rstd_out};

@@ -53,48 +53,38 @@ __global__ void __launch_bounds__(512)
 attn_fwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk,
                     const bf16* __restrict__ v, int64_t ldv, bf16* __restrict__ o, int64_t ldo,
                     const uint8_t* __restrict__ mask, float* __restrict__ stats, int heads, int Lq,
-                    int Lk, int LqPad, int LkPad) {
+                    int Lk, int QR, int KC, int q_tiles) {
+  // QR = query rows per CTA (16 per warp), KC = keys staged per chunk (multiple of KT).
+  // Lk <= KC: whole sequence in one tile (self-attention, L = 151/129/128).  Lk > KC: the keys are
+  // streamed chunk by chunk under the same online softmax (latents <- tracks cross-attention,
+  // 128 queries x N keys, track_autoencoder_3d.py:200-201).
   constexpr int LDS = DH + 8;    // padded smem row, elements (16 B pad)
   constexpr int CH = DH / 8;     // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
-  bf16* Ks = Qs + (size_t)LqPad * LDS;
-  bf16* Vs = Ks + (size_t)LkPad * LDS;
-  uint8_t* Ms = reinterpret_cast<uint8_t*>(Vs + (size_t)LkPad * LDS);  // 1 keep, 0 masked, 2 absent
+  bf16* Ks = Qs + (size_t)QR * LDS;
+  bf16* Vs = Ks + (size_t)KC * LDS;
+  uint8_t* Ms = reinterpret_cast<uint8_t*>(Vs + (size_t)KC * LDS);  // 1 keep, 0 masked, 2 absent
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
-  const int64_t b = blockIdx.x / heads;
-  const int h = blockIdx.x % heads;
-  const bf16* qg = q + (b * Lq) * ldq + (int64_t)h * DH;
+  const int qt = blockIdx.x % q_tiles;
+  const int64_t bh = blockIdx.x / q_tiles;
+  const int64_t b = bh / heads;
+  const int h = (int)(bh % heads);
+  const int q0 = qt * QR;
+  const bf16* qg = q + (b * Lq + q0) * ldq + (int64_t)h * DH;
   const bf16* kg = k + (b * Lk) * ldk + (int64_t)h * DH;
   const bf16* vg = v + (b * Lk) * ldv + (int64_t)h * DH;
 
-  for (int idx = tid; idx < LqPad * CH; idx += nthr) {
+  for (int idx = tid; idx < QR * CH; idx += nthr) {
     int r = idx / CH, c = idx % CH;
     bf16* dst = Qs + r * LDS + c * 8;
-    if (r < Lq) __pipeline_memcpy_async(dst, qg + (int64_t)r * ldq + c * 8, 16);
+    if (q0 + r < Lq) __pipeline_memcpy_async(dst, qg + (int64_t)r * ldq + c * 8, 16);
     else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
-  for (int idx = tid; idx < LkPad * CH; idx += nthr) {
-    int r = idx / CH, c = idx % CH;
-    bf16* dk = Ks + r * LDS + c * 8;
-    bf16* dv = Vs + r * LDS + c * 8;
-    if (r < Lk) {
-      __pipeline_memcpy_async(dk, kg + (int64_t)r * ldk + c * 8, 16);
-      __pipeline_memcpy_async(dv, vg + (int64_t)r * ldv + c * 8, 16);
-    } else {
-      *reinterpret_cast<uint4*>(dk) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(dv) = make_uint4(0, 0, 0, 0);
-    }
-  }
-  for (int j = tid; j < LkPad; j += nthr)
-    Ms[j] = j < Lk ? (mask == nullptr ? 1 : (mask[b * Lk + j] != 0 ? 1 : 0)) : 2;
-  __pipeline_commit();
-  __pipeline_wait_prior(0);
-  __syncthreads();
 
   const int r0 = warp * 16;
-  if (r0 >= Lq) return;  // no block-wide sync below this point
+  const bool active = q0 + r0 < Lq;
   const int g = lane >> 2, tq = lane & 3;
 
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
@@ -108,7 +98,29 @@ attn_fwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restr
   const int vb_row = (lane & 7) + ((lane >> 3) & 1) * 8, vb_col = (lane >> 4) * 8;     // B from V (.trans)
   constexpr float LOG2E = 1.4426950408889634f;
 
-  for (int kt = 0; kt < LkPad; kt += KT) {
+  for (int kc0 = 0; kc0 < Lk; kc0 += KC) {
+    if (kc0 > 0) __syncthreads();  // every warp is done with the previous chunk
+    const int kn = min(KC, (Lk - kc0 + KT - 1) / KT * KT);  // staged rows of this chunk (padded to KT)
+    for (int idx = tid; idx < kn * CH; idx += nthr) {
+      int r = idx / CH, c = idx % CH;
+      bf16* dk = Ks + r * LDS + c * 8;
+      bf16* dv = Vs + r * LDS + c * 8;
+      if (kc0 + r < Lk) {
+        __pipeline_memcpy_async(dk, kg + (int64_t)(kc0 + r) * ldk + c * 8, 16);
+        __pipeline_memcpy_async(dv, vg + (int64_t)(kc0 + r) * ldv + c * 8, 16);
+      } else {
+        *reinterpret_cast<uint4*>(dk) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dv) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    for (int j = tid; j < kn; j += nthr)
+      Ms[j] = kc0 + j < Lk ? (mask == nullptr ? 1 : (mask[b * Lk + kc0 + j] != 0 ? 1 : 0)) : 2;
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    if (!active) continue;
+
+  for (int kt = 0; kt < kn; kt += KT) {
     float s[KT / 8][4];
 #pragma unroll
     for (int i = 0; i < KT / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -176,6 +188,8 @@ attn_fwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restr
       }
     }
   }
+  }  // key chunks
+  if (!active) return;  // no block-wide sync below this point
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -191,16 +205,16 @@ attn_fwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restr
     *reinterpret_cast<uint32_t*>(Os + (g + 8) * LDS + i * 8 + tq * 2) = pack_bf16(oacc[i][2] * i1, oacc[i][3] * i1);
   }
   __syncwarp();
-  bf16* og = o + (b * Lq) * ldo + (int64_t)h * DH;
+  bf16* og = o + (b * Lq + q0) * ldo + (int64_t)h * DH;
   for (int idx = lane; idx < 16 * CH; idx += 32) {
     int r = idx / CH, c = idx % CH;
-    if (r0 + r < Lq)
+    if (q0 + r0 + r < Lq)
       *reinterpret_cast<uint4*>(og + (int64_t)(r0 + r) * ldo + c * 8) = *reinterpret_cast<const uint4*>(Os + r * LDS + c * 8);
   }
   if (stats != nullptr && tq == 0) {
-    int64_t base = (b * heads + h) * Lq;
-    if (r0 + g < Lq) { stats[(base + r0 + g) * 2] = m0; stats[(base + r0 + g) * 2 + 1] = i0; }
-    if (r0 + g + 8 < Lq) { stats[(base + r0 + g + 8) * 2] = m1; stats[(base + r0 + g + 8) * 2 + 1] = i1; }
+    int64_t base = (b * heads + h) * Lq + q0;
+    if (q0 + r0 + g < Lq) { stats[(base + r0 + g) * 2] = m0; stats[(base + r0 + g) * 2 + 1] = i0; }
+    if (q0 + r0 + g + 8 < Lq) { stats[(base + r0 + g + 8) * 2] = m1; stats[(base + r0 + g + 8) * 2 + 1] = i1; }
   }
 }
 
@@ -208,18 +222,24 @@ template <int DH>
 static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                   void* o, int64_t ldo, const uint8_t* mask, float* stats, int64_t batch, int heads,
                   int Lq, int Lk, cudaStream_t st) {
-  int LqPad = (Lq + 15) / 16 * 16, LkPad = (Lk + KT - 1) / KT * KT;
-  size_t smem = (size_t)(LqPad + 2 * LkPad) * (DH + 8) * 2 + LkPad;
+  // whole-sequence tile when the keys fit (self-attention); otherwise 32 query rows per CTA and
+  // the keys streamed in chunks of 128 (more CTAs, two or more resident per SM)
+  const bool one_tile = Lk <= 256;
+  const int LqPad = (Lq + 15) / 16 * 16;
+  const int QR = one_tile ? LqPad : 32;
+  const int KC = one_tile ? (Lk + KT - 1) / KT * KT : 128;
+  const int q_tiles = (Lq + QR - 1) / QR;
+  size_t smem = (size_t)(QR + 2 * KC) * (DH + 8) * 2 + KC;
   static size_t max_set = 0;
   if (smem > max_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_mma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SPA3D_REQUIRE(e == cudaSuccess, "attention_mma: smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
     max_set = smem;
   }
-  int64_t blocks = batch * heads;
+  int64_t blocks = batch * heads * q_tiles;
   SPA3D_REQUIRE(blocks < (1ll << 31), "attention_mma: grid too large");
-  attn_fwd_mma_kernel<DH><<<(unsigned)blocks, LqPad * 2, smem, st>>>(
-      (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, mask, stats, heads, Lq, Lk, LqPad, LkPad);
+  attn_fwd_mma_kernel<DH><<<(unsigned)blocks, QR * 2, smem, st>>>(
+      (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, mask, stats, heads, Lq, Lk, QR, KC, q_tiles);
   return check_launch("attention_fwd_mma");
 }
 
@@ -229,7 +249,7 @@ bool attention_fwd_mma_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq
                                   int64_t ldv, int64_t ldo) {
   if (dtype != SPA3D_BF16) return false;
   if (Dh != 64 && Dh != 96) return false;
-  if (Lq > 256 || Lk > 256) return false;
+  if (Lq > 256 && Lk <= 256) return false;  // one-tile mode keeps all queries of a sequence in one CTA
   return (ldq % 8 == 0) && (ldk % 8 == 0) && (ldv % 8 == 0) && (ldo % 8 == 0);
 }
 

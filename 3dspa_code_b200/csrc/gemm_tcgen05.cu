@@ -3,33 +3,29 @@
 // This is the throughput path for every Dense / DenseGeneral of the 3DSPA hot path
 // (attention.py:106-107,154-183; track_autoencoder_3d.py:73-115), 90+ % of its FLOPs.
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0      TMA producer  : cp.async.bulk.tensor 2D loads of the A (128 x 64) and Wt
 //                               (BN x 64) K-blocks into a STAGES-deep 128B-swizzled smem ring,
 //                               completion signalled on mbarriers (expect_tx).
 //   warp 1      MMA issuer    : one thread issues tcgen05.mma.cta_group::1.kind::f16
 //                               (M=128, N=BN, K=16) x4 per K-block, accumulating fp32 in TMEM;
 //                               tcgen05.commit releases smem slots and publishes accumulators.
-//   warps 2..5  epilogue      : tcgen05.ld 32 lanes x 32 columns at a time (thread = output row),
-//                               bias / tanh-GELU / residual / per-head RMSNorm in registers, then
-//                               each warp stages its 32 rows x 128 B in a 128B-swizzled smem slab
-//                               (conflict-free st.shared.v4) and one lane issues a TMA store
-//                               (cp.async.bulk.tensor.2d.global.shared), double buffered.  A
-//                               row-per-thread st.global would touch 32 cache lines per
-//                               instruction and made the epilogue, not the MMAs, the pace-setter.
+//   warps 2..9  epilogue      : two warps per TMEM lane quarter, each owning half of the tile's
+//                               columns.  tcgen05.ld 32 lanes x 32 columns at a time (thread = output
+//                               row), software pipelined (the load of chunk c+1 is in flight while
+//                               chunk c is processed); bias / tanh-GELU / per-head RMSNorm run on
+//                               packed fp32x2 instructions.  Stores never go row-per-thread to
+//                               global memory (32 cache lines per instruction): every chunk is
+//                               transposed through a swizzled smem slab and leaves either as a TMA
+//                               store (bf16 outputs) or as 128-byte-per-row coalesced stores with the
+//                               residual read the same coalesced way (fp32 / residual outputs).
 // The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.  Out-of-range rows / columns / K are zero-filled by TMA and masked in
 // the epilogue, so M, N need no padding (K % 8 == 0 for the 16-byte TMA stride rule).
 //
-// Operand reuse (CL = 2): the kernel is L2->smem bound, not MMA bound (a 128 x 256 tile needs 48 KB
-// of operands per 512 MMA cycles).  With CL = 2 the two CTAs of a cluster work on vertically
-// adjacent M tiles of the same N tile; each loads half of the weight tile and multicasts it to
-// both (cp.async.bulk.tensor ... .multicast::cluster), so weight traffic from L2 halves.  The smem
-// slot of a stage is released by BOTH CTAs' MMA warps (tcgen05.commit ... multicast::cluster).
-//
-// Fused per-head RMSNorm (attention.py:166-167): with BN a multiple of the head width every
-// accumulator row holds whole heads in one thread, so q/k normalisation (+ q/sqrt(Dh)) is two
-// passes over TMEM inside the epilogue and the separate in-place pass over q,k disappears.
+// Fused per-head RMSNorm (attention.py:166-167): BN/2 is a multiple of the head width, so every
+// epilogue thread holds whole heads of its row in registers: q/k normalisation (+ q/sqrt(Dh)) is a
+// sum of squares and a scale on values already loaded from TMEM.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -40,7 +36,8 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -83,32 +80,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1,
-                                               uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
-        "r"(c1), "h"(mask)
-      : "memory");
-}
-
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, single CTA
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -127,14 +104,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(mask)
-      : "memory");
-}
-
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
 // (cute::UMMA::SmemDescriptor: start>>4 @0, LBO>>4 @16, SBO>>4 @32, version=1 @46, layout @61)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -168,21 +137,27 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
 constexpr int tmem_cols_for(int bn) {
   int need = 2 * bn;
   return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
 }
+
+// epilogue flavours (template parameter EPI)
+constexpr int EPI_TMA = 0;     // bf16 output, no residual: swizzled slab -> TMA store
+constexpr int EPI_DIRECT = 1;  // fp32 output and/or residual: slab transpose -> coalesced ld/st.global
+constexpr int EPI_RMS = 2;     // bf16 output with fused per-head RMSNorm of the q / k columns
 
 template <int BN>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
-  static constexpr int SCALE_BYTES = 2 * 128 * 4;  // RMSNorm scales (q, k)
-  static constexpr int BUDGET = 227 * 1024 - EPI_BYTES - SCALE_BYTES - 256 - 1024;
-  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * 4096;  // one 4 KB slab (or 2 x 2 KB) per epilogue warp
+  static constexpr int SCALE_BYTES = 2 * 128 * 4;         // RMSNorm scales (q, k)
   static constexpr int BAR_BYTES = 256;
+  static constexpr int BUDGET = 227 * 1024 - EPI_BYTES - SCALE_BYTES - BAR_BYTES - 1024;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + SCALE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
@@ -196,26 +171,69 @@ struct EpiParams {
   int c_dtype;
   int act;
   // fused per-head RMSNorm: columns [0,q_cols) use scale_q * q_mul, [q_cols, q_cols+k_cols) use
-  // scale_k, the rest is stored as is.  rms_dh == 0 disables it.
-  int rms_dh;
+  // scale_k, the rest is stored as is.
   int q_cols;
   int k_cols;
   const float* scale_q;
   const float* scale_k;
   float q_mul;
-  float* rstd_out;   // [M, (q_cols+k_cols)/rms_dh] or null
+  float* rstd_out;   // [M, (q_cols+k_cols)/DH] or null
+  int debug_skip;    // SPA3D_GEMM_SKIP_EPI=1: accumulators are drained but nothing is computed or stored
 };
+
+// ---- packed fp32x2 arithmetic (sm_100: two fp32 lanes per instruction) ----
+__device__ __forceinline__ uint64_t pk(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pku(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(uint64_t v) {
+  float a, b;
+  upk(v, a, b);
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// flax nn.gelu(approximate=True) with the hardware tanh (bf16 outputs only)
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float k = 0.7978845608028654f;
-  float u = k * fmaf(0.044715f * x, x * x, x);
-  return 0.5f * x * (1.0f + tanh_fast(u));
+// flax nn.gelu(approximate=True) on two values, hardware tanh (bf16 outputs only)
+__device__ __forceinline__ uint64_t gelu2_fast(uint64_t x) {
+  constexpr float k = 0.7978845608028654f;
+  const uint64_t c1 = pk(k * 0.044715f, k * 0.044715f), c0 = pk(k, k), half = pk(0.5f, 0.5f);
+  uint64_t t = mul2(x, x);
+  uint64_t p = fma2(t, c1, c0);
+  uint64_t u = mul2(p, x);
+  float u0, u1;
+  upk(u, u0, u1);
+  uint64_t th = pk(tanh_fast(u0), tanh_fast(u1));
+  uint64_t hx = mul2(x, half);
+  return fma2(hx, th, hx);
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
@@ -233,57 +251,51 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// bias / GELU / residual on 8 consecutive columns of one output row (registers only)
-__device__ __forceinline__ void epi_math8(const EpiParams& ep, float (&v)[8], int64_t row, int col, bool row_ok) {
+// bias + activation on one 32-column chunk of an output row held in registers (v = packed pairs)
+__device__ __forceinline__ void epi_bias_act(const EpiParams& ep, uint64_t (&v)[16], int col0, int N) {
   if (ep.bias) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
-  if (ep.act == SPA3D_ACT_GELU_TANH) {
-    if (ep.c_dtype == SPA3D_BF16) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
-    }
-  }
-  if (ep.residual && row_ok) {
-    if (ep.r_dtype == SPA3D_F32) {
-      const float* rp = reinterpret_cast<const float*>(ep.residual) + row * ep.ldr + col;
-      const float4 r0 = *reinterpret_cast<const float4*>(rp);
-      const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-      v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-    } else {
-      const uint4 rr = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.residual) + row * ep.ldr + col);
-      const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-        v[2 * i] += __low2float(h);
-        v[2 * i + 1] += __high2float(h);
+    for (int g = 0; g < 8; ++g) {
+      if (col0 + 4 * g < N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 4 * g));
+        v[2 * g] = add2(v[2 * g], pk(b.x, b.y));
+        v[2 * g + 1] = add2(v[2 * g + 1], pk(b.z, b.w));
       }
     }
   }
+  if (ep.act == SPA3D_ACT_GELU_TANH) {   // bf16 outputs only (api.cu routes fp32 + GELU to the SIMT path)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = gelu2_fast(v[i]);
+  }
 }
 
-template <int BN, int CL>
+// 32 bf16 of this lane's row -> 64-byte row of a [32 x 64 B] slab laid out for a SWIZZLE_64B TMA store
+__device__ __forceinline__ void slab_store_bf16(uint8_t* slab, int lane, const uint64_t (&v)[16]) {
+  uint8_t* srow = slab + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 w = make_uint4(pack_bf16x2(v[4 * j]), pack_bf16x2(v[4 * j + 1]), pack_bf16x2(v[4 * j + 2]),
+                         pack_bf16x2(v[4 * j + 3]));
+    *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = w;
+  }
+}
+
+template <int BN, int EPI, int DH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, EpiParams ep, int64_t M, int N, int K) {
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
   constexpr int TMEM_COLS = tmem_cols_for(BN);
-  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
+  constexpr int HC = BN / 2;     // columns per epilogue warp
+  constexpr int NCH = HC / 32;   // 32-column chunks per epilogue warp
+  static_assert(HC % 32 == 0, "tile halves must be whole 32-column chunks");
   extern __shared__ uint8_t smem_raw[];
-  // identical offsets in every CTA of a cluster (multicast writes land at the same smem offset)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * L::A_BYTES;
-  uint8_t* smem_epi = smem + STAGES * L::STAGE_BYTES;                    // [4 warps][2][4096], 1024-aligned
+  uint8_t* smem_epi = smem + STAGES * L::STAGE_BYTES;                    // [8 warps][4096], 1024-aligned
   float* smem_scale = reinterpret_cast<float*>(smem_epi + L::EPI_BYTES);  // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + L::EPI_BYTES + L::SCALE_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
@@ -296,23 +308,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_kb = (K + BK - 1) / BK;
   const int n_tiles = (N + BN - 1) / BN;
   const int64_t m_tiles = (M + BM - 1) / BM;
-  const int64_t m_groups = (m_tiles + CL - 1) / CL;
-  const int64_t num_groups = m_groups * n_tiles;      // a group = CL vertically adjacent tiles
-  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
-  const int64_t cluster_id = blockIdx.x / CL;
-  const int64_t num_clusters = gridDim.x / CL;
+  const int64_t num_tiles = m_tiles * n_tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    if (EPI != EPI_DIRECT) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);   // one tcgen05.commit from every CTA of the cluster
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], NUM_EPI_WARPS * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -323,15 +331,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (ep.rms_dh > 0 && threadIdx.x >= 64) {
-    for (int i = threadIdx.x - 64; i < ep.rms_dh; i += NUM_THREADS - 64) {
+  if (EPI == EPI_RMS && threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < DH; i += NUM_THREADS - 64) {
       smem_scale[i] = ep.scale_q ? ep.scale_q[i] * ep.q_mul : 0.f;
       smem_scale[128 + i] = ep.scale_k ? ep.scale_k[i] : 0.f;
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast lands
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -340,19 +347,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t g = cluster_id; g < num_groups; g += num_clusters) {
-        const int m_blk = (int)(g / n_tiles) * CL + (int)crank, n_blk = (int)(g % n_tiles);
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           tma_load_2d(smem_a + stage * L::A_BYTES, &tmA, kb * BK, m_blk * BM, &full_bar[stage]);
-          if (CL == 1) {
-            tma_load_2d(smem_b + stage * L::B_BYTES, &tmB, kb * BK, n_blk * BN, &full_bar[stage]);
-          } else {
-            // this CTA fetches rows [crank*BN/CL, (crank+1)*BN/CL) of the weight tile for everyone
-            tma_load_2d_mc(smem_b + stage * L::B_BYTES + crank * (L::B_BYTES / CL), &tmB, kb * BK,
-                           n_blk * BN + (int)crank * (BN / CL), &full_bar[stage], MC_MASK);
-          }
+          tma_load_2d(smem_b + stage * L::B_BYTES, &tmB, kb * BK, n_blk * BN, &full_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -364,7 +365,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int64_t g = cluster_id; g < num_groups; g += num_clusters, ++it) {
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
@@ -381,127 +382,243 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                       (kb > 0 || k > 0) ? 1u : 0u);
           }
-          // smem slot reusable (in every CTA that multicasts into it) once these MMAs have read it
-          if (CL == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_mc(&empty_bar[stage], MC_MASK);
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[as]);  // accumulator complete
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    uint8_t* slab = smem_epi + (size_t)quarter * 2 * 4096;
+    const int half = ew >> 2;      // which half of the tile's columns
+    uint8_t* slab = smem_epi + (size_t)ew * 4096;
     const bool out_f32 = ep.c_dtype == SPA3D_F32;
-    const int box_cols = out_f32 ? 32 : 64;     // 128 bytes of output per row and box
     int sbuf = 0;
     int it = 0;
-    for (int64_t g = cluster_id; g < num_groups; g += num_clusters, ++it) {
-      const int m_blk = (int)(g / n_tiles) * CL + (int)crank, n_blk = (int)(g % n_tiles);
+    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[as], aphase);
-      tcgen05_fence_after();
       const int row0 = m_blk * BM + quarter * 32;
       const int64_t row = (int64_t)row0 + lane;
-      const bool row_ok = row < M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
-      // fused per-head RMSNorm, pass 1: 1/rms of every normalised head of this row
-      float rstd_h[8];
-      const int dh = ep.rms_dh;
-      const int nq = ep.q_cols + ep.k_cols;
-      if (dh > 0) {
-#pragma unroll 1
-        for (int hh = 0; hh * dh < BN; ++hh) {
-          const int gcol = n_blk * BN + hh * dh;
-          float rs = 1.f;
-          if (gcol < nq && gcol < N) {
-            float ss = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < dh; c0 += 32) {
-              uint32_t r[32];
-              tmem_ld32(taddr + (uint32_t)(hh * dh + c0), r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float x = __uint_as_float(r[i]);
-                ss = fmaf(x, x, ss);
-              }
-            }
-            rs = rsqrtf(ss / (float)dh + kNormEps);
-            if (ep.rstd_out && row_ok) ep.rstd_out[row * (nq / dh) + gcol / dh] = rs;
-          }
-          rstd_h[hh & 7] = rs;
-        }
-      }
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int col0 = n_blk * BN + c0;
-        if (col0 >= N) break;
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        const int cb = c0 % box_cols;  // column offset inside the current 128-byte box
-        if (cb == 0) {
-          // the buffer we are about to fill was handed to a TMA store two boxes ago
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-        }
-        float mul = 1.f;
-        const float* sc = nullptr;
-        if (dh > 0 && col0 < nq) {
-          mul = rstd_h[(c0 / dh) & 7];
-          sc = smem_scale + (col0 < ep.q_cols ? 0 : 128) + (c0 % dh);
-        }
-        uint8_t* srow = slab + sbuf * 4096 + lane * 128;
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          float v[8];
+      const int colbase = n_blk * BN + half * HC;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * HC);
+
+      if constexpr (EPI == EPI_DIRECT) {
+        // ---- fp32 / residual outputs -------------------------------------------------------------
+        // coalesced view of a 32 x 32 chunk: pass i covers rows 4i..4i+3, lane -> (row 4i + lane/8,
+        // 4 columns at (lane%8)*4): every 8 lanes touch one 128-byte (fp32) row segment.
+        const int cr = lane >> 3, cc = lane & 7;
+        uint4 res[8];
+        auto load_res = [&](int c) {
+          const int col = colbase + c * 32 + cc * 4;
+          const int esz_r = ep.r_dtype == SPA3D_F32 ? 4 : 2;
+          const char* rp = reinterpret_cast<const char*>(ep.residual) + (((int64_t)row0 + cr) * ep.ldr + col) * esz_r;
+          const int64_t rstep = 4 * ep.ldr * esz_r;
+          const int rows_ok = (ep.residual && col < N) ? (int)min((int64_t)32, M - row0) : 0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float x = __uint_as_float(r[gq * 8 + i]);
-            v[i] = sc ? x * mul * sc[gq * 8 + i] : x;
-          }
-          const int col = col0 + gq * 8;
-          if (col < N) epi_math8(ep, v, row, col, row_ok);
-          if (out_f32) {
-            // 8 floats = two 16-byte chunks j = 2*gq, 2*gq+1 of the 128-byte row; swizzle j ^ (row & 7)
-            const int j0 = 2 * gq, j1 = 2 * gq + 1;
-            *reinterpret_cast<float4*>(srow + ((j0 ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(srow + ((j1 ^ (lane & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-            uint32_t w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            res[i] = make_uint4(0, 0, 0, 0);
+            if (i * 4 + cr < rows_ok) {
+              if (ep.r_dtype == SPA3D_F32) {
+                res[i] = *reinterpret_cast<const uint4*>(rp);
+              } else {
+                const uint2 h = *reinterpret_cast<const uint2*>(rp);
+                res[i].x = h.x;
+                res[i].y = h.y;
+              }
             }
-            const int j = (cb >> 3) + gq;  // 8 bf16 = one 16-byte chunk
-            *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            rp += rstep;
+          }
+        };
+        if (!ep.debug_skip) {
+          load_res(0);   // in flight while the MMAs of this tile still run
+          // pull the residual of this CTA's next tile into L2 (one prefetch per 128-byte line)
+          const int64_t tn = t + gridDim.x;
+          if (ep.residual && tn < num_tiles) {
+            const int64_t prow = (int64_t)(tn / n_tiles) * BM + quarter * 32 + lane;
+            const int pcol = (int)(tn % n_tiles) * BN + half * HC;
+            const int esz = ep.r_dtype == SPA3D_F32 ? 4 : 2;
+            if (prow < M) {
+              const char* pp = reinterpret_cast<const char*>(ep.residual) + (prow * ep.ldr + pcol) * esz;
+              for (int b = 0; b < HC * esz && pcol + b / esz < N; b += 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + b));
+            }
           }
         }
-        const bool box_done = (cb + 32 == box_cols) || (c0 + 32 >= BN) || (col0 + 32 >= N);
-        if (box_done) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, slab + sbuf * 4096, col0 - cb, row0);
-            bulk_commit();
+        mbar_wait(&tfull_bar[as], aphase);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tbase + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+          if (c == NCH - 1) {
+            tcgen05_fence_before();
+            mbar_arrive(&tempty_bar[as]);   // every value of this accumulator is in registers
           }
-          sbuf ^= 1;
+          const int col0 = colbase + c * 32;
+          if (col0 < N && !ep.debug_skip) {
+            uint64_t v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = pku(r[2 * i], r[2 * i + 1]);
+            epi_bias_act(ep, v, col0, N);
+            uint8_t* srow = slab + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a0, a1, a2, a3;
+              upk(v[2 * j], a0, a1);
+              upk(v[2 * j + 1], a2, a3);
+              *reinterpret_cast<float4*>(srow + ((j ^ (lane & 7)) << 4)) = make_float4(a0, a1, a2, a3);
+            }
+            __syncwarp();
+            const int col = col0 + cc * 4;
+            const int esz_c = out_f32 ? 4 : 2;
+            char* cp = reinterpret_cast<char*>(ep.C) + (((int64_t)row0 + cr) * ep.ldc + col) * esz_c;
+            const int64_t cstep = 4 * ep.ldc * esz_c;
+            const int rows_ok = col < N ? (int)min((int64_t)32, M - row0) : 0;   // rows of this chunk inside the matrix
+            // row 4i + cr sits at chunk cc ^ ((4i + cr) & 7) = cc ^ cr ^ 4(i & 1): odd passes flip 64 bytes
+            const uint8_t* sp = slab + cr * 128 + ((cc ^ cr) << 4);
+            const int odd_off = (cc & 4) ? -64 : 64;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 a = *reinterpret_cast<const float4*>(sp + i * 512 + ((i & 1) ? odd_off : 0));
+              const uint4 q = res[i];
+              if (ep.residual) {
+                if (ep.r_dtype == SPA3D_F32) {
+                  a.x += __uint_as_float(q.x); a.y += __uint_as_float(q.y);
+                  a.z += __uint_as_float(q.z); a.w += __uint_as_float(q.w);
+                } else {
+                  const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+                  const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+                  a.x += __low2float(h0); a.y += __high2float(h0);
+                  a.z += __low2float(h1); a.w += __high2float(h1);
+                }
+              }
+              if (i * 4 + cr < rows_ok) {
+                if (out_f32) {
+                  *reinterpret_cast<float4*>(cp) = a;
+                } else {
+                  __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+                  *reinterpret_cast<uint2*>(cp) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                }
+              }
+              cp += cstep;
+            }
+            __syncwarp();   // slab is rewritten by the next chunk
+          }
+          if (c + 1 < NCH && !ep.debug_skip) load_res(c + 1);
+        }
+      } else if constexpr (EPI == EPI_TMA) {
+        // ---- bf16 outputs: slab -> TMA store, two 2 KB buffers per warp --------------------------
+        mbar_wait(&tfull_bar[as], aphase);
+        tcgen05_fence_after();
+        uint32_t r[2][32];
+        tmem_ld32(tbase, r[0]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < NCH) {
+            tmem_ld32(tbase + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+          } else {
+            tcgen05_fence_before();
+            mbar_arrive(&tempty_bar[as]);
+          }
+          const int col0 = colbase + c * 32;
+          if (col0 < N && !ep.debug_skip) {
+            uint64_t v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = pku(r[c & 1][2 * i], r[c & 1][2 * i + 1]);
+            epi_bias_act(ep, v, col0, N);
+            if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago has left this buffer
+            __syncwarp();
+            slab_store_bf16(slab + sbuf * 2048, lane, v);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, slab + sbuf * 2048, col0, row0);
+              bulk_commit();
+            }
+            sbuf ^= 1;
+          }
+        }
+      } else {
+        // ---- bf16 outputs with per-head RMSNorm: whole heads of this row live in registers ---------
+        constexpr int HPW = HC / DH;     // heads per warp
+        constexpr int NCHH = DH / 32;    // chunks per head
+        static_assert(HC % DH == 0 && DH % 32 == 0, "tile half must hold whole heads");
+        const int nq = ep.q_cols + ep.k_cols;
+        mbar_wait(&tfull_bar[as], aphase);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < HPW; ++hh) {
+          const int gcol = colbase + hh * DH;
+          uint32_t r[NCHH][32];
+#pragma unroll
+          for (int c = 0; c < NCHH; ++c) tmem_ld32(tbase + (uint32_t)(hh * DH + c * 32), r[c]);
+          tmem_ld_wait();
+          if (hh == HPW - 1) {
+            tcgen05_fence_before();
+            mbar_arrive(&tempty_bar[as]);
+          }
+          if (gcol >= N || ep.debug_skip) continue;
+          const int kind = gcol < ep.q_cols ? 0 : (gcol < nq ? 1 : 2);   // q / k / v columns (warp uniform)
+          uint64_t rs2 = pk(1.f, 1.f);
+          if (kind < 2) {
+            uint64_t acc0 = pk(0.f, 0.f), acc1 = pk(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < NCHH; ++c) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                const uint64_t x0 = pku(r[c][2 * i], r[c][2 * i + 1]), x1 = pku(r[c][2 * i + 2], r[c][2 * i + 3]);
+                acc0 = fma2(x0, x0, acc0);
+                acc1 = fma2(x1, x1, acc1);
+              }
+            }
+            float s0, s1;
+            upk(add2(acc0, acc1), s0, s1);
+            const float rs = rsqrtf((s0 + s1) / (float)DH + kNormEps);
+            if (ep.rstd_out && row < M) ep.rstd_out[row * (nq / DH) + gcol / DH] = rs;
+            rs2 = pk(rs, rs);
+          }
+          const float* sc = smem_scale + kind * 128;
+#pragma unroll
+          for (int c = 0; c < NCHH; ++c) {
+            uint64_t v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = pku(r[c][2 * i], r[c][2 * i + 1]);
+            if (kind < 2) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 s4 = *reinterpret_cast<const float4*>(sc + c * 32 + g * 4);
+                v[2 * g] = mul2(mul2(v[2 * g], rs2), pk(s4.x, s4.y));
+                v[2 * g + 1] = mul2(mul2(v[2 * g + 1], rs2), pk(s4.z, s4.w));
+              }
+            }
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            slab_store_bf16(slab + sbuf * 2048, lane, v);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, slab + sbuf * 2048, gcol + c * 32, row0);
+              bulk_commit();
+            }
+            sbuf ^= 1;
+          }
         }
       }
-      tcgen05_fence_before();
-      mbar_arrive(&tempty_bar[as]);
     }
-    if (lane == 0) bulk_wait_read<0>();
-    __syncwarp();
+    if (EPI != EPI_DIRECT) {
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+    }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into its smem
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -528,18 +645,17 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// output map: [M, N] of bf16 / f32, box = {128 bytes of columns, 32 rows}, 128B swizzle
-static int make_map_c(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int c_dtype) {
+// bf16 output map: [M, N], box = {32 columns (64 bytes), 32 rows}, 64B swizzle
+static int make_map_c(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn fn = get_encode_fn();
   SPA3D_REQUIRE(fn != nullptr, "gemm_tcgen05: cuTensorMapEncodeTiled not available from the driver");
-  const int esz = c_dtype == SPA3D_F32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 32u};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32u, 32u};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, c_dtype == SPA3D_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SPA3D_REQUIRE(r == CUDA_SUCCESS, "gemm_tcgen05: cuTensorMapEncodeTiled (C) failed (%d)", (int)r);
   return 0;
 }
@@ -560,59 +676,57 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
   return 0;
 }
 
-static int g_cluster = 2;  // weight-tile multicast width (1 = off); SPA3D_GEMM_CLUSTER overrides
-
-static int cluster_width() {
-  static bool init = false;
-  if (!init) {
-    const char* e = getenv("SPA3D_GEMM_CLUSTER");
-    if (e) g_cluster = atoi(e) == 1 ? 1 : 2;
-    init = true;
+static int debug_skip_epilogue() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPA3D_GEMM_SKIP_EPI");
+    v = (e && atoi(e) == 1) ? 1 : 0;
   }
-  return g_cluster;
+  return v;
 }
 
-template <int BN, int CL>
-static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, const EpiParams& ep,
-                  int64_t M, int N, int K, cudaStream_t st) {
+template <int BN, int EPI, int DH>
+static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiParams ep, int64_t M,
+                  int N, int K, cudaStream_t st) {
   using L = SmemLayout<BN>;
   CUtensorMap tmA, tmB, tmC;
   if (make_map(&tmA, A, M, K, lda, BM)) return 1;
-  if (make_map(&tmB, Wt, N, K, ldw, BN / CL)) return 1;
-  if (make_map_c(&tmC, ep.C, M, N, ep.ldc, ep.c_dtype)) return 1;
+  if (make_map(&tmB, Wt, N, K, ldw, BN)) return 1;
+  if (EPI == EPI_DIRECT) tmC = tmA;  // unused
+  else if (make_map_c(&tmC, ep.C, M, N, ep.ldc)) return 1;
+  ep.debug_skip = debug_skip_epilogue();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     SPA3D_REQUIRE(e == cudaSuccess, "gemm_tcgen05: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  int64_t m_tiles = (M + BM - 1) / BM;
-  int64_t groups = ((m_tiles + CL - 1) / CL) * ((N + BN - 1) / BN);
-  int max_clusters = num_sms() / CL;
-  int clusters = (int)(groups < max_clusters ? groups : max_clusters);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * CL));
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = L::TOTAL;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CL>, tmA, tmB, tmC, ep, M, N, K);
-  SPA3D_REQUIRE(e == cudaSuccess, "gemm_tcgen05 launch: %s", cudaGetErrorString(e));
+  int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  gemm_tcgen05_kernel<BN, EPI, DH><<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, ep, M, N, K);
   return check_launch("gemm_tcgen05");
 }
 
-template <int BN>
-static int launch_cl(const void* A, int64_t lda, const void* Wt, int64_t ldw, const EpiParams& ep,
+template <int EPI>
+static int launch_bn(int bn, const void* A, int64_t lda, const void* Wt, int64_t ldw, const EpiParams& ep,
                      int64_t M, int N, int K, cudaStream_t st) {
-  // multicast pays only when there are at least two M tiles to pair up
-  if (cluster_width() == 2 && M > BM) return launch<BN, 2>(A, lda, Wt, ldw, ep, M, N, K, st);
-  return launch<BN, 1>(A, lda, Wt, ldw, ep, M, N, K, st);
+  switch (bn) {
+    case 256: return launch<256, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st);
+    case 192: return launch<192, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st);
+    case 128: return launch<128, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st);
+    default: return launch<64, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st);
+  }
+}
+
+// tile width: the candidate of {256,192,128} with the least padded N (ties -> the widest); 64 for N <= 64
+static int pick_bn(int N) {
+  if (N <= 64) return 64;
+  int best = 256, best_pad = (N + 255) / 256 * 256;
+  for (int bn : {192, 128}) {
+    int pad = (N + bn - 1) / bn * bn;
+    if (pad < best_pad) { best = bn; best_pad = pad; }
+  }
+  return best;
 }
 
 }  // namespace tc
@@ -624,7 +738,8 @@ bool gemm_tcgen05_applicable(const void* A, int64_t lda, const void* Wt, int64_t
          M > 0 && M < (1ll << 31);
 }
 
-bool gemm_tcgen05_rms_applicable(int N, int dh, int q_cols, int k_cols) {
+bool gemm_tcgen05_rms_applicable(int N, int dh, int q_cols, int k_cols, int c_dtype) {
+  if (c_dtype != SPA3D_BF16) return false;
   if (dh != 64 && dh != 96 && dh != 32 && dh != 128) return false;
   return q_cols % dh == 0 && k_cols % dh == 0 && N % dh == 0;
 }
@@ -640,27 +755,26 @@ int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const 
     SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(residual) & 15) == 0 && ldr % (r_dtype == SPA3D_F32 ? 4 : 8) == 0,
                   "gemm_tcgen05: residual must be 16-byte aligned with 16-byte row pitch");
   if (bias) SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm_tcgen05: bias must be 16-byte aligned");
-  EpiParams ep{bias, residual, ldr, r_dtype, C, ldc, c_dtype, act, 0, 0, 0, nullptr, nullptr, 1.f, nullptr};
+  EpiParams ep{bias, residual, ldr, r_dtype, C, ldc, c_dtype, act, 0, 0, nullptr, nullptr, 1.f, nullptr, 0};
   if (rms && rms->dh > 0) {
-    ep.rms_dh = rms->dh; ep.q_cols = rms->q_cols; ep.k_cols = rms->k_cols;
+    SPA3D_REQUIRE(c_dtype == SPA3D_BF16 && !bias && !residual && act == 0, "gemm_tcgen05: fused RMSNorm is bf16, no bias/act/residual");
+    ep.q_cols = rms->q_cols; ep.k_cols = rms->k_cols;
     ep.scale_q = rms->scale_q; ep.scale_k = rms->scale_k; ep.q_mul = rms->q_mul; ep.rstd_out = rms->rstd_out;
-    // tile width must hold whole heads
-    const int dh = rms->dh;
-    if (dh == 96) return launch_cl<192>(A, lda, Wt, ldw, ep, M, N, K, st);
-    if (dh == 64 || dh == 128 || dh == 32) {
-      if (N % 256 == 0) return launch_cl<256>(A, lda, Wt, ldw, ep, M, N, K, st);
-      return launch_cl<128>(A, lda, Wt, ldw, ep, M, N, K, st);
+    // every half tile must hold whole heads
+    const bool wide = N % 256 == 0;
+    switch (rms->dh) {
+      case 96: return launch<192, EPI_RMS, 96>(A, lda, Wt, ldw, ep, M, N, K, st);
+      case 128: return launch<256, EPI_RMS, 128>(A, lda, Wt, ldw, ep, M, N, K, st);
+      case 64: return wide ? launch<256, EPI_RMS, 64>(A, lda, Wt, ldw, ep, M, N, K, st)
+                           : launch<128, EPI_RMS, 64>(A, lda, Wt, ldw, ep, M, N, K, st);
+      case 32: return wide ? launch<256, EPI_RMS, 32>(A, lda, Wt, ldw, ep, M, N, K, st)
+                           : launch<64, EPI_RMS, 32>(A, lda, Wt, ldw, ep, M, N, K, st);
+      default: SPA3D_REQUIRE(false, "gemm_tcgen05: fused RMSNorm needs a head width of 32, 64, 96 or 128");
     }
-    SPA3D_REQUIRE(false, "gemm_tcgen05: fused RMSNorm needs a head width of 32, 64, 96 or 128");
   }
-  // tile width: the widest of {256,192,128} that divides N, else the narrowest tile covering N
-  if (N % 256 == 0) return launch_cl<256>(A, lda, Wt, ldw, ep, M, N, K, st);
-  if (N % 192 == 0) return launch_cl<192>(A, lda, Wt, ldw, ep, M, N, K, st);
-  if (N % 128 == 0) return launch_cl<128>(A, lda, Wt, ldw, ep, M, N, K, st);
-  if (N <= 64) return launch_cl<64>(A, lda, Wt, ldw, ep, M, N, K, st);
-  // 96-wide tiles only for f32 outputs: a bf16 store box spans 64 columns and must not straddle tiles
-  if (N <= 96 && c_dtype == SPA3D_F32) return launch_cl<96>(A, lda, Wt, ldw, ep, M, N, K, st);
-  return launch_cl<128>(A, lda, Wt, ldw, ep, M, N, K, st);
+  const int bn = pick_bn(N);
+  if (c_dtype == SPA3D_BF16 && !residual) return launch_bn<EPI_TMA>(bn, A, lda, Wt, ldw, ep, M, N, K, st);
+  return launch_bn<EPI_DIRECT>(bn, A, lda, Wt, ldw, ep, M, N, K, st);
 }
 
 }  // namespace spa3d

@@ -126,10 +126,10 @@ def test_gemm_shapes(spa, impl):
         wt = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(dtype)
         bias = torch.randn(N, device="cuda")
         res = torch.randn(M, N, device="cuda")
-        for variant in range(4):
+        for variant in range(5):
             b = bias if variant in (1, 2, 3) else None
             act = ops.ACT_GELU if variant == 2 else ops.ACT_NONE
-            r = res if variant == 3 else None
+            r = res if variant == 3 else (res.to(dtype) if variant == 4 else None)  # 4: residual in the compute dtype (backward)
             odt = torch.float32 if variant in (0, 3) else dtype
             y = ops.gemm(a, wt, b, act, r, out_dtype=odt, impl=code)
             ref = _gemm_ref(a, wt, b, act, r)
@@ -217,6 +217,7 @@ def _attn_ref(q, k, v, mask, batch, H, Lq, Lk, Dh):
     (torch.float32, 151, 151, 96), (torch.float32, 128, 300, 96), (torch.float32, 13, 13, 64),
     (torch.bfloat16, 151, 151, 96), (torch.bfloat16, 129, 129, 96), (torch.bfloat16, 128, 128, 64),
     (torch.bfloat16, 16, 16, 96), (torch.bfloat16, 37, 37, 64), (torch.bfloat16, 128, 2048, 96),
+    (torch.bfloat16, 40, 300, 64), (torch.bfloat16, 128, 4096, 96),
 ])
 def test_attention_fwd(spa, dtype, Lq, Lk, Dh):
     ops = spa.ops
@@ -411,8 +412,8 @@ def test_gemm_fused_head_rmsnorm(spa, impl, Dh):
     assert rel_err(q0, ref[: rows * 7 : 7, :A]) < tol
 
 
-def test_gemm_cluster_multicast_matches_single(spa, monkeypatch):
-    """CL=2 weight-tile multicast (default) vs many M-tile counts incl. odd tails."""
+def test_gemm_persistent_tile_counts(spa):
+    """Persistent tile loop: fewer / more tiles than SMs, odd M tails."""
     ops = spa.ops
     torch.manual_seed(14)
     for M in (129, 256, 257, 128 * 7 + 5, 128 * 300 + 1):
