@@ -88,6 +88,24 @@ int spa3d_gemm_rmsnorm(const void* A, int64_t lda, const void* Wt, int64_t ldw, 
   return rc;
 }
 
+int spa3d_gemm_dw(const void* dY, int64_t lddy, const void* X, int64_t ldx, int dtype, float* dW,
+                  int64_t lddw, int64_t M, int N, int K, int accumulate, int impl, void* stream) {
+  using namespace spa3d;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_dw: bad shape");
+  bool tc_ok = dtype == SPA3D_BF16 && gemm_tcgen05_dw_applicable(dY, lddy, X, ldx, M, N, K, dW, lddw);
+  if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok || M == 0, "gemm_dw: tcgen05 path not applicable");
+  if (!accumulate) {
+    cudaError_t e = cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)K * 4, (size_t)N, st);
+    SPA3D_REQUIRE(e == cudaSuccess, "gemm_dw: memset: %s", cudaGetErrorString(e));
+  }
+  if (M == 0) return 0;
+  if (impl != SPA3D_GEMM_SIMT && tc_ok) return gemm_tcgen05_dw(dY, lddy, X, ldx, dW, lddw, M, N, K, st);
+  // SIMT: A(n,m) = dY[m*lddy + n], B(m,k) = X[m*ldx + k]
+  return gemm_simt(dY, 1, lddy, dtype, X, ldx, 1, dtype, nullptr, 0, nullptr, 0, 0, dW, lddw, SPA3D_F32, N,
+                   K, M, 1, st);
+}
+
 int spa3d_gemm_strided(const void* A, int64_t sam, int64_t sak, int a_dtype, const void* B,
                        int64_t sbk, int64_t sbn, int b_dtype, void* C, int64_t ldc, int c_dtype,
                        int64_t M, int N, int64_t K, int accumulate, void* stream) {

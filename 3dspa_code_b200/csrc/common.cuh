@@ -113,6 +113,10 @@ bool gemm_tcgen05_rms_applicable(int N, int dh, int q_cols, int k_cols, int c_dt
 int head_rmsnorm_fwd_impl(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
                           float* rstd_out, int64_t rstd_ld, int64_t rows, int heads, int Dh,
                           cudaStream_t st);
+bool gemm_tcgen05_dw_applicable(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t M,
+                                int N, int K, const void* dW, int64_t lddw);
+int gemm_tcgen05_dw(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
+                    int64_t M, int N, int K, cudaStream_t st);
 bool gemm_tcgen05_applicable(const void* A, int64_t lda, const void* Wt, int64_t ldw, int64_t M,
                              int N, int K);
 

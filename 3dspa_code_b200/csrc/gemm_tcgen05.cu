@@ -116,9 +116,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-// cute::UMMA::InstrDescriptor for kind::f16: c=f32, a=b=bf16, both K-major, M=128, N=BN
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// MN-major, 128B-swizzled operand tile (the token-major operands of the weight-gradient GEMM):
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units - 64 MN-elements per 128-byte row,
+// 8 K-rows per 1024-byte atom; the next 8 K-rows are SBO away, the next 64 MN-elements LBO away.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: c=f32, a=b=bf16, M=128, N=BN; both operands K-major
+// (mn_major = false) or both MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t make_idesc(int bn, bool mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(bn >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -178,6 +193,7 @@ struct EpiParams {
   const float* scale_k;
   float q_mul;
   float* rstd_out;   // [M, (q_cols+k_cols)/DH] or null
+  int atomic_add;    // EPI_DIRECT, fp32 C: C += tile with red.global.add.v4.f32 (split-K weight gradients)
   int debug_skip;    // SPA3D_GEMM_SKIP_EPI=1: accumulators are drained but nothing is computed or stored
 };
 
@@ -281,10 +297,16 @@ __device__ __forceinline__ void slab_store_bf16(uint8_t* slab, int lane, const u
   }
 }
 
-template <int BN, int EPI, int DH>
+// TN = false: C[M,N] = A[M,K] . Wt[N,K]^T (both operands K-major, boxes of 64 K-elements).
+// TN = true : C[M,N] = P[K,M]^T . Q[K,N]  (weight gradient dW = dY^T X: the reduction runs over
+//             tokens, both operands are token-major = MN-major for the MMA; boxes of 64 tokens x
+//             64 columns).  The reduction is split over `splits` CTAs per tile which add their
+//             partial tiles into C with vector atomics.
+template <int BN, int EPI, int DH, bool TN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, EpiParams ep, int64_t M, int N, int K) {
+                    const __grid_constant__ CUtensorMap tmC, EpiParams ep, int64_t M, int N, int64_t K,
+                    int splits) {
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
   constexpr int TMEM_COLS = tmem_cols_for(BN);
@@ -305,10 +327,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (K + BK - 1) / BK;
+  const int num_kb_all = (int)((K + BK - 1) / BK);
+  const int kb_per_split = (num_kb_all + splits - 1) / splits;
   const int n_tiles = (N + BN - 1) / BN;
   const int64_t m_tiles = (M + BM - 1) / BM;
-  const int64_t num_tiles = m_tiles * n_tiles;
+  const int64_t num_tiles = m_tiles * n_tiles * splits;   // work items: (output tile, K split)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -348,12 +371,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int64_t tile = t / splits;
+        const int sp = (int)(t % splits);
+        const int m_blk = (int)(tile / n_tiles), n_blk = (int)(tile % n_tiles);
+        const int kb0 = sp * kb_per_split, kb1 = min(num_kb_all, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_2d(smem_a + stage * L::A_BYTES, &tmA, kb * BK, m_blk * BM, &full_bar[stage]);
-          tma_load_2d(smem_b + stage * L::B_BYTES, &tmB, kb * BK, n_blk * BN, &full_bar[stage]);
+          if constexpr (!TN) {
+            tma_load_2d(smem_a + stage * L::A_BYTES, &tmA, kb * BK, m_blk * BM, &full_bar[stage]);
+            tma_load_2d(smem_b + stage * L::B_BYTES, &tmB, kb * BK, n_blk * BN, &full_bar[stage]);
+          } else {
+            // 64 tokens x 64 columns per box; column chunk c lands 8 KB after chunk c-1 (= LBO)
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d(smem_a + stage * L::A_BYTES + c * 8192, &tmA, m_blk * BM + c * 64, kb * BK, &full_bar[stage]);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(smem_b + stage * L::B_BYTES + c * 8192, &tmB, n_blk * BN + c * 64, kb * BK, &full_bar[stage]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -361,26 +397,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+      constexpr uint32_t idesc = make_idesc(BN, TN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        const int sp = (int)(t % splits);
+        const int kb0 = sp * kb_per_split, kb1 = min(num_kb_all, kb0 + kb_per_split);
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * L::A_BYTES));
-          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * L::B_BYTES));
+          if constexpr (!TN) {
+            const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * L::A_BYTES));
+            const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * L::B_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the 128B swizzle atom: +2 in the >>4 field
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 32 bytes (16 bf16) along K inside the 128B swizzle atom: +2 in the >>4 field
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+            const uint64_t da = make_smem_desc_mn(smem_u32(smem_a + stage * L::A_BYTES), 8192);
+            const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + stage * L::B_BYTES), 8192);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 tokens = 16 rows of 128 bytes = 2048 bytes: +128 in the >>4 field
+              umma_bf16(tmem_d, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -398,7 +447,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int sbuf = 0;
     int it = 0;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int m_blk = (int)(t / n_tiles), n_blk = (int)(t % n_tiles);
+      const int64_t tile = t / splits;
+      const int m_blk = (int)(tile / n_tiles), n_blk = (int)(tile % n_tiles);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = m_blk * BM + quarter * 32;
@@ -436,8 +486,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (!ep.debug_skip) {
           load_res(0);   // in flight while the MMAs of this tile still run
           // pull the residual of this CTA's next tile into L2 (one prefetch per 128-byte line)
-          const int64_t tn = t + gridDim.x;
-          if (ep.residual && tn < num_tiles) {
+          const int64_t tn = (t + gridDim.x) / splits;
+          if (ep.residual && t + gridDim.x < num_tiles) {
             const int64_t prow = (int64_t)(tn / n_tiles) * BM + quarter * 32 + lane;
             const int pcol = (int)(tn % n_tiles) * BN + half * HC;
             const int esz = ep.r_dtype == SPA3D_F32 ? 4 : 2;
@@ -498,7 +548,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
               }
               if (i * 4 + cr < rows_ok) {
-                if (out_f32) {
+                if (ep.atomic_add) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(a.x), "f"(a.y), "f"(a.z),
+                               "f"(a.w)
+                               : "memory");
+                } else if (out_f32) {
                   *reinterpret_cast<float4*>(cp) = a;
                 } else {
                   __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
@@ -685,25 +739,44 @@ static int debug_skip_epilogue() {
   return v;
 }
 
-template <int BN, int EPI, int DH>
+template <int BN, int EPI, int DH, bool TN = false>
 static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiParams ep, int64_t M,
-                  int N, int K, cudaStream_t st) {
+                  int N, int64_t K, cudaStream_t st) {
   using L = SmemLayout<BN>;
   CUtensorMap tmA, tmB, tmC;
-  if (make_map(&tmA, A, M, K, lda, BM)) return 1;
-  if (make_map(&tmB, Wt, N, K, ldw, BN)) return 1;
+  if (TN) {
+    // operands are [K tokens, M] and [K tokens, N], boxes of 64 tokens x 64 columns
+    if (make_map(&tmA, A, K, M, lda, 64)) return 1;
+    if (make_map(&tmB, Wt, K, N, ldw, 64)) return 1;
+  } else {
+    if (make_map(&tmA, A, M, K, lda, BM)) return 1;
+    if (make_map(&tmB, Wt, N, K, ldw, BN)) return 1;
+  }
   if (EPI == EPI_DIRECT) tmC = tmA;  // unused
   else if (make_map_c(&tmC, ep.C, M, N, ep.ldc)) return 1;
   ep.debug_skip = debug_skip_epilogue();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, DH, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     SPA3D_REQUIRE(e == cudaSuccess, "gemm_tcgen05: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  gemm_tcgen05_kernel<BN, EPI, DH><<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, ep, M, N, K);
+  const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int splits = 1;
+  if (TN) {
+    // split the token reduction so that every SM has work: about two waves of work items, at
+    // least 16 K-blocks (1024 tokens) per item, no empty split
+    const int num_kb = (int)((K + BK - 1) / BK);
+    int want = (int)((2 * (int64_t)num_sms() + tiles - 1) / tiles);
+    int max_by_len = num_kb / 16 > 0 ? num_kb / 16 : 1;
+    splits = want < max_by_len ? want : max_by_len;
+    if (splits < 1) splits = 1;
+    const int per = (num_kb + splits - 1) / splits;
+    splits = (num_kb + per - 1) / per;
+  }
+  const int64_t items = tiles * splits;
+  int grid = (int)(items < num_sms() ? items : num_sms());
+  gemm_tcgen05_kernel<BN, EPI, DH, TN><<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, ep, M, N, K, splits);
   return check_launch("gemm_tcgen05");
 }
 
@@ -755,7 +828,7 @@ int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const 
     SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(residual) & 15) == 0 && ldr % (r_dtype == SPA3D_F32 ? 4 : 8) == 0,
                   "gemm_tcgen05: residual must be 16-byte aligned with 16-byte row pitch");
   if (bias) SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm_tcgen05: bias must be 16-byte aligned");
-  EpiParams ep{bias, residual, ldr, r_dtype, C, ldc, c_dtype, act, 0, 0, nullptr, nullptr, 1.f, nullptr, 0};
+  EpiParams ep{bias, residual, ldr, r_dtype, C, ldc, c_dtype, act, 0, 0, nullptr, nullptr, 1.f, nullptr, 0, 0};
   if (rms && rms->dh > 0) {
     SPA3D_REQUIRE(c_dtype == SPA3D_BF16 && !bias && !residual && act == 0, "gemm_tcgen05: fused RMSNorm is bf16, no bias/act/residual");
     ep.q_cols = rms->q_cols; ep.k_cols = rms->k_cols;
@@ -775,6 +848,35 @@ int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const 
   const int bn = pick_bn(N);
   if (c_dtype == SPA3D_BF16 && !residual) return launch_bn<EPI_TMA>(bn, A, lda, Wt, ldw, ep, M, N, K, st);
   return launch_bn<EPI_DIRECT>(bn, A, lda, Wt, ldw, ep, M, N, K, st);
+}
+
+// Weight gradient on the tensor cores: dW[N,K] += dY[M,N]^T . X[M,K]  (fp32 accumulate into dW;
+// the reduction over the M tokens is split across CTAs, partial tiles are added atomically).
+bool gemm_tcgen05_dw_applicable(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t M,
+                                int N, int K, const void* dW, int64_t lddw) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return al16(dY) && al16(X) && al16(dW) && (lddy % 8 == 0) && (ldx % 8 == 0) && (lddw % 4 == 0) &&
+         (N % 8 == 0) && (K % 8 == 0) && M > 0 && M < (1ll << 31);
+}
+
+int gemm_tcgen05_dw(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
+                    int64_t M, int N, int K, cudaStream_t st) {
+  using namespace tc;
+  EpiParams ep{nullptr, nullptr, 0, 0, dW, lddw, SPA3D_F32, 0, 0, 0, nullptr, nullptr, 1.f, nullptr, 1, 0};
+  // output tile = 128 rows of dW (N) x BN columns of dW (K); BN a multiple of the 64-column box
+  int bn = K <= 64 ? 64 : 256, best_pad = K <= 64 ? 64 : (K + 255) / 256 * 256;
+  if (K > 64) {
+    for (int c : {192, 128}) {
+      int pad = (K + c - 1) / c * c;
+      if (pad < best_pad) { bn = c; best_pad = pad; }
+    }
+  }
+  switch (bn) {
+    case 256: return launch<256, EPI_DIRECT, 32, true>(dY, lddy, X, ldx, ep, N, K, M, st);
+    case 192: return launch<192, EPI_DIRECT, 32, true>(dY, lddy, X, ldx, ep, N, K, M, st);
+    case 128: return launch<128, EPI_DIRECT, 32, true>(dY, lddy, X, ldx, ep, N, K, M, st);
+    default: return launch<64, EPI_DIRECT, 32, true>(dY, lddy, X, ldx, ep, N, K, M, st);
+  }
 }
 
 }  // namespace spa3d

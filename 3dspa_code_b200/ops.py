@@ -118,6 +118,15 @@ def gemm(a, wt, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=None
     return out
 
 
+def gemm_dw(dy, x, dw, accumulate=True, impl=GEMM_AUTO):
+    """dw[N,K] (+)= dy[M,N]^T @ x[M,K]  (fp32 dw; weight gradient in the packed [out,in] layout)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == M and dw.shape == (N, K) and dw.dtype == torch.float32 and dy.dtype == x.dtype
+    _call("spa3d_gemm_dw", _p(dy), _ld(dy), _p(x), _ld(x), dt(dy), _p(dw), _ld(dw), M, N, K, int(accumulate), int(impl), _stream())
+    return dw
+
+
 def gemm_strided(a, sam, sak, b, sbk, sbn, out, M, N, K, accumulate=False):
     _call("spa3d_gemm_strided", _p(a), int(sam), int(sak), dt(a), _p(b), int(sbk), int(sbn), dt(b), _p(out), _ld(out),
           dt(out), int(M), int(N), int(K), int(accumulate), _stream())

@@ -91,9 +91,7 @@ class ParamStore(DeviceWeights):
 
     def accum_dw(self, name, g, x):
         """grad[name] ([N,K], fp32) += g[M,N]^T x[M,K]  (reduction over tokens)."""
-        M, N = g.shape
-        K = x.shape[1]
-        ops.gemm_strided(g, 1, g.stride(0), x, x.stride(0), 1, self.g[name], N, K, M, accumulate=True)
+        ops.gemm_dw(g, x, self.g[name], accumulate=True)
 
     def accum_bias(self, name, dy):
         ops.colsum(dy, self.g[name], accumulate=True)

@@ -92,6 +92,14 @@ int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dt
                void* C, int64_t ldc, int c_dtype, int64_t M, int N, int K, int impl,
                void* stream);
 
+/* Weight gradient of a Dense layer (backward of attention.py:106-107,154-183 and
+ * track_autoencoder_3d.py:73-115 under jax.value_and_grad, train.py:161-162):
+ *   dW[N,K] (+)= dY[M,N]^T . X[M,K]     dY, X in `dtype` (row-major, lddy / ldx), dW f32 (lddw),
+ * in the packed [out,in] layout of Wt.  The reduction runs over the M tokens.  bf16 operands take
+ * the tcgen05 kernel (token-major = MN-major operands, split-K with vector atomics into dW). */
+int spa3d_gemm_dw(const void* dY, int64_t lddy, const void* X, int64_t ldx, int dtype, float* dW,
+                  int64_t lddw, int64_t M, int N, int K, int accumulate, int impl, void* stream);
+
 /* General strided fp32-accumulate GEMM used by the backward pass:
  *   C[m,n] (+)= sum_k A(m,k) * B(k,n),  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].
  * accumulate != 0 adds into C (C must be f32 then). */

@@ -421,3 +421,25 @@ def test_gemm_persistent_tile_counts(spa):
         wt = (torch.randn(768, 384, device="cuda") / 20).to(torch.bfloat16)
         y = ops.gemm(a, wt, out_dtype=torch.float32, impl=ops.GEMM_TCGEN05)
         assert rel_err(y, a.double() @ wt.double().t()) < 2e-5, M
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_gemm_dw_weight_gradient(spa, impl):
+    """dW[N,K] += dY[M,N]^T X[M,K] (backward of every Dense): token-major operands on tcgen05 with
+    split-K atomics vs fp64 of the same bf16 operands; ragged M / N / K, strided views, accumulation."""
+    ops = spa.ops
+    torch.manual_seed(21)
+    code = ops.GEMM_TCGEN05 if impl == "tcgen05" else ops.GEMM_SIMT
+    dtype = torch.bfloat16 if impl == "tcgen05" else torch.float32
+    shapes = [(300, 72, 136), (5000, 384, 1280), (1000, 600, 1280), (777, 2304, 384), (4096 + 13, 96, 512),
+              (2000, 1152, 96), (64, 128, 64), (20000, 1536, 384), (129, 8, 8)]
+    for (M, N, K) in shapes:
+        big = torch.randn(M, N + 16, device="cuda").to(dtype)
+        dy = big[:, 8 : 8 + N]                      # strided view (a column block of a wider buffer)
+        x = torch.randn(M, K, device="cuda").to(dtype)
+        ref = dy.double().t() @ x.double()
+        dw = torch.full((N, K), 3.0, device="cuda")
+        ops.gemm_dw(dy, x, dw, accumulate=False, impl=code)
+        assert rel_err(dw, ref) < 5e-5, (impl, M, N, K, rel_err(dw, ref))
+        ops.gemm_dw(dy, x, dw, accumulate=True, impl=code)
+        assert rel_err(dw, 2 * ref) < 5e-5, (impl, M, N, K, "accumulate")
