@@ -358,6 +358,15 @@ int attention_fwd_simt(const void* q, int64_t ldq, const void* k, int64_t ldk, c
   return check_launch("attention_fwd_simt");
 }
 
+int attention_delta(const void* o, int64_t ldo, const void* d_o, int64_t lddo, int dtype, float* delta_ws,
+                    int64_t batch, int heads, int Lq, int Dh, cudaStream_t st) {
+  int64_t rows = batch * Lq;
+  SPA3D_DISPATCH(dtype, T, {
+    attn_delta_kernel<T><<<(unsigned)((rows * heads + 7) / 8), 256, 0, st>>>((const T*)o, ldo, (const T*)d_o, lddo, delta_ws, rows, heads, Lq, Dh);
+  });
+  return check_launch("attention_delta");
+}
+
 int attention_bwd_simt(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                        int64_t ldv, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
                        void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,

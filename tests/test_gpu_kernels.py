@@ -240,11 +240,14 @@ def test_attention_fwd(spa, dtype, Lq, Lk, Dh):
     assert rel_err(o, ref) < tol, rel_err(o, ref)
 
 
-@pytest.mark.parametrize("dtype,Lq,Lk", [(torch.float32, 40, 40), (torch.float32, 16, 70), (torch.bfloat16, 151, 151)])
-def test_attention_bwd(spa, dtype, Lq, Lk):
+@pytest.mark.parametrize("dtype,Lq,Lk,Dh", [
+    (torch.float32, 40, 40, 96), (torch.float32, 16, 70, 96), (torch.bfloat16, 151, 151, 96), (torch.bfloat16, 129, 129, 96),
+    (torch.bfloat16, 128, 128, 64), (torch.bfloat16, 23, 23, 64), (torch.bfloat16, 128, 150, 96), (torch.bfloat16, 64, 300, 96),
+])
+def test_attention_bwd(spa, dtype, Lq, Lk, Dh):
     ops = spa.ops
     torch.manual_seed(6)
-    batch, H, Dh = 3, 4, 96
+    batch, H = 3, 4
     A = H * Dh
     q = (torch.randn(batch * Lq, A, device="cuda") / math.sqrt(Dh)).to(dtype)
     k = torch.randn(batch * Lk, A, device="cuda").to(dtype)
@@ -253,6 +256,7 @@ def test_attention_bwd(spa, dtype, Lq, Lk):
     if Lq == Lk:
         mask = (torch.rand(batch, Lk, device="cuda") < 0.7).to(torch.uint8)
         mask[:, 0] = 1
+        mask[2] = 0  # a fully masked sequence: uniform weights, value gradient only
     qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
     ref = _attn_ref(qd, kd, vd, mask, batch, H, Lq, Lk, Dh)
     d_o = torch.randn(batch * Lq, A, device="cuda").to(dtype)
