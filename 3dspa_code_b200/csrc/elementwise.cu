@@ -147,6 +147,88 @@ __global__ void layernorm_bwd_kernel(const TX* __restrict__ x, int64_t ldx,
   for (int i = threadIdx.x; i < d; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * d + i] = s_ds[i];
 }
 
+
+// Bandwidth version for fp32 x / dx with d = 128*J: one warp per row, lane owns the float4 chunks
+// lane + 32j (128-bit loads), the row stays in registers between the statistics and the output
+// pass, the scale gradient is accumulated in per-lane registers across the grid-stride loop.
+// dx_lowp (optional) receives a bf16 copy of the final dx - the operand of the next backward GEMMs.
+template <int J, typename TDY>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ scale,
+                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const TDY* __restrict__ dy, int64_t lddy, float* __restrict__ dx, int64_t lddx,
+                          int dx_accumulate, bf16* __restrict__ dx_lowp, int64_t ldl,
+                          float* __restrict__ dscale_partial, int64_t rows) {
+  constexpr int D = 128 * J;
+  __shared__ float s_ds[D];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) s_ds[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float4 sc[J], acc[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    sc[j] = *reinterpret_cast<const float4*>(scale + (lane + 32 * j) * 4);
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
+    const float* xr = x + row * ldx;
+    const TDY* dyr = dy + row * lddy;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[J], g[J];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = (lane + 32 * j) * 4;
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      float4 dv;
+      if constexpr (sizeof(TDY) == 4) {
+        dv = *reinterpret_cast<const float4*>(dyr + c);
+      } else {
+        const uint2 w = *reinterpret_cast<const uint2*>(dyr + c);
+        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w.x);
+        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
+        dv = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
+      }
+      xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      g[j] = make_float4(dv.x * sc[j].x, dv.y * sc[j].y, dv.z * sc[j].z, dv.w * sc[j].w);
+      sg += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+      sgx += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+      acc[j].x = fmaf(dv.x, xh[j].x, acc[j].x);
+      acc[j].y = fmaf(dv.y, xh[j].y, acc[j].y);
+      acc[j].z = fmaf(dv.z, xh[j].z, acc[j].z);
+      acc[j].w = fmaf(dv.w, xh[j].w, acc[j].w);
+    }
+    sg = warp_sum(sg) * (1.f / D);
+    sgx = warp_sum(sgx) * (1.f / D);
+    float* dxr = dx + row * lddx;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = (lane + 32 * j) * 4;
+      float4 v = make_float4(rs * (g[j].x - sg - xh[j].x * sgx), rs * (g[j].y - sg - xh[j].y * sgx),
+                             rs * (g[j].z - sg - xh[j].z * sgx), rs * (g[j].w - sg - xh[j].w * sgx));
+      if (dx_accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(dxr + c);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *reinterpret_cast<float4*>(dxr + c) = v;
+      if (dx_lowp) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(dx_lowp + row * ldl + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c = (lane + 32 * j) * 4;
+    atomicAdd(&s_ds[c], acc[j].x);
+    atomicAdd(&s_ds[c + 1], acc[j].y);
+    atomicAdd(&s_ds[c + 2], acc[j].z);
+    atomicAdd(&s_ds[c + 3], acc[j].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * D + i] = s_ds[i];
+}
+
 // ------------------------------------------------------------------------------------------
 // per-head RMSNorm (attention.py:166-167), in place; one warp per (row, head)
 // ------------------------------------------------------------------------------------------
@@ -210,6 +292,99 @@ __global__ void head_rmsnorm_bwd_kernel(const TY* __restrict__ y, int64_t ldy,
   }
   __syncthreads();
   for (int i = threadIdx.x; i < Dh; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * Dh + i] = s_ds[i];
+}
+
+
+// Bandwidth version of the above for bf16 buffers: 4 lanes per (row, head), each lane owns CPL =
+// Dh/32 16-byte chunks (chunks lane, lane+4, ...), the head's statistics are two shuffles, the
+// scale gradient lives in per-lane registers for the whole grid-stride loop (no atomics inside).
+template <int CPL>
+__global__ void __launch_bounds__(256)
+head_rmsnorm_bwd_fast_kernel(const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ scale,
+                             float out_mul, const float* __restrict__ rstd, int64_t rstd_ld,
+                             bf16* __restrict__ d_io, int64_t ldd, float* __restrict__ dscale_partial,
+                             int64_t rows, int heads) {
+  constexpr int DH = CPL * 32;
+  __shared__ float s_ds[DH];
+  for (int i = threadIdx.x; i < DH; i += blockDim.x) s_ds[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2;
+  float sm[CPL][8], ism[CPL][8], acc[CPL][8];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = scale[(sub + 4 * c) * 8 + e] * out_mul;
+      sm[c][e] = v;
+      ism[c][e] = v != 0.f ? 1.f / v : 0.f;
+      acc[c][e] = 0.f;
+    }
+  const int64_t total = rows * heads;
+  const int64_t gstride = (int64_t)gridDim.x * (blockDim.x >> 2);
+  for (int64_t wb = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8; wb < total; wb += gstride) {
+    // a warp takes 8 consecutive (row, head) pairs; groups beyond the end idle but stay in the shuffles
+    const int64_t wid = wb + grp;
+    const bool live = wid < total;
+    const int64_t r = live ? wid / heads : 0;
+    const int h = live ? (int)(wid % heads) : 0;
+    const bf16* yp = y + r * ldy + (int64_t)h * DH;
+    bf16* dp = d_io + r * ldd + (int64_t)h * DH;
+    float xh[CPL][8], g[CPL][8];
+    float sgx = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      uint4 yv = make_uint4(0, 0, 0, 0), dv = make_uint4(0, 0, 0, 0);
+      if (live) {
+        yv = *reinterpret_cast<const uint4*>(yp + (sub + 4 * c) * 8);
+        dv = *reinterpret_cast<const uint4*>(dp + (sub + 4 * c) * 8);
+      }
+      const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        const __nv_bfloat162 yh = *reinterpret_cast<const __nv_bfloat162*>(&yw[e2]);
+        const __nv_bfloat162 dh = *reinterpret_cast<const __nv_bfloat162*>(&dw[e2]);
+        const float y0 = __low2float(yh), y1 = __high2float(yh), d0 = __low2float(dh), d1 = __high2float(dh);
+        xh[c][2 * e2] = y0 * ism[c][2 * e2];
+        xh[c][2 * e2 + 1] = y1 * ism[c][2 * e2 + 1];
+        g[c][2 * e2] = d0 * sm[c][2 * e2];
+        g[c][2 * e2 + 1] = d1 * sm[c][2 * e2 + 1];
+        sgx = fmaf(g[c][2 * e2], xh[c][2 * e2], sgx);
+        sgx = fmaf(g[c][2 * e2 + 1], xh[c][2 * e2 + 1], sgx);
+        acc[c][2 * e2] = fmaf(d0 * out_mul, xh[c][2 * e2], acc[c][2 * e2]);
+        acc[c][2 * e2 + 1] = fmaf(d1 * out_mul, xh[c][2 * e2 + 1], acc[c][2 * e2 + 1]);
+      }
+    }
+    sgx += __shfl_xor_sync(0xffffffffu, sgx, 1);
+    sgx += __shfl_xor_sync(0xffffffffu, sgx, 2);
+    sgx *= 1.f / DH;
+    if (live) {
+      const float rs = rstd[r * rstd_ld + h];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          __nv_bfloat162 o = __floats2bfloat162_rn(rs * (g[c][2 * e2] - xh[c][2 * e2] * sgx),
+                                                   rs * (g[c][2 * e2 + 1] - xh[c][2 * e2 + 1] * sgx));
+          w[e2] = *reinterpret_cast<uint32_t*>(&o);
+        }
+        *reinterpret_cast<uint4*>(dp + (sub + 4 * c) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  // reduce the per-lane scale gradients: across the 8 groups of a warp, then across warps
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = acc[c][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (grp == 0) atomicAdd(&s_ds[(sub + 4 * c) * 8 + e], v);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DH; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * DH + i] = s_ds[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -565,14 +740,36 @@ int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* sc
 int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
                         const float* mean, const float* rstd, const void* dy, int64_t lddy,
                         int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int dx_accumulate,
-                        float* dscale_partial, int num_partials, int64_t rows, int d, void* stream) {
+                        void* dx_lowp, int64_t ldl, float* dscale_partial, int num_partials, int64_t rows,
+                        int d, void* stream) {
   SPA3D_REQUIRE(num_partials > 0, "layernorm_bwd: num_partials must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool fast = x_dtype == SPA3D_F32 && dx_dtype == SPA3D_F32 && d % 128 == 0 && d <= 1536 && ldx % 4 == 0 &&
+                    lddx % 4 == 0 && lddy % 4 == 0 && al16(x) && al16(dx) && al16(dy) && al16(scale) &&
+                    (!dx_lowp || (ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(dx_lowp) & 7) == 0));
+  if (fast) {
+#define SPA3D_LN_BWD_FAST(J)                                                                                   \
+  case J:                                                                                                      \
+    SPA3D_DISPATCH(dy_dtype, TDY, {                                                                            \
+      layernorm_bwd_fast_kernel<J, TDY><<<num_partials, 256, 0, st>>>((const float*)x, ldx, scale, mean, rstd, \
+          (const TDY*)dy, lddy, (float*)dx, lddx, dx_accumulate, (bf16*)dx_lowp, ldl, dscale_partial, rows);   \
+    });                                                                                                        \
+    return check_launch("layernorm_bwd_fast");
+    switch (d / 128) {
+      SPA3D_LN_BWD_FAST(1) SPA3D_LN_BWD_FAST(2) SPA3D_LN_BWD_FAST(3) SPA3D_LN_BWD_FAST(4) SPA3D_LN_BWD_FAST(8)
+      SPA3D_LN_BWD_FAST(9) SPA3D_LN_BWD_FAST(10) SPA3D_LN_BWD_FAST(12)
+      default: break;
+    }
+#undef SPA3D_LN_BWD_FAST
+  }
   SPA3D_DISPATCH(x_dtype, TX, SPA3D_DISPATCH(dy_dtype, TDY, SPA3D_DISPATCH(dx_dtype, TDX, {
     layernorm_bwd_kernel<TX, TDY, TDX><<<num_partials, 256, d * sizeof(float), st>>>(
         (const TX*)x, ldx, scale, mean, rstd, (const TDY*)dy, lddy, (TDX*)dx, lddx, dx_accumulate, dscale_partial, rows, d);
   })));
-  return check_launch("layernorm_bwd");
+  int rc = check_launch("layernorm_bwd");
+  if (rc || !dx_lowp) return rc;
+  return spa3d_convert(dx, lddx, dx_dtype, dx_lowp, ldl, SPA3D_BF16, rows, d, 0, stream);
 }
 
 int spa3d_head_rmsnorm_fwd(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
@@ -588,6 +785,21 @@ int spa3d_head_rmsnorm_bwd(const void* y, int64_t ldy, int y_dtype, const float*
                            void* stream) {
   SPA3D_REQUIRE(num_partials > 0, "head_rmsnorm_bwd: num_partials must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (y_dtype == SPA3D_BF16 && d_dtype == SPA3D_BF16 && Dh % 32 == 0 && Dh <= 128 && ldy % 8 == 0 && ldd % 8 == 0 &&
+      al16(y) && al16(dy_inout)) {
+#define SPA3D_RMS_BWD_FAST(CPL)                                                                              \
+  head_rmsnorm_bwd_fast_kernel<CPL><<<num_partials, 256, 0, st>>>((const bf16*)y, ldy, scale, out_mul, rstd, \
+                                                                  rstd_ld, (bf16*)dy_inout, ldd, dscale_partial, rows, heads)
+    switch (Dh / 32) {
+      case 1: SPA3D_RMS_BWD_FAST(1); break;
+      case 2: SPA3D_RMS_BWD_FAST(2); break;
+      case 3: SPA3D_RMS_BWD_FAST(3); break;
+      default: SPA3D_RMS_BWD_FAST(4); break;
+    }
+#undef SPA3D_RMS_BWD_FAST
+    return check_launch("head_rmsnorm_bwd_fast");
+  }
   SPA3D_DISPATCH(y_dtype, TY, SPA3D_DISPATCH(d_dtype, TD, {
     head_rmsnorm_bwd_kernel<TY, TD><<<num_partials, 256, Dh * sizeof(float), st>>>(
         (const TY*)y, ldy, scale, out_mul, rstd, rstd_ld, (TD*)dy_inout, ldd, dscale_partial, rows, heads, Dh);

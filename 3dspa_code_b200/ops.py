@@ -147,14 +147,16 @@ def layernorm_fwd(x, scale, out_dtype, rows=None, ldx=None, d=None, stats=False,
     return (out, mean, rstd) if stats else out
 
 
-def layernorm_bwd(x, scale, mean, rstd, dy, dx, rows=None, ldx=None, lddx=None, d=None, accumulate=False, num_partials=296):
+def layernorm_bwd(x, scale, mean, rstd, dy, dx, rows=None, ldx=None, lddx=None, d=None, accumulate=False, num_partials=296,
+                  dx_lowp=None):
     rows = x.shape[0] if rows is None else rows
     d = x.shape[-1] if d is None else d
     ldx = _ld(x) if ldx is None else ldx
     lddx = _ld(dx) if lddx is None else lddx
     partial = torch.empty(num_partials, d, device=x.device, dtype=torch.float32)
     _call("spa3d_layernorm_bwd", _p(x), int(ldx), dt(x), _p(scale), _p(mean), _p(rstd), _p(dy), _ld(dy), dt(dy), _p(dx), int(lddx),
-          dt(dx), int(accumulate), _p(partial), num_partials, int(rows), int(d), _stream())
+          dt(dx), int(accumulate), _p(dx_lowp), _ld(dx_lowp) if dx_lowp is not None else 0, _p(partial), num_partials, int(rows), int(d),
+          _stream())
     dscale = torch.empty(d, device=x.device, dtype=torch.float32)
     colsum(partial, dscale)
     return dscale

@@ -72,6 +72,7 @@ class ParamStore(DeviceWeights):
         self.g = g
         self.ct: Dict[str, torch.Tensor] = {}
         self.step_count = 0
+        self.lowp: Dict[int, torch.Tensor] = {}   # fp32 gradient data_ptr -> bf16 copy written by the producer kernel
         self.refresh()
 
     def is_matrix(self, k):
@@ -105,10 +106,24 @@ class ParamStore(DeviceWeights):
 
 
 def _c(st, t):
-    """activation gradient in the compute dtype (bf16 path: one conversion pass)."""
+    """activation gradient in the compute dtype.  The LayerNorm backward that produced ``t`` has
+    usually written the bf16 copy in the same pass (``_lowp_out``); otherwise one conversion pass."""
     if t.dtype == st.cdt:
         return t if t.is_contiguous() else t.contiguous()
+    hit = st.lowp.pop(t.data_ptr(), None)
+    if hit is not None and hit.shape == t.shape:
+        return hit
     return ops.convert(t, torch.empty(t.shape, device=t.device, dtype=st.cdt))
+
+
+def _lowp_out(st, t):
+    """bf16 side output for the fp32 gradient tensor ``t`` (consumed by the next block's ``_c``)."""
+    if st.cdt == torch.float32:
+        return None
+    st.lowp.clear()  # at most one pending copy: the gradient handed to the next backward
+    buf = torch.empty(t.shape, device=t.device, dtype=st.cdt)
+    st.lowp[t.data_ptr()] = buf
+    return buf
 
 
 # ---- residual sub-blocks ---------------------------------------------------------------------------
@@ -176,7 +191,8 @@ class AttnBlockFn(torch.autograd.Function):
         st.accum_dw(pre + "self.Wqkv_t", dqkv, s["xn"])
         dxn = ops.gemm(dqkv, st.ct[pre + "self.Wqkv_t"], residual=dxn)
         # dx = da + LN'(dxn): accumulate into da's buffer (da has no other consumer)
-        ops.axpy(st.g[pre + "norm_q"], ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, da, accumulate=True))
+        ops.axpy(st.g[pre + "norm_q"], ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, da, accumulate=True,
+                                                         dx_lowp=_lowp_out(st, da)))
         ctx.saved = None
         return da, dkv, None, None, None, None, None, None, None, None
 
@@ -208,7 +224,8 @@ class MlpBlockFn(torch.autograd.Function):
         st.accum_bias(pre + "b1", dz)
         st.accum_dw(pre + "W1_t", dz, s["an"])
         dan = ops.gemm(dz, st.ct[pre + "W1_t"])
-        ops.axpy(st.g[pre + "norm_attn"], ops.layernorm_bwd(s["a"], st.f32[pre + "norm_attn"], s["mean"], s["rstd"], dan, dy, accumulate=True))
+        ops.axpy(st.g[pre + "norm_attn"], ops.layernorm_bwd(s["a"], st.f32[pre + "norm_attn"], s["mean"], s["rstd"], dan, dy, accumulate=True,
+                                                            dx_lowp=_lowp_out(st, dy)))
         ctx.saved = None
         return dy, None, None, None
 

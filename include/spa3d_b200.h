@@ -115,11 +115,14 @@ int spa3d_gemm_strided(const void* A, int64_t sam, int64_t sak, int a_dtype,
 int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
                         void* y, int64_t ldy, int y_dtype, float* mean_out, float* rstd_out,
                         int64_t rows, int d, void* stream);
+/* Backward: dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*scale; dscale_partial
+ * [num_partials, d] receives per-block partial sums of dy*xhat.  dx_lowp (bf16 [rows,d], ldl) may be
+ * NULL; otherwise it receives a bf16 copy of the final dx (the operand of the next backward GEMMs). */
 int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
                         const float* mean, const float* rstd, const void* dy, int64_t lddy,
                         int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int dx_accumulate,
-                        float* dscale_partial, int num_partials, int64_t rows, int d,
-                        void* stream);
+                        void* dx_lowp, int64_t ldl, float* dscale_partial, int num_partials,
+                        int64_t rows, int d, void* stream);
 
 /* ---- per-head RMSNorm of q and k (attention.py:166-167) + q/sqrt(Dh) (flax attention) ------
  * In place on a packed projection buffer: for every row and head h < heads,

@@ -178,6 +178,16 @@ def test_layernorm_fwd_bwd(spa, d):
     dx = torch.empty_like(dy)
     dscale = ops.layernorm_bwd(x.detach(), scale.detach(), mean, rstd, dy, dx)
     assert rel_err(dx, x.grad) < 1e-4 and rel_err(dscale, scale.grad) < 1e-4
+    # bf16 dy (what the bf16 backward feeds), accumulation into dx and the bf16 side copy of dx
+    dx2 = torch.ones_like(dy)
+    low = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    dyb = dy.to(torch.bfloat16)
+    x.grad = None
+    scale.grad = None
+    om.layer_norm(x.double(), scale.double()).backward(dyb.double())
+    dscale2 = ops.layernorm_bwd(x.detach(), scale.detach(), mean, rstd, dyb, dx2, accumulate=True, dx_lowp=low)
+    assert rel_err(dx2, x.grad + 1) < 1e-4 and rel_err(dscale2, scale.grad) < 1e-4
+    assert rel_err(low, x.grad + 1) < 6e-3
     # bf16 output and "first token of each sequence" addressing
     yb = ops.layernorm_fwd(x.detach(), scale.detach(), torch.bfloat16, rows=rows // 7, ldx=7 * d, d=d)
     assert rel_err(yb, ref[::7]) < 6e-3
@@ -199,6 +209,31 @@ def test_head_rmsnorm_fwd_bwd(spa):
     d_io = dy.clone()
     dscale = ops.head_rmsnorm_bwd(q, scale.detach(), 1 / math.sqrt(Dh), rstd, d_io, H, Dh)
     assert rel_err(d_io, x.grad) < 1e-4 and rel_err(dscale, scale.grad) < 1e-4
+
+
+@pytest.mark.parametrize("Dh,H,rows", [(96, 8, 1003), (64, 8, 500), (32, 2, 77), (128, 4, 260)])
+def test_head_rmsnorm_bwd_bf16_fast_path(spa, Dh, H, rows):
+    """bf16 buffers (4 lanes per head, register-resident scale gradient) vs autograd in fp64 on the
+    same bf16-rounded normalised output."""
+    ops = spa.ops
+    torch.manual_seed(40)
+    A = H * Dh
+    scale = (1 + 0.2 * torch.randn(Dh, device="cuda")).requires_grad_(True)
+    x = torch.randn(rows, A, device="cuda").requires_grad_(True)
+    mul = 1 / math.sqrt(Dh)
+    ref = om.rms_norm(x.double().view(rows, H, Dh), scale.double()) * mul
+    buf = torch.zeros(rows, 3 * A, device="cuda", dtype=torch.bfloat16)
+    y = buf[:, A : 2 * A]
+    y.copy_(ref.reshape(rows, A))
+    rstd = torch.rsqrt((x.detach().view(rows, H, Dh) ** 2).mean(-1) + 1e-6).contiguous()
+    dy = torch.randn(rows, A, device="cuda").to(torch.bfloat16)
+    ref.backward(dy.double().view(rows, H, Dh))
+    dbuf = torch.zeros(rows, 3 * A, device="cuda", dtype=torch.bfloat16)
+    d_io = dbuf[:, A : 2 * A]
+    d_io.copy_(dy)
+    dscale = ops.head_rmsnorm_bwd(y, scale.detach(), mul, rstd, d_io, H, Dh)
+    assert rel_err(d_io, x.grad) < 1.5e-2 and rel_err(dscale, scale.grad) < 1e-2
+    assert float(dbuf[:, :A].abs().max()) == 0 and float(dbuf[:, 2 * A :].abs().max()) == 0
 
 
 # ---- attention ---------------------------------------------------------------------------------
