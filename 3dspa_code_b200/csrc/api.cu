@@ -88,6 +88,45 @@ int spa3d_gemm_rmsnorm(const void* A, int64_t lda, const void* Wt, int64_t ldw, 
   return rc;
 }
 
+int spa3d_gemm_gelu(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
+                    const float* bias, void* Z, int64_t ldz, void* H, int64_t ldh, int64_t M, int N, int K,
+                    int impl, void* stream) {
+  using namespace spa3d;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_gelu: bad shape");
+  if (M == 0) return 0;
+  bool tc_ok = (a_dtype == SPA3D_BF16) && gemm_tcgen05_applicable(A, lda, Wt, ldw, M, N, K) &&
+               (reinterpret_cast<uintptr_t>(Z) & 15) == 0 && ldz % 8 == 0;
+  if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_gelu: tcgen05 path not applicable");
+  if (impl != SPA3D_GEMM_SIMT && tc_ok)
+    return gemm_tcgen05(A, lda, Wt, ldw, bias, SPA3D_ACT_GELU_TANH, nullptr, 0, 0, H, ldh, a_dtype, M, N, K, nullptr, st,
+                        0, Z, ldz);
+  int rc = spa3d_gemm(A, lda, Wt, ldw, a_dtype, bias, 0, nullptr, 0, 0, Z, ldz, a_dtype, M, N, K,
+                      impl == SPA3D_GEMM_SIMT ? SPA3D_GEMM_SIMT : SPA3D_GEMM_AUTO, stream);
+  if (rc) return rc;
+  return spa3d_gelu_fwd(Z, ldz, a_dtype, H, ldh, a_dtype, M, N, stream);
+}
+
+int spa3d_gemm_gelu_bwd(const void* dH_in, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
+                        const void* Z, int64_t ldz, void* dZ, int64_t lddz, int64_t M, int N, int K,
+                        int impl, void* stream) {
+  using namespace spa3d;
+  cudaStream_t st = (cudaStream_t)stream;
+  SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_gelu_bwd: bad shape");
+  if (M == 0) return 0;
+  bool tc_ok = (a_dtype == SPA3D_BF16) && gemm_tcgen05_applicable(dH_in, lda, Wt, ldw, M, N, K) &&
+               (reinterpret_cast<uintptr_t>(Z) & 15) == 0 && ldz % 8 == 0 &&
+               (reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && lddz % 8 == 0;
+  if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_gelu_bwd: tcgen05 path not applicable");
+  if (impl != SPA3D_GEMM_SIMT && tc_ok)
+    return gemm_tcgen05(dH_in, lda, Wt, ldw, nullptr, 0, Z, ldz, a_dtype, dZ, lddz, a_dtype, M, N, K, nullptr, st, 1,
+                        nullptr, 0);
+  int rc = spa3d_gemm(dH_in, lda, Wt, ldw, a_dtype, nullptr, 0, nullptr, 0, 0, dZ, lddz, a_dtype, M, N, K,
+                      impl == SPA3D_GEMM_SIMT ? SPA3D_GEMM_SIMT : SPA3D_GEMM_AUTO, stream);
+  if (rc) return rc;
+  return spa3d_gelu_bwd(Z, ldz, a_dtype, dZ, lddz, a_dtype, dZ, lddz, a_dtype, M, N, stream);
+}
+
 int spa3d_gemm_dw(const void* dY, int64_t lddy, const void* X, int64_t ldx, int dtype, float* dW,
                   int64_t lddw, int64_t M, int N, int K, int accumulate, int impl, void* stream) {
   using namespace spa3d;

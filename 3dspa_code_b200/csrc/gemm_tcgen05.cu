@@ -193,6 +193,8 @@ struct EpiParams {
   const float* scale_k;
   float q_mul;
   float* rstd_out;   // [M, (q_cols+k_cols)/DH] or null
+  int aux_pre;       // EPI_TMA + GELU: also store the pre-activation (bf16) through the aux tensor map
+  int res_op;        // EPI_DIRECT: 0 = C = f(acc) + residual; 1 = C = acc * gelu'(residual) (residual = saved pre-activation)
   int atomic_add;    // EPI_DIRECT, fp32 C: C += tile with red.global.add.v4.f32 (split-K weight gradients)
   int debug_skip;    // SPA3D_GEMM_SKIP_EPI=1: accumulators are drained but nothing is computed or stored
 };
@@ -267,8 +269,8 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// bias + activation on one 32-column chunk of an output row held in registers (v = packed pairs)
-__device__ __forceinline__ void epi_bias_act(const EpiParams& ep, uint64_t (&v)[16], int col0, int N) {
+// bias on one 32-column chunk of an output row held in registers (v = packed pairs)
+__device__ __forceinline__ void epi_bias(const EpiParams& ep, uint64_t (&v)[16], int col0, int N) {
   if (ep.bias) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -279,10 +281,21 @@ __device__ __forceinline__ void epi_bias_act(const EpiParams& ep, uint64_t (&v)[
       }
     }
   }
-  if (ep.act == SPA3D_ACT_GELU_TANH) {   // bf16 outputs only (api.cu routes fp32 + GELU to the SIMT path)
+}
+// activation (bf16 outputs only: api.cu routes fp32 + GELU to the SIMT path)
+__device__ __forceinline__ void epi_act(const EpiParams& ep, uint64_t (&v)[16]) {
+  if (ep.act == SPA3D_ACT_GELU_TANH) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = gelu2_fast(v[i]);
   }
+}
+// d/dx of flax nn.gelu(approximate=True), hardware tanh
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  constexpr float k = 0.7978845608028654f;
+  const float x2 = x * x;
+  const float t = tanh_fast(k * fmaf(0.044715f * x, x2, x));
+  const float du = k * fmaf(3.0f * 0.044715f, x2, 1.0f);
+  return fmaf(0.5f * x * (1.0f - t * t), du, 0.5f * (1.0f + t));
 }
 
 // 32 bf16 of this lane's row -> 64-byte row of a [32 x 64 B] slab laid out for a SWIZZLE_64B TMA store
@@ -305,8 +318,8 @@ __device__ __forceinline__ void slab_store_bf16(uint8_t* slab, int lane, const u
 template <int BN, int EPI, int DH, bool TN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, EpiParams ep, int64_t M, int N, int64_t K,
-                    int splits) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
+                    EpiParams ep, int64_t M, int N, int64_t K, int splits) {
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
   constexpr int TMEM_COLS = tmem_cols_for(BN);
@@ -514,7 +527,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint64_t v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = pku(r[2 * i], r[2 * i + 1]);
-            epi_bias_act(ep, v, col0, N);
+            epi_bias(ep, v, col0, N);
+            epi_act(ep, v);
             uint8_t* srow = slab + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -537,14 +551,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float4 a = *reinterpret_cast<const float4*>(sp + i * 512 + ((i & 1) ? odd_off : 0));
               const uint4 q = res[i];
               if (ep.residual) {
+                float4 rv;
                 if (ep.r_dtype == SPA3D_F32) {
-                  a.x += __uint_as_float(q.x); a.y += __uint_as_float(q.y);
-                  a.z += __uint_as_float(q.z); a.w += __uint_as_float(q.w);
+                  rv = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
                 } else {
                   const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
                   const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
-                  a.x += __low2float(h0); a.y += __high2float(h0);
-                  a.z += __low2float(h1); a.w += __high2float(h1);
+                  rv = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
+                }
+                if (ep.res_op == 0) {
+                  a.x += rv.x; a.y += rv.y; a.z += rv.z; a.w += rv.w;
+                } else {   // dz = dh * gelu'(z)
+                  a.x *= gelu_grad_fast(rv.x); a.y *= gelu_grad_fast(rv.y);
+                  a.z *= gelu_grad_fast(rv.z); a.w *= gelu_grad_fast(rv.w);
                 }
               }
               if (i * 4 + cr < rows_ok) {
@@ -585,7 +604,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint64_t v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = pku(r[c & 1][2 * i], r[c & 1][2 * i + 1]);
-            epi_bias_act(ep, v, col0, N);
+            epi_bias(ep, v, col0, N);
+            if (ep.aux_pre) {   // pre-activation z (saved for the backward pass) leaves through its own map
+              if (lane == 0) bulk_wait_read<1>();
+              __syncwarp();
+              slab_store_bf16(slab + sbuf * 2048, lane, v);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmAux, slab + sbuf * 2048, col0, row0);
+                bulk_commit();
+              }
+              sbuf ^= 1;
+            }
+            epi_act(ep, v);
             if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago has left this buffer
             __syncwarp();
             slab_store_bf16(slab + sbuf * 2048, lane, v);
@@ -741,9 +773,9 @@ static int debug_skip_epilogue() {
 
 template <int BN, int EPI, int DH, bool TN = false>
 static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiParams ep, int64_t M,
-                  int N, int64_t K, cudaStream_t st) {
+                  int N, int64_t K, cudaStream_t st, void* aux = nullptr, int64_t ld_aux = 0) {
   using L = SmemLayout<BN>;
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmAux;
   if (TN) {
     // operands are [K tokens, M] and [K tokens, N], boxes of 64 tokens x 64 columns
     if (make_map(&tmA, A, K, M, lda, 64)) return 1;
@@ -754,6 +786,12 @@ static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiPa
   }
   if (EPI == EPI_DIRECT) tmC = tmA;  // unused
   else if (make_map_c(&tmC, ep.C, M, N, ep.ldc)) return 1;
+  tmAux = tmC;
+  ep.aux_pre = 0;
+  if (EPI == EPI_TMA && aux != nullptr) {
+    if (make_map_c(&tmAux, aux, M, N, ld_aux)) return 1;
+    ep.aux_pre = 1;
+  }
   ep.debug_skip = debug_skip_epilogue();
   static bool attr_set = false;
   if (!attr_set) {
@@ -776,18 +814,18 @@ static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiPa
   }
   const int64_t items = tiles * splits;
   int grid = (int)(items < num_sms() ? items : num_sms());
-  gemm_tcgen05_kernel<BN, EPI, DH, TN><<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, ep, M, N, K, splits);
+  gemm_tcgen05_kernel<BN, EPI, DH, TN><<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, tmAux, ep, M, N, K, splits);
   return check_launch("gemm_tcgen05");
 }
 
 template <int EPI>
 static int launch_bn(int bn, const void* A, int64_t lda, const void* Wt, int64_t ldw, const EpiParams& ep,
-                     int64_t M, int N, int K, cudaStream_t st) {
+                     int64_t M, int N, int K, cudaStream_t st, void* aux = nullptr, int64_t ld_aux = 0) {
   switch (bn) {
-    case 256: return launch<256, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st);
-    case 192: return launch<192, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st);
-    case 128: return launch<128, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st);
-    default: return launch<64, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st);
+    case 256: return launch<256, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st, aux, ld_aux);
+    case 192: return launch<192, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st, aux, ld_aux);
+    case 128: return launch<128, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st, aux, ld_aux);
+    default: return launch<64, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st, aux, ld_aux);
   }
 }
 
@@ -819,7 +857,8 @@ bool gemm_tcgen05_rms_applicable(int N, int dh, int q_cols, int k_cols, int c_dt
 
 int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias, int act,
                  const void* residual, int64_t ldr, int r_dtype, void* C, int64_t ldc, int c_dtype,
-                 int64_t M, int N, int K, const RmsEpilogue* rms, cudaStream_t st) {
+                 int64_t M, int N, int K, const RmsEpilogue* rms, cudaStream_t st, int res_op, void* aux_pre,
+                 int64_t ld_aux) {
   using namespace tc;
   SPA3D_REQUIRE(c_dtype == SPA3D_F32 || c_dtype == SPA3D_BF16, "gemm_tcgen05: bad C dtype");
   SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % (c_dtype == SPA3D_F32 ? 4 : 8) == 0,
@@ -828,7 +867,11 @@ int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const 
     SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(residual) & 15) == 0 && ldr % (r_dtype == SPA3D_F32 ? 4 : 8) == 0,
                   "gemm_tcgen05: residual must be 16-byte aligned with 16-byte row pitch");
   if (bias) SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm_tcgen05: bias must be 16-byte aligned");
-  EpiParams ep{bias, residual, ldr, r_dtype, C, ldc, c_dtype, act, 0, 0, nullptr, nullptr, 1.f, nullptr, 0, 0};
+  EpiParams ep{bias, residual, ldr, r_dtype, C, ldc, c_dtype, act, 0, 0, nullptr, nullptr, 1.f, nullptr, 0, res_op, 0, 0};
+  if (aux_pre)
+    SPA3D_REQUIRE(c_dtype == SPA3D_BF16 && !residual && (reinterpret_cast<uintptr_t>(aux_pre) & 15) == 0 && ld_aux % 8 == 0,
+                  "gemm_tcgen05: the pre-activation side output needs a bf16 C, no residual, 16-byte aligned rows");
+  if (res_op) SPA3D_REQUIRE(residual != nullptr, "gemm_tcgen05: res_op needs the saved pre-activation");
   if (rms && rms->dh > 0) {
     SPA3D_REQUIRE(c_dtype == SPA3D_BF16 && !bias && !residual && act == 0, "gemm_tcgen05: fused RMSNorm is bf16, no bias/act/residual");
     ep.q_cols = rms->q_cols; ep.k_cols = rms->k_cols;
@@ -846,7 +889,7 @@ int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const 
     }
   }
   const int bn = pick_bn(N);
-  if (c_dtype == SPA3D_BF16 && !residual) return launch_bn<EPI_TMA>(bn, A, lda, Wt, ldw, ep, M, N, K, st);
+  if (c_dtype == SPA3D_BF16 && !residual) return launch_bn<EPI_TMA>(bn, A, lda, Wt, ldw, ep, M, N, K, st, aux_pre, ld_aux);
   return launch_bn<EPI_DIRECT>(bn, A, lda, Wt, ldw, ep, M, N, K, st);
 }
 
@@ -862,7 +905,7 @@ bool gemm_tcgen05_dw_applicable(const void* dY, int64_t lddy, const void* X, int
 int gemm_tcgen05_dw(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
                     int64_t M, int N, int K, cudaStream_t st) {
   using namespace tc;
-  EpiParams ep{nullptr, nullptr, 0, 0, dW, lddw, SPA3D_F32, 0, 0, 0, nullptr, nullptr, 1.f, nullptr, 1, 0};
+  EpiParams ep{nullptr, nullptr, 0, 0, dW, lddw, SPA3D_F32, 0, 0, 0, nullptr, nullptr, 1.f, nullptr, 0, 0, 1, 0};
   // output tile = 128 rows of dW (N) x BN columns of dW (K); BN a multiple of the 64-column box
   int bn = K <= 64 ? 64 : 256, best_pad = K <= 64 ? 64 : (K + 255) / 256 * 256;
   if (K > 64) {

@@ -204,8 +204,7 @@ class MlpBlockFn(torch.autograd.Function):
     def forward(ctx, a, anchor, st, pre):
         f, w, cdt = st.f32, st.c, st.cdt
         an, mean, rstd = ops.layernorm_fwd(a, f[pre + "norm_attn"], cdt, stats=True)
-        z = ops.gemm(an, w[pre + "W1_t"], f[pre + "b1"])
-        h = ops.gelu_fwd(z, torch.empty_like(z))
+        z, h = ops.gemm_gelu(an, w[pre + "W1_t"], f[pre + "b1"])
         y = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=a, out_dtype=torch.float32)
         ctx.saved = dict(a=a, mean=mean, rstd=rstd, an=an, z=z, h=h)
         ctx.args = (st, pre)
@@ -219,8 +218,7 @@ class MlpBlockFn(torch.autograd.Function):
         dyc = _c(st, dy)
         st.accum_bias(pre + "b2", dy)
         st.accum_dw(pre + "W2_t", dyc, s["h"])
-        dh = ops.gemm(dyc, st.ct[pre + "W2_t"])
-        dz = ops.gelu_bwd(s["z"], dh, dh)  # in place
+        dz = ops.gemm_gelu_bwd(dyc, st.ct[pre + "W2_t"], s["z"])
         st.accum_bias(pre + "b1", dz)
         st.accum_dw(pre + "W1_t", dz, s["an"])
         dan = ops.gemm(dz, st.ct[pre + "W1_t"])

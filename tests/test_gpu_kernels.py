@@ -482,3 +482,28 @@ def test_gemm_dw_weight_gradient(spa, impl):
         assert rel_err(dw, ref) < 5e-5, (impl, M, N, K, rel_err(dw, ref))
         ops.gemm_dw(dy, x, dw, accumulate=True, impl=code)
         assert rel_err(dw, 2 * ref) < 5e-5, (impl, M, N, K, "accumulate")
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_gemm_gelu_fused_forward_and_backward(spa, impl):
+    """MLP_in + tanh-GELU with the pre-activation as a side output, and the backward through MLP_out
+    and the activation in one epilogue (attention.py:103-108 under autodiff)."""
+    ops = spa.ops
+    torch.manual_seed(31)
+    dtype = torch.bfloat16 if impl == "tcgen05" else torch.float32
+    code = ops.GEMM_TCGEN05 if impl == "tcgen05" else ops.GEMM_SIMT
+    for (M, d, Mh) in [(1000 + 13, 384, 1536), (300, 1280, 1536), (129, 64, 200)]:
+        a = torch.randn(M, d, device="cuda").to(dtype)
+        w1t = (torch.randn(Mh, d, device="cuda") / math.sqrt(d)).to(dtype)
+        b1 = torch.randn(Mh, device="cuda")
+        z, h = ops.gemm_gelu(a, w1t, b1, impl=code)
+        zref = a.double() @ w1t.double().t() + b1.double()
+        href = torch.nn.functional.gelu(zref, approximate="tanh")
+        tol = 6e-3 if impl == "tcgen05" else 2e-5
+        assert rel_err(z, zref) < tol and rel_err(h, href) < tol, (M, d, Mh)
+        dy = torch.randn(M, d, device="cuda").to(dtype)
+        w2 = (torch.randn(Mh, d, device="cuda") / math.sqrt(Mh)).to(dtype)   # MLP_out kernel [Mh, d] as Flax stores it
+        dz = ops.gemm_gelu_bwd(dy, w2, z, impl=code)
+        zz = z.double().requires_grad_(True)
+        torch.nn.functional.gelu(zz, approximate="tanh").backward(dy.double() @ w2.double().t())
+        assert rel_err(dz, zz.grad) < (1e-2 if impl == "tcgen05" else 2e-5), (M, d, Mh, rel_err(dz, zz.grad))
