@@ -78,6 +78,8 @@ class Engine:
         self.w = weights
         self.cdt = weights.cdt
         self.exact = (weights.cdt == torch.float32) if exact_sin is None else exact_sin
+        self.stream_chunk = 256     # support tracks per host->device pipeline stage (0 = one-shot upload)
+        self._copy_stream = None
         self.dev = weights.f32["latents_init"].device
 
     # ---- transformer blocks (attention.py:11-185) ---------------------------------------------
@@ -181,30 +183,82 @@ class Engine:
         """encode (track_autoencoder_3d.py:190-204 / track_autoencoder.py:234-246) -> [B,128,latent] f32."""
         meta = self.w.meta
         dev = self.dev
-        tracks = _as_dev(inputs["support_tracks"], torch.float32, dev)
-        visible = _as_dev(inputs["support_tracks_visible"], torch.float32, dev)
-        boundary = _as_dev(inputs["boundary_frame"], torch.int32, dev)
-        B, N, T, _ = tracks.shape
         three_d = meta["coords"] == 3
+        boundary = _as_dev(inputs["boundary_frame"], torch.int32, dev)
+        B, N, T, _ = inputs["support_tracks"].shape
+        # host-resident inputs: overlap the host->device copies (1.26 GB of fp32 features per clip,
+        # PCIe-bound) with the per-track work, chunk by chunk - tracks are independent until pooling
+        streamed = three_d and self.stream_chunk > 0 and N >= 2 * self.stream_chunk and all(
+            isinstance(inputs.get(k), torch.Tensor) and not inputs[k].is_cuda
+            for k in ("support_tracks", "support_tracks_visible"))
+        tracks = visible = None
+        if not streamed:
+            tracks = _as_dev(inputs["support_tracks"], torch.float32, dev)
+            visible = _as_dev(inputs["support_tracks_visible"], torch.float32, dev)
         dino = depth = None
-        if three_d and self.cfg.use_dino and meta["has_dino"] and inputs.get("dino_features") is not None:
+        if streamed:
+            pass
+        elif three_d and self.cfg.use_dino and meta["has_dino"] and inputs.get("dino_features") is not None:
             dino = _as_dev(inputs["dino_features"], torch.float32, dev)
         if three_d and self.cfg.use_depth and meta["has_depth"] and inputs.get("depth_features") is not None:
             depth = _as_dev(inputs["depth_features"], torch.float32, dev)
-        x = self.embed_tracks(tracks, dino, depth, readout=three_d)
-        key_mask = ops.build_key_mask(visible, boundary, has_readout=three_d)
-        L = T + (1 if three_d else 0)
-        if three_d:
-            st = self.transformer("itt", x, B * N, L, key_mask, out_rows="first")  # [B*N, W]
+        if streamed:
+            st = self._encode_tracks_streamed(inputs, boundary, B, N, T)
+        elif three_d:
+            x = self.embed_tracks(tracks, dino, depth, readout=True)
+            key_mask = ops.build_key_mask(visible, boundary, has_readout=True)
+            st = self.transformer("itt", x, B * N, T + 1, key_mask, out_rows="first")  # [B*N, W]
         else:
-            tok = self.transformer("itt", x, B * N, L, key_mask)  # [B*N*T, W]
+            x = self.embed_tracks(tracks, dino, depth, readout=False)
+            key_mask = ops.build_key_mask(visible, boundary, has_readout=False)
+            tok = self.transformer("itt", x, B * N, T, key_mask)  # [B*N*T, W]
             st = self._masked_mean(tok, visible, B * N, T)
-        del x
+            del tok
         nl, E = meta["latent_tokens"], meta["E"]
         lat = self.w.f32["latents_init"].unsqueeze(0).expand(B, nl, E).reshape(B * nl, E).contiguous()
         lat = self.transformer("t2l", lat, B, nl, kv=st, Lkv=N)
         z = ops.gemm(lat, self.w.c["compressor.Wt"], self.w.f32["compressor.b"], out_dtype=torch.float32)
         return z.view(B, nl, meta["latent_dim"])
+
+    def _encode_tracks_streamed(self, inputs, boundary, B, N, T):
+        """encode_tracks (track_autoencoder_3d.py:151-188) on host-resident inputs, in chunks of
+        ``stream_chunk`` support tracks: the copy of chunk i+1 (side stream, pinned source) runs under
+        the embedding + temporal transformer of chunk i.  Same arithmetic per track as the one-shot path."""
+        meta, dev, cfg = self.w.meta, self.dev, self.cfg
+        cur = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        cs.wait_stream(cur)
+        use_dino = cfg.use_dino and meta["has_dino"] and inputs.get("dino_features") is not None
+        use_depth = cfg.use_depth and meta["has_depth"] and inputs.get("depth_features") is not None
+        keys = ["support_tracks", "support_tracks_visible"] + (["dino_features"] if use_dino else []) + (["depth_features"] if use_depth else [])
+        host = {k: (inputs[k] if inputs[k].dtype == torch.float32 else inputs[k].float()) for k in keys}
+        pieces = [(b, n0, min(n0 + self.stream_chunk, N)) for b in range(B) for n0 in range(0, N, self.stream_chunk)]
+
+        def upload(piece):
+            b, n0, n1 = piece
+            with torch.cuda.stream(cs):
+                dv = {k: host[k][b : b + 1, n0:n1].to(dev, non_blocking=True) for k in keys}
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return dv, ev
+
+        out = torch.empty(B * N, meta["W"], device=dev, dtype=self.cdt)
+        nxt = upload(pieces[0])
+        for i, (b, n0, n1) in enumerate(pieces):
+            dv, ev = nxt
+            if i + 1 < len(pieces):
+                nxt = upload(pieces[i + 1])
+            cur.wait_event(ev)
+            for t in dv.values():
+                t.record_stream(cur)
+            x = self.embed_tracks(dv["support_tracks"], dv.get("dino_features"), dv.get("depth_features"), readout=True)
+            km = ops.build_key_mask(dv["support_tracks_visible"], boundary[b : b + 1], has_readout=True)
+            st = self.transformer("itt", x, n1 - n0, T + 1, km, out_rows="first")
+            out[b * N + n0 : b * N + n1].copy_(st)
+            del x, st, dv
+        return out
 
     def _masked_mean(self, tok, visible, seqs, T):
         """TRAJAN pooling (track_autoencoder.py:230-232): sum(tok*vis)/max(1,sum vis)."""

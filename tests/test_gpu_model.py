@@ -138,3 +138,27 @@ def test_trajan_2d_forward(spa):
     assert rel_err(got.tracks, ref.tracks) < 1e-4
     assert rel_err(got.visible_logits, ref.visible_logits) < 1e-4
     assert rel_err(got.certain_logits, ref.certain_logits) < 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_streamed_host_inputs_equal_one_shot_upload(spa, precision):
+    """Host-resident (pinned) inputs are uploaded chunk by chunk under the per-track transformer;
+    the latents must equal the one-shot path bit for bit (tracks are independent until pooling)."""
+    c = small_cfg()
+    model = spa.TrackAutoEncoder3D(**{k: getattr(c, k) for k in om.Config3D.__dataclass_fields__})
+    inp, noise = make_inputs(c, B=2, N=11, Q=6)
+    inp["boundary_frame"] = np.array([c.num_output_frames - 3, c.num_output_frames], np.int32)
+    variables = model.init(5, inp, arch=SMALL_ARCH)
+    randomize(variables["params"], 5)
+    eng = model.bind(variables, precision)
+    dev_inp = {k: torch.as_tensor(v).cuda() for k, v in inp.items()}
+    with torch.no_grad():
+        ref = eng.encode(dev_inp)
+        host_inp = {k: torch.as_tensor(v).pin_memory() for k, v in inp.items()}
+        eng.stream_chunk = 4          # 11 tracks -> chunks of 4, 4, 3 per clip
+        got = eng.encode(host_inp)
+        eng.stream_chunk = 256
+    assert torch.equal(got, ref)
+    res_a = model.apply(variables, host_inp, noise=noise, precision=precision)
+    res_b = model.apply(variables, dev_inp, noise=torch.as_tensor(noise).cuda(), precision=precision)
+    assert torch.equal(res_a.tracks, res_b.tracks) and torch.equal(res_a.visible_logits, res_b.visible_logits)
