@@ -18,6 +18,7 @@ SOURCES = [
     "lift.cu",
     "gemm_simt.cu",
     "gemm_tcgen05.cu",
+    "embed_tcgen05.cu",
     "attention_simt.cu",
     "attention_mma.cu",
     "attention_api.cu",

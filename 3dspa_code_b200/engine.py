@@ -78,6 +78,7 @@ class Engine:
         self.w = weights
         self.cdt = weights.cdt
         self.exact = (weights.cdt == torch.float32) if exact_sin is None else exact_sin
+        self.fused_embed = True     # bf16 path: fused Fourier + feature conversion + first projection (K1)
         self.stream_chunk = 256     # support tracks per host->device pipeline stage (0 = one-shot upload)
         self._copy_stream = None
         self.dev = weights.f32["latents_init"].device
@@ -162,6 +163,16 @@ class Engine:
                 cols += list(range(off, off + meta["depth_dim"]))
                 ops.axpy(bias, self.w.f32["embed.b_depth"])
             wt = wt[:, cols].contiguous()
+        if (ro and self.cdt == torch.bfloat16 and self.fused_embed and cfg.num_frequencies == 32 and C == 3
+                and ops.embed_fused_applicable(wt.shape[0], K, dino.shape[-1] if dino is not None else 0,
+                                               depth.shape[-1] if depth is not None else 0, C)):
+            # K1: Fourier features + fp32->bf16 feature conversion inside the GEMM's operand producers
+            x = torch.empty(B * N * (T + 1), wt.shape[0], device=self.dev, dtype=torch.float32)
+            ops.embed_fused(tracks.view(rows, C), dino.view(rows, -1) if dino is not None else None,
+                            depth.view(rows, -1) if depth is not None else None, wt, bias, x, T, cfg.num_frequencies,
+                            cfg.track_scale_factor)
+            ops.set_rows(x, T + 1, self.w.f32["readout_token"].view(-1), B * N)
+            return x
         grp = T if ro else 0
         a = torch.empty(B * N * (T + ro), K, device=self.dev, dtype=self.cdt)
         if ro:

@@ -94,6 +94,19 @@ def fourier_features(x, out, num_freq=32, scale_factor=1.0, append_time=0, tail_
     return out
 
 
+def embed_fused_applicable(W, K_total, dino_dim, depth_dim, coords):
+    return bool(_lib.lib().spa3d_embed_fused_applicable(int(W), int(K_total), int(dino_dim), int(depth_dim), int(coords)))
+
+
+def embed_fused(tracks, dino, depth, wt, bias, out, T, num_freq, scale_factor):
+    """out[r + r//T + 1] = [Fourier(tracks[r], t/T) | dino[r] | depth[r]] @ wt^T + bias (fp32 out)."""
+    rows = tracks.shape[0]
+    _call("spa3d_embed_fused", _p(tracks), _p(dino), _p(depth), _p(wt), _ld(wt), _p(bias), _p(out), _ld(out), rows, int(T),
+          dino.shape[1] if dino is not None else 0, depth.shape[1] if depth is not None else 0, wt.shape[0], int(num_freq),
+          float(scale_factor), _stream())
+    return out
+
+
 def convert(src, dst, out_row_group=0):
     rows, cols = src.shape
     _call("spa3d_convert", _p(src), _ld(src), dt(src), _p(dst), _ld(dst), dt(dst), rows, cols, int(out_row_group), _stream())

@@ -68,6 +68,19 @@ int spa3d_fourier_features(const float* x, int64_t ldx, void* out, int64_t ldo, 
                            int append_time, int tail_zero, int exact, int out_row_group,
                            void* stream);
 
+/* ---- K1 fused: track embedding without staging the concatenated features -----------------------
+ * (track_autoencoder_3d.py:123-149): for every (track, frame) row r of tracks [rows,3] (f32),
+ *   out[r + r/T + 1, 0:W] = [Fourier(x,y,z,t/T) | dino[r] | depth[r]] . Wt^T + bias
+ * Wt [W, 256+dino_dim+depth_dim] bf16 (the three Flax kernels stacked along K, transposed), bias [W]
+ * f32 (sum of the three biases), dino / depth f32 [rows, dim] or NULL with dim 0, out f32 with the
+ * read-out slot (row 0 of every T+1 rows) left untouched.  bf16 tensor-core path (sin.approx
+ * Fourier features); spa3d_embed_fused_applicable tells whether the widths are supported. */
+int spa3d_embed_fused_applicable(int W, int K_total, int dino_dim, int depth_dim, int coords);
+int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth, const void* Wt,
+                      int64_t ldw, const float* bias, float* out, int64_t ldo, int64_t rows, int T,
+                      int dino_dim, int depth_dim, int W, int num_freq, float track_scale_factor,
+                      void* stream);
+
 /* Row-wise dtype conversion / strided copy: dst[r', 0:cols] = (dst_dtype) src[r, 0:cols],
  * r' = r (+ r/out_row_group + 1 when out_row_group > 0). */
 int spa3d_convert(const void* src, int64_t lds, int src_dtype, void* dst, int64_t ldd,

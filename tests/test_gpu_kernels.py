@@ -507,3 +507,33 @@ def test_gemm_gelu_fused_forward_and_backward(spa, impl):
         zz = z.double().requires_grad_(True)
         torch.nn.functional.gelu(zz, approximate="tanh").backward(dy.double() @ w2.double().t())
         assert rel_err(dz, zz.grad) < (1e-2 if impl == "tcgen05" else 2e-5), (M, d, Mh, rel_err(dz, zz.grad))
+
+
+@pytest.mark.parametrize("N,T,Dd,Dz,W", [(40, 7, 768, 256, 384), (3, 150, 768, 256, 384), (33, 12, 64, 0, 256), (9, 5, 0, 128, 192)])
+def test_embed_fused_matches_unfused_math(spa, N, T, Dd, Dz, W):
+    """K1 fused embedding (Fourier + fp32->bf16 features + first projection in one tcgen05 kernel)
+    vs the oracle's SinusoidalEmbedding + the stacked Dense in fp64 on bf16-rounded operands
+    (track_autoencoder_3d.py:123-149); read-out slots must be left untouched."""
+    ops = spa.ops
+    torch.manual_seed(50)
+    R = N * T
+    tracks = (torch.rand(R, 3, device="cuda") * 2 - 1)
+    dino = torch.randn(R, Dd, device="cuda") if Dd else None
+    depth = torch.randn(R, Dz, device="cuda") if Dz else None
+    K = 256 + Dd + Dz
+    wt = (torch.randn(W, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(W, device="cuda")
+    assert ops.embed_fused_applicable(W, K, Dd, Dz, 3)
+    out = torch.full((N * (T + 1), W), -7.0, device="cuda")
+    ops.embed_fused(tracks, dino, depth, wt, bias, out, T, 32, 1.0)
+    t = (torch.arange(R, device="cuda") % T).float() / T
+    feats = om.sinusoidal_embedding(torch.cat([tracks, t[:, None]], -1).cpu(), 32).cuda()
+    parts = [feats.float().to(torch.bfloat16).double()]
+    if Dd:
+        parts.append(dino.to(torch.bfloat16).double())
+    if Dz:
+        parts.append(depth.to(torch.bfloat16).double())
+    ref = torch.cat(parts, -1) @ wt.double().t() + bias.double()
+    got = out.view(N, T + 1, W)
+    assert float((got[:, 0] + 7.0).abs().max()) == 0.0          # read-out slots untouched
+    assert rel_err(got[:, 1:].reshape(R, W), ref) < 3e-3, rel_err(got[:, 1:].reshape(R, W), ref)
