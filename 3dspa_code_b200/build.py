@@ -21,6 +21,7 @@ SOURCES = [
     "embed_tcgen05.cu",
     "attention_simt.cu",
     "attention_mma.cu",
+    "attention_tc.cu",
     "attention_api.cu",
 ]
 

@@ -17,6 +17,11 @@ bool attention_fwd_mma_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq
 int attention_fwd_mma(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                       int64_t ldv, void* o, int64_t ldo, const uint8_t* key_mask, float* lse_out,
                       int64_t batch, int heads, int Lq, int Lk, int Dh, cudaStream_t st);
+bool attention_fwd_tc_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                 const void* q, const void* k, const void* v, const void* o);
+int attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                     int64_t ldo, const uint8_t* key_mask, float* stats, int64_t batch, int heads, int L, int Dh,
+                     cudaStream_t st);
 int attention_delta(const void* o, int64_t ldo, const void* d_o, int64_t lddo, int dtype, float* delta_ws,
                     int64_t batch, int heads, int Lq, int Dh, cudaStream_t st);
 bool attention_bwd_mma_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq, int64_t ldk, int64_t ldv,
@@ -38,6 +43,8 @@ int spa3d_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   if (batch == 0 || Lq == 0) return 0;
   SPA3D_REQUIRE(Lk > 0, "attention: Lk must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
+  if (attention_fwd_tc_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, ldo, q, k, v, o))
+    return attention_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse_out, batch, heads, Lq, Dh, st);
   if (attention_fwd_mma_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, ldo))
     return attention_fwd_mma(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse_out, batch, heads, Lq, Lk,
                              Dh, st);

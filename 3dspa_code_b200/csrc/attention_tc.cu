@@ -1,0 +1,358 @@
+// Short-sequence self-attention core on the 5th-gen tensor cores (tcgen05 + TMEM), bf16:
+//   o = softmax(q k^T [+ key mask]) v   per (sequence, head), whole sequence in one CTA pass.
+//
+// The per-track temporal self-attention (L = T+1 = 151, track_autoencoder_3d.py:182-184), the
+// decoder read-out attention (L = 129, :285) and the latent self-attentions (L = 128) all fit one
+// tile: S = Q K^T is one UMMA per 16 head channels with N = L (padded to 160) accumulating in TMEM,
+// the softmax reads S straight from TMEM with one thread per query row (no shuffles, no online
+// rescaling: the whole row is there), P goes back through shared memory as the K-major A operand
+// of O = P V, and V is consumed in place as an MN-major B operand (no transpose).
+//
+// Persistent CTA, one item = (sequence, head):
+//   warp 0      TMA: Q,K (3 + 3 boxes of 32 channels x L rows, 64B swizzle) then V, 3-D tensor maps
+//               [channels, L, sequences] so rows past the sequence end are zero-filled / clipped.
+//   warp 1      MMA issuer: S MMAs (both 128-row query tiles), later the P V MMAs.
+//   warps 2..9  softmax + epilogue, thread = query row (tile = warp/4, TMEM lane quarter = warp%4).
+// Q/K/V are single-buffered but released early (tcgen05.commit -> mbarrier), so the loads of item
+// i+1 run under the softmax / PV / epilogue of item i.
+//
+// Mask semantics (attention.py:175, flax dot_product_attention): masked logits become
+// finfo(float32).min, so an all-masked row is uniform; keys beyond L do not exist (-inf).
+#include "tc_ptx.cuh"
+
+namespace spa3d {
+namespace ta {
+
+using namespace tc;
+
+constexpr int THREADS = 320;
+constexpr int SM_WARPS = 8;
+
+__device__ __forceinline__ uint64_t desc_k64(uint32_t addr) {   // K-major, 64B swizzle: 8 rows x 64 B atoms
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;   // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_mn64(uint32_t addr, uint32_t lbo_bytes) {   // MN-major, 64B swizzle
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// kind::f16, fp32 accumulate, bf16 operands, M = 128; b_mn: B operand MN-major
+__host__ __device__ constexpr uint32_t idesc_attn(int n, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DH, int LPAD, int MT>   // head width, padded sequence length (multiple of 32), 128-row query tiles
+__global__ void __launch_bounds__(THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                   const uint8_t* __restrict__ mask, float* __restrict__ stats, int64_t items, int heads, int L) {
+  constexpr int DA = DH / 32;          // 32-channel atoms per operand row
+  constexpr int KA = LPAD / 32;        // 32-key atoms per P row
+  constexpr int QROWS = MT * 128;
+  constexpr int Q_BYTES = DA * QROWS * 64, K_BYTES = DA * LPAD * 64, P_BYTES = KA * 128 * 64;
+  constexpr int S_COL = 0, O_COL = MT * LPAD;
+  static_assert(MT * (LPAD + DH) <= 512, "TMEM: S and O accumulators of every query tile");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + K_BYTES;
+  uint8_t* sP = sV + K_BYTES;                      // [MT][KA][128 rows][64 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + MT * P_BYTES);
+  uint64_t* qk_full = bars, *qk_empty = bars + 1, *v_full = bars + 2, *v_empty = bars + 3;
+  uint64_t* s_full = bars + 4, *s_empty = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+    mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, SM_WARPS * 32); mbar_init(p_full, SM_WARPS * 32); mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA loads =====================
+    if (lane == 0) {
+      uint32_t ph = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
+        const int b = (int)(it / heads), h = (int)(it % heads);
+        mbar_wait(qk_empty, ph ^ 1);
+        mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * DA * LPAD * 64));
+#pragma unroll
+        for (int a = 0; a < DA; ++a) {
+          tma_load_3d(sQ + a * (QROWS * 64), &tmQ, h * DH + a * 32, 0, b, qk_full);
+          tma_load_3d(sK + a * (LPAD * 64), &tmK, h * DH + a * 32, 0, b, qk_full);
+        }
+        mbar_wait(v_empty, ph ^ 1);
+        mbar_arrive_expect_tx(v_full, (uint32_t)(DA * LPAD * 64));
+#pragma unroll
+        for (int a = 0; a < DA; ++a) tma_load_3d(sV + a * (LPAD * 64), &tmV, h * DH + a * 32, 0, b, v_full);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idS = idesc_attn(LPAD, false), idO = idesc_attn(DH, true);
+      uint32_t ph = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
+        mbar_wait(qk_full, ph);
+        mbar_wait(s_empty, ph ^ 1);   // the softmax of the previous item has finished reading S
+        tcgen05_fence_after();
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) {
+            const uint64_t da = desc_k64(smem_u32(sQ + (kk >> 1) * (QROWS * 64) + mt * (128 * 64) + (kk & 1) * 32));
+            const uint64_t db = desc_k64(smem_u32(sK + (kk >> 1) * (LPAD * 64) + (kk & 1) * 32));
+            umma_bf16(tmem_base + (uint32_t)(S_COL + mt * LPAD), da, db, idS, kk > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(s_full);
+        umma_commit(qk_empty);
+        mbar_wait(v_full, ph);
+        mbar_wait(p_full, ph);        // P is in shared memory (and O of the previous item has been drained)
+        tcgen05_fence_after();
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int ks = 0; ks < LPAD / 16; ++ks) {
+            const uint64_t da = desc_k64(smem_u32(sP + mt * P_BYTES + (ks >> 1) * (128 * 64) + (ks & 1) * 32));
+            const uint64_t db = desc_mn64(smem_u32(sV + ks * (16 * 64)), (uint32_t)(LPAD * 64));
+            umma_bf16(tmem_base + (uint32_t)(O_COL + mt * DH), da, db, idO, ks > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(o_full);
+        umma_commit(v_empty);
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue: thread = query row =====================
+    const int sw = warp - 2;
+    const int mt = sw >> 2;            // query tile
+    const int quarter = warp & 3;      // TMEM lane quarter of this warp
+    const int row = mt * 128 + quarter * 32 + lane;
+    const bool warp_live = mt < MT && mt * 128 + quarter * 32 < L;   // any valid row in this warp
+    const uint32_t tS = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(S_COL + mt * LPAD);
+    const uint32_t tO = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(O_COL + mt * DH);
+    uint8_t* pRow = sP + mt * P_BYTES + (quarter * 32 + lane) * 64;   // this thread's 64 B in every 32-key atom
+    const int sw64 = (lane >> 1) & 3;
+    uint32_t* kmask = reinterpret_cast<uint32_t*>(bars + 16) + sw * 16;   // [2*KA] keep / absent bit masks of this warp
+    constexpr float LOG2E = 1.4426950408889634f;
+    uint32_t ph = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
+      const int b = (int)(it / heads), h = (int)(it % heads);
+      // key classes of this sequence as two bit masks per 32-key chunk (keep / absent); lane = key
+      // (kept in this warp's private smem words so the chunk loops can stay rolled)
+#pragma unroll
+      for (int c = 0; c < KA; ++c) {
+        const int key = c * 32 + lane;
+        const bool ab = key >= L;
+        const bool kp = !ab && (mask == nullptr || mask[(int64_t)b * L + key] != 0);
+        const uint32_t kb = __ballot_sync(0xffffffffu, kp), abm = __ballot_sync(0xffffffffu, ab);
+        if (lane == 0) {
+          kmask[2 * c] = kb;
+          kmask[2 * c + 1] = abm;
+        }
+      }
+      __syncwarp();
+      mbar_wait(s_full, ph);
+      tcgen05_fence_after();
+      float mx = -INFINITY, lsum = 0.f;
+      if (warp_live) {
+        // pass 1: row maximum (masked logits are finfo.min, absent keys -inf)
+#pragma unroll 1
+        for (int c = 0; c < KA; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tS + (uint32_t)(c * 32), r);
+          const uint32_t keep = kmask[2 * c], absent = kmask[2 * c + 1];
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = ((keep >> i) & 1u) ? __uint_as_float(r[i]) : (((absent >> i) & 1u) ? -INFINITY : -FLT_MAX);
+            mx = fmaxf(mx, v);
+          }
+        }
+        // pass 2: probabilities -> bf16 P rows (K-major, 64B-swizzled atoms of 32 keys)
+#pragma unroll 1
+        for (int c = 0; c < KA; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tS + (uint32_t)(c * 32), r);
+          const uint32_t keep = kmask[2 * c], absent = kmask[2 * c + 1];
+          tmem_ld_wait();
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v0 = ((keep >> (2 * i)) & 1u) ? __uint_as_float(r[2 * i]) : (((absent >> (2 * i)) & 1u) ? -INFINITY : -FLT_MAX);
+            const float v1 = ((keep >> (2 * i + 1)) & 1u) ? __uint_as_float(r[2 * i + 1]) : (((absent >> (2 * i + 1)) & 1u) ? -INFINITY : -FLT_MAX);
+            const float p0 = ex2_fast((v0 - mx) * LOG2E), p1 = ex2_fast((v1 - mx) * LOG2E);
+            lsum += p0 + p1;
+            __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+            w[i] = *reinterpret_cast<uint32_t*>(&hb);
+          }
+          uint8_t* dst = pRow + c * (128 * 64);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(s_empty);
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+      // epilogue: O / l -> bf16 -> staging -> TMA store (rows past L are clipped by the tensor map).
+      // Staging reuses this warp's own 32 P rows of the first DA atoms (free once P V has completed).
+      mbar_wait(o_full, ph);
+      tcgen05_fence_after();
+      if (warp_live) {
+        const float inv = 1.f / lsum;
+#pragma unroll
+        for (int c = 0; c < DA; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tO + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+          uint8_t* dst = pRow + c * (128 * 64);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * e]) * inv, __uint_as_float(r[j * 8 + 2 * e + 1]) * inv);
+              w[e] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+            *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < DA; ++c)
+            tma_store_3d(&tmO, sP + mt * P_BYTES + c * (128 * 64) + quarter * 2048, h * DH + c * 32, mt * 128 + quarter * 32, b);
+          bulk_commit();
+        }
+        if (stats != nullptr && row < L) {
+          const int64_t base = (((int64_t)b * heads + h) * L + row) * 2;
+          stats[base] = mx;
+          stats[base + 1] = inv;
+        }
+        if (lane == 0) bulk_wait_read<0>();   // the staging rows are P rows of the next item
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// [cols, L rows, batch] view of a token-major matrix; box = {32 channels, box_rows, 1}, 64B swizzle
+static int make_map3(CUtensorMap* map, const void* ptr, int cols, int L, int64_t batch, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  SPA3D_REQUIRE(fn != nullptr, "attention_tc: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * (cuuint64_t)ld * 2};
+  cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SPA3D_REQUIRE(r == CUDA_SUCCESS, "attention_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+template <int DH, int LPAD, int MT>
+static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                  const uint8_t* mask, float* stats, int64_t batch, int heads, int L, cudaStream_t st) {
+  constexpr int DA = DH / 32, KA = LPAD / 32;
+  constexpr int SMEM = DA * MT * 128 * 64 + 2 * DA * LPAD * 64 + MT * KA * 128 * 64 + 128 + 512 + 1024;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  const int cols = heads * DH;
+  if (make_map3(&tmQ, q, cols, L, batch, ldq, LPAD)) return 1;
+  if (make_map3(&tmK, k, cols, L, batch, ldk, LPAD)) return 1;
+  if (make_map3(&tmV, v, cols, L, batch, ldv, LPAD)) return 1;
+  if (make_map3(&tmO, o, cols, L, batch, ldo, 32)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, LPAD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    SPA3D_REQUIRE(e == cudaSuccess, "attention_tc: smem attribute (%d B): %s", SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t items = batch * heads;
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  attn_fwd_tc_kernel<DH, LPAD, MT><<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, tmO, mask, stats, items, heads, L);
+  return check_launch("attention_fwd_tc");
+}
+
+}  // namespace ta
+
+bool attention_fwd_tc_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                 const void* q, const void* k, const void* v, const void* o) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("SPA3D_ATTN_TC");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!enabled || dtype != SPA3D_BF16 || Lq != Lk || Lq < 2 || Lq > 160) return false;
+  if (Dh != 96 && Dh != 64) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return al16(q) && al16(k) && al16(v) && al16(o) && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0;
+}
+
+int attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                     int64_t ldo, const uint8_t* key_mask, float* stats, int64_t batch, int heads, int L, int Dh,
+                     cudaStream_t st) {
+  using namespace ta;
+  if (Dh == 96) {
+    if (L <= 128) return launch<96, 128, 1>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+    return launch<96, 160, 2>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+  }
+  if (L <= 128) return launch<64, 128, 1>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+  return launch<64, 160, 2>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+}
+
+}  // namespace spa3d

@@ -78,18 +78,14 @@ struct EpiParams {
   int debug_skip;    // SPA3D_GEMM_SKIP_EPI=1: accumulators are drained but nothing is computed or stored
 };
 
-// bias on one 32-column chunk of an output row held in registers (v = packed pairs)
-__device__ __forceinline__ void epi_bias(const EpiParams& ep, uint64_t (&v)[16], int col0, int N) {
-  if (ep.bias) {
+// bias on one 32-column chunk of an output row held in registers (v = packed pairs).  Lane i holds
+// the bias of column i of the chunk (loaded while the MMAs of the tile were still running: a global
+// load here would sit on the critical path, L1 is nearly all carved out as shared memory); every
+// thread owns a whole row, so the 32 values are broadcast with shuffles.
+__device__ __forceinline__ void epi_bias(uint64_t (&v)[16], float breg) {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (col0 + 4 * g < N) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 4 * g));
-        v[2 * g] = add2(v[2 * g], pk(b.x, b.y));
-        v[2 * g + 1] = add2(v[2 * g + 1], pk(b.z, b.w));
-      }
-    }
-  }
+  for (int i = 0; i < 16; ++i)
+    v[i] = add2(v[i], pk(__shfl_sync(0xffffffffu, breg, 2 * i), __shfl_sync(0xffffffffu, breg, 2 * i + 1)));
 }
 // activation (bf16 outputs only: api.cu routes fp32 + GELU to the SIMT path)
 __device__ __forceinline__ void epi_act(const EpiParams& ep, uint64_t (&v)[16]) {
@@ -305,6 +301,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             rp += rstep;
           }
         };
+        // bias of the 4 columns this lane stores in the coalesced pass, one float4 per chunk
+        float4 bq[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col = colbase + c * 32 + cc * 4;
+          bq[c] = (ep.bias && col < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (!ep.debug_skip) {
           load_res(0);   // in flight while the MMAs of this tile still run
           // pull the residual of this CTA's next tile into L2 (one prefetch per 128-byte line)
@@ -333,20 +336,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           const int col0 = colbase + c * 32;
           if (col0 < N && !ep.debug_skip) {
-            uint64_t v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = pku(r[2 * i], r[2 * i + 1]);
-            epi_bias(ep, v, col0, N);
-            epi_act(ep, v);
             uint8_t* srow = slab + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float a0, a1, a2, a3;
-              upk(v[2 * j], a0, a1);
-              upk(v[2 * j + 1], a2, a3);
-              *reinterpret_cast<float4*>(srow + ((j ^ (lane & 7)) << 4)) = make_float4(a0, a1, a2, a3);
-            }
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
             __syncwarp();
+            float4 bcur = bq[0];
+#pragma unroll
+            for (int c2 = 1; c2 < NCH; ++c2)
+              if (c == c2) bcur = bq[c2];
             const int col = col0 + cc * 4;
             const int esz_c = out_f32 ? 4 : 2;
             char* cp = reinterpret_cast<char*>(ep.C) + (((int64_t)row0 + cr) * ep.ldc + col) * esz_c;
@@ -358,6 +356,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               float4 a = *reinterpret_cast<const float4*>(sp + i * 512 + ((i & 1) ? odd_off : 0));
+              a.x += bcur.x; a.y += bcur.y; a.z += bcur.z; a.w += bcur.w;
+              if (ep.act == SPA3D_ACT_GELU_TANH) {
+                uint64_t g0 = gelu2_fast(pk(a.x, a.y)), g1 = gelu2_fast(pk(a.z, a.w));
+                upk(g0, a.x, a.y);
+                upk(g1, a.z, a.w);
+              }
               const uint4 q = res[i];
               if (ep.residual) {
                 float4 rv;
@@ -395,6 +399,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       } else if constexpr (EPI == EPI_TMA) {
         // ---- bf16 outputs: slab -> TMA store, two 2 KB buffers per warp --------------------------
+        float breg[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col = colbase + c * 32 + lane;
+          breg[c] = (ep.bias && col < N) ? __ldg(ep.bias + col) : 0.f;
+        }
         mbar_wait(&tfull_bar[as], aphase);
         tcgen05_fence_after();
         uint32_t r[2][32];
@@ -413,7 +423,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint64_t v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = pku(r[c & 1][2 * i], r[c & 1][2 * i + 1]);
-            epi_bias(ep, v, col0, N);
+            if (ep.bias) epi_bias(v, breg[c]);
             if (ep.aux_pre) {   // pre-activation z (saved for the backward pass) leaves through its own map
               if (lane == 0) bulk_wait_read<1>();
               __syncwarp();
