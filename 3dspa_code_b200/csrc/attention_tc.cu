@@ -16,8 +16,12 @@
 // Q/K/V are single-buffered but released early (tcgen05.commit -> mbarrier), so the loads of item
 // i+1 run under the softmax / PV / epilogue of item i.
 //
-// Mask semantics (attention.py:175, flax dot_product_attention): masked logits become
-// finfo(float32).min, so an all-masked row is uniform; keys beyond L do not exist (-inf).
+// Mask semantics (attention.py:175, flax dot_product_attention): masked logits become a huge negative
+// constant, so an all-masked row is uniform; keys beyond L do not exist (-inf).  The mask costs the
+// softmax nothing: it is one extra K-step of the S MMA, a rank-1 update ones[q] x bias[k] with
+// bias = 0 / -1e30 / -inf per key (a 32-byte-per-row operand pair built by an otherwise idle warp).
+// -1e30 instead of finfo.min: any finite logit is absorbed by rounding (ulp(1e30) = 7.6e22), so
+// masked keys are the same constant as in the reference, and (s - max) stays exact.
 #include "tc_ptx.cuh"
 
 namespace spa3d {
@@ -26,7 +30,7 @@ namespace ta {
 using namespace tc;
 
 constexpr int THREADS = 320;
-constexpr int SM_WARPS = 8;
+constexpr int SM_WARPS = 7;   // softmax / epilogue warps 2..8; warp 9 builds the key-bias operand
 
 __device__ __forceinline__ uint64_t desc_k64(uint32_t addr) {   // K-major, 64B swizzle: 8 rows x 64 B atoms
   uint64_t d = 0;
@@ -35,6 +39,15 @@ __device__ __forceinline__ uint64_t desc_k64(uint32_t addr) {   // K-major, 64B 
   d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)4 << 61;   // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_k32(uint32_t addr) {   // K-major, 32B swizzle: 8 rows x 32 B atoms (one K-step wide)
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;   // SWIZZLE_32B
   return d;
 }
 __device__ __forceinline__ uint64_t desc_mn64(uint32_t addr, uint32_t lbo_bytes) {   // MN-major, 64B swizzle
@@ -86,10 +99,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sK = sQ + Q_BYTES;
   uint8_t* sV = sK + K_BYTES;
   uint8_t* sP = sV + K_BYTES;                      // [MT][KA][128 rows][64 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + MT * P_BYTES);
+  uint8_t* sE = sP + MT * P_BYTES;                 // ones operand [QROWS][32 B], 32B-swizzled, constant
+  uint8_t* sB = sE + QROWS * 32;                   // [2][LPAD][32 B] per-item key bias operand
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * LPAD * 32);
   uint64_t* qk_full = bars, *qk_empty = bars + 1, *v_full = bars + 2, *v_empty = bars + 3;
   uint64_t* s_full = bars + 4, *s_empty = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* m_full = bars + 8, *m_empty = bars + 10;   // [2] each
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -99,12 +115,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
     mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
     mbar_init(s_full, 1); mbar_init(s_empty, SM_WARPS * 32); mbar_init(p_full, SM_WARPS * 32); mbar_init(o_full, 1);
+    mbar_init(&m_full[0], 1); mbar_init(&m_full[1], 1); mbar_init(&m_empty[0], 1); mbar_init(&m_empty[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // ones operand: element 0 of every row = 1.0 (logical chunk 0 sits at physical chunk (row >> 2) & 1)
+  for (int r = threadIdx.x; r < QROWS; r += THREADS) {
+    const int pc = (r >> 2) & 1;
+    *reinterpret_cast<uint4*>(sE + r * 32 + pc * 16) = make_uint4(0x3F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sE + r * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -134,8 +158,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idS = idesc_attn(LPAD, false), idO = idesc_attn(DH, true);
       uint32_t ph = 0;
-      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
+      int n = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1, ++n) {
+        const int mb = n & 1;
         mbar_wait(qk_full, ph);
+        mbar_wait(&m_full[mb], (n >> 1) & 1);
         mbar_wait(s_empty, ph ^ 1);   // the softmax of the previous item has finished reading S
         tcgen05_fence_after();
 #pragma unroll
@@ -146,9 +173,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint64_t db = desc_k64(smem_u32(sK + (kk >> 1) * (LPAD * 64) + (kk & 1) * 32));
             umma_bf16(tmem_base + (uint32_t)(S_COL + mt * LPAD), da, db, idS, kk > 0 ? 1u : 0u);
           }
+          // S += ones[q] x bias[k]: the key mask as one more K-step
+          umma_bf16(tmem_base + (uint32_t)(S_COL + mt * LPAD), desc_k32(smem_u32(sE + mt * (128 * 32))),
+                    desc_k32(smem_u32(sB + mb * (LPAD * 32))), idS, 1u);
         }
         umma_commit(s_full);
         umma_commit(qk_empty);
+        umma_commit(&m_empty[mb]);
         mbar_wait(v_full, ph);
         mbar_wait(p_full, ph);        // P is in shared memory (and O of the previous item has been drained)
         tcgen05_fence_after();
@@ -165,6 +196,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(v_empty);
       }
     }
+  } else if (warp == 2 + SM_WARPS) {
+    // ===================== key-bias operand builder (one warp, runs one item ahead) =====================
+    const uint32_t NEG_BIG = 0xF14Au;   // bf16(-1e30)
+    const uint32_t NEG_INF = 0xFF80u;
+    int n = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int b = (int)(it / heads);
+      const int mb = n & 1;
+      if (lane == 0) mbar_wait(&m_empty[mb], ((n >> 1) & 1) ^ 1);
+      __syncwarp();
+      uint8_t* dstb = sB + mb * (LPAD * 32);
+      for (int j = lane; j < LPAD; j += 32) {
+        uint32_t val = NEG_INF;                                              // key does not exist
+        if (j < L) val = (mask == nullptr || mask[(int64_t)b * L + j] != 0) ? 0u : NEG_BIG;
+        const int pc = (j >> 2) & 1;
+        *reinterpret_cast<uint4*>(dstb + j * 32 + pc * 16) = make_uint4(val, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dstb + j * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&m_full[mb]);
+    }
   } else {
     // ===================== softmax + epilogue: thread = query row =====================
     const int sw = warp - 2;
@@ -176,56 +229,44 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tO = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(O_COL + mt * DH);
     uint8_t* pRow = sP + mt * P_BYTES + (quarter * 32 + lane) * 64;   // this thread's 64 B in every 32-key atom
     const int sw64 = (lane >> 1) & 3;
-    uint32_t* kmask = reinterpret_cast<uint32_t*>(bars + 16) + sw * 16;   // [2*KA] keep / absent bit masks of this warp
     constexpr float LOG2E = 1.4426950408889634f;
     uint32_t ph = 0;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
       const int b = (int)(it / heads), h = (int)(it % heads);
-      // key classes of this sequence as two bit masks per 32-key chunk (keep / absent); lane = key
-      // (kept in this warp's private smem words so the chunk loops can stay rolled)
-#pragma unroll
-      for (int c = 0; c < KA; ++c) {
-        const int key = c * 32 + lane;
-        const bool ab = key >= L;
-        const bool kp = !ab && (mask == nullptr || mask[(int64_t)b * L + key] != 0);
-        const uint32_t kb = __ballot_sync(0xffffffffu, kp), abm = __ballot_sync(0xffffffffu, ab);
-        if (lane == 0) {
-          kmask[2 * c] = kb;
-          kmask[2 * c + 1] = abm;
-        }
-      }
-      __syncwarp();
       mbar_wait(s_full, ph);
       tcgen05_fence_after();
       float mx = -INFINITY, lsum = 0.f;
       if (warp_live) {
-        // pass 1: row maximum (masked logits are finfo.min, absent keys -inf)
+        // pass 1: row maximum (the mask is already in the logits)
 #pragma unroll 1
         for (int c = 0; c < KA; ++c) {
           uint32_t r[32];
           tmem_ld32(tS + (uint32_t)(c * 32), r);
-          const uint32_t keep = kmask[2 * c], absent = kmask[2 * c + 1];
           tmem_ld_wait();
+          float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = ((keep >> i) & 1u) ? __uint_as_float(r[i]) : (((absent >> i) & 1u) ? -INFINITY : -FLT_MAX);
-            mx = fmaxf(mx, v);
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[i]));
+            m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
           }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         }
         // pass 2: probabilities -> bf16 P rows (K-major, 64B-swizzled atoms of 32 keys)
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
         for (int c = 0; c < KA; ++c) {
           uint32_t r[32];
           tmem_ld32(tS + (uint32_t)(c * 32), r);
-          const uint32_t keep = kmask[2 * c], absent = kmask[2 * c + 1];
           tmem_ld_wait();
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float v0 = ((keep >> (2 * i)) & 1u) ? __uint_as_float(r[2 * i]) : (((absent >> (2 * i)) & 1u) ? -INFINITY : -FLT_MAX);
-            const float v1 = ((keep >> (2 * i + 1)) & 1u) ? __uint_as_float(r[2 * i + 1]) : (((absent >> (2 * i + 1)) & 1u) ? -INFINITY : -FLT_MAX);
-            const float p0 = ex2_fast((v0 - mx) * LOG2E), p1 = ex2_fast((v1 - mx) * LOG2E);
-            lsum += p0 + p1;
+            const float p0 = ex2_fast((__uint_as_float(r[2 * i]) - mx) * LOG2E);
+            const float p1 = ex2_fast((__uint_as_float(r[2 * i + 1]) - mx) * LOG2E);
+            l0 += p0;
+            l1 += p1;
             __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
             w[i] = *reinterpret_cast<uint32_t*>(&hb);
           }
@@ -234,6 +275,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         }
+        lsum = l0 + l1;
       }
       tcgen05_fence_before();
       mbar_arrive(s_empty);
@@ -309,7 +351,7 @@ template <int DH, int LPAD, int MT>
 static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                   const uint8_t* mask, float* stats, int64_t batch, int heads, int L, cudaStream_t st) {
   constexpr int DA = DH / 32, KA = LPAD / 32;
-  constexpr int SMEM = DA * MT * 128 * 64 + 2 * DA * LPAD * 64 + MT * KA * 128 * 64 + 128 + 512 + 1024;
+  constexpr int SMEM = DA * MT * 128 * 64 + 2 * DA * LPAD * 64 + MT * KA * 128 * 64 + MT * 128 * 32 + 2 * LPAD * 32 + 128 + 1024;
   CUtensorMap tmQ, tmK, tmV, tmO;
   const int cols = heads * DH;
   if (make_map3(&tmQ, q, cols, L, batch, ldq, LPAD)) return 1;
