@@ -600,7 +600,10 @@ __global__ void zero_kernel(float* __restrict__ p, int64_t n) {
   if (i < n) p[i] = 0.f;
 }
 
-__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+// sum of squares in a FIXED order (per-block partials, then one block adds them in index order):
+// every data-parallel replica must derive the identical clip scale from the identical all-reduced
+// gradient, or the replicas drift apart bit by bit.
+__global__ void sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partial) {
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = g[i];
@@ -615,7 +618,22 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __re
     int nw = blockDim.x >> 5;
     acc = lane < nw ? sh[lane] : 0.f;
     acc = warp_sum(acc);
-    if (lane == 0) atomicAdd(out, acc);
+    if (lane == 0) partial[blockIdx.x] = acc;
+  }
+}
+__global__ void sumsq_final_kernel(const float* __restrict__ partial, int nb, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += partial[i];
+  acc = warp_sum(acc);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh[w] = acc;
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    acc = lane < nw ? sh[lane] : 0.f;
+    acc = warp_sum(acc);
+    if (lane == 0) *out += acc;
   }
 }
 
@@ -932,12 +950,13 @@ int spa3d_axpy(float* y, const float* x, float alpha, int64_t n, void* stream) {
   return check_launch("axpy");
 }
 
-int spa3d_sumsq(const float* g, int64_t n, float* sumsq, void* stream) {
+int spa3d_sumsq(const float* g, int64_t n, float* sumsq, float* workspace, void* stream) {
   if (n == 0) return 0;
+  SPA3D_REQUIRE(workspace != nullptr, "sumsq: workspace of SPA3D_SUMSQ_WORKSPACE floats required");
   unsigned nb = blocks_for(n, 1024);
-  unsigned cap = (unsigned)num_sms() * 8;
-  if (nb > cap) nb = cap;
-  sumsq_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(g, n, sumsq);
+  if (nb > SPA3D_SUMSQ_WORKSPACE) nb = SPA3D_SUMSQ_WORKSPACE;
+  sumsq_partial_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(g, n, workspace);
+  sumsq_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, (int)nb, sumsq);
   return check_launch("sumsq");
 }
 

@@ -317,7 +317,9 @@ def axpy(y, x, alpha=1.0):
 
 
 def sumsq(g, out):
-    _call("spa3d_sumsq", _p(g), g.numel(), _p(out), _stream())
+    """out += sum(g*g), summed in a fixed order (identical on every data-parallel replica)."""
+    ws = torch.empty(1024, device=g.device, dtype=torch.float32)
+    _call("spa3d_sumsq", _p(g), g.numel(), _p(out), _p(ws), _stream())
 
 
 def adamw_step(p, g, m, v, sumsq_t, clip_norm, lr, b1, b2, eps, wd, step):

@@ -72,8 +72,16 @@ class ParamStore(DeviceWeights):
         self.g = g
         self.ct: Dict[str, torch.Tensor] = {}
         self.step_count = 0
+        self.progress_cb = None   # called with a layer prefix when that layer's backward has finished (DP overlap)
         self.lowp: Dict[int, torch.Tensor] = {}   # fp32 gradient data_ptr -> bf16 copy written by the producer kernel
         self.refresh()
+
+    def frontier(self, prefix):
+        """End offset (elements) of the flat buffers up to and including the parameters of ``prefix``:
+        the buffers are laid out in backward-completion order, so everything below is final once the
+        backward of that layer has run."""
+        ends = [self.offsets[n] + (self.f32[n].numel() + 63) // 64 * 64 for n in self.names if n.startswith(prefix)]
+        return max(ends) if ends else 0
 
     def is_matrix(self, k):
         return self.f32[k].dim() == 2 and (k.endswith("_t") or k.endswith(".Wt"))
@@ -194,6 +202,8 @@ class AttnBlockFn(torch.autograd.Function):
         ops.axpy(st.g[pre + "norm_q"], ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, da, accumulate=True,
                                                          dx_lowp=_lowp_out(st, da)))
         ctx.saved = None
+        if st.progress_cb is not None:
+            st.progress_cb(pre)   # every parameter of this layer (and of everything after it) now has its final gradient
         return da, dkv, None, None, None, None, None, None, None, None
 
 
@@ -482,17 +492,33 @@ class Trainer:
         self.bucket_elems = bucket_mb * (1 << 20) // 4
         self.comm_stream = torch.cuda.Stream(device=device) if self.world > 1 and torch.device(device).type == "cuda" else None
         self.step_idx = 0
+        self.overlap = True
+        self._sent = 0
 
     # -- gradient all-reduce -----------------------------------------------------------------------------
-    def _allreduce_grads(self):
-        """Sum-all-reduce the flat gradient buffer in buckets (contiguous, backward-completion order)."""
-        if self.world == 1:
+    def _reduce_upto(self, frontier):
+        """All-reduce (sum) the complete buckets below ``frontier`` on the side stream; they were
+        finished by kernels already enqueued on the compute stream."""
+        b = self.bucket_elems
+        hi = self.store.total if frontier >= self.store.total else (frontier // b) * b
+        if hi <= self._sent:
             return
         cur = torch.cuda.current_stream()
-        self.comm_stream.wait_stream(cur)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
-            dp.bucketed_allreduce(self.store.grad, self.bucket_elems, self.group)
-        cur.wait_stream(self.comm_stream)
+            dp.bucketed_allreduce(self.store.grad[self._sent : hi], self.bucket_elems, self.group)
+        self._sent = hi
+
+    def _progress(self, prefix):
+        self._reduce_upto(self.store.frontier(prefix))
+
+    def _allreduce_rest(self):
+        if self.world == 1:
+            return
+        self._reduce_upto(self.store.total)
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def train_step(self, batch, noise):
         """batch: this rank's clips (dict of arrays with leading axis B_local, incl. query_tracks /
@@ -506,10 +532,16 @@ class Trainer:
         ops.colsum(tv.reshape(-1, 1), cnt)  # local visible count; summed over ranks below
         denom = dp.global_denominator(cnt, self.group)
         sums = torch.zeros(3, device=dev)
+        self._sent = 0
         for s in range(0, Bl, self.micro):
             mb = {k: (v[s : s + self.micro] if hasattr(v, "shape") and len(v.shape) > 0 and v.shape[0] == Bl else v) for k, v in batch.items()}
+            # gradients are final only in the last micro-batch: overlap the all-reduce with ITS backward,
+            # bucket by bucket, as the layers complete (the flat buffer is in backward-completion order)
+            last = s + self.micro >= Bl
+            st.progress_cb = self._progress if (last and self.world > 1 and self.overlap) else None
             self.engine.loss_and_backward(mb, noise[s : s + self.micro], denom, sums=sums)
-        self._allreduce_grads()
+        st.progress_cb = None
+        self._allreduce_rest()
         if self.world > 1:
             dist.all_reduce(sums, group=self.group)
         lr = learning_rate(self.step_idx, **self.hp)

@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 T, S, Q = 150, 2048, 512
+TRAIN_GLOBAL_BATCH = 64   # BASELINE.json configs[2]
 FWD_TFLOP_PER_CLIP = 9.413  # SURVEY.md Appendix D / BASELINE.md section 3 (algorithmic, forward)
 METRIC = "3dspa_infer_query_tracks_per_s"
 UNIT = "query-tracks/s"
@@ -121,6 +122,86 @@ def cpu_oracle_rate(sample_s=256, sample_q=64, threads=None):
         om.forward_3d(tree, cfg, inp, noise, True)
     dt = time.perf_counter() - t0
     return sample_q / dt, dt, f"oracle fp32 forward on 1 clip of {sample_s} support / {sample_q} query tracks, T={T} (same 4:1 ratio as cfg2; rate = queries / wall time)"
+
+
+def synth_train_batch(B, seed, dev):
+    """cfg3 micro data on the device: B clips with targets (held-out query tracks + visibility)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    r = lambda *sh: torch.rand(*sh, generator=g, device=dev)
+    batch = {
+        "support_tracks": r(B, S, T, 3) * 2 - 1,
+        "support_tracks_visible": (r(B, S, T, 1) < 0.9).float(),
+        "query_points": torch.cat([torch.randint(0, T, (B, Q, 1), generator=g, device=dev).float(), r(B, Q, 3) * 2 - 1], -1),
+        "boundary_frame": torch.full((B,), T, dtype=torch.int32, device=dev),
+        "dino_features": torch.randn(B, S, T, 768, generator=g, device=dev),
+        "depth_features": torch.randn(B, S, T, 256, generator=g, device=dev),
+        "query_tracks": r(B, Q, T, 3) * 2 - 1,
+        "query_tracks_visible": (r(B, Q, T, 1) < 0.9).float(),
+    }
+    return batch, r(B, 128, 96)
+
+
+def run_train_leg(args, spa, model, variables, world, rank, dev, barrier):
+    """cfg3: one optimiser step over a global batch of 64 clips, 64/N clips per rank in micro-batches of
+    one clip, gradients summed over NCCL (overlapped with the last backward), AdamW on every rank."""
+    import torch.distributed as dist
+
+    te = importlib.import_module("3dspa_code_b200.train_engine")
+    dp = importlib.import_module("3dspa_code_b200.dp")
+    lo, hi = dp.shard_range(args.train_batch, world, rank)
+    trainer = te.Trainer(model, variables["params"], precision="bf16", device=dev, micro_batch=1)
+    batch, noise = synth_train_batch(hi - lo, 1000 + rank, dev)
+    l0 = spa.ops.launch_count
+    trainer.train_step(batch, noise)   # warm-up (allocator, NCCL communicator)
+    launches = spa.ops.launch_count - l0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        log = trainer.train_step(batch, noise)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.train_steps
+    peak_tf, _, _ = measured_peaks()
+    tf = 3 * FWD_TFLOP_PER_CLIP * args.train_batch / (ms * 1e-3)   # algorithmic TFLOP/s, whole job (fwd + 2x bwd)
+    del trainer, batch
+    torch.cuda.empty_cache()
+    return {"metric": "3dspa_train_clips_per_s", "value": args.train_batch / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms,
+            "global_batch": args.train_batch, "clips_per_gpu": hi - lo, "micro_batch": 1, "steps": args.train_steps, "warmup": 1,
+            "scaling": "strong", "dtype": "bf16", "model_tflops_per_gpu": tf / world, "frac_of_sustained_peak_per_gpu": tf / world / peak_tf,
+            "gpu_launches_per_step": int(launches), "loss": log["total_loss"],
+            "config": "cfg3: fwd+bwd+AdamW, B=64 global, T=150, S=2048, Q=512, DINO+depth, NCCL gradient all-reduce overlapped with backward"}
+
+
+def run_lifting_leg(spa, dev):
+    """cfg4 (K0): bilinear DINO / depth sampling + unprojection for a 64x64 track grid over 150 frames."""
+    g = torch.Generator(device=dev).manual_seed(4)
+    N, H, W, Hp, Wp = 4096, 518, 518, 37, 37
+    gy, gx = torch.meshgrid(torch.arange(64, device=dev), torch.arange(64, device=dev), indexing="ij")
+    base = torch.stack([(gx.reshape(-1) + 0.5) * W / 64, (gy.reshape(-1) + 0.5) * H / 64], -1).float()
+    walk = torch.cumsum(torch.randn(N, T, 2, generator=g, device=dev) * 1.5, 1)
+    tracks = (base[:, None] + walk).contiguous()
+    depth = torch.rand(T, H, W, 1, generator=g, device=dev) * 9.5 + 0.5
+    dino = torch.randn(T, Hp, Wp, 768, generator=g, device=dev)
+    fn = lambda: spa.ops.lift_sample(tracks, depth=depth, dino=dino, video_hw=(H, W))
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    nbytes = dino.numel() * 4 + depth.numel() * 4 + tracks.numel() * 4 + N * T * (3 + 768 + 256) * 4   # SURVEY 8(d): 3.32 GB
+    _, peak_bw, src = measured_peaks()
+    return {"workload": "cfg4: lift + sample 4096 tracks x 150 frames, 518x518 video, DINO map 37x37x768 (fp32 out)", "ms": ms,
+            "bound": "hbm", "algorithmic_bytes": int(nbytes), "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak_bw, "unit": "GB/s",
+            "frac": nbytes / (ms * 1e-3) / 1e9 / peak_bw, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})",
+            "points_per_s": N * T / (ms * 1e-3)}
 
 
 def run_reference(args):
@@ -255,6 +336,18 @@ def run_ours(args):
             v, dt, sample = cpu_oracle_rate()
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                                     "seconds": dt}
+    # ---- the other half of BASELINE.json's metric: train clips/s (cfg3), and the K0 gather (cfg4) ----
+    train = lifting = None
+    if not args.no_train:
+        torch.cuda.empty_cache()
+        train = run_train_leg(args, spa, model, variables, world, rank, dev, barrier)
+    if rank == 0 and not args.no_train:
+        lifting = run_lifting_leg(spa, dev)
+    if rank == 0:
+        if train is not None:
+            line["train"] = train
+        if lifting is not None:
+            line["lifting"] = lifting
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -267,6 +360,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the cfg3 training leg and the cfg4 gather leg")
+    ap.add_argument("--train-batch", type=int, default=TRAIN_GLOBAL_BATCH, help="global batch of the training leg (clips)")
+    ap.add_argument("--train-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

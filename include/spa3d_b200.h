@@ -33,6 +33,7 @@ extern "C" {
 #define SPA3D_ACT_NONE 0
 #define SPA3D_ACT_GELU_TANH 1 /* flax nn.gelu(approximate=True), attention.py:106 */
 
+#define SPA3D_SUMSQ_WORKSPACE 1024 /* floats of scratch for spa3d_sumsq (deterministic two-stage sum) */
 #define SPA3D_GEMM_AUTO 0   /* tcgen05 when operands are bf16 and shapes allow, else SIMT fp32 */
 #define SPA3D_GEMM_SIMT 1   /* fp32 FMA path (the "fp32-accumulate" accurate mode)           */
 #define SPA3D_GEMM_TCGEN05 2 /* force the tcgen05/TMEM/TMA kernel; error if not applicable   */
@@ -256,7 +257,7 @@ int spa3d_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
 
 /* ---- a16: optimiser (train.py:41-57,239-243; optax adamw + clip_by_global_norm) ------------
  * sumsq[0] += sum g^2 ;  then adamw with clip factor computed on device from sumsq. */
-int spa3d_sumsq(const float* g, int64_t n, float* sumsq, void* stream);
+int spa3d_sumsq(const float* g, int64_t n, float* sumsq, float* workspace, void* stream);
 int spa3d_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
                      float clip_norm, float lr, float b1, float b2, float eps, float wd,
                      int step, void* stream);
