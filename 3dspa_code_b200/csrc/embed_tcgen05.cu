@@ -38,7 +38,8 @@ struct EmbedParams {
   int64_t ldo;
   int64_t R;
   int T, Dd, Dz, W;
-  float scale;           // track_scale_factor
+  float inv_scale;       // 1 / track_scale_factor
+  float inv_T;           // 1 / T
   float fs[32];          // 2^(i/3)
 };
 
@@ -53,7 +54,8 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_BYTES;
   uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;            // [4 warps][4096]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + NUM_EPI * 4096);
+  float* smem_bias = reinterpret_cast<float*>(smem_epi + NUM_EPI * 4096);   // [NB*BNH]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + NB * BNH);
   uint64_t* full_bar = bars;                 // [STAGES]  1 TMA arrive (expect_tx) + 8 producer warps
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // accumulator complete
@@ -80,6 +82,7 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < NB * BNH; i += THREADS) smem_bias[i] = p.bias[i];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -137,6 +140,13 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
     int it = 0;
     for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
       const int64_t row0 = t * BM + quarter * 32;
+      // output rows of the 8 coalesced passes (row remap r -> r + r/T + 1), once per tile
+      float* orow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t r_ = row0 + i * 4 + cr;
+        orow[i] = r_ < p.R ? p.out + (r_ + (int64_t)((uint32_t)r_ / (uint32_t)p.T) + 1) * p.ldo + cc * 4 : nullptr;
+      }
       mbar_wait(tfull_bar, it & 1);
       tcgen05_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -153,21 +163,17 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
         const int col0 = c * 32;
         uint8_t* srow = slab + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
-          *reinterpret_cast<float4*>(srow + ((j ^ (lane & 7)) << 4)) =
-              make_float4(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y,
-                          __uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
-        }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
+        const float4 b = *reinterpret_cast<const float4*>(smem_bias + col0 + cc * 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + cr;
-          const int64_t r_ = row0 + rr;
-          if (r_ < p.R) {
-            const float4 a = *reinterpret_cast<const float4*>(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
-            const int64_t ro = r_ + r_ / p.T + 1;   // slot 0 of every sequence is the read-out token
-            *reinterpret_cast<float4*>(p.out + ro * p.ldo + col0 + cc * 4) = a;
+          if (orow[i] != nullptr) {
+            float4 a = *reinterpret_cast<const float4*>(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            *reinterpret_cast<float4*>(orow[i] + col0) = a;
           }
         }
         __syncwarp();
@@ -175,62 +181,105 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
     }
   } else {
     // ===================== A-tile producers (8 warps, 256 threads) =====================
+    // Software pipelined over the flat (tile, K-block) sequence: the 128-bit loads of item i+1 are
+    // in flight while item i is converted and written to shared memory (two register buffers), so
+    // every producer thread keeps 2 x 8 x 16 B of HBM reads outstanding.
     const int ptid = threadIdx.x - (2 + NUM_EPI) * 32;   // 0..255
     const int rsub = ptid >> 4, l16 = ptid & 15;         // 16 lanes per row segment, 16 rows per pass
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-      const int64_t row_base = t * BM;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
-        __syncwarp();
-        uint8_t* at = smem_a + stage * A_BYTES;
-        if (kb < 4) {
-          // Fourier features of coordinate kb: features f = l16*4 .. +3 (f < 32: sin(v s_f), else sin(v s_f + pi/2))
-          const int f0 = (l16 * 4) & 31;
-          const float ph = l16 >= 8 ? 1.57079632679489661923f : 0.f;
-          const float s0 = p.fs[f0], s1 = p.fs[f0 + 1], s2 = p.fs[f0 + 2], s3 = p.fs[f0 + 3];
+    const int64_t my_tiles = blockIdx.x < m_tiles ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_items = my_tiles * num_kb;
+
+    auto issue = [&](int64_t idx, float4 (&v)[8]) {
+      if (idx >= n_items) return;
+      const int kb = (int)(idx % num_kb);
+      const int64_t row_base = (blockIdx.x + (idx / num_kb) * gridDim.x) * BM;
+      if (kb < 4) {
+        // Fourier block: only the coordinate of each row is loaded (x, y, z) or derived (t / T);
+        // issued one item ahead like the feature loads, so its HBM latency is off the critical path
 #pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int row = ps * 16 + rsub;
-            const int64_t r_ = row_base + row;
-            float v = 0.f;
-            if (r_ < p.R) v = kb < 3 ? p.tracks[r_ * 3 + kb] : __fdiv_rn((float)(r_ % p.T), (float)p.T);
-            v = __fdiv_rn(v, p.scale);
-            float o0, o1, o2, o3;
-            asm("sin.approx.f32 %0, %1;" : "=f"(o0) : "f"(__fadd_rn(__fmul_rn(v, s0), ph)));
-            asm("sin.approx.f32 %0, %1;" : "=f"(o1) : "f"(__fadd_rn(__fmul_rn(v, s1), ph)));
-            asm("sin.approx.f32 %0, %1;" : "=f"(o2) : "f"(__fadd_rn(__fmul_rn(v, s2), ph)));
-            asm("sin.approx.f32 %0, %1;" : "=f"(o3) : "f"(__fadd_rn(__fmul_rn(v, s3), ph)));
-            if (r_ >= p.R) o0 = o1 = o2 = o3 = 0.f;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
-            *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
-                make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-          }
-        } else {
-          const bool is_dino = kb < kb_depth0;
-          const float* src = is_dino ? p.dino : p.depth;
-          const int64_t ld = is_dino ? p.Dd : p.Dz;
-          const int col = (is_dino ? kb - kb_dino0 : kb - kb_depth0) * 64 + l16 * 4;
-          float4 v[8];
-#pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int64_t r_ = row_base + ps * 16 + rsub;
-            v[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r_ < p.R) v[ps] = __ldcs(reinterpret_cast<const float4*>(src + r_ * ld + col));   // streamed once
-          }
-#pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int row = ps * 16 + rsub;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[ps].x, v[ps].y), h1 = __floats2bfloat162_rn(v[ps].z, v[ps].w);
-            *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
-                make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-          }
+        for (int ps = 0; ps < 8; ++ps) {
+          const int64_t r_ = row_base + ps * 16 + rsub;
+          float x = 0.f;
+          if (r_ < p.R) x = kb < 3 ? __ldg(p.tracks + r_ * 3 + kb) : (float)((uint32_t)r_ % (uint32_t)p.T) * p.inv_T;
+          v[ps].x = x * p.inv_scale;
         }
-        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        return;
+      }
+      const bool is_dino = kb < kb_depth0;
+      const float* src = is_dino ? p.dino : p.depth;
+      const int64_t ld = is_dino ? p.Dd : p.Dz;
+      const int col = (is_dino ? kb - kb_dino0 : kb - kb_depth0) * 64 + l16 * 4;
+#pragma unroll
+      for (int ps = 0; ps < 8; ++ps) {
+        const int64_t r_ = row_base + ps * 16 + rsub;
+        v[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r_ < p.R) v[ps] = __ldcs(reinterpret_cast<const float4*>(src + r_ * ld + col));   // streamed once
+      }
+    };
+    auto consume = [&](int64_t idx, const float4 (&v)[8]) {
+      const int kb = (int)(idx % num_kb);
+      const int stage = (int)(idx % STAGES);
+      const uint32_t phase = (uint32_t)((idx / STAGES) & 1);
+      const int64_t row_base = (blockIdx.x + (idx / num_kb) * gridDim.x) * BM;
+      if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+      __syncwarp();
+      uint8_t* at = smem_a + stage * A_BYTES;
+      if (kb < 4) {
+        // Fourier features of coordinate kb: features f = l16*4 .. +3 (f < 32: sin(v s_f), else sin(v s_f + pi/2))
+        const int f0 = (l16 * 4) & 31;
+        const float ph = l16 >= 8 ? 1.57079632679489661923f : 0.f;
+        const float s0 = p.fs[f0], s1 = p.fs[f0 + 1], s2 = p.fs[f0 + 2], s3 = p.fs[f0 + 3];
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+          const int row = ps * 16 + rsub;
+          const int64_t r_ = row_base + row;
+          const float x = v[ps].x;
+          float o0, o1, o2, o3;
+          asm("sin.approx.f32 %0, %1;" : "=f"(o0) : "f"(__fadd_rn(__fmul_rn(x, s0), ph)));
+          asm("sin.approx.f32 %0, %1;" : "=f"(o1) : "f"(__fadd_rn(__fmul_rn(x, s1), ph)));
+          asm("sin.approx.f32 %0, %1;" : "=f"(o2) : "f"(__fadd_rn(__fmul_rn(x, s2), ph)));
+          asm("sin.approx.f32 %0, %1;" : "=f"(o3) : "f"(__fadd_rn(__fmul_rn(x, s3), ph)));
+          if (r_ >= p.R) o0 = o1 = o2 = o3 = 0.f;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+          *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+      } else {
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+          const int row = ps * 16 + rsub;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[ps].x, v[ps].y), h1 = __floats2bfloat162_rn(v[ps].z, v[ps].w);
+          *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    };
+
+    // DRAM-friendly order: the 256-byte-per-row slices of one K-block touch a different DRAM page
+    // per row; pulling every row's whole feature vector (3 KB + 1 KB contiguous) into L2 ahead of
+    // time turns the HBM side into long sequential reads and the slices into L2 hits.
+    auto prefetch_tile = [&](int64_t tile_iter) {
+      if (tile_iter >= my_tiles) return;
+      const int64_t r_ = (blockIdx.x + tile_iter * gridDim.x) * BM + (ptid >> 1);
+      if (r_ >= p.R) return;
+      const float* src = (ptid & 1) ? p.depth : p.dino;
+      const int64_t w = (ptid & 1) ? p.Dz : p.Dd;
+      if (src != nullptr && w > 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + r_ * w), "r"((uint32_t)(w * 4)) : "memory");
+    };
+    prefetch_tile(0);
+    float4 va[8], vb[8];
+    issue(0, va);
+    for (int64_t i = 0; i < n_items; i += 2) {
+      if (i % num_kb == (num_kb & ~1) - 6 || (i + 1) % num_kb == (num_kb & ~1) - 6) prefetch_tile(i / num_kb + 1);
+      issue(i + 1, vb);
+      consume(i, va);
+      if (i + 1 < n_items) {
+        issue(i + 2, va);
+        consume(i + 1, vb);
       }
     }
   }
@@ -245,7 +294,7 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
 
 template <int NB, int BNH>
 static int launch(const CUtensorMap& tmB, const EmbedParams& p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + NB * BNH * BK * 2) + NUM_EPI * 4096 + 256 + 1024;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + NB * BNH * BK * 2) + NUM_EPI * 4096 + NB * BNH * 4 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(embed_fused_kernel<NB, BNH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -282,9 +331,10 @@ int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth
   SPA3D_REQUIRE(al16(dino) && al16(depth) && al16(Wt) && al16(out) && al16(bias) && ldw % 8 == 0 && ldo % 4 == 0,
                 "embed_fused: operands must be 16-byte aligned");
   if (rows == 0) return 0;
+  SPA3D_REQUIRE(rows < (1ll << 31), "embed_fused: too many rows");
   EmbedParams p;
   p.tracks = tracks; p.dino = dino; p.depth = depth; p.bias = bias; p.out = out; p.ldo = ldo; p.R = rows;
-  p.T = T; p.Dd = dino_dim; p.Dz = depth_dim; p.W = W; p.scale = track_scale_factor;
+  p.T = T; p.Dd = dino_dim; p.Dz = depth_dim; p.W = W; p.inv_scale = (float)(1.0 / (double)track_scale_factor); p.inv_T = (float)(1.0 / (double)T);
   for (int i = 0; i < 32; ++i) p.fs[i] = (float)pow(2.0, (double)i / 3.0);
   const int K = 256 + dino_dim + depth_dim;
   CUtensorMap tmB;

@@ -222,7 +222,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: 3DSPA inference forward, B=1, T=150, S=2048, Q=512 (CPU arm runs a bounded 128/32 sample per step)"},
+        "config": {"workload": "cfg2: 3DSPA inference forward, 1 clip per GPU, T=150, S=2048 support, Q=512 query, DINO 768 + depth 256, bf16",
+                   "reference_arm": "fp32 torch-CPU oracle restatement on all host cores; each step = a bounded 128-support / 32-query sample of the same clip shape"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is JAX/Flax (not installable here); this arm is the torch-CPU oracle restatement",
