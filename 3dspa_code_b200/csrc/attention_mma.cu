@@ -12,8 +12,9 @@
 // tile, the core is 2-9 % of the layer FLOPs, and at Dh = 96 it is bound by the HBM traffic of
 // q/k/v/o, not by the tensor pipe.  The dense projections around it use tcgen05.
 //
-// Mask semantics (attention.py:175, flax dot_product_attention): masked logits become
-// finfo(float32).min, so an all-masked row is uniform; keys beyond Lk do not exist (-inf).
+// Mask semantics (attention.py:175, flax dot_product_attention): masked logits become one huge
+// negative constant (finfo.min there, bf16(-1e30) here, see common.cuh), so an all-masked row is
+// uniform; keys beyond Lk do not exist (-inf).
 #include <cuda_pipeline.h>
 
 #include "common.cuh"
@@ -143,8 +144,8 @@ attn_fwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restr
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         uint8_t mk = Ms[kt + nt * 8 + tq * 2 + e];
-        float lo = mk == 1 ? s[nt][e] : (mk == 0 ? -FLT_MAX : -INFINITY);
-        float hi = mk == 1 ? s[nt][2 + e] : (mk == 0 ? -FLT_MAX : -INFINITY);
+        float lo = mk == 1 ? s[nt][e] : (mk == 0 ? masked_logit_bf16() : -INFINITY);
+        float hi = mk == 1 ? s[nt][2 + e] : (mk == 0 ? masked_logit_bf16() : -INFINITY);
         s[nt][e] = lo;
         s[nt][2 + e] = hi;
         tmax0 = fmaxf(tmax0, lo);
@@ -334,7 +335,7 @@ attn_bwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restr
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const uint8_t mk = Ms[j0 + nt * 8 + tq * 2 + e];
-          const float lo = mk == 1 ? s[nt][e] : -FLT_MAX, hi = mk == 1 ? s[nt][2 + e] : -FLT_MAX;
+          const float lo = mk == 1 ? s[nt][e] : masked_logit_bf16(), hi = mk == 1 ? s[nt][2 + e] : masked_logit_bf16();
           const float p0 = mk != 2 ? exp2f((lo - m0) * LOG2E) * i0 : 0.f;
           const float p1 = mk != 2 ? exp2f((hi - m1) * LOG2E) * i1 : 0.f;
           dsv[e] = mk == 1 ? p0 * (dp[nt][e] - e0) : 0.f;
@@ -400,7 +401,7 @@ attn_bwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restr
         for (int e = 0; e < 2; ++e) {
           const int qi = r0 + nt * 8 + tq * 2 + e;       // query index = column of S^T
           const float m = mS[qi], il = iS[qi], dl = dS[qi];
-          const float lo = mk0 == 1 ? s[nt][e] : -FLT_MAX, hi = mk1 == 1 ? s[nt][2 + e] : -FLT_MAX;
+          const float lo = mk0 == 1 ? s[nt][e] : masked_logit_bf16(), hi = mk1 == 1 ? s[nt][2 + e] : masked_logit_bf16();
           pv[e] = mk0 != 2 ? exp2f((lo - m) * LOG2E) * il : 0.f;
           pv[2 + e] = mk1 != 2 ? exp2f((hi - m) * LOG2E) * il : 0.f;
           dsv[e] = mk0 == 1 ? pv[e] * (dp[nt][e] - dl) : 0.f;

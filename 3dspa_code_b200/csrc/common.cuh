@@ -67,6 +67,12 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // flax nn.gelu(approximate=True)
+// Logit of a masked key in the bf16 attention kernels: bf16(-1e30) widened to fp32, the value the
+// tcgen05 forward adds as a key bias (attention_tc.cu).  Any finite logit is absorbed by rounding, so
+// masked keys are one constant as with the reference's finfo.min, and the backward kernels that
+// recompute P from the saved row maximum must use the very same constant.
+__device__ __forceinline__ float masked_logit_bf16() { return __uint_as_float(0xF14A0000u); }
+
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k = 0.7978845608028654f;  // sqrt(2/pi)
   float u = k * (x + 0.044715f * x * x * x);
