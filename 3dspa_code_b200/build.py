@@ -22,6 +22,7 @@ SOURCES = [
     "attention_simt.cu",
     "attention_mma.cu",
     "attention_tc.cu",
+    "attention_tc_bwd.cu",
     "attention_api.cu",
 ]
 

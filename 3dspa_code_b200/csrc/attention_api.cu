@@ -22,6 +22,12 @@ bool attention_fwd_tc_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq,
 int attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                      int64_t ldo, const uint8_t* key_mask, float* stats, int64_t batch, int heads, int L, int Dh,
                      cudaStream_t st);
+bool attention_bwd_tc_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddo,
+                                 int64_t lddq, int64_t lddk, int64_t lddv);
+int attention_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                     int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                     const uint8_t* key_mask, const float* stats, const float* delta, int64_t batch, int heads, int L,
+                     int Dh, cudaStream_t st);
 int attention_delta(const void* o, int64_t ldo, const void* d_o, int64_t lddo, int dtype, float* delta_ws,
                     int64_t batch, int heads, int Lq, int Dh, cudaStream_t st);
 bool attention_bwd_mma_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq, int64_t ldk, int64_t ldv,
@@ -60,6 +66,12 @@ int spa3d_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   using namespace spa3d;
   if (batch == 0 || Lq == 0) return 0;
   SPA3D_REQUIRE(lse != nullptr && delta_ws != nullptr, "attention_bwd: lse/delta_ws required");
+  if (attention_bwd_tc_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, lddo, lddq, lddk, lddv)) {
+    int rc = attention_delta(o, ldo, d_o, lddo, dtype, delta_ws, batch, heads, Lq, Dh, (cudaStream_t)stream);
+    if (rc) return rc;
+    return attention_bwd_tc(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, lse, delta_ws,
+                            batch, heads, Lq, Dh, (cudaStream_t)stream);
+  }
   if (attention_bwd_mma_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, lddo, lddq, lddk, lddv)) {
     int rc = attention_delta(o, ldo, d_o, lddo, dtype, delta_ws, batch, heads, Lq, Dh, (cudaStream_t)stream);
     if (rc) return rc;
