@@ -445,6 +445,259 @@ attn_bwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// backward for long key sequences (the 128 x N latents<-tracks cross-attention): same math as above,
+// split in two launches so that no partial sums cross CTAs:
+//   MODE 0 (dQ)    : CTA = (sequence, head, 32 query rows); the keys are streamed in chunks of KW.
+//   MODE 1 (dK, dV): CTA = (sequence, head, KW keys); all Lq <= 160 query rows sit in shared memory.
+// ------------------------------------------------------------------------------------------
+template <int DH, int MODE>
+__global__ void __launch_bounds__(256)
+attn_bwd_win_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk,
+                        const bf16* __restrict__ v, int64_t ldv, const bf16* __restrict__ d_o, int64_t lddo,
+                        bf16* __restrict__ dq, int64_t lddq, bf16* __restrict__ dk, int64_t lddk,
+                        bf16* __restrict__ dv, int64_t lddv, const uint8_t* __restrict__ mask,
+                        const float* __restrict__ stats, const float* __restrict__ delta, int heads, int Lq,
+                        int Lk, int QW, int KW, int parts) {
+  constexpr int LDS = DH + 8;
+  constexpr int CH = DH / 8;
+  constexpr float LOG2E = 1.4426950408889634f;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int nwarps = blockDim.x >> 5;
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* Gs = Qs + (size_t)QW * LDS;
+  bf16* Ks = Gs + (size_t)QW * LDS;
+  bf16* Vs = Ks + (size_t)KW * LDS;
+  bf16* Os = Vs + (size_t)KW * LDS;          // per-warp output staging [nwarps][16][LDS]
+  float* mS = reinterpret_cast<float*>(Os + (size_t)nwarps * 16 * LDS);
+  float* iS = mS + QW;
+  float* dS = iS + QW;
+  uint8_t* Ms = reinterpret_cast<uint8_t*>(dS + QW);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  const int part = blockIdx.x % parts;
+  const int64_t bh = blockIdx.x / parts;
+  const int64_t b = bh / heads;
+  const int h = (int)(bh % heads);
+  const int q0 = MODE == 0 ? part * QW : 0;
+  const bf16* qg = q + (b * Lq) * ldq + (int64_t)h * DH;
+  const bf16* gg = d_o + (b * Lq) * lddo + (int64_t)h * DH;
+  const bf16* kg = k + (b * Lk) * ldk + (int64_t)h * DH;
+  const bf16* vg = v + (b * Lk) * ldv + (int64_t)h * DH;
+
+  for (int idx = tid; idx < QW * CH; idx += nthr) {
+    int r = idx / CH, c = idx % CH;
+    bf16* d0 = Qs + r * LDS + c * 8;
+    bf16* d1 = Gs + r * LDS + c * 8;
+    if (q0 + r < Lq) {
+      __pipeline_memcpy_async(d0, qg + (int64_t)(q0 + r) * ldq + c * 8, 16);
+      __pipeline_memcpy_async(d1, gg + (int64_t)(q0 + r) * lddo + c * 8, 16);
+    } else {
+      *reinterpret_cast<uint4*>(d0) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(d1) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  {
+    const int64_t base = (b * heads + h) * Lq;
+    for (int r = tid; r < QW; r += nthr) {
+      const bool ok = q0 + r < Lq;
+      mS[r] = ok ? stats[(base + q0 + r) * 2] : 0.f;
+      iS[r] = ok ? stats[(base + q0 + r) * 2 + 1] : 0.f;
+      dS[r] = ok ? delta[base + q0 + r] : 0.f;
+    }
+  }
+  const int g = lane >> 2, tq = lane & 3;
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;
+  const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;
+  const int t_row = (lane & 7) + ((lane >> 3) & 1) * 8, t_col = (lane >> 4) * 8;
+  bf16* Ow = Os + (size_t)warp * 16 * LDS;
+
+  float acc[DH / 8][4], acc2[MODE == 1 ? DH / 8 : 1][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+  for (int i = 0; i < (MODE == 1 ? DH / 8 : 1); ++i) acc2[i][0] = acc2[i][1] = acc2[i][2] = acc2[i][3] = 0.f;
+
+  const int k_begin = MODE == 0 ? 0 : part * KW;
+  const int k_end = MODE == 0 ? Lk : min(Lk, k_begin + KW);
+  for (int kc0 = k_begin; kc0 < k_end; kc0 += KW) {
+    if (kc0 > k_begin) __syncthreads();
+    for (int idx = tid; idx < KW * CH; idx += nthr) {
+      int r = idx / CH, c = idx % CH;
+      bf16* d0 = Ks + r * LDS + c * 8;
+      bf16* d1 = Vs + r * LDS + c * 8;
+      if (kc0 + r < Lk) {
+        __pipeline_memcpy_async(d0, kg + (int64_t)(kc0 + r) * ldk + c * 8, 16);
+        __pipeline_memcpy_async(d1, vg + (int64_t)(kc0 + r) * ldv + c * 8, 16);
+      } else {
+        *reinterpret_cast<uint4*>(d0) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(d1) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    for (int j = tid; j < KW; j += nthr)
+      Ms[j] = kc0 + j < Lk ? (mask == nullptr ? 1 : (mask[b * Lk + kc0 + j] != 0 ? 1 : 0)) : 2;
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
+
+    if (MODE == 0) {
+      // warp = 16 query rows of the window, keys of this chunk
+      if (warp * 16 < QW) {
+        const int r0 = warp * 16;
+        const float m0 = mS[r0 + g], m1 = mS[r0 + g + 8], i0 = iS[r0 + g], i1 = iS[r0 + g + 8];
+        const float e0 = dS[r0 + g], e1 = dS[r0 + g + 8];
+        for (int j0 = 0; j0 < KW; j0 += 16) {
+          if (kc0 + j0 >= Lk) break;
+          float s[2][4], dp[2][4];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) {
+            uint32_t a[4], bb[4];
+            ldsm_x4(a, Qs + (r0 + a_row) * LDS + kk * 16 + a_col);
+            ldsm_x4(bb, Ks + (j0 + b_row) * LDS + kk * 16 + b_col);
+            mma_bf16(s[0], a, bb[0], bb[1]);
+            mma_bf16(s[1], a, bb[2], bb[3]);
+            ldsm_x4(a, Gs + (r0 + a_row) * LDS + kk * 16 + a_col);
+            ldsm_x4(bb, Vs + (j0 + b_row) * LDS + kk * 16 + b_col);
+            mma_bf16(dp[0], a, bb[0], bb[1]);
+            mma_bf16(dp[1], a, bb[2], bb[3]);
+          }
+          uint32_t pa[4];
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            float dsv[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const uint8_t mk = Ms[j0 + nt * 8 + tq * 2 + e];
+              const float lo = mk == 1 ? s[nt][e] : masked_logit_bf16(), hi = mk == 1 ? s[nt][2 + e] : masked_logit_bf16();
+              const float p0 = mk != 2 ? exp2f((lo - m0) * LOG2E) * i0 : 0.f;
+              const float p1 = mk != 2 ? exp2f((hi - m1) * LOG2E) * i1 : 0.f;
+              dsv[e] = mk == 1 ? p0 * (dp[nt][e] - e0) : 0.f;
+              dsv[2 + e] = mk == 1 ? p1 * (dp[nt][2 + e] - e1) : 0.f;
+            }
+            pa[nt * 2] = pack_bf16(dsv[0], dsv[1]);
+            pa[nt * 2 + 1] = pack_bf16(dsv[2], dsv[3]);
+          }
+#pragma unroll
+          for (int nd2 = 0; nd2 < DH / 16; ++nd2) {
+            uint32_t bb[4];
+            ldsm_x4_t(bb, Ks + (j0 + t_row) * LDS + nd2 * 16 + t_col);
+            mma_bf16(acc[nd2 * 2], pa, bb[0], bb[1]);
+            mma_bf16(acc[nd2 * 2 + 1], pa, bb[2], bb[3]);
+          }
+        }
+      }
+    } else {
+      // warp = 16 keys of the window, all query rows
+      if (warp * 16 < KW && kc0 + warp * 16 < Lk) {
+        const int j0 = warp * 16;
+        const uint8_t mk0 = Ms[j0 + g], mk1 = Ms[j0 + g + 8];
+        for (int r0 = 0; r0 < QW; r0 += 16) {
+          float s[2][4], dp[2][4];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) {
+            uint32_t a[4], bb[4];
+            ldsm_x4(a, Ks + (j0 + a_row) * LDS + kk * 16 + a_col);
+            ldsm_x4(bb, Qs + (r0 + b_row) * LDS + kk * 16 + b_col);
+            mma_bf16(s[0], a, bb[0], bb[1]);
+            mma_bf16(s[1], a, bb[2], bb[3]);
+            ldsm_x4(a, Vs + (j0 + a_row) * LDS + kk * 16 + a_col);
+            ldsm_x4(bb, Gs + (r0 + b_row) * LDS + kk * 16 + b_col);
+            mma_bf16(dp[0], a, bb[0], bb[1]);
+            mma_bf16(dp[1], a, bb[2], bb[3]);
+          }
+          uint32_t pp[4], pd[4];
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            float pv[4], dsv[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int qi = r0 + nt * 8 + tq * 2 + e;
+              const float m = mS[qi], il = iS[qi], dl = dS[qi];
+              const float lo = mk0 == 1 ? s[nt][e] : masked_logit_bf16(), hi = mk1 == 1 ? s[nt][2 + e] : masked_logit_bf16();
+              pv[e] = mk0 != 2 ? exp2f((lo - m) * LOG2E) * il : 0.f;
+              pv[2 + e] = mk1 != 2 ? exp2f((hi - m) * LOG2E) * il : 0.f;
+              dsv[e] = mk0 == 1 ? pv[e] * (dp[nt][e] - dl) : 0.f;
+              dsv[2 + e] = mk1 == 1 ? pv[2 + e] * (dp[nt][2 + e] - dl) : 0.f;
+            }
+            pp[nt * 2] = pack_bf16(pv[0], pv[1]);
+            pp[nt * 2 + 1] = pack_bf16(pv[2], pv[3]);
+            pd[nt * 2] = pack_bf16(dsv[0], dsv[1]);
+            pd[nt * 2 + 1] = pack_bf16(dsv[2], dsv[3]);
+          }
+#pragma unroll
+          for (int nd2 = 0; nd2 < DH / 16; ++nd2) {
+            uint32_t bb[4];
+            ldsm_x4_t(bb, Gs + (r0 + t_row) * LDS + nd2 * 16 + t_col);
+            mma_bf16(acc2[(MODE == 1 ? nd2 * 2 : 0)], pp, bb[0], bb[1]);
+            mma_bf16(acc2[(MODE == 1 ? nd2 * 2 + 1 : 0)], pp, bb[2], bb[3]);
+            ldsm_x4_t(bb, Qs + (r0 + t_row) * LDS + nd2 * 16 + t_col);
+            mma_bf16(acc[nd2 * 2], pd, bb[0], bb[1]);
+            mma_bf16(acc[nd2 * 2 + 1], pd, bb[2], bb[3]);
+          }
+        }
+      }
+    }
+  }
+  // outputs: MODE 0 -> dq rows of the window (acc); MODE 1 -> dk (acc), dv (acc2) rows of the key window
+  const int npass = MODE == 0 ? 1 : 2;
+  const int row0 = (MODE == 0 ? q0 : k_begin) + warp * 16;
+  const int row_lim = MODE == 0 ? Lq : Lk;
+  const bool has_rows = warp * 16 < (MODE == 0 ? QW : KW);
+  for (int pass = 0; pass < npass; ++pass) {
+    bf16* outp = MODE == 0 ? dq : (pass == 0 ? dk : dv);
+    const int64_t ldo_ = MODE == 0 ? lddq : (pass == 0 ? lddk : lddv);
+    if (has_rows) {
+#pragma unroll
+      for (int i = 0; i < DH / 8; ++i) {
+        const float(&a)[4] = (MODE == 1 && pass == 1) ? acc2[MODE == 1 ? i : 0] : acc[i];
+        *reinterpret_cast<uint32_t*>(Ow + g * LDS + i * 8 + tq * 2) = pack_bf16(a[0], a[1]);
+        *reinterpret_cast<uint32_t*>(Ow + (g + 8) * LDS + i * 8 + tq * 2) = pack_bf16(a[2], a[3]);
+      }
+      __syncwarp();
+      bf16* og = outp + (b * row_lim) * ldo_ + (int64_t)h * DH;
+      for (int idx = lane; idx < 16 * CH; idx += 32) {
+        int r = idx / CH, c = idx % CH;
+        if (row0 + r < row_lim)
+          *reinterpret_cast<uint4*>(og + (int64_t)(row0 + r) * ldo_ + c * 8) = *reinterpret_cast<const uint4*>(Ow + r * LDS + c * 8);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int DH>
+static int launch_bwd_win(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                          void* dv, int64_t lddv, const uint8_t* mask, const float* stats, const float* delta,
+                          int64_t batch, int heads, int Lq, int Lk, cudaStream_t st) {
+  const int LqPad = (Lq + 15) / 16 * 16;
+  const int KW = 128;
+  auto smem_for = [&](int QW, int nwarps) { return (size_t)(2 * QW + 2 * KW + nwarps * 16) * (DH + 8) * 2 + (size_t)QW * 12 + KW; };
+  {   // dQ: 32 query rows per CTA (2 compute warps, 4 loading warps), keys streamed
+    const int QW = 32, threads = 128, parts = (Lq + QW - 1) / QW;
+    size_t smem = smem_for(QW, threads / 32);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_win_mma_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SPA3D_REQUIRE(e == cudaSuccess, "attention_bwd_win: smem attribute: %s", cudaGetErrorString(e));
+    attn_bwd_win_mma_kernel<DH, 0><<<(unsigned)(batch * heads * parts), threads, smem, st>>>(
+        (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (const bf16*)d_o, lddo, (bf16*)dq, lddq, (bf16*)dk, lddk,
+        (bf16*)dv, lddv, mask, stats, delta, heads, Lq, Lk, QW, KW, parts);
+  }
+  {   // dK, dV: 128 keys per CTA (8 warps), every query row in shared memory
+    const int QW = LqPad, threads = 256, parts = (Lk + KW - 1) / KW;
+    size_t smem = smem_for(QW, threads / 32);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_win_mma_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SPA3D_REQUIRE(e == cudaSuccess, "attention_bwd_win: smem attribute: %s", cudaGetErrorString(e));
+    attn_bwd_win_mma_kernel<DH, 1><<<(unsigned)(batch * heads * parts), threads, smem, st>>>(
+        (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (const bf16*)d_o, lddo, (bf16*)dq, lddq, (bf16*)dk, lddk,
+        (bf16*)dv, lddv, mask, stats, delta, heads, Lq, Lk, QW, KW, parts);
+  }
+  return check_launch("attention_bwd_win_mma");
+}
+
 template <int DH>
 static int launch_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                       const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk,
@@ -515,7 +768,7 @@ bool attention_bwd_mma_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq
                                   int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv) {
   if (dtype != SPA3D_BF16) return false;
   if (Dh != 64 && Dh != 96) return false;
-  if (Lq > 160 || Lk > 160) return false;   // whole sequence (q, dO, k, v + staging) in one CTA's shared memory
+  if (Lq > 160) return false;   // every query row (q, dO) of a sequence sits in one CTA's shared memory
   return (ldq % 8 == 0) && (ldk % 8 == 0) && (ldv % 8 == 0) && (lddo % 8 == 0) && (lddq % 8 == 0) &&
          (lddk % 8 == 0) && (lddv % 8 == 0);
 }
@@ -527,6 +780,11 @@ int attention_bwd_mma(const void* q, int64_t ldq, const void* k, int64_t ldk, co
                       cudaStream_t st) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   SPA3D_REQUIRE(al(q) && al(k) && al(v) && al(d_o) && al(dq) && al(dk) && al(dv), "attention_bwd_mma: operands must be 16-byte aligned");
+  if (Lk > 160) {   // long key sequences: dQ and dK/dV as two launches over query / key windows
+    if (Dh == 96)
+      return am::launch_bwd_win<96>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, batch, heads, Lq, Lk, st);
+    return am::launch_bwd_win<64>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, batch, heads, Lq, Lk, st);
+  }
   if (Dh == 96)
     return am::launch_bwd<96>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, batch, heads, Lq, Lk, st);
   return am::launch_bwd<64>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, batch, heads, Lq, Lk, st);

@@ -278,6 +278,7 @@ def test_attention_fwd(spa, dtype, Lq, Lk, Dh):
 @pytest.mark.parametrize("dtype,Lq,Lk,Dh", [
     (torch.float32, 40, 40, 96), (torch.float32, 16, 70, 96), (torch.bfloat16, 151, 151, 96), (torch.bfloat16, 129, 129, 96),
     (torch.bfloat16, 128, 128, 64), (torch.bfloat16, 23, 23, 64), (torch.bfloat16, 128, 150, 96), (torch.bfloat16, 64, 300, 96),
+    (torch.bfloat16, 128, 2048, 96), (torch.bfloat16, 40, 500, 64),
 ])
 def test_attention_bwd(spa, dtype, Lq, Lk, Dh):
     ops = spa.ops
