@@ -67,8 +67,7 @@ int spa3d_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   if (batch == 0 || Lq == 0) return 0;
   SPA3D_REQUIRE(lse != nullptr && delta_ws != nullptr, "attention_bwd: lse/delta_ws required");
   if (attention_bwd_tc_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, lddo, lddq, lddk, lddv)) {
-    int rc = attention_delta(o, ldo, d_o, lddo, dtype, delta_ws, batch, heads, Lq, Dh, (cudaStream_t)stream);
-    if (rc) return rc;
+    // delta is computed inside the kernel from P and dP
     return attention_bwd_tc(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, lse, delta_ws,
                             batch, heads, Lq, Dh, (cudaStream_t)stream);
   }

@@ -1,8 +1,8 @@
 // Backward of the short-sequence self-attention core on tcgen05 + TMEM (bf16, L <= 160):
 //   P = exp(S - m) / l,  dP = dO V^T,  dS = P o (dP - delta),  dQ = dS K,  dK = dS^T Q,  dV = P^T dO
 // per (sequence, head), whole sequence in one CTA pass (attention.py:175 under jax.value_and_grad,
-// train.py:161-162).  m, 1/l come from the forward (row statistics), delta_i = sum_d O_id dO_id from
-// a small pre-pass.
+// train.py:161-162).  m, 1/l come from the forward (row statistics); delta_i = sum_d O_id dO_id is
+// evaluated in place as sum_j P_ij dP_ij, so the forward output O is not read at all.
 //
 // No operand is ever transposed in memory: P and dS are written once to shared memory as
 // [query][key] tiles (64B-swizzled atoms of 32 keys) and are read as the K-major A operand of
@@ -106,6 +106,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
   uint64_t* ld_full = bars, *ld_empty = bars + 1, *s_full = bars + 2, *p_done = bars + 3, *dp_full = bars + 4;
   uint64_t* ds_done = bars + 5, *dq_full = bars + 6, *dq_read = bars + 7, *m_full = bars + 8, *m_empty = bars + 10;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  float* dpart = reinterpret_cast<float*>(bars + 16);   // [2 halves][128 rows] partial row sums of P o dP
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -244,11 +245,10 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
         const uint32_t tp = tcount & 1;
         const int row = t * 128 + rloc;
         const bool tile_live = t * 128 + quarter * 32 < L;     // this warp has valid query rows in tile t
-        float m = 0.f, il = 0.f, dl = 0.f;
+        float m = 0.f, il = 0.f;
         if (row < L) {
           m = stats[(sbase + row) * 2];
           il = stats[(sbase + row) * 2 + 1];
-          dl = delta[sbase + row];
         }
         const bool row_grad = m > -1e29f;    // a fully masked row: its logits are constants, dS = 0
         // ---- phase A: P = exp(S - m) / l -> bf16, [query][key] tile ----
@@ -281,6 +281,29 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
         mbar_wait(dp_full, tp);
         tcgen05_fence_after();
         if (tile_live) {
+          // delta_i = sum_d O_id dO_id = sum_j P_ij dP_ij: a row sum over the keys, half of them in the
+          // partner warp of this lane quarter -> exchange through shared memory
+          float part = 0.f;
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c * 32), r);
+            const uint8_t* src = pRow + c * (128 * 64);
+            uint4 pw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pw[j] = *reinterpret_cast<const uint4*>(src + ((j ^ sw64) << 4));
+            tmem_ld_wait();
+            const uint32_t* pwu = reinterpret_cast<const uint32_t*>(pw);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
+              part = fmaf(__low2float(pb), __uint_as_float(r[2 * i]), part);
+              part = fmaf(__high2float(pb), __uint_as_float(r[2 * i + 1]), part);
+            }
+          }
+          dpart[half * 128 + rloc] = part;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+          const float dl = part + dpart[(half ^ 1) * 128 + rloc];
 #pragma unroll 1
           for (int c = c_lo; c < c_hi; ++c) {
             uint32_t r[32];
@@ -306,6 +329,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
           }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // dpart is rewritten for the next tile
         }
         tcgen05_fence_before();
         fence_proxy_async_smem();
@@ -405,7 +429,7 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
                   const uint8_t* mask, const float* stats, const float* delta, int64_t batch, int heads, int L,
                   cudaStream_t st) {
   constexpr int DA = DH / 32, KA = LPAD / 32;
-  constexpr int SMEM = 4 * DA * LPAD * 64 + 2 * KA * 128 * 64 + MT * 128 * 32 + 2 * LPAD * 32 + 128 + 1024;
+  constexpr int SMEM = 4 * DA * LPAD * 64 + 2 * KA * 128 * 64 + MT * 128 * 32 + 2 * LPAD * 32 + 128 + 1024 + 1024;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   Maps tm;
   const int cols = heads * DH;
