@@ -173,7 +173,7 @@ class AttnBlockFn(torch.autograd.Function):
         dkv = None
         dxn = None
         if "kv" in s:
-            st.accum_bias(pre + "cross.bo", da)
+            st.accum_bias(pre + "cross.bo", dac)   # the bf16 copy: half the bytes of the fp32 gradient
             st.accum_dw(pre + "cross.Wo_t", dac, s["oc"])
             d_oc = ops.gemm(dac, st.ct[pre + "cross.Wo_t"])
             dqc = torch.empty_like(s["qc"])
@@ -187,7 +187,7 @@ class AttnBlockFn(torch.autograd.Function):
             dxn = ops.gemm(dqc, st.ct[pre + "cross.Wq_t"])
             if kv_grad:
                 dkv = ops.gemm(dkvp, st.ct[pre + "cross.Wkv_t"])
-        st.accum_bias(pre + "self.bo", da)
+        st.accum_bias(pre + "self.bo", dac)
         st.accum_dw(pre + "self.Wo_t", dac, s["o"])
         d_o = ops.gemm(dac, st.ct[pre + "self.Wo_t"])
         qkv = s["qkv"]
@@ -226,7 +226,7 @@ class MlpBlockFn(torch.autograd.Function):
         s = ctx.saved
         dy = dy.contiguous()
         dyc = _c(st, dy)
-        st.accum_bias(pre + "b2", dy)
+        st.accum_bias(pre + "b2", dyc)
         st.accum_dw(pre + "W2_t", dyc, s["h"])
         dz = ops.gemm_gelu_bwd(dyc, st.ct[pre + "W2_t"], s["z"])
         st.accum_bias(pre + "b1", dz)
