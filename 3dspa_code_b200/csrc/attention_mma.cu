@@ -85,7 +85,7 @@ attn_fwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restr
   }
 
   const int r0 = warp * 16;
-  const bool active = q0 + r0 < Lq;
+  const bool active = r0 < QR && q0 + r0 < Lq;
   const int g = lane >> 2, tq = lane & 3;
 
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
@@ -740,7 +740,10 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   }
   int64_t blocks = batch * heads * q_tiles;
   SPA3D_REQUIRE(blocks < (1ll << 31), "attention_mma: grid too large");
-  attn_fwd_mma_kernel<DH><<<(unsigned)blocks, QR * 2, smem, st>>>(
+  // at least 4 warps per CTA: with few query rows (the pruned last layer has ONE) the extra warps
+  // only help staging K and V, but a 1-warp CTA leaves the SM at 3 resident warps
+  const int threads = QR * 2 < 128 ? 128 : QR * 2;
+  attn_fwd_mma_kernel<DH><<<(unsigned)blocks, threads, smem, st>>>(
       (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, mask, stats, heads, Lq, Lk, QR, KC, q_tiles);
   return check_launch("attention_fwd_mma");
 }

@@ -81,6 +81,7 @@ class Engine:
         self.fused_embed = True     # bf16 path: fused Fourier + feature conversion + first projection (K1)
         self.stream_chunk = 256     # support tracks per host->device pipeline stage (0 = one-shot upload)
         self._copy_stream = None
+        self._stage = {}            # (input key, slot) -> persistent device staging buffer
         self.dev = weights.f32["latents_init"].device
 
     # ---- transformer blocks (attention.py:11-185) ---------------------------------------------
@@ -207,12 +208,11 @@ class Engine:
             tracks = _as_dev(inputs["support_tracks"], torch.float32, dev)
             visible = _as_dev(inputs["support_tracks_visible"], torch.float32, dev)
         dino = depth = None
-        if streamed:
-            pass
-        elif three_d and self.cfg.use_dino and meta["has_dino"] and inputs.get("dino_features") is not None:
-            dino = _as_dev(inputs["dino_features"], torch.float32, dev)
-        if three_d and self.cfg.use_depth and meta["has_depth"] and inputs.get("depth_features") is not None:
-            depth = _as_dev(inputs["depth_features"], torch.float32, dev)
+        if three_d and not streamed:
+            if self.cfg.use_dino and meta["has_dino"] and inputs.get("dino_features") is not None:
+                dino = _as_dev(inputs["dino_features"], torch.float32, dev)
+            if self.cfg.use_depth and meta["has_depth"] and inputs.get("depth_features") is not None:
+                depth = _as_dev(inputs["depth_features"], torch.float32, dev)
         if streamed:
             st = self._encode_tracks_streamed(inputs, boundary, B, N, T)
         elif three_d:
@@ -247,27 +247,46 @@ class Engine:
         host = {k: (inputs[k] if inputs[k].dtype == torch.float32 else inputs[k].float()) for k in keys}
         pieces = [(b, n0, min(n0 + self.stream_chunk, N)) for b in range(B) for n0 in range(0, N, self.stream_chunk)]
 
-        def upload(piece):
-            b, n0, n1 = piece
+        # two persistent staging slots per input (no allocator traffic across streams: a tensor
+        # allocated on the copy stream and freed after use on the compute stream makes the caching
+        # allocator wait on cross-stream events and fall back to cudaMalloc, which stalls everything)
+        C = self.stream_chunk
+        for slot in (0, 1):
+            for k in keys:
+                shp = (1, C) + tuple(host[k].shape[2:])
+                cur_buf = self._stage.get((k, slot))
+                if cur_buf is None or cur_buf.shape != shp:
+                    self._stage[(k, slot)] = torch.empty(shp, device=dev, dtype=torch.float32)
+        done = [None, None]   # compute-finished events per slot
+
+        def upload(i):
+            b, n0, n1 = pieces[i]
+            slot = i & 1
+            if done[slot] is not None:
+                cs.wait_event(done[slot])          # the chunk that used this slot two steps ago has been consumed
             with torch.cuda.stream(cs):
-                dv = {k: host[k][b : b + 1, n0:n1].to(dev, non_blocking=True) for k in keys}
+                dv = {}
+                for k in keys:
+                    view = self._stage[(k, slot)][:, : n1 - n0]
+                    view.copy_(host[k][b : b + 1, n0:n1], non_blocking=True)
+                    dv[k] = view
                 ev = torch.cuda.Event()
                 ev.record(cs)
             return dv, ev
 
         out = torch.empty(B * N, meta["W"], device=dev, dtype=self.cdt)
-        nxt = upload(pieces[0])
+        nxt = upload(0)
         for i, (b, n0, n1) in enumerate(pieces):
             dv, ev = nxt
             if i + 1 < len(pieces):
-                nxt = upload(pieces[i + 1])
+                nxt = upload(i + 1)
             cur.wait_event(ev)
-            for t in dv.values():
-                t.record_stream(cur)
             x = self.embed_tracks(dv["support_tracks"], dv.get("dino_features"), dv.get("depth_features"), readout=True)
             km = ops.build_key_mask(dv["support_tracks_visible"], boundary[b : b + 1], has_readout=True)
             st = self.transformer("itt", x, n1 - n0, T + 1, km, out_rows="first")
             out[b * N + n0 : b * N + n1].copy_(st)
+            done[i & 1] = torch.cuda.Event()
+            done[i & 1].record(cur)
             del x, st, dv
         return out
 
