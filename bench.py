@@ -322,6 +322,8 @@ def run_ours(args):
 
     if rank == 0:
         peak_tf, peak_bw, src = measured_peaks()
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        traffic = json.load(open(tpath)) if os.path.isfile(tpath) else {}
         achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -336,7 +338,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all bf16 dense contractions of the step)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "traffic": traffic.get("dram_bytes_per_launch"),
+                         "traffic_kernel": traffic.get("kernel"), "traffic_algorithmic_bytes": traffic.get("algorithmic_bytes_per_launch"),
                          "gemm_share_of_step": gemm_ms / (ms_total) if ms_total else None,
                          "step_model_tflops": FWD_TFLOP_PER_CLIP / (ms_step * 1e-3), "launches_timed": len(gemm_log)},
         }
