@@ -70,13 +70,39 @@ def synth_clip(seed, device=None, pinned=False, s=S, q=Q, t=T):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML through
+    nvidia_ml_py (a query takes ~1 ms, so a 130 ms timed region gets several samples); falls back to
+    polling the nvidia-smi CLI when NVML cannot be loaded."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            while not self._halt.is_set():
+                try:
+                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    smax = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    self.rows.append((float(sm), float(smax), int(mask)))
+                except Exception:
+                    pass
+                self._halt.wait(0.01)
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._halt.is_set():
@@ -84,7 +110,9 @@ class ClockSampler(threading.Thread):
                 r = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=5)
                 if r.returncode == 0:
-                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+                    c = [x.strip() for x in r.stdout.strip().split(",")]
+                    mask = sum(bit for (name, bit), val in zip(self.REASONS, c[2:6]) if val.lower().startswith("active"))
+                    self.rows.append((float(c[0]), float(c[1]), mask))
             except Exception:
                 pass
             self._halt.wait(0.2)
@@ -92,18 +120,14 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm, smax, reasons = [], 0, set()
-        for row in self.rows:
-            try:
-                sm.append(float(row[0]))
-                smax = max(smax, float(row[1]))
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), row[2:6]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        smax = max([r[1] for r in self.rows], default=0)
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        reasons = sorted(name for name, bit in self.REASONS if mask & bit)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -155,12 +179,16 @@ def run_train_leg(args, spa, model, variables, world, rank, dev, barrier):
     trainer.train_step(batch, noise)   # warm-up (allocator, NCCL communicator)
     launches = spa.ops.launch_count - l0
     barrier()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
     e0.record()
     for _ in range(args.train_steps):
         log = trainer.train_step(batch, noise)
     e1.record()
     barrier()
+    clocks = sampler.stop() if sampler else None
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -172,7 +200,7 @@ def run_train_leg(args, spa, model, variables, world, rank, dev, barrier):
     return {"metric": "3dspa_train_clips_per_s", "value": args.train_batch / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms,
             "global_batch": args.train_batch, "clips_per_gpu": hi - lo, "micro_batch": 1, "steps": args.train_steps, "warmup": 1,
             "scaling": "strong", "dtype": "bf16", "model_tflops_per_gpu": tf / world, "frac_of_sustained_peak_per_gpu": tf / world / peak_tf,
-            "gpu_launches_per_step": int(launches), "loss": log["total_loss"],
+            "gpu_launches_per_step": int(launches), "loss": log["total_loss"], "clocks": clocks,
             "config": "cfg3: fwd+bwd+AdamW, B=64 global, T=150, S=2048, Q=512, DINO+depth, NCCL gradient all-reduce overlapped with backward"}
 
 
