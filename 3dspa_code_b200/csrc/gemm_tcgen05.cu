@@ -264,6 +264,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool out_f32 = ep.c_dtype == SPA3D_F32;
     int sbuf = 0;
     int it = 0;
+    float4 bq_next[NCH];
+    auto load_bias_direct = [&](int64_t tt, float4 (&dst)[NCH]) {
+      if (EPI != EPI_DIRECT) return;
+      const int nb = (int)((tt / splits) % n_tiles);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = nb * BN + half * HC + c * 32 + (lane & 7) * 4;
+        dst[c] = (ep.bias && tt < num_tiles && col < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_bias_direct(blockIdx.x, bq_next);
+    float breg_next[NCH];
+    auto load_bias_tma = [&](int64_t tt, float (&dst)[NCH]) {
+      if (EPI != EPI_TMA) return;
+      const int nb = (int)((tt / splits) % n_tiles);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = nb * BN + half * HC + c * 32 + lane;
+        dst[c] = (ep.bias && tt < num_tiles && col < N) ? __ldg(ep.bias + col) : 0.f;
+      }
+    };
+    load_bias_tma(blockIdx.x, breg_next);
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int64_t tile = t / splits;
       const int m_blk = (int)(tile / n_tiles), n_blk = (int)(tile % n_tiles);
@@ -301,13 +324,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             rp += rstep;
           }
         };
-        // bias of the 4 columns this lane stores in the coalesced pass, one float4 per chunk
+        // bias of the 4 columns this lane stores in the coalesced pass, one float4 per chunk; the
+        // loads for the NEXT tile are issued now (L1 is carved out as smem: a bias load is an L2 round
+        // trip, and the epilogue is the pace-setter for these shapes)
         float4 bq[NCH];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col = colbase + c * 32 + cc * 4;
-          bq[c] = (ep.bias && col < N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int c = 0; c < NCH; ++c) bq[c] = bq_next[c];
+        load_bias_direct(t + gridDim.x, bq_next);
         if (!ep.debug_skip) {
           load_res(0);   // in flight while the MMAs of this tile still run
           // pull the residual of this CTA's next tile into L2 (one prefetch per 128-byte line)
@@ -401,10 +424,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ---- bf16 outputs: slab -> TMA store, two 2 KB buffers per warp --------------------------
         float breg[NCH];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col = colbase + c * 32 + lane;
-          breg[c] = (ep.bias && col < N) ? __ldg(ep.bias + col) : 0.f;
-        }
+        for (int c = 0; c < NCH; ++c) breg[c] = breg_next[c];
+        load_bias_tma(t + gridDim.x, breg_next);   // next tile's bias: its L2 latency hides under this tile
         mbar_wait(&tfull_bar[as], aphase);
         tcgen05_fence_after();
         uint32_t r[2][32];
