@@ -340,8 +340,11 @@ class Engine:
         dq = ctx.decoder_query.reshape(B * Q, -1)
         qfeat = torch.empty(B * Q, meta["query_in"], device=dev, dtype=self.cdt)
         # query_frame // time_scale_factor (:268-269) is 0 for every in-range frame: tail_zero
-        if int(ctx.query_frame.max().item()) >= cfg.time_scale_factor or int(ctx.query_frame.min().item()) < 0:
-            raise ValueError("query frames outside [0, time_scale_factor) are not supported")
+        # (validated on the host once; a stream that is being captured into a CUDA graph cannot synchronise,
+        # and the token-assembly kernel is memory safe for any frame index)
+        if not torch.cuda.is_current_stream_capturing():
+            if int(ctx.query_frame.max().item()) >= cfg.time_scale_factor or int(ctx.query_frame.min().item()) < 0:
+                raise ValueError("query frames outside [0, time_scale_factor) are not supported")
         ops.fourier_features(dq, qfeat, cfg.num_frequencies, cfg.track_scale_factor, tail_zero=True, exact=self.exact)
         qe = ops.gemm(qfeat, w["query_encoder.Wt"], f["query_encoder.b"], out_dtype=torch.float32)
         tokens = torch.empty(B * Q * (nl + 1), meta["D"], device=dev, dtype=torch.float32)

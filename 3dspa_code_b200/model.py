@@ -57,6 +57,8 @@ class _ModuleBase:
 
     def __post_init__(self):
         self._bound = {}  # (id(tree), precision) -> (weakref-able holder, Engine)
+        self.cuda_graph = False   # replay the whole forward as ONE CUDA graph when the same device buffers are passed again
+        self._graphs = {}
 
     # -- Flax-style API ---------------------------------------------------------------------------
     def init(self, rng=0, batch=None, arch=None):
@@ -106,6 +108,8 @@ class _ModuleBase:
                 lat = method_kwargs.get("latents")
                 return self._results(eng, eng.decode(lat, ctx, noise, method_kwargs.get("discretize", discretize)), ctx)
             raise ValueError(f"unknown method {name}")
+        if self.cuda_graph and self._graphable(inputs, noise, discretize):
+            return self._forward_graphed(eng, inputs, noise, discretize, precision)
         return self._forward(eng, inputs, noise, discretize)
 
     def __call__(self, variables, inputs, **kw):
@@ -121,6 +125,39 @@ class _ModuleBase:
     def decode(self, variables, latents, decoder_context, discretize=True, noise=None, precision="bf16"):
         eng = self.bind(variables, precision)
         return self._results(eng, eng.decode(latents, decoder_context, noise, discretize), decoder_context)
+
+    # -- CUDA-graph replay of the forward ---------------------------------------------------------------
+    def _graphable(self, inputs, noise, discretize):
+        if self.decoder_scan_chunk_size is not None or inputs.get("query_points") is None:
+            return False
+        ts = [v for v in inputs.values() if v is not None] + ([noise] if discretize else [])
+        return all(isinstance(t, torch.Tensor) and t.is_cuda for t in ts)
+
+    def _forward_graphed(self, eng, inputs, noise, discretize, precision):
+        """The ~145 launches of a forward (90 of them under 20 us) captured once into a CUDA graph and
+        replayed: the graph is keyed on the addresses and shapes of the device input buffers, so a
+        pipeline that refills the same buffers pays one launch per clip.  The returned tensors are
+        owned by the graph and are overwritten by the next replay with the same buffers."""
+        ts = {k: v for k, v in inputs.items() if isinstance(v, torch.Tensor)}
+        key = (id(eng), precision, bool(discretize), noise.data_ptr() if discretize else 0,
+               tuple(sorted((k, t.data_ptr(), tuple(t.shape), str(t.dtype)) for k, t in ts.items())))
+        hit = self._graphs.get(key)
+        if hit is None:
+            self._forward(eng, inputs, noise, discretize)   # eager once: lazy init, input validation
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._forward(eng, inputs, noise, discretize)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                res = self._forward(eng, inputs, noise, discretize)
+            if len(self._graphs) >= 2:   # each graph pins its activations (a few GB): keep two
+                self._graphs.pop(next(iter(self._graphs)))
+            hit = (g, res, dict(inputs), noise)
+            self._graphs[key] = hit
+        hit[0].replay()
+        return hit[1]
 
     # -- internals ------------------------------------------------------------------------------------
     def _results(self, eng, head_out, ctx):

@@ -162,3 +162,31 @@ def test_streamed_host_inputs_equal_one_shot_upload(spa, precision):
     res_a = model.apply(variables, host_inp, noise=noise, precision=precision)
     res_b = model.apply(variables, dev_inp, noise=torch.as_tensor(noise).cuda(), precision=precision)
     assert torch.equal(res_a.tracks, res_b.tracks) and torch.equal(res_a.visible_logits, res_b.visible_logits)
+
+
+def test_cuda_graph_replay_equals_eager(spa):
+    """model.cuda_graph = True replays the whole forward as one CUDA graph when the same device buffers
+    are passed again; results must equal the eager launches bit for bit, also after the buffers are
+    refilled with another clip."""
+    c = small_cfg()
+    fields = {k: getattr(c, k) for k in om.Config3D.__dataclass_fields__}
+    model = spa.TrackAutoEncoder3D(**fields)
+    gmodel = spa.TrackAutoEncoder3D(**fields)
+    gmodel.cuda_graph = True
+    inp, noise = make_inputs(c, B=2, N=10, Q=6, seed=1)
+    variables = model.init(6, inp, arch=SMALL_ARCH)
+    randomize(variables["params"], 6)
+    dev_inp = {k: torch.as_tensor(v).cuda() for k, v in inp.items()}
+    dev_noise = torch.as_tensor(noise).cuda()
+    ref = model.apply(variables, dev_inp, noise=dev_noise, precision="bf16")
+    got = gmodel.apply(variables, dev_inp, noise=dev_noise, precision="bf16")      # capture + first replay
+    assert torch.equal(got.tracks, ref.tracks) and torch.equal(got.visible_logits, ref.visible_logits)
+    inp2, noise2 = make_inputs(c, B=2, N=10, Q=6, seed=2)
+    for k, v in inp2.items():
+        dev_inp[k].copy_(torch.as_tensor(v))                                        # refill the same buffers
+    dev_noise.copy_(torch.as_tensor(noise2))
+    ref2 = model.apply(variables, dev_inp, noise=dev_noise, precision="bf16")
+    got2 = gmodel.apply(variables, dev_inp, noise=dev_noise, precision="bf16")     # pure replay
+    assert len(gmodel._graphs) == 1
+    assert torch.equal(got2.tracks, ref2.tracks) and torch.equal(got2.visible_logits, ref2.visible_logits)
+    assert not torch.equal(ref2.tracks, ref.tracks)
