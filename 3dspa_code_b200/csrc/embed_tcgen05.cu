@@ -17,6 +17,8 @@
 //   warp 0      TMA producer (weights)     warp 1      MMA issuer
 //   warps 2..5  epilogue: TMEM -> +bias -> smem transpose -> coalesced fp32 stores (row remap)
 //   warps 6..13 A-tile producers
+#include <cuda_pipeline.h>
+
 #include "tc_ptx.cuh"
 
 namespace spa3d {
@@ -41,6 +43,7 @@ struct EmbedParams {
   float inv_scale;       // 1 / track_scale_factor
   float inv_T;           // 1 / T
   float fs[32];          // 2^(i/3)
+  int l2_prefetch;       // pull whole feature rows into L2 one tile ahead (SPA3D_EMBED_L2_PREFETCH=1 enables; measured slower)
 };
 
 template <int NB, int BNH>   // W = NB * BNH output columns, BNH <= 256
@@ -55,7 +58,8 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
   uint8_t* smem_b = smem + STAGES * A_BYTES;
   uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;            // [4 warps][4096]
   float* smem_bias = reinterpret_cast<float*>(smem_epi + NUM_EPI * 4096);   // [NB*BNH]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + NB * BNH);
+  float* smem_trk = smem_bias + NB * BNH;                                     // [2][128 rows][3] coordinates of a tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_trk + 2 * BM * 3);
   uint64_t* full_bar = bars;                 // [STAGES]  1 TMA arrive (expect_tx) + 8 producer warps
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // accumulator complete
@@ -187,24 +191,11 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
     const int ptid = threadIdx.x - (2 + NUM_EPI) * 32;   // 0..255
     const int rsub = ptid >> 4, l16 = ptid & 15;         // 16 lanes per row segment, 16 rows per pass
     const int64_t my_tiles = blockIdx.x < m_tiles ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t n_items = my_tiles * num_kb;
 
-    auto issue = [&](int64_t idx, float4 (&v)[8]) {
-      if (idx >= n_items) return;
-      const int kb = (int)(idx % num_kb);
-      const int64_t row_base = (blockIdx.x + (idx / num_kb) * gridDim.x) * BM;
-      if (kb < 4) {
-        // Fourier block: only the coordinate of each row is loaded (x, y, z) or derived (t / T);
-        // issued one item ahead like the feature loads, so its HBM latency is off the critical path
-#pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-          const int64_t r_ = row_base + ps * 16 + rsub;
-          float x = 0.f;
-          if (r_ < p.R) x = kb < 3 ? __ldg(p.tracks + r_ * 3 + kb) : (float)((uint32_t)r_ % (uint32_t)p.T) * p.inv_T;
-          v[ps].x = x * p.inv_scale;
-        }
-        return;
-      }
+    // feature K-blocks: straight-line load / convert code with no data-dependent branch between the
+    // issue of a load and its use (a branch there makes ptxas wait for every outstanding load)
+    auto issue = [&](int64_t tile_iter, int kb, float4 (&v)[8]) {
+      const int64_t row_base = (blockIdx.x + tile_iter * gridDim.x) * BM;
       const bool is_dino = kb < kb_depth0;
       const float* src = is_dino ? p.dino : p.depth;
       const int64_t ld = is_dino ? p.Dd : p.Dz;
@@ -212,57 +203,83 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
 #pragma unroll
       for (int ps = 0; ps < 8; ++ps) {
         const int64_t r_ = row_base + ps * 16 + rsub;
-        v[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r_ < p.R) v[ps] = __ldcs(reinterpret_cast<const float4*>(src + r_ * ld + col));   // streamed once
+        const float* ptr = src + (r_ < p.R ? r_ : 0) * ld + col;      // clamped: always a valid address
+        v[ps] = __ldcs(reinterpret_cast<const float4*>(ptr));
       }
     };
-    auto consume = [&](int64_t idx, const float4 (&v)[8]) {
-      const int kb = (int)(idx % num_kb);
+    auto acquire = [&](int64_t idx) -> uint8_t* {
       const int stage = (int)(idx % STAGES);
       const uint32_t phase = (uint32_t)((idx / STAGES) & 1);
-      const int64_t row_base = (blockIdx.x + (idx / num_kb) * gridDim.x) * BM;
       if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
       __syncwarp();
-      uint8_t* at = smem_a + stage * A_BYTES;
-      if (kb < 4) {
-        // Fourier features of coordinate kb: features f = l16*4 .. +3 (f < 32: sin(v s_f), else sin(v s_f + pi/2))
-        const int f0 = (l16 * 4) & 31;
-        const float ph = l16 >= 8 ? 1.57079632679489661923f : 0.f;
-        const float s0 = p.fs[f0], s1 = p.fs[f0 + 1], s2 = p.fs[f0 + 2], s3 = p.fs[f0 + 3];
-#pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-          const int row = ps * 16 + rsub;
-          const int64_t r_ = row_base + row;
-          const float x = v[ps].x;
-          float o0, o1, o2, o3;
-          asm("sin.approx.f32 %0, %1;" : "=f"(o0) : "f"(__fadd_rn(__fmul_rn(x, s0), ph)));
-          asm("sin.approx.f32 %0, %1;" : "=f"(o1) : "f"(__fadd_rn(__fmul_rn(x, s1), ph)));
-          asm("sin.approx.f32 %0, %1;" : "=f"(o2) : "f"(__fadd_rn(__fmul_rn(x, s2), ph)));
-          asm("sin.approx.f32 %0, %1;" : "=f"(o3) : "f"(__fadd_rn(__fmul_rn(x, s3), ph)));
-          if (r_ >= p.R) o0 = o1 = o2 = o3 = 0.f;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
-          *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
-              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-        }
-      } else {
-#pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-          const int row = ps * 16 + rsub;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[ps].x, v[ps].y), h1 = __floats2bfloat162_rn(v[ps].z, v[ps].w);
-          *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
-              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-        }
-      }
+      return smem_a + stage * A_BYTES;
+    };
+    auto publish = [&](int64_t idx) {
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      if (lane == 0) mbar_arrive(&full_bar[(int)(idx % STAGES)]);
     };
-
-    // DRAM-friendly order: the 256-byte-per-row slices of one K-block touch a different DRAM page
-    // per row; pulling every row's whole feature vector (3 KB + 1 KB contiguous) into L2 ahead of
-    // time turns the HBM side into long sequential reads and the slices into L2 hits.
+    auto consume = [&](int64_t tile_iter, int kb, const float4 (&v)[8]) {
+      const int64_t idx = tile_iter * num_kb + kb;
+      const int64_t row_base = (blockIdx.x + tile_iter * gridDim.x) * BM;
+      uint8_t* at = acquire(idx);
+#pragma unroll
+      for (int ps = 0; ps < 8; ++ps) {
+        const int row = ps * 16 + rsub;
+        const bool ok = row_base + row < p.R;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(ok ? v[ps].x : 0.f, ok ? v[ps].y : 0.f);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(ok ? v[ps].z : 0.f, ok ? v[ps].w : 0.f);
+        *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+      publish(idx);
+    };
+    // coordinates (x, y, z) of the tile's 128 rows: 1.5 KB copied global -> shared with cp.async one
+    // tile ahead (no registers held, no latency in the Fourier blocks)
+    auto load_tracks = [&](int64_t tile_iter) {
+      if (ptid < BM * 3 / 4) {
+        const int64_t f0 = (blockIdx.x + tile_iter * gridDim.x) * BM * 3 + ptid * 4;   // first of 4 floats
+        float* dst = smem_trk + (tile_iter & 1) * (BM * 3) + ptid * 4;
+        if (f0 + 4 <= p.R * 3) {
+          __pipeline_memcpy_async(dst, p.tracks + f0, 16);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dst[e] = f0 + e < p.R * 3 ? p.tracks[f0 + e] : 0.f;
+        }
+      }
+      __pipeline_commit();
+    };
+    auto fourier = [&](int64_t tile_iter, int kb) {
+      // Fourier features of coordinate kb: features f = l16*4 .. +3 (f < 32: sin(v s_f), else sin(v s_f + pi/2))
+      const int64_t idx = tile_iter * num_kb + kb;
+      const int64_t row_base = (blockIdx.x + tile_iter * gridDim.x) * BM;
+      uint8_t* at = acquire(idx);
+      const float* trk = smem_trk + (tile_iter & 1) * (BM * 3);
+      const int f0 = (l16 * 4) & 31;
+      const float ph = l16 >= 8 ? 1.57079632679489661923f : 0.f;
+      const float s0 = p.fs[f0], s1 = p.fs[f0 + 1], s2 = p.fs[f0 + 2], s3 = p.fs[f0 + 3];
+#pragma unroll
+      for (int ps = 0; ps < 8; ++ps) {
+        const int row = ps * 16 + rsub;
+        const int64_t r_ = row_base + row;
+        float x = kb < 3 ? trk[row * 3 + kb] : (float)((uint32_t)r_ % (uint32_t)p.T) * p.inv_T;
+        x *= p.inv_scale;
+        float o0, o1, o2, o3;
+        asm("sin.approx.f32 %0, %1;" : "=f"(o0) : "f"(__fadd_rn(__fmul_rn(x, s0), ph)));
+        asm("sin.approx.f32 %0, %1;" : "=f"(o1) : "f"(__fadd_rn(__fmul_rn(x, s1), ph)));
+        asm("sin.approx.f32 %0, %1;" : "=f"(o2) : "f"(__fadd_rn(__fmul_rn(x, s2), ph)));
+        asm("sin.approx.f32 %0, %1;" : "=f"(o3) : "f"(__fadd_rn(__fmul_rn(x, s3), ph)));
+        if (r_ >= p.R) o0 = o1 = o2 = o3 = 0.f;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+        *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+      publish(idx);
+    };
+    // Optional experiment (off): pull every row's whole feature vector (3 KB + 1 KB contiguous) into L2 one
+    // tile ahead so the 256-byte-per-row slices become L2 hits.  Measured slower than plain demand loads.
     auto prefetch_tile = [&](int64_t tile_iter) {
-      if (tile_iter >= my_tiles) return;
+      if (tile_iter >= my_tiles || !p.l2_prefetch) return;
       const int64_t r_ = (blockIdx.x + tile_iter * gridDim.x) * BM + (ptid >> 1);
       if (r_ >= p.R) return;
       const float* src = (ptid & 1) ? p.depth : p.dino;
@@ -270,16 +287,30 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
       if (src != nullptr && w > 0)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + r_ * w), "r"((uint32_t)(w * 4)) : "memory");
     };
-    prefetch_tile(0);
+
     float4 va[8], vb[8];
-    issue(0, va);
-    for (int64_t i = 0; i < n_items; i += 2) {
-      if (i % num_kb == (num_kb & ~1) - 6 || (i + 1) % num_kb == (num_kb & ~1) - 6) prefetch_tile(i / num_kb + 1);
-      issue(i + 1, vb);
-      consume(i, va);
-      if (i + 1 < n_items) {
-        issue(i + 2, va);
-        consume(i + 1, vb);
+    const bool has_feat = num_kb > 4;
+    if (my_tiles > 0) {
+      prefetch_tile(0);
+      load_tracks(0);
+      if (has_feat) issue(0, 4, va);
+    }
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      prefetch_tile(ti + 1);
+      __pipeline_wait_prior(0);                              // this tile's coordinates have landed ...
+      asm volatile("bar.sync 2, 256;" ::: "memory");        // ... for every producer warp
+      if (ti + 1 < my_tiles) load_tracks(ti + 1);           // other half of the double buffer
+      for (int kb = 0; kb < 4; ++kb) fourier(ti, kb);
+      for (int kb = 4; kb < num_kb; kb += 2) {
+        if (kb + 1 < num_kb) issue(ti, kb + 1, vb);
+        consume(ti, kb, va);
+        if (kb + 1 < num_kb) {
+          if (kb + 2 < num_kb) issue(ti, kb + 2, va);
+          else if (ti + 1 < my_tiles) issue(ti + 1, 4, va);   // first feature block of the next tile, over its Fourier phase
+          consume(ti, kb + 1, vb);
+        } else if (ti + 1 < my_tiles) {
+          issue(ti + 1, 4, va);
+        }
       }
     }
   }
@@ -294,7 +325,7 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
 
 template <int NB, int BNH>
 static int launch(const CUtensorMap& tmB, const EmbedParams& p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + NB * BNH * BK * 2) + NUM_EPI * 4096 + NB * BNH * 4 + 256 + 1024;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + NB * BNH * BK * 2) + NUM_EPI * 4096 + NB * BNH * 4 + 2 * BM * 3 * 4 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(embed_fused_kernel<NB, BNH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -336,6 +367,10 @@ int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth
   p.tracks = tracks; p.dino = dino; p.depth = depth; p.bias = bias; p.out = out; p.ldo = ldo; p.R = rows;
   p.T = T; p.Dd = dino_dim; p.Dz = depth_dim; p.W = W; p.inv_scale = (float)(1.0 / (double)track_scale_factor); p.inv_T = (float)(1.0 / (double)T);
   for (int i = 0; i < 32; ++i) p.fs[i] = (float)pow(2.0, (double)i / 3.0);
+  {
+    const char* e = getenv("SPA3D_EMBED_L2_PREFETCH");
+    p.l2_prefetch = (e && atoi(e) == 1) ? 1 : 0;   // measured: 0.54 ms with, 0.48 ms without - off by default
+  }
   const int K = 256 + dino_dim + depth_dim;
   CUtensorMap tmB;
   const int bnh = W > 256 ? W / 2 : W;
