@@ -53,7 +53,7 @@ template <typename TO>
 __device__ __forceinline__ void store4(TO* p, float4 v);
 template <>
 __device__ __forceinline__ void store4<float>(float* p, float4 v) {
-  *reinterpret_cast<float4*>(p) = v;
+  __stcs(reinterpret_cast<float4*>(p), v);   // streaming: written once, keep the L2 for the DINO maps
 }
 template <>
 __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
@@ -61,7 +61,7 @@ __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
   uint2 u;
   u.x = *reinterpret_cast<uint32_t*>(&lo);
   u.y = *reinterpret_cast<uint32_t*>(&hi);
-  *reinterpret_cast<uint2*>(p) = u;
+  __stcs(reinterpret_cast<uint2*>(p), u);
 }
 
 template <typename TO>
@@ -91,9 +91,14 @@ lift_sample_kernel(const float* __restrict__ tracks, const float* __restrict__ d
         grad = __fsub_rn(z, zp);
       }
       TO* o = depth_out + pt * Cd;
-      for (int c = lane; c < Cd; c += 32) {
-        float v = c == 0 ? z : (c == 1 ? __fdiv_rn(z, 10.f) : (c == 2 ? grad : 0.f));
-        stf<TO>(o + c, v);
+      if ((Cd & 3) == 0) {   // 128-bit stores: (z, z/10, dz, 0) then zeros (inference.py:437-443)
+        for (int c = lane * 4; c < Cd; c += 128)
+          store4<TO>(o + c, c == 0 ? make_float4(z, __fdiv_rn(z, 10.f), grad, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f));
+      } else {
+        for (int c = lane; c < Cd; c += 32) {
+          float v = c == 0 ? z : (c == 1 ? __fdiv_rn(z, 10.f) : (c == 2 ? grad : 0.f));
+          stf<TO>(o + c, v);
+        }
       }
     }
   }
