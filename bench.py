@@ -131,7 +131,7 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_oracle_rate(sample_s=256, sample_q=64, threads=None):
+def cpu_oracle_rate(sample_s=1024, sample_q=256, threads=None):
     """Time the fp32 oracle restatement on the host cores on a bounded sample (same S:Q ratio)."""
     from oracle import model as om
 
