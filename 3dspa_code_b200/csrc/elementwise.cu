@@ -113,7 +113,7 @@ __global__ void layernorm_bwd_kernel(const TX* __restrict__ x, int64_t ldx,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const TDY* __restrict__ dy, int64_t lddy, TDX* __restrict__ dx,
                                      int64_t lddx, int dx_accumulate,
-                                     float* __restrict__ dscale_partial, int64_t rows, int d) {
+                                     float* __restrict__ dscale_partial, int ds_accum, int64_t rows, int d) {
   // grid-stride over rows, one warp per row; per-block partial dscale accumulated in smem
   extern __shared__ float s_ds[];  // [d]
   for (int i = threadIdx.x; i < d; i += blockDim.x) s_ds[i] = 0.f;
@@ -144,7 +144,10 @@ __global__ void layernorm_bwd_kernel(const TX* __restrict__ x, int64_t ldx,
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < d; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * d + i] = s_ds[i];
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    if (ds_accum) atomicAdd(&dscale_partial[i], s_ds[i]);   // straight into the gradient of the scale
+    else dscale_partial[(int64_t)blockIdx.x * d + i] = s_ds[i];
+  }
 }
 
 
@@ -158,7 +161,7 @@ layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float*
                           const float* __restrict__ mean, const float* __restrict__ rstd,
                           const TDY* __restrict__ dy, int64_t lddy, float* __restrict__ dx, int64_t lddx,
                           int dx_accumulate, bf16* __restrict__ dx_lowp, int64_t ldl,
-                          float* __restrict__ dscale_partial, int64_t rows) {
+                          float* __restrict__ dscale_partial, int ds_accum, int64_t rows) {
   constexpr int D = 128 * J;
   __shared__ float s_ds[D];
   for (int i = threadIdx.x; i < D; i += blockDim.x) s_ds[i] = 0.f;
@@ -226,7 +229,10 @@ layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float*
     atomicAdd(&s_ds[c + 3], acc[j].w);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * D + i] = s_ds[i];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (ds_accum) atomicAdd(&dscale_partial[i], s_ds[i]);   // straight into the gradient of the scale
+    else dscale_partial[(int64_t)blockIdx.x * D + i] = s_ds[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -261,7 +267,7 @@ __global__ void head_rmsnorm_bwd_kernel(const TY* __restrict__ y, int64_t ldy,
                                         const float* __restrict__ scale, float out_mul,
                                         const float* __restrict__ rstd, int64_t rstd_ld,
                                         TD* __restrict__ d_io, int64_t ldd,
-                                        float* __restrict__ dscale_partial, int64_t rows, int heads,
+                                        float* __restrict__ dscale_partial, int ds_accum, int64_t rows, int heads,
                                         int Dh) {
   extern __shared__ float s_ds[];  // [Dh]
   for (int i = threadIdx.x; i < Dh; i += blockDim.x) s_ds[i] = 0.f;
@@ -291,7 +297,10 @@ __global__ void head_rmsnorm_bwd_kernel(const TY* __restrict__ y, int64_t ldy,
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Dh; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * Dh + i] = s_ds[i];
+  for (int i = threadIdx.x; i < Dh; i += blockDim.x) {
+    if (ds_accum) atomicAdd(&dscale_partial[i], s_ds[i]);   // straight into the gradient of the scale
+    else dscale_partial[(int64_t)blockIdx.x * Dh + i] = s_ds[i];
+  }
 }
 
 
@@ -302,7 +311,7 @@ template <int CPL>
 __global__ void __launch_bounds__(256)
 head_rmsnorm_bwd_fast_kernel(const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ scale,
                              float out_mul, const float* __restrict__ rstd, int64_t rstd_ld,
-                             bf16* __restrict__ d_io, int64_t ldd, float* __restrict__ dscale_partial,
+                             bf16* __restrict__ d_io, int64_t ldd, float* __restrict__ dscale_partial, int ds_accum,
                              int64_t rows, int heads) {
   constexpr int DH = CPL * 32;
   __shared__ float s_ds[DH];
@@ -384,7 +393,10 @@ head_rmsnorm_bwd_fast_kernel(const bf16* __restrict__ y, int64_t ldy, const floa
       if (grp == 0) atomicAdd(&s_ds[(sub + 4 * c) * 8 + e], v);
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < DH; i += blockDim.x) dscale_partial[(int64_t)blockIdx.x * DH + i] = s_ds[i];
+  for (int i = threadIdx.x; i < DH; i += blockDim.x) {
+    if (ds_accum) atomicAdd(&dscale_partial[i], s_ds[i]);   // straight into the gradient of the scale
+    else dscale_partial[(int64_t)blockIdx.x * DH + i] = s_ds[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -812,8 +824,8 @@ int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* sc
 int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
                         const float* mean, const float* rstd, const void* dy, int64_t lddy,
                         int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int dx_accumulate,
-                        void* dx_lowp, int64_t ldl, float* dscale_partial, int num_partials, int64_t rows,
-                        int d, void* stream) {
+                        void* dx_lowp, int64_t ldl, float* dscale_partial, int num_partials, int accumulate_dscale,
+                        int64_t rows, int d, void* stream) {
   SPA3D_REQUIRE(num_partials > 0, "layernorm_bwd: num_partials must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -825,7 +837,7 @@ int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* sc
   case J:                                                                                                      \
     SPA3D_DISPATCH(dy_dtype, TDY, {                                                                            \
       layernorm_bwd_fast_kernel<J, TDY><<<num_partials, 256, 0, st>>>((const float*)x, ldx, scale, mean, rstd, \
-          (const TDY*)dy, lddy, (float*)dx, lddx, dx_accumulate, (bf16*)dx_lowp, ldl, dscale_partial, rows);   \
+          (const TDY*)dy, lddy, (float*)dx, lddx, dx_accumulate, (bf16*)dx_lowp, ldl, dscale_partial, accumulate_dscale, rows); \
     });                                                                                                        \
     return check_launch("layernorm_bwd_fast");
     switch (d / 128) {
@@ -837,7 +849,7 @@ int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* sc
   }
   SPA3D_DISPATCH(x_dtype, TX, SPA3D_DISPATCH(dy_dtype, TDY, SPA3D_DISPATCH(dx_dtype, TDX, {
     layernorm_bwd_kernel<TX, TDY, TDX><<<num_partials, 256, d * sizeof(float), st>>>(
-        (const TX*)x, ldx, scale, mean, rstd, (const TDY*)dy, lddy, (TDX*)dx, lddx, dx_accumulate, dscale_partial, rows, d);
+        (const TX*)x, ldx, scale, mean, rstd, (const TDY*)dy, lddy, (TDX*)dx, lddx, dx_accumulate, dscale_partial, accumulate_dscale, rows, d);
   })));
   int rc = check_launch("layernorm_bwd");
   if (rc || !dx_lowp) return rc;
@@ -853,7 +865,7 @@ int spa3d_head_rmsnorm_fwd(void* buf, int64_t ld, int dtype, const float* scale,
 
 int spa3d_head_rmsnorm_bwd(const void* y, int64_t ldy, int y_dtype, const float* scale, float out_mul,
                            const float* rstd, int64_t rstd_ld, void* dy_inout, int64_t ldd, int d_dtype,
-                           float* dscale_partial, int num_partials, int64_t rows, int heads, int Dh,
+                           float* dscale_partial, int num_partials, int accumulate_dscale, int64_t rows, int heads, int Dh,
                            void* stream) {
   SPA3D_REQUIRE(num_partials > 0, "head_rmsnorm_bwd: num_partials must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
@@ -862,7 +874,7 @@ int spa3d_head_rmsnorm_bwd(const void* y, int64_t ldy, int y_dtype, const float*
       al16(y) && al16(dy_inout)) {
 #define SPA3D_RMS_BWD_FAST(CPL)                                                                              \
   head_rmsnorm_bwd_fast_kernel<CPL><<<num_partials, 256, 0, st>>>((const bf16*)y, ldy, scale, out_mul, rstd, \
-                                                                  rstd_ld, (bf16*)dy_inout, ldd, dscale_partial, rows, heads)
+                                                                  rstd_ld, (bf16*)dy_inout, ldd, dscale_partial, accumulate_dscale, rows, heads)
     switch (Dh / 32) {
       case 1: SPA3D_RMS_BWD_FAST(1); break;
       case 2: SPA3D_RMS_BWD_FAST(2); break;
@@ -874,7 +886,7 @@ int spa3d_head_rmsnorm_bwd(const void* y, int64_t ldy, int y_dtype, const float*
   }
   SPA3D_DISPATCH(y_dtype, TY, SPA3D_DISPATCH(d_dtype, TD, {
     head_rmsnorm_bwd_kernel<TY, TD><<<num_partials, 256, Dh * sizeof(float), st>>>(
-        (const TY*)y, ldy, scale, out_mul, rstd, rstd_ld, (TD*)dy_inout, ldd, dscale_partial, rows, heads, Dh);
+        (const TY*)y, ldy, scale, out_mul, rstd, rstd_ld, (TD*)dy_inout, ldd, dscale_partial, accumulate_dscale, rows, heads, Dh);
   }));
   return check_launch("head_rmsnorm_bwd");
 }

@@ -180,15 +180,19 @@ def layernorm_fwd(x, scale, out_dtype, rows=None, ldx=None, d=None, stats=False,
 
 
 def layernorm_bwd(x, scale, mean, rstd, dy, dx, rows=None, ldx=None, lddx=None, d=None, accumulate=False, num_partials=296,
-                  dx_lowp=None):
+                  dx_lowp=None, dscale_accum=None):
+    """dscale_accum: the [d] fp32 gradient of the scale; when given the kernel adds into it directly and
+    nothing is returned (no partial buffer, no reduction pass)."""
     rows = x.shape[0] if rows is None else rows
     d = x.shape[-1] if d is None else d
     ldx = _ld(x) if ldx is None else ldx
     lddx = _ld(dx) if lddx is None else lddx
-    partial = torch.empty(num_partials, d, device=x.device, dtype=torch.float32)
+    partial = dscale_accum if dscale_accum is not None else torch.empty(num_partials, d, device=x.device, dtype=torch.float32)
     _call("spa3d_layernorm_bwd", _p(x), int(ldx), dt(x), _p(scale), _p(mean), _p(rstd), _p(dy), _ld(dy), dt(dy), _p(dx), int(lddx),
-          dt(dx), int(accumulate), _p(dx_lowp), _ld(dx_lowp) if dx_lowp is not None else 0, _p(partial), num_partials, int(rows), int(d),
-          _stream())
+          dt(dx), int(accumulate), _p(dx_lowp), _ld(dx_lowp) if dx_lowp is not None else 0, _p(partial), num_partials,
+          int(dscale_accum is not None), int(rows), int(d), _stream())
+    if dscale_accum is not None:
+        return None
     dscale = torch.empty(d, device=x.device, dtype=torch.float32)
     colsum(partial, dscale)
     return dscale
@@ -213,12 +217,14 @@ def gemm_rmsnorm(a, wt, Dh, q_cols, k_cols, scale_q, scale_k, save_rstd=False, i
     return (out, rstd) if save_rstd else out
 
 
-def head_rmsnorm_bwd(y, scale, out_mul, rstd, d_io, heads, Dh, num_partials=296):
-    """rstd: a [rows, >=heads] view (row stride = rstd.stride(0))."""
+def head_rmsnorm_bwd(y, scale, out_mul, rstd, d_io, heads, Dh, num_partials=296, dscale_accum=None):
+    """rstd: a [rows, >=heads] view (row stride = rstd.stride(0)).  dscale_accum: see layernorm_bwd."""
     rows = y.shape[0]
-    partial = torch.empty(num_partials, Dh, device=y.device, dtype=torch.float32)
+    partial = dscale_accum if dscale_accum is not None else torch.empty(num_partials, Dh, device=y.device, dtype=torch.float32)
     _call("spa3d_head_rmsnorm_bwd", _p(y), _ld(y), dt(y), _p(scale), float(out_mul), _p(rstd), rstd.stride(0), _p(d_io), _ld(d_io), dt(d_io),
-          _p(partial), num_partials, rows, heads, Dh, _stream())
+          _p(partial), num_partials, int(dscale_accum is not None), rows, heads, Dh, _stream())
+    if dscale_accum is not None:
+        return None
     dscale = torch.empty(Dh, device=y.device, dtype=torch.float32)
     colsum(partial, dscale)
     return dscale

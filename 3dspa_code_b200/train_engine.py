@@ -180,8 +180,8 @@ class AttnBlockFn(torch.autograd.Function):
             dkvp = torch.empty_like(s["kvp"])
             ops.attention_bwd(s["qc"], s["kvp"][:, :A], s["kvp"][:, A:], s["oc"], d_oc, dqc, dkvp[:, :A], dkvp[:, A:], s["stc"],
                               batch, H, L, Lkv, Dh, None)
-            ops.axpy(st.g[pre + "cross.norm_query"], ops.head_rmsnorm_bwd(s["qc"], f[pre + "cross.norm_query"], 1.0 / math.sqrt(Dh), s["rqc"], dqc, H, Dh))
-            ops.axpy(st.g[pre + "cross.norm_key"], ops.head_rmsnorm_bwd(s["kvp"][:, :A], f[pre + "cross.norm_key"], 1.0, s["rkc"], dkvp[:, :A], H, Dh))
+            ops.head_rmsnorm_bwd(s["qc"], f[pre + "cross.norm_query"], 1.0 / math.sqrt(Dh), s["rqc"], dqc, H, Dh, dscale_accum=st.g[pre + "cross.norm_query"])
+            ops.head_rmsnorm_bwd(s["kvp"][:, :A], f[pre + "cross.norm_key"], 1.0, s["rkc"], dkvp[:, :A], H, Dh, dscale_accum=st.g[pre + "cross.norm_key"])
             st.accum_dw(pre + "cross.Wq_t", dqc, s["xn"])
             st.accum_dw(pre + "cross.Wkv_t", dkvp, s["kv"])
             dxn = ops.gemm(dqc, st.ct[pre + "cross.Wq_t"])
@@ -194,13 +194,13 @@ class AttnBlockFn(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :A], qkv[:, A : 2 * A], qkv[:, 2 * A :], s["o"], d_o, dqkv[:, :A], dqkv[:, A : 2 * A], dqkv[:, 2 * A :],
                           s["stats"], batch, H, L, L, Dh, key_mask)
-        ops.axpy(st.g[pre + "self.norm_query"], ops.head_rmsnorm_bwd(qkv[:, :A], f[pre + "self.norm_query"], 1.0 / math.sqrt(Dh), s["rq"], dqkv[:, :A], H, Dh))
-        ops.axpy(st.g[pre + "self.norm_key"], ops.head_rmsnorm_bwd(qkv[:, A : 2 * A], f[pre + "self.norm_key"], 1.0, s["rk"], dqkv[:, A : 2 * A], H, Dh))
+        ops.head_rmsnorm_bwd(qkv[:, :A], f[pre + "self.norm_query"], 1.0 / math.sqrt(Dh), s["rq"], dqkv[:, :A], H, Dh, dscale_accum=st.g[pre + "self.norm_query"])
+        ops.head_rmsnorm_bwd(qkv[:, A : 2 * A], f[pre + "self.norm_key"], 1.0, s["rk"], dqkv[:, A : 2 * A], H, Dh, dscale_accum=st.g[pre + "self.norm_key"])
         st.accum_dw(pre + "self.Wqkv_t", dqkv, s["xn"])
         dxn = ops.gemm(dqkv, st.ct[pre + "self.Wqkv_t"], residual=dxn)
         # dx = da + LN'(dxn): accumulate into da's buffer (da has no other consumer)
-        ops.axpy(st.g[pre + "norm_q"], ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, da, accumulate=True,
-                                                         dx_lowp=_lowp_out(st, da)))
+        ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, da, accumulate=True, dx_lowp=_lowp_out(st, da),
+                          dscale_accum=st.g[pre + "norm_q"])
         ctx.saved = None
         if st.progress_cb is not None:
             st.progress_cb(pre)   # every parameter of this layer (and of everything after it) now has its final gradient
@@ -232,8 +232,8 @@ class MlpBlockFn(torch.autograd.Function):
         st.accum_bias(pre + "b1", dz)
         st.accum_dw(pre + "W1_t", dz, s["an"])
         dan = ops.gemm(dz, st.ct[pre + "W1_t"])
-        ops.axpy(st.g[pre + "norm_attn"], ops.layernorm_bwd(s["a"], st.f32[pre + "norm_attn"], s["mean"], s["rstd"], dan, dy, accumulate=True,
-                                                            dx_lowp=_lowp_out(st, dy)))
+        ops.layernorm_bwd(s["a"], st.f32[pre + "norm_attn"], s["mean"], s["rstd"], dan, dy, accumulate=True, dx_lowp=_lowp_out(st, dy),
+                          dscale_accum=st.g[pre + "norm_attn"])
         ctx.saved = None
         return dy, None, None, None
 

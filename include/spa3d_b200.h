@@ -142,12 +142,14 @@ int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* sc
                         int64_t rows, int d, void* stream);
 /* Backward: dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*scale; dscale_partial
  * [num_partials, d] receives per-block partial sums of dy*xhat.  dx_lowp (bf16 [rows,d], ldl) may be
- * NULL; otherwise it receives a bf16 copy of the final dx (the operand of the next backward GEMMs). */
+ * NULL; otherwise it receives a bf16 copy of the final dx (the operand of the next backward GEMMs).
+ * accumulate_dscale != 0: dscale_partial is the [d] gradient of the scale itself and every block adds
+ * its partial sum into it atomically (no separate reduction pass). */
 int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
                         const float* mean, const float* rstd, const void* dy, int64_t lddy,
                         int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int dx_accumulate,
                         void* dx_lowp, int64_t ldl, float* dscale_partial, int num_partials,
-                        int64_t rows, int d, void* stream);
+                        int accumulate_dscale, int64_t rows, int d, void* stream);
 
 /* ---- per-head RMSNorm of q and k (attention.py:166-167) + q/sqrt(Dh) (flax attention) ------
  * In place on a packed projection buffer: for every row and head h < heads,
@@ -158,7 +160,7 @@ int spa3d_head_rmsnorm_fwd(void* buf, int64_t ld, int dtype, const float* scale,
                            void* stream);
 int spa3d_head_rmsnorm_bwd(const void* y, int64_t ldy, int y_dtype, const float* scale,
                            float out_mul, const float* rstd, int64_t rstd_ld, void* dy_inout,
-                           int64_t ldd, int d_dtype, float* dscale_partial, int num_partials,
+                           int64_t ldd, int d_dtype, float* dscale_partial, int num_partials, int accumulate_dscale,
                            int64_t rows, int heads, int Dh, void* stream);
 
 /* QKV projection with the per-head RMSNorm fused into the GEMM epilogue (attention.py:154-173):
