@@ -308,26 +308,27 @@ __global__ void head_rmsnorm_bwd_kernel(const TY* __restrict__ y, int64_t ldy,
 // Dh/32 16-byte chunks (chunks lane, lane+4, ...), the head's statistics are two shuffles, the
 // scale gradient lives in per-lane registers for the whole grid-stride loop (no atomics inside).
 template <int CPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_rmsnorm_bwd_fast_kernel(const bf16* __restrict__ y, int64_t ldy, const float* __restrict__ scale,
                              float out_mul, const float* __restrict__ rstd, int64_t rstd_ld,
                              bf16* __restrict__ d_io, int64_t ldd, float* __restrict__ dscale_partial, int ds_accum,
                              int64_t rows, int heads) {
   constexpr int DH = CPL * 32;
   __shared__ float s_ds[DH];
-  for (int i = threadIdx.x; i < DH; i += blockDim.x) s_ds[i] = 0.f;
+  __shared__ __align__(16) float s_sm[DH], s_ism[DH];   // scale*mul and its reciprocal
+  for (int i = threadIdx.x; i < DH; i += blockDim.x) {
+    s_ds[i] = 0.f;
+    const float v = scale[i] * out_mul;
+    s_sm[i] = v;
+    s_ism[i] = v != 0.f ? 1.f / v : 0.f;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2;
-  float sm[CPL][8], ism[CPL][8], acc[CPL][8];
+  float acc[CPL][8];
 #pragma unroll
   for (int c = 0; c < CPL; ++c)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float v = scale[(sub + 4 * c) * 8 + e] * out_mul;
-      sm[c][e] = v;
-      ism[c][e] = v != 0.f ? 1.f / v : 0.f;
-      acc[c][e] = 0.f;
-    }
+    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
   const int64_t total = rows * heads;
   const int64_t gstride = (int64_t)gridDim.x * (blockDim.x >> 2);
   for (int64_t wb = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8; wb < total; wb += gstride) {
@@ -338,29 +339,32 @@ head_rmsnorm_bwd_fast_kernel(const bf16* __restrict__ y, int64_t ldy, const floa
     const int h = live ? (int)(wid % heads) : 0;
     const bf16* yp = y + r * ldy + (int64_t)h * DH;
     bf16* dp = d_io + r * ldd + (int64_t)h * DH;
-    float xh[CPL][8], g[CPL][8];
+    uint4 yv[CPL], dv[CPL];   // the row stays packed (bf16) in registers between the two passes
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      yv[c] = make_uint4(0, 0, 0, 0);
+      dv[c] = make_uint4(0, 0, 0, 0);
+      if (live) {
+        yv[c] = *reinterpret_cast<const uint4*>(yp + (sub + 4 * c) * 8);
+        dv[c] = *reinterpret_cast<const uint4*>(dp + (sub + 4 * c) * 8);
+      }
+    }
     float sgx = 0.f;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      uint4 yv = make_uint4(0, 0, 0, 0), dv = make_uint4(0, 0, 0, 0);
-      if (live) {
-        yv = *reinterpret_cast<const uint4*>(yp + (sub + 4 * c) * 8);
-        dv = *reinterpret_cast<const uint4*>(dp + (sub + 4 * c) * 8);
-      }
-      const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+      const uint32_t yw[4] = {yv[c].x, yv[c].y, yv[c].z, yv[c].w}, dw[4] = {dv[c].x, dv[c].y, dv[c].z, dv[c].w};
+      const float* smp = s_sm + (sub + 4 * c) * 8;
+      const float* isp = s_ism + (sub + 4 * c) * 8;
 #pragma unroll
       for (int e2 = 0; e2 < 4; ++e2) {
         const __nv_bfloat162 yh = *reinterpret_cast<const __nv_bfloat162*>(&yw[e2]);
         const __nv_bfloat162 dh = *reinterpret_cast<const __nv_bfloat162*>(&dw[e2]);
-        const float y0 = __low2float(yh), y1 = __high2float(yh), d0 = __low2float(dh), d1 = __high2float(dh);
-        xh[c][2 * e2] = y0 * ism[c][2 * e2];
-        xh[c][2 * e2 + 1] = y1 * ism[c][2 * e2 + 1];
-        g[c][2 * e2] = d0 * sm[c][2 * e2];
-        g[c][2 * e2 + 1] = d1 * sm[c][2 * e2 + 1];
-        sgx = fmaf(g[c][2 * e2], xh[c][2 * e2], sgx);
-        sgx = fmaf(g[c][2 * e2 + 1], xh[c][2 * e2 + 1], sgx);
-        acc[c][2 * e2] = fmaf(d0 * out_mul, xh[c][2 * e2], acc[c][2 * e2]);
-        acc[c][2 * e2 + 1] = fmaf(d1 * out_mul, xh[c][2 * e2 + 1], acc[c][2 * e2 + 1]);
+        const float d0 = __low2float(dh), d1 = __high2float(dh);
+        const float x0 = __low2float(yh) * isp[2 * e2], x1 = __high2float(yh) * isp[2 * e2 + 1];
+        sgx = fmaf(d0 * smp[2 * e2], x0, sgx);
+        sgx = fmaf(d1 * smp[2 * e2 + 1], x1, sgx);
+        acc[c][2 * e2] = fmaf(d0 * out_mul, x0, acc[c][2 * e2]);
+        acc[c][2 * e2 + 1] = fmaf(d1 * out_mul, x1, acc[c][2 * e2 + 1]);
       }
     }
     sgx += __shfl_xor_sync(0xffffffffu, sgx, 1);
@@ -370,11 +374,17 @@ head_rmsnorm_bwd_fast_kernel(const bf16* __restrict__ y, int64_t ldy, const floa
       const float rs = rstd[r * rstd_ld + h];
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
+        const uint32_t yw[4] = {yv[c].x, yv[c].y, yv[c].z, yv[c].w}, dw[4] = {dv[c].x, dv[c].y, dv[c].z, dv[c].w};
+        const float* smp = s_sm + (sub + 4 * c) * 8;
+        const float* isp = s_ism + (sub + 4 * c) * 8;
         uint32_t w[4];
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
-          __nv_bfloat162 o = __floats2bfloat162_rn(rs * (g[c][2 * e2] - xh[c][2 * e2] * sgx),
-                                                   rs * (g[c][2 * e2 + 1] - xh[c][2 * e2 + 1] * sgx));
+          const __nv_bfloat162 yh = *reinterpret_cast<const __nv_bfloat162*>(&yw[e2]);
+          const __nv_bfloat162 dh = *reinterpret_cast<const __nv_bfloat162*>(&dw[e2]);
+          const float x0 = __low2float(yh) * isp[2 * e2], x1 = __high2float(yh) * isp[2 * e2 + 1];
+          const float g0 = __low2float(dh) * smp[2 * e2], g1 = __high2float(dh) * smp[2 * e2 + 1];
+          __nv_bfloat162 o = __floats2bfloat162_rn(rs * (g0 - x0 * sgx), rs * (g1 - x1 * sgx));
           w[e2] = *reinterpret_cast<uint32_t*>(&o);
         }
         *reinterpret_cast<uint4*>(dp + (sub + 4 * c) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
