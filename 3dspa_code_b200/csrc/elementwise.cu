@@ -156,50 +156,68 @@ __global__ void layernorm_bwd_kernel(const TX* __restrict__ x, int64_t ldx,
 // pass, the scale gradient is accumulated in per-lane registers across the grid-stride loop.
 // dx_lowp (optional) receives a bf16 copy of the final dx - the operand of the next backward GEMMs.
 template <int J, typename TDY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (J >= 8 ? 2 : 1))
 layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ scale,
                           const float* __restrict__ mean, const float* __restrict__ rstd,
                           const TDY* __restrict__ dy, int64_t lddy, float* __restrict__ dx, int64_t lddx,
                           int dx_accumulate, bf16* __restrict__ dx_lowp, int64_t ldl,
                           float* __restrict__ dscale_partial, int ds_accum, int64_t rows) {
   constexpr int D = 128 * J;
+  constexpr bool DYF = sizeof(TDY) == 4;
   __shared__ float s_ds[D];
-  for (int i = threadIdx.x; i < D; i += blockDim.x) s_ds[i] = 0.f;
+  __shared__ __align__(16) float s_sc[D];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    s_ds[i] = 0.f;
+    s_sc[i] = scale[i];
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  float4 sc[J], acc[J];
+  float4 acc[J];
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    sc[j] = *reinterpret_cast<const float4*>(scale + (lane + 32 * j) * 4);
-    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int j = 0; j < J; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto unpack = [](const uint4& w) -> float4 {   // dy chunk as loaded (fp32: 4 floats; bf16: 4 values in .x,.y)
+    if constexpr (DYF) {
+      return make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+    } else {
+      const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w.x);
+      const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
+      return make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
+    }
+  };
   for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
     const float* xr = x + row * ldx;
     const TDY* dyr = dy + row * lddy;
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[J], g[J];
+    // the row stays in registers as loaded (x fp32, dy packed) between the statistics and the output pass
+    float4 xv[J];
+    uint2 dp[J];
+    uint2 dq[DYF ? J : 1];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = (lane + 32 * j) * 4;
+      xv[j] = *reinterpret_cast<const float4*>(xr + c);
+      if constexpr (DYF) {
+        const uint4 w = *reinterpret_cast<const uint4*>(dyr + c);
+        dp[j] = make_uint2(w.x, w.y);
+        dq[j] = make_uint2(w.z, w.w);
+      } else {
+        dp[j] = *reinterpret_cast<const uint2*>(dyr + c);
+      }
+    }
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const int c = (lane + 32 * j) * 4;
-      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
-      float4 dv;
-      if constexpr (sizeof(TDY) == 4) {
-        dv = *reinterpret_cast<const float4*>(dyr + c);
-      } else {
-        const uint2 w = *reinterpret_cast<const uint2*>(dyr + c);
-        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w.x);
-        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
-        dv = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
-      }
-      xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      g[j] = make_float4(dv.x * sc[j].x, dv.y * sc[j].y, dv.z * sc[j].z, dv.w * sc[j].w);
-      sg += (g[j].x + g[j].y) + (g[j].z + g[j].w);
-      sgx += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
-      acc[j].x = fmaf(dv.x, xh[j].x, acc[j].x);
-      acc[j].y = fmaf(dv.y, xh[j].y, acc[j].y);
-      acc[j].z = fmaf(dv.z, xh[j].z, acc[j].z);
-      acc[j].w = fmaf(dv.w, xh[j].w, acc[j].w);
+      const float4 dv = unpack(make_uint4(dp[j].x, dp[j].y, DYF ? dq[DYF ? j : 0].x : 0u, DYF ? dq[DYF ? j : 0].y : 0u));
+      const float4 sc = *reinterpret_cast<const float4*>(s_sc + c);
+      const float4 xh = make_float4((xv[j].x - mu) * rs, (xv[j].y - mu) * rs, (xv[j].z - mu) * rs, (xv[j].w - mu) * rs);
+      const float4 g = make_float4(dv.x * sc.x, dv.y * sc.y, dv.z * sc.z, dv.w * sc.w);
+      sg += (g.x + g.y) + (g.z + g.w);
+      sgx += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+      acc[j].x = fmaf(dv.x, xh.x, acc[j].x);
+      acc[j].y = fmaf(dv.y, xh.y, acc[j].y);
+      acc[j].z = fmaf(dv.z, xh.z, acc[j].z);
+      acc[j].w = fmaf(dv.w, xh.w, acc[j].w);
     }
     sg = warp_sum(sg) * (1.f / D);
     sgx = warp_sum(sgx) * (1.f / D);
@@ -207,8 +225,11 @@ layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float*
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const int c = (lane + 32 * j) * 4;
-      float4 v = make_float4(rs * (g[j].x - sg - xh[j].x * sgx), rs * (g[j].y - sg - xh[j].y * sgx),
-                             rs * (g[j].z - sg - xh[j].z * sgx), rs * (g[j].w - sg - xh[j].w * sgx));
+      const float4 dv = unpack(make_uint4(dp[j].x, dp[j].y, DYF ? dq[DYF ? j : 0].x : 0u, DYF ? dq[DYF ? j : 0].y : 0u));
+      const float4 sc = *reinterpret_cast<const float4*>(s_sc + c);
+      const float4 xh = make_float4((xv[j].x - mu) * rs, (xv[j].y - mu) * rs, (xv[j].z - mu) * rs, (xv[j].w - mu) * rs);
+      float4 v = make_float4(rs * (dv.x * sc.x - sg - xh.x * sgx), rs * (dv.y * sc.y - sg - xh.y * sgx),
+                             rs * (dv.z * sc.z - sg - xh.z * sgx), rs * (dv.w * sc.w - sg - xh.w * sgx));
       if (dx_accumulate) {
         const float4 o = *reinterpret_cast<const float4*>(dxr + c);
         v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
