@@ -149,7 +149,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int kb_per_split = (num_kb_all + splits - 1) / splits;
   const int n_tiles = (N + BN - 1) / BN;
   const int64_t m_tiles = (M + BM - 1) / BM;
-  const int64_t num_tiles = m_tiles * n_tiles * splits;   // work items: (output tile, K split)
+  const int64_t tiles_mn = m_tiles * n_tiles;
+  const int64_t num_tiles = tiles_mn * splits;            // work items: (output tile, K split)
+  // Work item -> (tile, split).  Split-major: the CTAs that run together share one token range and
+  // differ in the output tile, so every operand block they stream is reused through L2 by all the
+  // tiles of that range (a tile-major order would have each CTA stream its own range: no reuse).
+  auto item_tile = [&](int64_t t) -> int64_t { return t % tiles_mn; };
+  auto item_split = [&](int64_t t) -> int { return (int)(t / tiles_mn); };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -189,8 +195,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int64_t tile = t / splits;
-        const int sp = (int)(t % splits);
+        const int64_t tile = item_tile(t);
+        const int sp = item_split(t);
         const int m_blk = (int)(tile / n_tiles), n_blk = (int)(tile % n_tiles);
         const int kb0 = sp * kb_per_split, kb1 = min(num_kb_all, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -222,7 +228,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        const int sp = (int)(t % splits);
+        const int sp = item_split(t);
         const int kb0 = sp * kb_per_split, kb1 = min(num_kb_all, kb0 + kb_per_split);
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
@@ -267,7 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float4 bq_next[NCH];
     auto load_bias_direct = [&](int64_t tt, float4 (&dst)[NCH]) {
       if (EPI != EPI_DIRECT) return;
-      const int nb = (int)((tt / splits) % n_tiles);
+      const int nb = (int)(item_tile(tt) % n_tiles);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int col = nb * BN + half * HC + c * 32 + (lane & 7) * 4;
@@ -279,7 +285,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float breg_next[NCH];
     auto load_bias_tma = [&](int64_t tt, float (&dst)[NCH]) {
       if (EPI != EPI_TMA) return;
-      const int nb = (int)((tt / splits) % n_tiles);
+      const int nb = (int)(item_tile(tt) % n_tiles);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int col = nb * BN + half * HC + c * 32 + lane;
@@ -288,7 +294,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     };
     load_bias_tma(blockIdx.x, breg_next);
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int64_t tile = t / splits;
+      const int64_t tile = item_tile(t);
       const int m_blk = (int)(tile / n_tiles), n_blk = (int)(tile % n_tiles);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -334,7 +340,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (!ep.debug_skip) {
           load_res(0);   // in flight while the MMAs of this tile still run
           // pull the residual of this CTA's next tile into L2 (one prefetch per 128-byte line)
-          const int64_t tn = (t + gridDim.x) / splits;
+          const int64_t tn = item_tile(t + gridDim.x);
           if (ep.residual && t + gridDim.x < num_tiles) {
             const int64_t prow = (int64_t)(tn / n_tiles) * BM + quarter * 32 + lane;
             const int pcol = (int)(tn % n_tiles) * BN + half * HC;
