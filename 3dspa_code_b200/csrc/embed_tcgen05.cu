@@ -37,6 +37,8 @@ struct EmbedParams {
   const float* depth;    // [R, Dz] or null
   const float* bias;     // [W] summed biases
   float* out;            // [R + R/T, W] token matrix (row remap r -> r + r/T + 1)
+  bf16* acat;            // optional [R + R/T, K] bf16 copy of the concatenated features (training: operand of dW), same row remap
+  int64_t lda;
   int64_t ldo;
   int64_t R;
   int T, Dd, Dz, W;
@@ -229,8 +231,12 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
         const bool ok = row_base + row < p.R;
         __nv_bfloat162 h0 = __floats2bfloat162_rn(ok ? v[ps].x : 0.f, ok ? v[ps].y : 0.f);
         __nv_bfloat162 h1 = __floats2bfloat162_rn(ok ? v[ps].z : 0.f, ok ? v[ps].w : 0.f);
-        *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
-            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        const uint2 w2 = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) = w2;
+        if (p.acat != nullptr && ok) {   // 16 lanes x 8 B = one 128-byte line of the row
+          const uint32_t r32 = (uint32_t)(row_base + row);
+          *reinterpret_cast<uint2*>(p.acat + ((int64_t)r32 + r32 / (uint32_t)p.T + 1) * p.lda + kb * 64 + l16 * 4) = w2;
+        }
       }
       publish(idx);
     };
@@ -271,8 +277,12 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
         asm("sin.approx.f32 %0, %1;" : "=f"(o3) : "f"(__fadd_rn(__fmul_rn(x, s3), ph)));
         if (r_ >= p.R) o0 = o1 = o2 = o3 = 0.f;
         __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
-        *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) =
-            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        const uint2 w2 = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) = w2;
+        if (p.acat != nullptr && r_ < p.R) {
+          const uint32_t r32 = (uint32_t)r_;
+          *reinterpret_cast<uint2*>(p.acat + ((int64_t)r32 + r32 / (uint32_t)p.T + 1) * p.lda + kb * 64 + l16 * 4) = w2;
+        }
       }
       publish(idx);
     };
@@ -352,8 +362,8 @@ int spa3d_embed_fused_applicable(int W, int K_total, int dino_dim, int depth_dim
 }
 
 int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth, const void* Wt, int64_t ldw,
-                      const float* bias, float* out, int64_t ldo, int64_t rows, int T, int dino_dim, int depth_dim,
-                      int W, int num_freq, float track_scale_factor, void* stream) {
+                      const float* bias, float* out, int64_t ldo, void* a_cat, int64_t lda, int64_t rows, int T,
+                      int dino_dim, int depth_dim, int W, int num_freq, float track_scale_factor, void* stream) {
   using namespace spa3d::te;
   SPA3D_REQUIRE(num_freq == 32, "embed_fused: 32 frequencies per coordinate (one 64-column K block each)");
   SPA3D_REQUIRE(spa3d_embed_fused_applicable(W, 256 + dino_dim + depth_dim, dino_dim, depth_dim, 3), "embed_fused: unsupported widths");
@@ -365,6 +375,8 @@ int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth
   SPA3D_REQUIRE(rows < (1ll << 31), "embed_fused: too many rows");
   EmbedParams p;
   p.tracks = tracks; p.dino = dino; p.depth = depth; p.bias = bias; p.out = out; p.ldo = ldo; p.R = rows;
+  p.acat = reinterpret_cast<bf16*>(a_cat); p.lda = lda;
+  SPA3D_REQUIRE(a_cat == nullptr || (lda % 4 == 0 && (reinterpret_cast<uintptr_t>(a_cat) & 7) == 0), "embed_fused: a_cat must be 8-byte aligned");
   p.T = T; p.Dd = dino_dim; p.Dz = depth_dim; p.W = W; p.inv_scale = (float)(1.0 / (double)track_scale_factor); p.inv_T = (float)(1.0 / (double)T);
   for (int i = 0; i < 32; ++i) p.fs[i] = (float)pow(2.0, (double)i / 3.0);
   {

@@ -98,10 +98,12 @@ def embed_fused_applicable(W, K_total, dino_dim, depth_dim, coords):
     return bool(_lib.lib().spa3d_embed_fused_applicable(int(W), int(K_total), int(dino_dim), int(depth_dim), int(coords)))
 
 
-def embed_fused(tracks, dino, depth, wt, bias, out, T, num_freq, scale_factor):
-    """out[r + r//T + 1] = [Fourier(tracks[r], t/T) | dino[r] | depth[r]] @ wt^T + bias (fp32 out)."""
+def embed_fused(tracks, dino, depth, wt, bias, out, T, num_freq, scale_factor, a_cat=None):
+    """out[r + r//T + 1] = [Fourier(tracks[r], t/T) | dino[r] | depth[r]] @ wt^T + bias (fp32 out); a_cat (bf16,
+    optional) receives the concatenated features at the same rows."""
     rows = tracks.shape[0]
-    _call("spa3d_embed_fused", _p(tracks), _p(dino), _p(depth), _p(wt), _ld(wt), _p(bias), _p(out), _ld(out), rows, int(T),
+    _call("spa3d_embed_fused", _p(tracks), _p(dino), _p(depth), _p(wt), _ld(wt), _p(bias), _p(out), _ld(out), _p(a_cat),
+          _ld(a_cat) if a_cat is not None else 0, rows, int(T),
           dino.shape[1] if dino is not None else 0, depth.shape[1] if depth is not None else 0, wt.shape[0], int(num_freq),
           float(scale_factor), _stream())
     return out

@@ -273,8 +273,9 @@ class EmbedFn(torch.autograd.Function):
     """tokens = [readout ; A_cat . W_embed + b]   (track_autoencoder_3d.py:123-165); A_cat is data."""
 
     @staticmethod
-    def forward(ctx, anchor, st, a_cat, wt, bias, bias_names, seqs, T, ro):
-        x = ops.gemm(a_cat, wt, bias, out_dtype=torch.float32)
+    def forward(ctx, anchor, st, a_cat, wt, bias, bias_names, seqs, T, ro, x=None):
+        if x is None:   # a_cat was built by the unfused kernels; otherwise the fused K1 kernel produced x and a_cat together
+            x = ops.gemm(a_cat, wt, bias, out_dtype=torch.float32)
         if ro:
             ops.set_rows(x, T + 1, st.f32["readout_token"].view(-1), seqs)
         ctx.saved = a_cat
@@ -301,7 +302,7 @@ class EmbedFn(torch.autograd.Function):
             raise NotImplementedError("training with a feature missing from the batch but present in the tree")
         st.accum_dw("embed.Wt", _c(st, dx), a_cat)
         ctx.saved = None
-        return (None,) * 9
+        return (None,) * 10
 
 
 class LatentInitFn(torch.autograd.Function):
@@ -414,18 +415,26 @@ class TrainEngine(Engine):
         K = st.c["embed.Wt"].shape[1]
         a_cat = torch.empty(B * N * (T + 1), K, device=dev, dtype=self.cdt)
         a_cat.view(B * N, T + 1, K)[:, 0].zero_()
-        ops.fourier_features(tracks.view(rows, C3), a_cat, cfg.num_frequencies, cfg.track_scale_factor, append_time=T,
-                             exact=self.exact, out_row_group=T)
-        off = meta["fourier_in"]
-        bias_names = ["embed.b_track"]
-        if dino is not None:
-            ops.convert(dino.view(rows, -1), a_cat[:, off : off + meta["dino_dim"]], out_row_group=T)
-            off += meta["dino_dim"]
-            bias_names.append("embed.b_dino")
-        if depth is not None:
-            ops.convert(depth.view(rows, -1), a_cat[:, off : off + meta["depth_dim"]], out_row_group=T)
-            bias_names.append("embed.b_depth")
-        x = EmbedFn.apply(self.anchor, st, a_cat, st.c["embed.Wt"], st.embed_bias, bias_names, B * N, T, True)
+        bias_names = ["embed.b_track"] + (["embed.b_dino"] if dino is not None else []) + (["embed.b_depth"] if depth is not None else [])
+        x0 = None
+        W = st.c["embed.Wt"].shape[0]
+        if (self.cdt == torch.bfloat16 and self.fused_embed and cfg.num_frequencies == 32 and C3 == 3
+                and ops.embed_fused_applicable(W, K, dino.shape[-1] if dino is not None else 0, depth.shape[-1] if depth is not None else 0, C3)):
+            # K1: one kernel produces the tokens AND the bf16 concatenated features the weight gradient needs
+            x0 = torch.empty(B * N * (T + 1), W, device=dev, dtype=torch.float32)
+            ops.embed_fused(tracks.view(rows, C3), dino.view(rows, -1) if dino is not None else None,
+                            depth.view(rows, -1) if depth is not None else None, st.c["embed.Wt"], st.embed_bias, x0, T,
+                            cfg.num_frequencies, cfg.track_scale_factor, a_cat=a_cat)
+        else:
+            ops.fourier_features(tracks.view(rows, C3), a_cat, cfg.num_frequencies, cfg.track_scale_factor, append_time=T,
+                                 exact=self.exact, out_row_group=T)
+            off = meta["fourier_in"]
+            if dino is not None:
+                ops.convert(dino.view(rows, -1), a_cat[:, off : off + meta["dino_dim"]], out_row_group=T)
+                off += meta["dino_dim"]
+            if depth is not None:
+                ops.convert(depth.view(rows, -1), a_cat[:, off : off + meta["depth_dim"]], out_row_group=T)
+        x = EmbedFn.apply(self.anchor, st, a_cat, st.c["embed.Wt"], st.embed_bias, bias_names, B * N, T, True, x0)
         key_mask = ops.build_key_mask(visible, boundary, True)
         stok = self._transformer_t("itt", x, B * N, T + 1, key_mask, first=True)
         nl = meta["latent_tokens"]

@@ -74,13 +74,15 @@ int spa3d_fourier_features(const float* x, int64_t ldx, void* out, int64_t ldo, 
  *   out[r + r/T + 1, 0:W] = [Fourier(x,y,z,t/T) | dino[r] | depth[r]] . Wt^T + bias
  * Wt [W, 256+dino_dim+depth_dim] bf16 (the three Flax kernels stacked along K, transposed), bias [W]
  * f32 (sum of the three biases), dino / depth f32 [rows, dim] or NULL with dim 0, out f32 with the
- * read-out slot (row 0 of every T+1 rows) left untouched.  bf16 tensor-core path (sin.approx
+ * read-out slot (row 0 of every T+1 rows) left untouched.  a_cat (bf16 [rows + rows/T, 256+dino+depth], lda) may
+ * be NULL; otherwise it receives the concatenated bf16 features at the same remapped rows (training keeps
+ * them as the operand of the embedding's weight gradient).  bf16 tensor-core path (sin.approx
  * Fourier features); spa3d_embed_fused_applicable tells whether the widths are supported. */
 int spa3d_embed_fused_applicable(int W, int K_total, int dino_dim, int depth_dim, int coords);
 int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth, const void* Wt,
-                      int64_t ldw, const float* bias, float* out, int64_t ldo, int64_t rows, int T,
-                      int dino_dim, int depth_dim, int W, int num_freq, float track_scale_factor,
-                      void* stream);
+                      int64_t ldw, const float* bias, float* out, int64_t ldo, void* a_cat, int64_t lda,
+                      int64_t rows, int T, int dino_dim, int depth_dim, int W, int num_freq,
+                      float track_scale_factor, void* stream);
 
 /* Row-wise dtype conversion / strided copy: dst[r', 0:cols] = (dst_dtype) src[r, 0:cols],
  * r' = r (+ r/out_row_group + 1 when out_row_group > 0). */

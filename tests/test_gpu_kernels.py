@@ -526,7 +526,8 @@ def test_embed_fused_matches_unfused_math(spa, N, T, Dd, Dz, W):
     bias = torch.randn(W, device="cuda")
     assert ops.embed_fused_applicable(W, K, Dd, Dz, 3)
     out = torch.full((N * (T + 1), W), -7.0, device="cuda")
-    ops.embed_fused(tracks, dino, depth, wt, bias, out, T, 32, 1.0)
+    a_cat = torch.full((N * (T + 1), K), -3.0, device="cuda", dtype=torch.bfloat16)
+    ops.embed_fused(tracks, dino, depth, wt, bias, out, T, 32, 1.0, a_cat=a_cat)
     t = (torch.arange(R, device="cuda") % T).float() / T
     feats = om.sinusoidal_embedding(torch.cat([tracks, t[:, None]], -1).cpu(), 32).cuda()
     parts = [feats.float().to(torch.bfloat16).double()]
@@ -538,3 +539,9 @@ def test_embed_fused_matches_unfused_math(spa, N, T, Dd, Dz, W):
     got = out.view(N, T + 1, W)
     assert float((got[:, 0] + 7.0).abs().max()) == 0.0          # read-out slots untouched
     assert rel_err(got[:, 1:].reshape(R, W), ref) < 3e-3, rel_err(got[:, 1:].reshape(R, W), ref)
+    # side output for training: the bf16 concatenated features at the same (remapped) rows
+    ac = a_cat.view(N, T + 1, K)
+    assert float((ac[:, 0].float() + 3.0).abs().max()) == 0.0
+    cat = torch.cat(parts, -1)
+    assert rel_err(ac[:, 1:, :256].reshape(R, 256), cat[:, :256]) < 1e-2          # sin.approx + bf16 rounding
+    assert torch.equal(ac[:, 1:, 256:].reshape(R, K - 256).double(), cat[:, 256:])   # features: the same bf16 rounding
