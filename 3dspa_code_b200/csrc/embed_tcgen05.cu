@@ -48,7 +48,7 @@ struct EmbedParams {
   int l2_prefetch;       // pull whole feature rows into L2 one tile ahead (SPA3D_EMBED_L2_PREFETCH=1 enables; measured slower)
 };
 
-template <int NB, int BNH>   // W = NB * BNH output columns, BNH <= 256
+template <int NB, int BNH, bool ACAT>   // W = NB * BNH output columns, BNH <= 256; ACAT: also store the bf16 features
 __global__ void __launch_bounds__(THREADS, 1)
 embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p) {
   constexpr int A_BYTES = BM * BK * 2;
@@ -233,7 +233,7 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
         __nv_bfloat162 h1 = __floats2bfloat162_rn(ok ? v[ps].z : 0.f, ok ? v[ps].w : 0.f);
         const uint2 w2 = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
         *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) = w2;
-        if (p.acat != nullptr && ok) {   // 16 lanes x 8 B = one 128-byte line of the row
+        if (ACAT && ok) {   // 16 lanes x 8 B = one 128-byte line of the row
           const uint32_t r32 = (uint32_t)(row_base + row);
           *reinterpret_cast<uint2*>(p.acat + ((int64_t)r32 + r32 / (uint32_t)p.T + 1) * p.lda + kb * 64 + l16 * 4) = w2;
         }
@@ -279,7 +279,7 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
         __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
         const uint2 w2 = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
         *reinterpret_cast<uint2*>(at + row * 128 + (((l16 >> 1) ^ (row & 7)) << 4) + (l16 & 1) * 8) = w2;
-        if (p.acat != nullptr && r_ < p.R) {
+        if (ACAT && r_ < p.R) {
           const uint32_t r32 = (uint32_t)r_;
           *reinterpret_cast<uint2*>(p.acat + ((int64_t)r32 + r32 / (uint32_t)p.T + 1) * p.lda + kb * 64 + l16 * 4) = w2;
         }
@@ -333,19 +333,24 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
   }
 }
 
-template <int NB, int BNH>
-static int launch(const CUtensorMap& tmB, const EmbedParams& p, cudaStream_t st) {
+template <int NB, int BNH, bool ACAT>
+static int launch_v(const CUtensorMap& tmB, const EmbedParams& p, cudaStream_t st) {
   constexpr int SMEM = STAGES * (BM * BK * 2 + NB * BNH * BK * 2) + NUM_EPI * 4096 + NB * BNH * 4 + 2 * BM * 3 * 4 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(embed_fused_kernel<NB, BNH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(embed_fused_kernel<NB, BNH, ACAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     SPA3D_REQUIRE(e == cudaSuccess, "embed_fused: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int64_t m_tiles = (p.R + BM - 1) / BM;
   const int grid = (int)(m_tiles < num_sms() ? m_tiles : num_sms());
-  embed_fused_kernel<NB, BNH><<<grid, THREADS, SMEM, st>>>(tmB, p);
+  embed_fused_kernel<NB, BNH, ACAT><<<grid, THREADS, SMEM, st>>>(tmB, p);
   return check_launch("embed_fused");
+}
+
+template <int NB, int BNH>
+static int launch(const CUtensorMap& tmB, const EmbedParams& p, cudaStream_t st) {
+  return p.acat != nullptr ? launch_v<NB, BNH, true>(tmB, p, st) : launch_v<NB, BNH, false>(tmB, p, st);
 }
 
 }  // namespace te
