@@ -238,6 +238,83 @@ class MlpBlockFn(torch.autograd.Function):
         return dy, None, None, None
 
 
+class LastLayerFn(torch.autograd.Function):
+    """Last layer of a transformer whose output is read at token 0 only (the read-out token,
+    track_autoencoder_3d.py:187,286): keys and values are needed for every token, but the query,
+    the output projection, the MLP and everything downstream only for token 0 of each sequence.
+    Returns y0 [batch, d] = token 0 after both residual sub-blocks; the other rows are dead code in
+    the reference's graph too (XLA eliminates them), so forward and gradients are unchanged."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, st, pre, m, batch, L, key_mask):
+        f, w, cdt = st.f32, st.c, st.cdt
+        H, Dh = m["heads"], m["Dh"]
+        A, d = H * Dh, m["d"]
+        sq, sk = f[pre + "self.norm_query"], f[pre + "self.norm_key"]
+        wqkv = w[pre + "self.Wqkv_t"]
+        xn, mean, rstd = ops.layernorm_fwd(x, f[pre + "norm_q"], cdt, stats=True)
+        kvp, rk = ops.gemm_rmsnorm(xn, wqkv[A:], Dh, 0, A, sq, sk, save_rstd=True)             # keys, values: all tokens
+        xn0 = xn.view(batch, L * d)[:, :d]
+        q0, rq = ops.gemm_rmsnorm(xn0, wqkv[:A], Dh, A, 0, sq, sk, save_rstd=True)             # queries: token 0
+        o0 = torch.empty(batch, A, device=x.device, dtype=cdt)
+        stats = ops.attention_fwd(q0, kvp[:, :A], kvp[:, A:], o0, batch, H, 1, L, Dh, key_mask, save_stats=True)
+        a0 = ops.gemm(o0, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x.view(batch, L * d)[:, :d], out_dtype=torch.float32)
+        an0, mean2, rstd2 = ops.layernorm_fwd(a0, f[pre + "norm_attn"], cdt, stats=True)
+        z0, h0 = ops.gemm_gelu(an0, w[pre + "W1_t"], f[pre + "b1"])
+        y0 = ops.gemm(h0, w[pre + "W2_t"], f[pre + "b2"], residual=a0, out_dtype=torch.float32)
+        ctx.saved = dict(x=x, xn=xn, mean=mean, rstd=rstd, kvp=kvp, rk=rk, q0=q0, rq=rq, o0=o0, stats=stats, a0=a0, an0=an0,
+                         mean2=mean2, rstd2=rstd2, z0=z0, h0=h0)
+        ctx.args = (st, pre, m, batch, L, key_mask)
+        return y0
+
+    @staticmethod
+    def backward(ctx, dy0):
+        st, pre, m, batch, L, key_mask = ctx.args
+        s = ctx.saved
+        f, cdt = st.f32, st.cdt
+        H, Dh = m["heads"], m["Dh"]
+        A, d = H * Dh, m["d"]
+        dy0 = dy0.contiguous()
+        # ---- MLP sub-block on the token-0 rows ----
+        dyc = _c(st, dy0)
+        st.accum_bias(pre + "b2", dyc)
+        st.accum_dw(pre + "W2_t", dyc, s["h0"])
+        dz0 = ops.gemm_gelu_bwd(dyc, st.ct[pre + "W2_t"], s["z0"])
+        st.accum_bias(pre + "b1", dz0)
+        st.accum_dw(pre + "W1_t", dz0, s["an0"])
+        dan0 = ops.gemm(dz0, st.ct[pre + "W1_t"])
+        da0 = dy0.clone()
+        ops.layernorm_bwd(s["a0"], f[pre + "norm_attn"], s["mean2"], s["rstd2"], dan0, da0, accumulate=True, dscale_accum=st.g[pre + "norm_attn"])
+        # ---- attention sub-block: one query row per sequence ----
+        dac = _c(st, da0)
+        st.accum_bias(pre + "self.bo", dac)
+        st.accum_dw(pre + "self.Wo_t", dac, s["o0"])
+        d_o0 = ops.gemm(dac, st.ct[pre + "self.Wo_t"])
+        kvp = s["kvp"]
+        dq0 = torch.empty_like(s["q0"])
+        dkv = torch.empty_like(kvp)
+        ops.attention_bwd(s["q0"], kvp[:, :A], kvp[:, A:], s["o0"], d_o0, dq0, dkv[:, :A], dkv[:, A:], s["stats"], batch, H, 1, L, Dh, key_mask)
+        ops.head_rmsnorm_bwd(s["q0"], f[pre + "self.norm_query"], 1.0 / math.sqrt(Dh), s["rq"], dq0, H, Dh, dscale_accum=st.g[pre + "self.norm_query"])
+        ops.head_rmsnorm_bwd(kvp[:, :A], f[pre + "self.norm_key"], 1.0, s["rk"], dkv[:, :A], H, Dh, dscale_accum=st.g[pre + "self.norm_key"])
+        gw = st.g[pre + "self.Wqkv_t"]                      # [3A, d]: query rows, then key and value rows
+        xn = s["xn"]
+        xn0 = xn.view(batch, L * d)[:, :d]
+        ops.gemm_dw(dq0, xn0, gw[:A], accumulate=True)
+        ops.gemm_dw(dkv, xn, gw[A:], accumulate=True)
+        ct = st.ct[pre + "self.Wqkv_t"]                      # [d, 3A]
+        dxn = ops.gemm(dkv, ct[:, A:])                       # every token, through keys and values
+        dxn0 = dxn.view(batch, L * d)[:, :d]
+        ops.gemm(dq0, ct[:, :A], residual=dxn0, out=dxn0)    # token 0 also through its query
+        dx = torch.zeros_like(s["x"])
+        dx.view(batch, L * d)[:, :d].copy_(da0)              # the residual path reaches token 0 only
+        ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, dx, accumulate=True, dx_lowp=_lowp_out(st, dx),
+                          dscale_accum=st.g[pre + "norm_q"])
+        ctx.saved = None
+        if st.progress_cb is not None:
+            st.progress_cb(pre)
+        return dx, None, None, None, None, None, None, None
+
+
 class FinalNormFn(torch.autograd.Function):
     """norm_encoder (attention.py:49) on every token or only on token 0 of each sequence."""
 
@@ -392,12 +469,16 @@ class TrainEngine(Engine):
     def __init__(self, cfg, store: ParamStore):
         super().__init__(cfg, store)
         self.st = store
+        self.prune_last = True   # token-0-only last layer of the read-out transformers (same dead-code elimination as inference)
         self.anchor = torch.zeros((), device=self.dev, requires_grad=True)
 
     def _transformer_t(self, short, x, batch, L, key_mask=None, kv=None, Lkv=0, first=False):
         m = self.w.meta[short]
         for i in range(m["layers"]):
             pre = f"{short}.{i}."
+            if first and self.prune_last and i == m["layers"] - 1 and kv is None and L > 1:
+                y0 = LastLayerFn.apply(x, self.anchor, self.st, pre, m, batch, L, key_mask)
+                return FinalNormFn.apply(y0, self.anchor, self.st, f"{short}.norm_encoder", batch, 1, False)
             a = AttnBlockFn.apply(x, kv, self.anchor, self.st, pre, m, batch, L, Lkv, key_mask)
             x = MlpBlockFn.apply(a, self.anchor, self.st, pre)
         return FinalNormFn.apply(x, self.anchor, self.st, f"{short}.norm_encoder", batch, L, first)
