@@ -1,8 +1,10 @@
 """CPU restatement (torch, fp32 or fp64) of the reference model path.  TEST INFRASTRUCTURE.
 
-PARITY UNPINNED: the reference (JAX/Flax) cannot be run in this environment and ships no
-golden vectors; see ``oracle/__init__.py``.  Every function cites the reference lines it
-follows (paths relative to /root/reference).  Third-party semantics (Flax ``Dense``,
+Pinned (tests/test_oracle_golden_model.py, 1e-9 in float64) against golden vectors produced by
+executing the reference's own model files on NumPy stand-ins for the absent jax / flax / optax
+primitives (oracle/flax_shim.py, tests/golden/make_golden_model.py).  Not pinned: bit-level
+agreement with XLA's kernels and the threefry noise stream; see ``oracle/__init__.py``.
+Every function cites the reference lines it follows (paths relative to /root/reference).  Third-party semantics (Flax ``Dense``,
 ``LayerNorm``, ``RMSNorm``, ``dot_product_attention``, ``gelu``; flax>=0.7.5, jax>=0.4.20 per
 ``requirements.txt:2-6``, lower bounds only) are restated from their published definitions
 (SURVEY.md Appendix B).

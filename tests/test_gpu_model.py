@@ -190,3 +190,53 @@ def test_cuda_graph_replay_equals_eager(spa):
     assert len(gmodel._graphs) == 1
     assert torch.equal(got2.tracks, ref2.tracks) and torch.equal(got2.visible_logits, ref2.visible_logits)
     assert not torch.equal(ref2.tracks, ref.tracks)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_matches_reference_executed_golden(spa, precision, golden_dir):
+    """The CUDA path against numbers produced by the reference's OWN source (tests/golden/make_golden_model.py:
+    track_autoencoder_3d.py executed on NumPy stand-ins for flax, R2' widths, R1 key mask) - no oracle in between."""
+    import os
+
+    g = np.load(os.path.join(golden_dir, "model_3dspa.npz"))
+    F = int(g["dec/num_output_frames"])
+    model = spa.TrackAutoEncoder3D(num_output_frames=F, track_token_dim=768, depth_feature_dim=768)
+    cfg = om.Config3D(num_output_frames=F, track_token_dim=768, depth_feature_dim=768)
+    variables = {"params": om.init_params_3d(cfg, seed=int(g["full/seed"]), randomize_norms=True)}
+    inp = {k[8:]: np.asarray(g[k], np.int32 if k.endswith("boundary_frame") else np.float32) for k in g.files if k.startswith("full/in/")}
+    lat = model.apply(variables, inp, method="encode", precision=precision)
+    assert rel_err(lat, torch.from_numpy(g["full/latents"])) < TOL[precision], rel_err(lat, torch.from_numpy(g["full/latents"]))
+    # whole forward without the quantiser (a last-bit difference in a latent may flip a round(x*128) and move it by 1/128)
+    got = model.apply(variables, inp, discretize=False, precision=precision)
+    assert rel_err(got.tracks, torch.from_numpy(g["full/nodisc/tracks"])) < TOL[precision], rel_err(got.tracks, torch.from_numpy(g["full/nodisc/tracks"]))
+    assert rel_err(got.visible_logits, torch.from_numpy(g["full/nodisc/visible_logits"])) < TOL[precision]
+    # decoder as written (default widths) from the golden latents (float32-valued, so the quantiser rounds identically)
+    model_d = spa.TrackAutoEncoder3D(num_output_frames=F)
+    cfg_d = om.Config3D(num_output_frames=F)
+    vars_d = {"params": om.init_params_3d(cfg_d, seed=int(g["dec/seed"]), randomize_norms=True)}
+    inp_d = {k[7:]: np.asarray(g[k], np.int32 if k.endswith("boundary_frame") else np.float32) for k in g.files if k.startswith("dec/in/")}
+    ctx = model_d.apply(vars_d, inp_d, method="get_decoder_context", precision=precision)
+    lat_d = np.asarray(g["dec/latents"], np.float32)
+    res = model_d.decode(vars_d, lat_d, ctx, discretize=False, precision=precision)
+    assert rel_err(res.tracks, torch.from_numpy(g["dec/nodisc/tracks"])) < TOL[precision], rel_err(res.tracks, torch.from_numpy(g["dec/nodisc/tracks"]))
+    assert rel_err(res.visible_logits, torch.from_numpy(g["dec/nodisc/visible_logits"])) < TOL[precision]
+    res = model_d.decode(vars_d, lat_d, ctx, discretize=True, noise=np.asarray(g["dec/noise"], np.float32), precision=precision)
+    assert rel_err(res.tracks, torch.from_numpy(g["dec/tracks"])) < TOL[precision], rel_err(res.tracks, torch.from_numpy(g["dec/tracks"]))
+    assert rel_err(res.visible_logits, torch.from_numpy(g["dec/visible_logits"])) < TOL[precision]
+
+
+def test_trajan_matches_reference_executed_golden(spa, golden_dir):
+    """TRAJAN 2D end to end, as written (track_autoencoder.py executed on the flax stand-ins), fp32 path."""
+    import os
+
+    g = np.load(os.path.join(golden_dir, "model_trajan.npz"))
+    F = int(g["num_output_frames"])
+    model = spa.TrackAutoEncoder(num_output_frames=F)
+    variables = {"params": om.init_params_2d(om.Config2D(num_output_frames=F), seed=int(g["seed"]), randomize_norms=True)}
+    inp = {k[3:]: np.asarray(g[k], np.int32 if k.endswith("boundary_frame") else np.float32) for k in g.files if k.startswith("in/")}
+    got = model.apply(variables, inp, discretize=False, precision="fp32")   # quantiser off: no round(x*128) flips
+    for name in ("tracks", "visible_logits", "certain_logits"):
+        e = rel_err(getattr(got, name), torch.from_numpy(g["nodisc/" + name]))
+        assert e < 1e-4, (name, e)
+    lat = model.apply(variables, inp, method="encode", precision="fp32")
+    assert rel_err(lat, torch.from_numpy(g["latents"])) < 1e-4
