@@ -23,6 +23,7 @@ SOURCES = [
     "attention_mma.cu",
     "attention_tc.cu",
     "attention_tc_bwd.cu",
+    "attention_q1.cu",
     "attention_api.cu",
 ]
 

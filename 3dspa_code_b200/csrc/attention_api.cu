@@ -37,6 +37,13 @@ int attention_bwd_mma(const void* q, int64_t ldq, const void* k, int64_t ldk, co
                       void* dv, int64_t lddv, const uint8_t* key_mask, const float* stats,
                       const float* delta, int64_t batch, int heads, int Lq, int Lk, int Dh,
                       cudaStream_t st);
+bool attention_q1_applicable(int dtype, int Lq, int Lk, int Dh);
+int attention_q1_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                     int64_t ldo, const uint8_t* key_mask, float* stats, int64_t batch, int heads, int Lk, int Dh,
+                     cudaStream_t st);
+int attention_q1_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                     int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                     const uint8_t* key_mask, int64_t batch, int heads, int Lk, int Dh, cudaStream_t st);
 }  // namespace spa3d
 
 extern "C" {
@@ -49,6 +56,8 @@ int spa3d_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   if (batch == 0 || Lq == 0) return 0;
   SPA3D_REQUIRE(Lk > 0, "attention: Lk must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
+  if (attention_q1_applicable(dtype, Lq, Lk, Dh))   // one query per sequence: the pruned last layers
+    return attention_q1_fwd(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse_out, batch, heads, Lk, Dh, st);
   if (attention_fwd_tc_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, ldo, q, k, v, o))
     return attention_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse_out, batch, heads, Lq, Dh, st);
   if (attention_fwd_mma_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, ldo))
@@ -66,6 +75,9 @@ int spa3d_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   using namespace spa3d;
   if (batch == 0 || Lq == 0) return 0;
   SPA3D_REQUIRE(lse != nullptr && delta_ws != nullptr, "attention_bwd: lse/delta_ws required");
+  if (attention_q1_applicable(dtype, Lq, Lk, Dh))   // recomputes the softmax: neither lse nor delta is read
+    return attention_q1_bwd(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, batch, heads, Lk, Dh,
+                            (cudaStream_t)stream);
   if (attention_bwd_tc_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, lddo, lddq, lddk, lddv)) {
     // delta is computed inside the kernel from P and dP
     return attention_bwd_tc(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, lse, delta_ws,

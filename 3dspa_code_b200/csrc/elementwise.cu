@@ -106,6 +106,52 @@ __global__ void layernorm_fwd_kernel(const TX* __restrict__ x, int64_t ldx,
   }
 }
 
+// Bandwidth-shaped forward: fp32 rows of d = 128*J floats, one warp per row, the whole row in registers (J float4 per
+// lane, read once with 128-bit loads), bf16 or fp32 output with 8 / 16-byte stores.
+template <int J, typename TY>
+__global__ void __launch_bounds__(256) layernorm_fwd_fast_kernel(const float* __restrict__ x, int64_t ldx,
+                                                                 const float* __restrict__ scale, TY* __restrict__ y,
+                                                                 int64_t ldy, float* __restrict__ mean_out,
+                                                                 float* __restrict__ rstd_out, int64_t rows) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int d = 128 * J;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) v[j] = __ldcs(xr + j * 32 + lane);
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    ss += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  const float mean = s * (1.f / d);
+  const float var = fmaxf(ss * (1.f / d) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + kNormEps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const float4* sc = reinterpret_cast<const float4*>(scale);
+  TY* yr = y + row * ldy;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const float4 g = __ldg(sc + j * 32 + lane);
+    const float o0 = (v[j].x - mean) * rstd * g.x, o1 = (v[j].y - mean) * rstd * g.y;
+    const float o2 = (v[j].z - mean) * rstd * g.z, o3 = (v[j].w - mean) * rstd * g.w;
+    if constexpr (sizeof(TY) == 2) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+      *reinterpret_cast<uint2*>(yr + (j * 32 + lane) * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    } else {
+      *reinterpret_cast<float4*>(yr + (j * 32 + lane) * 4) = make_float4(o0, o1, o2, o3);
+    }
+  }
+}
+
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*scale;  dscale += dy*xhat
 template <typename TX, typename TDY, typename TDX>
 __global__ void layernorm_bwd_kernel(const TX* __restrict__ x, int64_t ldx,
@@ -846,6 +892,24 @@ int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* sc
                         int d, void* stream) {
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+    const bool ybf = y_dtype == SPA3D_BF16;
+    if (x_dtype == SPA3D_F32 && (ybf || y_dtype == SPA3D_F32) && d % 128 == 0 && d <= 1536 && ldx % 4 == 0 && ldy % 4 == 0 &&
+        al(x, 16) && al(scale, 16) && al(y, ybf ? 8 : 16)) {
+#define SPA3D_LN_FWD_FAST(J)                                                                                              \
+  case J:                                                                                                                 \
+    if (ybf) layernorm_fwd_fast_kernel<J, bf16><<<blocks_for(rows, 8), 256, 0, st>>>((const float*)x, ldx, scale, (bf16*)y, ldy, mean_out, rstd_out, rows); \
+    else layernorm_fwd_fast_kernel<J, float><<<blocks_for(rows, 8), 256, 0, st>>>((const float*)x, ldx, scale, (float*)y, ldy, mean_out, rstd_out, rows);   \
+    return check_launch("layernorm_fwd_fast");
+      switch (d / 128) {
+        SPA3D_LN_FWD_FAST(1) SPA3D_LN_FWD_FAST(2) SPA3D_LN_FWD_FAST(3) SPA3D_LN_FWD_FAST(4) SPA3D_LN_FWD_FAST(8)
+        SPA3D_LN_FWD_FAST(9) SPA3D_LN_FWD_FAST(10) SPA3D_LN_FWD_FAST(12)
+        default: break;
+      }
+#undef SPA3D_LN_FWD_FAST
+    }
+  }
   SPA3D_DISPATCH(x_dtype, TX, SPA3D_DISPATCH(y_dtype, TY, {
     layernorm_fwd_kernel<TX, TY><<<blocks_for(rows, 8), 256, 0, st>>>((const TX*)x, ldx, scale, (TY*)y, ldy, mean_out, rstd_out, rows, d);
   }));

@@ -163,7 +163,7 @@ def test_gemm_strided_backward_layouts(spa):
 
 
 # ---- norms -----------------------------------------------------------------------------------
-@pytest.mark.parametrize("d", [48, 384, 1280])
+@pytest.mark.parametrize("d", [48, 384, 512, 1152, 1280])
 def test_layernorm_fwd_bwd(spa, d):
     ops = spa.ops
     torch.manual_seed(3)
@@ -304,6 +304,33 @@ def test_attention_bwd(spa, dtype, Lq, Lk, Dh):
     tol = 1e-4 if dtype == torch.float32 else 2e-2
     for got, want in ((dq, qd.grad), (dk, kd.grad), (dv, vd.grad)):
         assert rel_err(got, want) < tol, rel_err(got, want)
+
+
+@pytest.mark.parametrize("Lk,Dh", [(151, 96), (129, 96), (160, 64), (7, 64), (1, 96)])
+def test_attention_one_query(spa, Lk, Dh):
+    """Lq = 1 (the pruned last layers): dedicated kernel, key mask incl. a fully masked sequence, forward + backward."""
+    ops = spa.ops
+    torch.manual_seed(16)
+    batch, H, dtype = 37, 8, torch.bfloat16
+    A = H * Dh
+    q = (torch.randn(batch, A, device="cuda") / math.sqrt(Dh)).to(dtype)
+    kv = torch.randn(batch * Lk, 2 * A, device="cuda").to(dtype)     # k and v as column slices of one buffer (ld = 2A)
+    k, v = kv[:, :A], kv[:, A:]
+    mask = (torch.rand(batch, Lk, device="cuda") < 0.7).to(torch.uint8)
+    mask[:, 0] = 1
+    mask[3] = 0
+    qd, kd, vd = (t.double().clone().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qd, kd, vd, mask, batch, H, 1, Lk, Dh)
+    d_o = torch.randn(batch, A, device="cuda").to(dtype)
+    ref.backward(d_o.double())
+    o = torch.empty(batch, A, device="cuda", dtype=dtype)
+    stats = ops.attention_fwd(q, k, v, o, batch, H, 1, Lk, Dh, mask, save_stats=True)
+    assert rel_err(o, ref) < 1e-2, rel_err(o, ref)
+    dq = torch.empty_like(q)
+    dkv = torch.full_like(kv, float("nan"))
+    ops.attention_bwd(q, k, v, o, d_o, dq, dkv[:, :A], dkv[:, A:], stats, batch, H, 1, Lk, Dh, mask)
+    for got, want in ((dq, qd.grad), (dkv[:, :A], kd.grad), (dkv[:, A:], vd.grad)):
+        assert rel_err(got, want) < 2e-2, rel_err(got, want)
 
 
 # ---- small kernels --------------------------------------------------------------------------------

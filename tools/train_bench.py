@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--support", type=int, default=S)
     ap.add_argument("--query", type=int, default=Q)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--detail", default="", help="comma-separated entry points whose per-call times are printed (last step)")
     args = ap.parse_args()
     spa = importlib.import_module("3dspa_code_b200")
     te = importlib.import_module("3dspa_code_b200.train_engine")
@@ -84,6 +85,10 @@ def main():
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
             print(f"{v:10.3f} ms  n={len(prof[k]) // args.steps:5d}  {k}")
         print(f"{sum(tot.values()):10.3f} ms  total in kernels")
+        for name in filter(None, args.detail.split(",")):
+            v = prof["spa3d_" + name]
+            per = len(v) // args.steps
+            print(name, " ".join(f"{s.elapsed_time(e):.3f}" for s, e in v[-per:]))
 
 
 if __name__ == "__main__":
