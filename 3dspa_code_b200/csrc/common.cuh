@@ -66,6 +66,25 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// bilinear sampling set-up shared by the lifting kernel and the sampled embedding (inference.py:307-322)
+struct Bilin {
+  int x0, y0, x1, y1;
+  float wx, wy;
+};
+
+__device__ __forceinline__ Bilin bilin_setup(float x, float y, int W, int H) {
+  Bilin b;
+  float fx = floorf(x), fy = floorf(y);
+  int x0 = (int)fx, y0 = (int)fy;
+  b.wx = __fsub_rn(x, fx);  // weights use the UNclamped floor (inference.py:312)
+  b.wy = __fsub_rn(y, fy);
+  b.x1 = min(max(x0 + 1, 0), W - 1);
+  b.y1 = min(max(y0 + 1, 0), H - 1);
+  b.x0 = min(max(x0, 0), W - 1);
+  b.y0 = min(max(y0, 0), H - 1);
+  return b;
+}
+
 // flax nn.gelu(approximate=True)
 // Logit of a masked key in the bf16 attention kernels: bf16(-1e30) widened to fp32, the value the
 // tcgen05 forward adds as a key bias (attention_tc.cu).  Any finite logit is absorbed by rounding, so

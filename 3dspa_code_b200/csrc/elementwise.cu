@@ -62,6 +62,30 @@ __global__ void convert_kernel(const TS* __restrict__ src, int64_t lds, TD* __re
   stf<TD>(dst + ro * ldd + c, ldf<TS>(src + r * lds + c));
 }
 
+// four elements per thread, 128-bit accesses on the fp32 side (cols % 4 == 0, 16 / 8-byte aligned rows)
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) convert_vec4_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, int64_t ldd,
+                                                           int64_t rows, int cols4, int out_group) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols4) return;
+  const int64_t r = idx / cols4;
+  const int c = (int)(idx % cols4) * 4;
+  const int64_t ro = out_group > 0 ? r + r / out_group + 1 : r;
+  float4 v;
+  if constexpr (sizeof(TS) == 4) {
+    v = __ldcs(reinterpret_cast<const float4*>(src + r * lds + c));
+  } else {
+    const uint2 u = __ldcs(reinterpret_cast<const uint2*>(src + r * lds + c));
+    v = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+  }
+  if constexpr (sizeof(TD) == 4) {
+    *reinterpret_cast<float4*>(dst + ro * ldd + c) = v;
+  } else {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + ro * ldd + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  }
+}
+
 template <typename TD>
 __global__ void set_rows_kernel(TD* __restrict__ dst, int64_t ld, int64_t row_stride,
                                 const float* __restrict__ vec, int64_t rows, int cols) {
@@ -881,6 +905,17 @@ int spa3d_convert(const void* src, int64_t lds, int src_dtype, void* dst, int64_
                   int64_t rows, int cols, int out_row_group, void* stream) {
   if (rows == 0 || cols == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    auto al = [](const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+    const size_t ss = src_dtype == SPA3D_F32 ? 4 : 2, ds = dst_dtype == SPA3D_F32 ? 4 : 2;
+    if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && al(src, 4 * ss) && al(dst, 4 * ds) &&
+        (src_dtype == SPA3D_F32 || src_dtype == SPA3D_BF16) && (dst_dtype == SPA3D_F32 || dst_dtype == SPA3D_BF16)) {
+      SPA3D_DISPATCH(src_dtype, TS, SPA3D_DISPATCH(dst_dtype, TD, {
+        convert_vec4_kernel<TS, TD><<<blocks_for(rows * (cols / 4), 256), 256, 0, st>>>((const TS*)src, lds, (TD*)dst, ldd, rows, cols / 4, out_row_group);
+      }));
+      return check_launch("convert_vec4");
+    }
+  }
   SPA3D_DISPATCH(src_dtype, TS, SPA3D_DISPATCH(dst_dtype, TD, {
     convert_kernel<TS, TD><<<blocks_for(rows * cols, 256), 256, 0, st>>>((const TS*)src, lds, (TD*)dst, ldd, rows, cols, out_row_group);
   }));

@@ -46,9 +46,17 @@ struct EmbedParams {
   float inv_T;           // 1 / T
   float fs[32];          // 2^(i/3)
   int l2_prefetch;       // pull whole feature rows into L2 one tile ahead (SPA3D_EMBED_L2_PREFETCH=1 enables; measured slower)
+  // SAMPLE variant ("project, then sample": the DINO projection is linear, so the patch map is projected ONCE per clip
+  // and every track row blends four projected patch rows instead of projecting its own blended 768-vector)
+  const bf16* proj;      // [T*Hp*Wp, W] projected DINO patch map
+  const float* trk2d;    // [R, 2] pixel coordinates of the row's track point
+  const float* dfeat;    // [R, 4] (d, d/10, d_t - d_{t-1}, 0): the three live depth-feature channels (inference.py:437-443), or null
+  const float* wdep;     // [3, W] rows 0..2 of the depth projection kernel (fp32), or null
+  int Hp, Wp;
+  float scale_w, scale_h;   // Wp / video_W, Hp / video_H (inference.py:367-368)
 };
 
-template <int NB, int BNH, bool ACAT>   // W = NB * BNH output columns, BNH <= 256; ACAT: also store the bf16 features
+template <int NB, int BNH, bool ACAT, bool SAMPLE>   // W = NB * BNH output columns, BNH <= 256; ACAT: also store the bf16 features
 __global__ void __launch_bounds__(THREADS, 1)
 embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p) {
   constexpr int A_BYTES = BM * BK * 2;
@@ -61,7 +69,9 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
   uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;            // [4 warps][4096]
   float* smem_bias = reinterpret_cast<float*>(smem_epi + NUM_EPI * 4096);   // [NB*BNH]
   float* smem_trk = smem_bias + NB * BNH;                                     // [2][128 rows][3] coordinates of a tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_trk + 2 * BM * 3);
+  float* smem_wdep = smem_trk + 2 * BM * 3;                                  // SAMPLE: [3][W] depth-projection rows
+  uint32_t* smem_smp = reinterpret_cast<uint32_t*>(smem_wdep + (SAMPLE ? 3 * NB * BNH : 0));   // SAMPLE: [4 warps][32 rows][12 words]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_smp + (SAMPLE ? NUM_EPI * 32 * 12 : 0));
   uint64_t* full_bar = bars;                 // [STAGES]  1 TMA arrive (expect_tx) + 8 producer warps
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // accumulator complete
@@ -71,7 +81,12 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_dino0 = 4, kb_depth0 = 4 + p.Dd / 64;
   const int num_kb = kb_depth0 + p.Dz / 64;
-  const int64_t m_tiles = (p.R + BM - 1) / BM;
+  // SAMPLE: tiles are frame-major - 128 tracks of ONE frame - so every gather of a tile (and of the ~148 tiles in flight)
+  // hits the same 1 MB slice of the projected map, which stays in L2 and is read from HBM once.  Row i of tile tt is
+  // track n = (tt % nt_n) * 128 + i at frame t = tt / nt_n; its data lives at flat row n*T + t like in the other variant.
+  const int Ntrk = (int)(p.R / p.T);
+  const int nt_n = (Ntrk + BM - 1) / BM;
+  const int64_t m_tiles = SAMPLE ? (int64_t)p.T * nt_n : (p.R + BM - 1) / BM;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -89,6 +104,8 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < NB * BNH; i += THREADS) smem_bias[i] = p.bias[i];
+  if constexpr (SAMPLE)
+    for (int i = threadIdx.x; i < 3 * NB * BNH; i += THREADS) smem_wdep[i] = p.wdep != nullptr ? p.wdep[i] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -146,19 +163,98 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
     int it = 0;
     for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
       const int64_t row0 = t * BM + quarter * 32;
+      const int tf = SAMPLE ? (int)(t / nt_n) : 0;                               // SAMPLE: the tile's frame ...
+      const int n0 = SAMPLE ? (int)(t % nt_n) * BM + quarter * 32 : 0;           // ... and this warp's first track
       // output rows of the 8 coalesced passes (row remap r -> r + r/T + 1), once per tile
       float* orow[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int64_t r_ = row0 + i * 4 + cr;
-        orow[i] = r_ < p.R ? p.out + (r_ + (int64_t)((uint32_t)r_ / (uint32_t)p.T) + 1) * p.ldo + cc * 4 : nullptr;
+        if constexpr (SAMPLE) {
+          const int n = n0 + i * 4 + cr;
+          orow[i] = n < Ntrk ? p.out + ((int64_t)n * (p.T + 1) + tf + 1) * p.ldo + cc * 4 : nullptr;
+        } else {
+          const int64_t r_ = row0 + i * 4 + cr;
+          orow[i] = r_ < p.R ? p.out + (r_ + (int64_t)((uint32_t)r_ / (uint32_t)p.T) + 1) * p.ldo + cc * 4 : nullptr;
+        }
+      }
+      uint32_t* smp = smem_smp + (warp - 2) * (32 * 12);
+      if constexpr (SAMPLE) {
+        // lane = row: bilinear set-up of this row's track point on the patch grid, once per tile
+        const int n = n0 + lane;
+        const int64_t r_ = (int64_t)n * p.T + tf;
+        uint32_t w[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (n < Ntrk) {
+          const float2 xy = *reinterpret_cast<const float2*>(p.trk2d + r_ * 2);
+          const int t = tf;
+          const Bilin b = bilin_setup(__fmul_rn(xy.x, p.scale_w), __fmul_rn(xy.y, p.scale_h), p.Wp, p.Hp);
+          const float omx = __fsub_rn(1.f, b.wx), omy = __fsub_rn(1.f, b.wy);
+          const int fb = t * p.Hp * p.Wp;
+          w[0] = (uint32_t)((fb + b.y0 * p.Wp + b.x0) * p.W);
+          w[1] = (uint32_t)((fb + b.y0 * p.Wp + b.x1) * p.W);
+          w[2] = (uint32_t)((fb + b.y1 * p.Wp + b.x0) * p.W);
+          w[3] = (uint32_t)((fb + b.y1 * p.Wp + b.x1) * p.W);
+          w[4] = __float_as_uint(omx * omy);
+          w[5] = __float_as_uint(b.wx * omy);
+          w[6] = __float_as_uint(omx * b.wy);
+          w[7] = __float_as_uint(b.wx * b.wy);
+          if (p.dfeat != nullptr) {
+            const float4 df = *reinterpret_cast<const float4*>(p.dfeat + r_ * 4);
+            w[8] = __float_as_uint(df.x);
+            w[9] = __float_as_uint(df.y);
+            w[10] = __float_as_uint(df.z);
+          }
+        }
+        __syncwarp();   // the previous tile's passes have read their parameters
+#pragma unroll
+        for (int j = 0; j < 3; ++j) *reinterpret_cast<uint4*>(smp + lane * 12 + j * 4) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        __syncwarp();
       }
       mbar_wait(tfull_bar, it & 1);
       tcgen05_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
       constexpr int NCH = NB * BNH / 32;
+      // SAMPLE: the gathers of the four projected patch rows are issued half a chunk (4 passes x 4 neighbours = 16 loads of
+      // 8 B per lane) ahead of their use and unconditionally (rows past the end carry offset 0), so their L2 latency runs
+      // under the TMEM read, the transpose and the other half's arithmetic instead of once per pass.
+      auto gather = [&](int c, int half, uint2 (&g)[4][4]) {
+        const bf16* pj = p.proj + c * 32 + cc * 4;
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const uint4 off = *reinterpret_cast<const uint4*>(smp + ((half * 4 + i4) * 4 + cr) * 12);
+          g[i4][0] = __ldg(reinterpret_cast<const uint2*>(pj + off.x));
+          g[i4][1] = __ldg(reinterpret_cast<const uint2*>(pj + off.y));
+          g[i4][2] = __ldg(reinterpret_cast<const uint2*>(pj + off.z));
+          g[i4][3] = __ldg(reinterpret_cast<const uint2*>(pj + off.w));
+        }
+      };
+      auto finish = [&](int c, int half, const uint2 (&g)[4][4], const float4& b) {
+        const int col0 = c * 32;
+        const float4 w0 = *reinterpret_cast<const float4*>(smem_wdep + col0 + cc * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(smem_wdep + NB * BNH + col0 + cc * 4);
+        const float4 w2 = *reinterpret_cast<const float4*>(smem_wdep + 2 * NB * BNH + col0 + cc * 4);
+        auto lo = [](uint32_t u) { return __uint_as_float(u << 16); };
+        auto hi = [](uint32_t u) { return __uint_as_float(u & 0xffff0000u); };
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int i = half * 4 + i4, rr = i * 4 + cr;
+          const float4 wq = *reinterpret_cast<const float4*>(smp + rr * 12 + 4);
+          const float4 dq = *reinterpret_cast<const float4*>(smp + rr * 12 + 8);
+          float4 a = *reinterpret_cast<const float4*>(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          a.x += b.x + lo(g[i4][0].x) * wq.x + lo(g[i4][1].x) * wq.y + lo(g[i4][2].x) * wq.z + lo(g[i4][3].x) * wq.w;
+          a.y += b.y + hi(g[i4][0].x) * wq.x + hi(g[i4][1].x) * wq.y + hi(g[i4][2].x) * wq.z + hi(g[i4][3].x) * wq.w;
+          a.z += b.z + lo(g[i4][0].y) * wq.x + lo(g[i4][1].y) * wq.y + lo(g[i4][2].y) * wq.z + lo(g[i4][3].y) * wq.w;
+          a.w += b.w + hi(g[i4][0].y) * wq.x + hi(g[i4][1].y) * wq.y + hi(g[i4][2].y) * wq.z + hi(g[i4][3].y) * wq.w;
+          a.x += dq.x * w0.x + dq.y * w1.x + dq.z * w2.x;
+          a.y += dq.x * w0.y + dq.y * w1.y + dq.z * w2.y;
+          a.z += dq.x * w0.z + dq.y * w1.z + dq.z * w2.z;
+          a.w += dq.x * w0.w + dq.y * w1.w + dq.z * w2.w;
+          if (orow[i] != nullptr) *reinterpret_cast<float4*>(orow[i] + col0) = a;
+        }
+      };
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
+        uint2 ga[4][4], gb[4][4];
+        if constexpr (SAMPLE) gather(c, 0, ga);
         uint32_t r[32];
         tmem_ld32(tbase + (uint32_t)(c * 32), r);
         tmem_ld_wait();
@@ -173,13 +269,19 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
           *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
         const float4 b = *reinterpret_cast<const float4*>(smem_bias + col0 + cc * 4);
+        if constexpr (SAMPLE) {
+          gather(c, 1, gb);
+          finish(c, 0, ga, b);
+          finish(c, 1, gb, b);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + cr;
-          if (orow[i] != nullptr) {
-            float4 a = *reinterpret_cast<const float4*>(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            *reinterpret_cast<float4*>(orow[i] + col0) = a;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + cr;
+            if (orow[i] != nullptr) {
+              float4 a = *reinterpret_cast<const float4*>(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
+              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+              *reinterpret_cast<float4*>(orow[i] + col0) = a;
+            }
           }
         }
         __syncwarp();
@@ -243,6 +345,19 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
     // coordinates (x, y, z) of the tile's 128 rows: 1.5 KB copied global -> shared with cp.async one
     // tile ahead (no registers held, no latency in the Fourier blocks)
     auto load_tracks = [&](int64_t tile_iter) {
+      if constexpr (SAMPLE) {
+        // frame-major tile: the 128 rows are 128 tracks at one frame, T*12 bytes apart
+        const int64_t tile = blockIdx.x + tile_iter * gridDim.x;
+        const int tf = (int)(tile / nt_n), n = (int)(tile % nt_n) * BM + (ptid >> 1);
+        if (ptid < 2 * BM) {   // two threads per row: 8 + 4 bytes
+          float* dst = smem_trk + (tile_iter & 1) * (BM * 3) + (ptid >> 1) * 3;
+          const float* src = p.tracks + ((int64_t)(n < Ntrk ? n : 0) * p.T + tf) * 3;
+          if (ptid & 1) __pipeline_memcpy_async(dst + 2, src + 2, 4);
+          else { __pipeline_memcpy_async(dst, src, 4); __pipeline_memcpy_async(dst + 1, src + 1, 4); }
+        }
+        __pipeline_commit();
+        return;
+      }
       if (ptid < BM * 3 / 4) {
         const int64_t f0 = (blockIdx.x + tile_iter * gridDim.x) * BM * 3 + ptid * 4;   // first of 4 floats
         float* dst = smem_trk + (tile_iter & 1) * (BM * 3) + ptid * 4;
@@ -267,8 +382,15 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
 #pragma unroll
       for (int ps = 0; ps < 8; ++ps) {
         const int row = ps * 16 + rsub;
-        const int64_t r_ = row_base + row;
-        float x = kb < 3 ? trk[row * 3 + kb] : (float)((uint32_t)r_ % (uint32_t)p.T) * p.inv_T;
+        int64_t r_ = row_base + row;
+        float x;
+        if constexpr (SAMPLE) {
+          const int64_t tile = blockIdx.x + tile_iter * gridDim.x;
+          x = kb < 3 ? trk[row * 3 + kb] : (float)(int)(tile / nt_n) * p.inv_T;
+          r_ = ((int)(tile % nt_n) * BM + row) < Ntrk ? 0 : p.R;   // only used for the validity test below
+        } else {
+          x = kb < 3 ? trk[row * 3 + kb] : (float)((uint32_t)r_ % (uint32_t)p.T) * p.inv_T;
+        }
         x *= p.inv_scale;
         float o0, o1, o2, o3;
         asm("sin.approx.f32 %0, %1;" : "=f"(o0) : "f"(__fadd_rn(__fmul_rn(x, s0), ph)));
@@ -333,18 +455,19 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
   }
 }
 
-template <int NB, int BNH, bool ACAT>
+template <int NB, int BNH, bool ACAT, bool SAMPLE = false>
 static int launch_v(const CUtensorMap& tmB, const EmbedParams& p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + NB * BNH * BK * 2) + NUM_EPI * 4096 + NB * BNH * 4 + 2 * BM * 3 * 4 + 256 + 1024;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + NB * BNH * BK * 2) + NUM_EPI * 4096 + NB * BNH * 4 + 2 * BM * 3 * 4 + 256 + 1024 +
+                       (SAMPLE ? 3 * NB * BNH * 4 + NUM_EPI * 32 * 12 * 4 : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(embed_fused_kernel<NB, BNH, ACAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(embed_fused_kernel<NB, BNH, ACAT, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     SPA3D_REQUIRE(e == cudaSuccess, "embed_fused: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int64_t m_tiles = (p.R + BM - 1) / BM;
+  const int64_t m_tiles = SAMPLE ? (int64_t)p.T * ((p.R / p.T + BM - 1) / BM) : (p.R + BM - 1) / BM;
   const int grid = (int)(m_tiles < num_sms() ? m_tiles : num_sms());
-  embed_fused_kernel<NB, BNH, ACAT><<<grid, THREADS, SMEM, st>>>(tmB, p);
+  embed_fused_kernel<NB, BNH, ACAT, SAMPLE><<<grid, THREADS, SMEM, st>>>(tmB, p);
   return check_launch("embed_fused");
 }
 
@@ -381,6 +504,7 @@ int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth
   EmbedParams p;
   p.tracks = tracks; p.dino = dino; p.depth = depth; p.bias = bias; p.out = out; p.ldo = ldo; p.R = rows;
   p.acat = reinterpret_cast<bf16*>(a_cat); p.lda = lda;
+  p.proj = nullptr; p.trk2d = nullptr; p.dfeat = nullptr; p.wdep = nullptr; p.Hp = p.Wp = 0; p.scale_w = p.scale_h = 0.f;
   SPA3D_REQUIRE(a_cat == nullptr || (lda % 4 == 0 && (reinterpret_cast<uintptr_t>(a_cat) & 7) == 0), "embed_fused: a_cat must be 8-byte aligned");
   p.T = T; p.Dd = dino_dim; p.Dz = depth_dim; p.W = W; p.inv_scale = (float)(1.0 / (double)track_scale_factor); p.inv_T = (float)(1.0 / (double)T);
   for (int i = 0; i < 32; ++i) p.fs[i] = (float)pow(2.0, (double)i / 3.0);
@@ -398,6 +522,47 @@ int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth
     case 256: return launch<1, 256>(tmB, p, st);
     case 192: return launch<1, 192>(tmB, p, st);
     default: return launch<1, 128>(tmB, p, st);
+  }
+}
+
+/* K1, "project then sample" form (inference.py:543-590): tokens for track points whose DINO / depth features
+ * are never materialised.  out[r'] = Fourier(xyz[r], t/T) . Wt[:, :256]^T + bias
+ *                                   + sum_k w_k(r) * proj[patch_k(r)]                  (bilinear blend of PROJECTED patch rows)
+ *                                   + dfeat[r, 0..2] . wdep[0..2]                      (the three live depth channels)
+ * proj = bf16(dino_map) . W_dino^T is computed once per clip by the caller (spa3d_gemm). */
+int spa3d_embed_sampled(const float* xyz, const float* tracks_2d, const float* dfeat, const void* proj, const void* Wt, int64_t ldw,
+                        const float* wdep, const float* bias, float* out, int64_t ldo, int64_t rows, int T, int Hp, int Wp,
+                        int video_H, int video_W, int W, int num_freq, float track_scale_factor, void* stream) {
+  using namespace spa3d::te;
+  SPA3D_REQUIRE(num_freq == 32, "embed_sampled: 32 frequencies per coordinate (one 64-column K block each)");
+  SPA3D_REQUIRE(W == 384 || W == 256 || W == 192 || W == 128, "embed_sampled: unsupported token width %d", W);
+  SPA3D_REQUIRE(xyz && tracks_2d && proj && Wt && bias && out, "embed_sampled: NULL operand");
+  SPA3D_REQUIRE((dfeat == nullptr) == (wdep == nullptr), "embed_sampled: dfeat and wdep come together");
+  SPA3D_REQUIRE(Hp > 0 && Wp > 0 && video_H > 0 && video_W > 0 && T > 0, "embed_sampled: bad geometry");
+  SPA3D_REQUIRE((int64_t)T * Hp * Wp * W < (1ll << 31), "embed_sampled: projected map too large for 32-bit offsets");
+  auto al = [](const void* q, int a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+  SPA3D_REQUIRE(al(Wt, 16) && al(out, 16) && al(bias, 16) && al(proj, 8) && al(tracks_2d, 8) && al(dfeat, 16) && al(wdep, 16) &&
+                    ldw % 8 == 0 && ldo % 4 == 0, "embed_sampled: operand alignment");
+  if (rows == 0) return 0;
+  SPA3D_REQUIRE(rows < (1ll << 31) && rows % T == 0, "embed_sampled: rows must be tracks x T");
+  EmbedParams p;
+  p.tracks = xyz; p.dino = nullptr; p.depth = nullptr; p.bias = bias; p.out = out; p.ldo = ldo; p.R = rows;
+  p.acat = nullptr; p.lda = 0;
+  p.T = T; p.Dd = 0; p.Dz = 0; p.W = W; p.inv_scale = (float)(1.0 / (double)track_scale_factor); p.inv_T = (float)(1.0 / (double)T);
+  for (int i = 0; i < 32; ++i) p.fs[i] = (float)pow(2.0, (double)i / 3.0);
+  p.l2_prefetch = 0;
+  p.proj = reinterpret_cast<const bf16*>(proj); p.trk2d = tracks_2d; p.dfeat = dfeat; p.wdep = wdep; p.Hp = Hp; p.Wp = Wp;
+  p.scale_w = (float)((double)Wp / (double)video_W);
+  p.scale_h = (float)((double)Hp / (double)video_H);
+  CUtensorMap tmB;
+  const int bnh = W > 256 ? W / 2 : W;
+  if (tc::make_map(&tmB, Wt, W, 256, ldw, bnh)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (W) {
+    case 384: return launch_v<2, 192, false, true>(tmB, p, st);
+    case 256: return launch_v<1, 256, false, true>(tmB, p, st);
+    case 192: return launch_v<1, 192, false, true>(tmB, p, st);
+    default: return launch_v<1, 128, false, true>(tmB, p, st);
   }
 }
 

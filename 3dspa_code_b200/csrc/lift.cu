@@ -12,24 +12,6 @@
 
 namespace spa3d {
 
-struct Bilin {
-  int x0, y0, x1, y1;
-  float wx, wy;
-};
-
-__device__ __forceinline__ Bilin bilin_setup(float x, float y, int W, int H) {
-  Bilin b;
-  float fx = floorf(x), fy = floorf(y);
-  int x0 = (int)fx, y0 = (int)fy;
-  b.wx = __fsub_rn(x, fx);  // weights use the UNclamped floor (inference.py:312)
-  b.wy = __fsub_rn(y, fy);
-  b.x1 = min(max(x0 + 1, 0), W - 1);
-  b.y1 = min(max(y0 + 1, 0), H - 1);
-  b.x0 = min(max(x0, 0), W - 1);
-  b.y0 = min(max(y0, 0), H - 1);
-  return b;
-}
-
 // z00*(1-wx)*(1-wy) + z01*wx*(1-wy) + z10*(1-wx)*wy + z11*wx*wy, left to right
 __device__ __forceinline__ float blend(float v00, float v01, float v10, float v11, float wx, float wy,
                                        float omx, float omy) {

@@ -191,6 +191,65 @@ class Engine:
             ops.set_rows(x, T + 1, self.w.f32["readout_token"].view(-1), B * N)
         return x
 
+    def embed_tracks_from_maps(self, tracks_2d, depth_map, dino_map, video_hw, intrinsics=None):
+        """The inference pipeline's lift -> sample -> embed (inference.py:543-557 + track_autoencoder_3d.py:123-165) without
+        the per-track features: one clip, tracks_2d [N,T,2] px, depth_map [T,H,W,(1)], dino_map [T,Hp,Wp,D] (device f32).
+        Returns (tokens fp32 [N*(T+1), W] with the read-out slot filled, xyz [N,T,3]).
+
+        "Project, then sample": bilinear sampling and the DINO Dense commute, so the patch map is projected once
+        (T*Hp*Wp rows instead of N*T) and each token adds a blend of four projected patch rows in the GEMM epilogue."""
+        cfg, meta = self.cfg, self.w.meta
+        if self.cdt != torch.bfloat16 or meta["coords"] != 3 or cfg.num_frequencies != 32:
+            raise ValueError("embed_tracks_from_maps: bf16 3D path with 32 frequencies only")
+        N, T = tracks_2d.shape[:2]
+        W = meta["W"]
+        wt = self.w.c["embed.Wt"]
+        use_dino = dino_map is not None and meta["has_dino"] and cfg.use_dino
+        use_depth = depth_map is not None and meta["has_depth"] and cfg.use_depth
+        if depth_map is None or not use_dino:
+            raise ValueError("embed_tracks_from_maps needs the depth map (lifting) and the DINO patch map")
+        xyz, _, dfeat = ops.lift_sample(tracks_2d, depth=depth_map, intrinsics=intrinsics, depth_feature_dim=4, want_dino=False)
+        off = meta["fourier_in"]
+        Tm, Hp, Wp, D = dino_map.shape
+        if Tm != T or D != meta["dino_dim"]:
+            raise ValueError(f"dino_map {tuple(dino_map.shape)} does not match T={T}, dino_dim={meta['dino_dim']}")
+        dm = ops.convert(dino_map.view(T * Hp * Wp, D), torch.empty(T * Hp * Wp, D, device=self.dev, dtype=self.cdt))
+        proj = ops.gemm(dm, wt[:, off : off + D])           # [T*Hp*Wp, W] bf16, no bias (added once per token)
+        del dm
+        bias = self.w.f32["embed.b_track"].clone()
+        ops.axpy(bias, self.w.f32["embed.b_dino"])
+        wdep = None
+        if use_depth:
+            ops.axpy(bias, self.w.f32["embed.b_depth"])
+            o2 = off + D
+            wdep = wt[:, o2 : o2 + 3].float().t().contiguous()   # [3, W]: only channels 0..2 of the depth feature are non-zero
+        x = torch.empty(N * (T + 1), W, device=self.dev, dtype=torch.float32)
+        ops.embed_sampled(xyz.view(N * T, 3), tracks_2d.reshape(N * T, 2), dfeat.view(N * T, 4) if use_depth else None, proj, wt,
+                          wdep, bias, x, T, Hp, Wp, video_hw, cfg.num_frequencies, cfg.track_scale_factor)
+        ops.set_rows(x, T + 1, self.w.f32["readout_token"].view(-1), N)
+        return x, xyz
+
+    def encode_from_maps(self, inputs):
+        """encode() for the inference pipeline's raw products (one clip): ``support_tracks_2d`` [N,T,2] px,
+        ``support_tracks_visible`` [N,T,1], ``depth`` [T,H,W,1], ``dino_map`` [T,Hp,Wp,D], ``video_shape`` (T,H,W,3),
+        optional ``intrinsics`` and ``boundary_frame``.  Returns (latents [1,128,latent] f32, support xyz [N,T,3])."""
+        meta, dev = self.w.meta, self.dev
+        tr2 = _as_dev(inputs["support_tracks_2d"], torch.float32, dev)
+        N, T = tr2.shape[:2]
+        vis = _as_dev(inputs["support_tracks_visible"], torch.float32, dev).reshape(1, N, T, 1)
+        depth = _as_dev(inputs["depth"], torch.float32, dev)
+        dino = _as_dev(inputs["dino_map"], torch.float32, dev)
+        _, H, Wv = inputs["video_shape"][:3]
+        boundary = _as_dev(inputs.get("boundary_frame", np.array([T], np.int32)), torch.int32, dev)
+        x, xyz = self.embed_tracks_from_maps(tr2, depth, dino, (H, Wv), inputs.get("intrinsics"))
+        key_mask = ops.build_key_mask(vis, boundary, has_readout=True)
+        st = self.transformer("itt", x, N, T + 1, key_mask, out_rows="first")
+        nl, E = meta["latent_tokens"], meta["E"]
+        lat = self.w.f32["latents_init"].unsqueeze(0).reshape(nl, E).contiguous()
+        lat = self.transformer("t2l", lat, 1, nl, kv=st, Lkv=N)
+        z = ops.gemm(lat, self.w.c["compressor.Wt"], self.w.f32["compressor.b"], out_dtype=torch.float32)
+        return z.view(1, nl, meta["latent_dim"]), xyz
+
     def encode(self, inputs):
         """encode (track_autoencoder_3d.py:190-204 / track_autoencoder.py:234-246) -> [B,128,latent] f32."""
         meta = self.w.meta

@@ -126,6 +126,19 @@ class _ModuleBase:
         eng = self.bind(variables, precision)
         return self._results(eng, eng.decode(latents, decoder_context, noise, discretize), decoder_context)
 
+    def apply_from_maps(self, variables, inputs, *, noise=None, discretize=True, precision="bf16"):
+        """The reference's run_inference model call (inference.py:543-623) fed with the pipeline's RAW products instead of
+        per-track features: ``support_tracks_2d`` [N,T,2] px, ``support_tracks_visible`` [N,T,1], ``depth`` [T,H,W,1],
+        ``dino_map`` [T,Hp,Wp,768], ``video_shape``, ``query_points`` [1,Q,4] (t,x,y,z) (+ ``intrinsics``, ``boundary_frame``).
+        Lifting, DINO / depth sampling and the embedding run fused: the [N,T,768] and [N,T,256] features are
+        never written.  Same result as lifting.lift_and_sample + apply within the bf16 tolerance."""
+        eng = self.bind(variables, precision)
+        with torch.no_grad():
+            latents, _ = eng.encode_from_maps(inputs)
+            ctx = eng.get_decoder_context({"query_points": inputs["query_points"],
+                                           "boundary_frame": inputs.get("boundary_frame", np.array([inputs["support_tracks_2d"].shape[1]], np.int32))})
+            return self._results(eng, eng.decode(latents, ctx, noise, discretize), ctx)
+
     # -- CUDA-graph replay of the forward ---------------------------------------------------------------
     def _graphable(self, inputs, noise, discretize):
         if self.decoder_scan_chunk_size is not None or inputs.get("query_points") is None:

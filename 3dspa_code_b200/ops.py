@@ -109,6 +109,14 @@ def embed_fused(tracks, dino, depth, wt, bias, out, T, num_freq, scale_factor, a
     return out
 
 
+def embed_sampled(xyz, tracks_2d, dfeat, proj, wt, wdep, bias, out, T, Hp, Wp, video_hw, num_freq, scale_factor):
+    """Tokens from track points + a PROJECTED patch map (see spa3d_embed_sampled in include/spa3d_b200.h)."""
+    rows = xyz.shape[0]
+    _call("spa3d_embed_sampled", _p(xyz), _p(tracks_2d), _p(dfeat), _p(proj), _p(wt), _ld(wt), _p(wdep), _p(bias), _p(out), _ld(out),
+          rows, int(T), int(Hp), int(Wp), int(video_hw[0]), int(video_hw[1]), wt.shape[0], int(num_freq), float(scale_factor), _stream())
+    return out
+
+
 def convert(src, dst, out_row_group=0):
     rows, cols = src.shape
     _call("spa3d_convert", _p(src), _ld(src), dt(src), _p(dst), _ld(dst), dt(dst), rows, cols, int(out_row_group), _stream())

@@ -84,6 +84,20 @@ int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth
                       int64_t rows, int T, int dino_dim, int depth_dim, int W, int num_freq,
                       float track_scale_factor, void* stream);
 
+/* K1, "project then sample" form (replaces sample_dino_features_for_tracks + sample_depth_features_for_tracks
+ * + embed_track_pos_visible, inference.py:339-447,543-557 + track_autoencoder_3d.py:123-149, for the inference pipeline):
+ * the DINO projection is linear, so the caller projects the PATCH MAP once per clip (proj = bf16(dino_map) . W_dino^T,
+ * [T*Hp*Wp, W] bf16, through spa3d_gemm) and every (track, frame) row r adds the bilinear blend of four projected patch
+ * rows; the [N,T,768] / [N,T,256] per-track features never exist.
+ *   out[r + r/T + 1] = Fourier(xyz[r], t/T) . Wt[:, 0:256]^T + bias + sum_k w_k(r) proj[patch_k(r)] + dfeat[r,0:3] . wdep
+ * xyz [rows,3] f32 (spa3d_lift_sample), tracks_2d [rows,2] f32 pixels, dfeat [rows,4] f32 = (d, d/10, d_t - d_{t-1}, 0)
+ * (spa3d_lift_sample with Cd = 4) or NULL, wdep [3,W] f32 = rows 0..2 of the depth projection kernel or NULL, Wt the
+ * stacked embedding kernel (only its first 256 columns are read; ldw in elements), bias [W] f32 (sum of the biases in play). */
+int spa3d_embed_sampled(const float* xyz, const float* tracks_2d, const float* dfeat, const void* proj, const void* Wt,
+                        int64_t ldw, const float* wdep, const float* bias, float* out, int64_t ldo, int64_t rows, int T,
+                        int Hp, int Wp, int video_H, int video_W, int W, int num_freq, float track_scale_factor,
+                        void* stream);
+
 /* Row-wise dtype conversion / strided copy: dst[r', 0:cols] = (dst_dtype) src[r, 0:cols],
  * r' = r (+ r/out_row_group + 1 when out_row_group > 0). */
 int spa3d_convert(const void* src, int64_t lds, int src_dtype, void* dst, int64_t ldd,

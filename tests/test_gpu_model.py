@@ -240,3 +240,44 @@ def test_trajan_matches_reference_executed_golden(spa, golden_dir):
         assert e < 1e-4, (name, e)
     lat = model.apply(variables, inp, method="encode", precision="fp32")
     assert rel_err(lat, torch.from_numpy(g["latents"])) < 1e-4
+
+
+def test_forward_from_maps_matches_feature_path_and_oracle(spa):
+    """SURVEY 8f-1: lift -> sample -> embed fused ("project, then sample").  The per-track features are never built;
+    tokens, and the final outputs, agree with (a) the unfused CUDA path fed with lifted features and (b) the oracle
+    (NumPy lifting restatement + torch model restatement) within the bf16 tolerance."""
+    from oracle import lifting as ol
+
+    rs = np.random.RandomState(12)
+    N, T, Q, H, W, Hp, Wp = 70, 150, 6, 20, 24, 5, 6
+    model = spa.TrackAutoEncoder3D()
+    c = om.Config3D()
+    tracks_2d = np.stack([rs.uniform(-2, W + 1, (N, T)), rs.uniform(-2, H + 1, (N, T))], -1).astype(np.float32)
+    depth = rs.uniform(0.5, 4.0, (T, H, W, 1)).astype(np.float32)
+    dino_map = rs.standard_normal((T, Hp, Wp, 768)).astype(np.float32)
+    visible = (rs.uniform(size=(N, T, 1)) < 0.85).astype(np.float32)
+    video_shape = (T, H, W, 3)
+    # the reference pipeline on the CPU oracle: lifted xyz + per-track features
+    xyz = ol.lift_2d_to_3d(tracks_2d, depth)
+    dfe = ol.sample_dino_features_for_tracks(dino_map, tracks_2d, video_shape)
+    zfe = ol.sample_depth_features_for_tracks(depth, tracks_2d)
+    qp = np.concatenate([rs.randint(0, T, (1, Q, 1)).astype(np.float32), rs.uniform(-1, 1, (1, Q, 3)).astype(np.float32)], -1)
+    feat_inputs = {"support_tracks": xyz[None], "support_tracks_visible": visible[None], "query_points": qp,
+                   "boundary_frame": np.array([T], np.int32), "dino_features": dfe[None], "depth_features": zfe[None]}
+    variables = model.init(21, feat_inputs)
+    randomize(variables["params"], 21)
+    maps_inputs = {"support_tracks_2d": tracks_2d, "support_tracks_visible": visible, "depth": depth, "dino_map": dino_map,
+                   "video_shape": video_shape, "query_points": qp}
+    eng = model.bind(variables, "bf16")
+    dev = "cuda"
+    x_f, xyz_dev = eng.embed_tracks_from_maps(torch.from_numpy(tracks_2d).to(dev), torch.from_numpy(depth).to(dev),
+                                              torch.from_numpy(dino_map).to(dev), (H, W))
+    np.testing.assert_array_equal(xyz_dev.cpu().numpy(), xyz)   # lifting stays bit-exact
+    x_u = eng.embed_tracks(torch.from_numpy(xyz[None]).to(dev), torch.from_numpy(dfe[None]).to(dev), torch.from_numpy(zfe[None]).to(dev), readout=True)
+    assert rel_err(x_f, x_u) < 1e-2, rel_err(x_f, x_u)
+    got = model.apply_from_maps(variables, maps_inputs, discretize=False)
+    unf = model.apply(variables, feat_inputs, discretize=False, precision="bf16")
+    ref = oracle_fwd(model, variables["params"], feat_inputs, np.zeros((1, 128, 96), np.float32), False)
+    assert rel_err(got.tracks, unf.tracks) < 2e-2, rel_err(got.tracks, unf.tracks)
+    assert rel_err(got.tracks, ref.tracks) < 2e-2, rel_err(got.tracks, ref.tracks)
+    assert rel_err(got.visible_logits, ref.visible_logits) < 2e-2, rel_err(got.visible_logits, ref.visible_logits)
