@@ -54,11 +54,21 @@ struct EmbedParams {
   const float* wdep;     // [3, W] rows 0..2 of the depth projection kernel (fp32), or null
   int Hp, Wp;
   float scale_w, scale_h;   // Wp / video_W, Hp / video_H (inference.py:367-368)
+  int debug;                // SPA3D_EMBED_DEBUG (timing experiments only): 1 = all gathers hit one patch row, 2 = no stores
 };
 
 template <int NB, int BNH, bool ACAT, bool SAMPLE>   // W = NB * BNH output columns, BNH <= 256; ACAT: also store the bf16 features
 __global__ void __launch_bounds__(THREADS, 1)
 embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p) {
+  // SAMPLE re-balances the warps: its A operand is the four Fourier K-blocks only (no feature streaming), while its epilogue
+  // gathers and blends projected patch rows, so it runs 8 epilogue warps (two per TMEM lane quarter, alternating 32-column
+  // chunks) and 4 producer warps on a 2-stage ring; the streaming variant keeps 4 + 8 on 3 stages.
+  constexpr int NEPI = SAMPLE ? 8 : NUM_EPI;               // epilogue warps 2 .. 2+NEPI-1
+  constexpr int NPW = SAMPLE ? 4 : NUM_PROD_WARPS;         // producer warps
+  constexpr int PT = NPW * 32;                             // producer threads
+  constexpr int RPP = PT / 16;                             // rows per producer pass (16 lanes per row segment)
+  constexpr int PASSES = BM / RPP;
+  constexpr int STAGES = SAMPLE ? 2 : te::STAGES;
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = NB * BNH * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -67,11 +77,11 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_BYTES;
   uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;            // [4 warps][4096]
-  float* smem_bias = reinterpret_cast<float*>(smem_epi + NUM_EPI * 4096);   // [NB*BNH]
+  float* smem_bias = reinterpret_cast<float*>(smem_epi + NEPI * 4096);   // [NB*BNH]
   float* smem_trk = smem_bias + NB * BNH;                                     // [2][128 rows][3] coordinates of a tile
   float* smem_wdep = smem_trk + 2 * BM * 3;                                  // SAMPLE: [3][W] depth-projection rows
-  uint32_t* smem_smp = reinterpret_cast<uint32_t*>(smem_wdep + (SAMPLE ? 3 * NB * BNH : 0));   // SAMPLE: [4 warps][32 rows][12 words]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_smp + (SAMPLE ? NUM_EPI * 32 * 12 : 0));
+  uint32_t* smem_smp = reinterpret_cast<uint32_t*>(smem_wdep + (SAMPLE ? 3 * NB * BNH : 0));   // SAMPLE: [8 warps][32 rows][12 words]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_smp + (SAMPLE ? NEPI * 32 * 12 : 0));
   uint64_t* full_bar = bars;                 // [STAGES]  1 TMA arrive (expect_tx) + 8 producer warps
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // accumulator complete
@@ -91,11 +101,11 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1 + NUM_PROD_WARPS);
+      mbar_init(&full_bar[i], 1 + NPW);
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, NUM_EPI * 32);
+    mbar_init(tempty_bar, NEPI * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -155,9 +165,11 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
         umma_commit(tfull_bar);
       }
     }
-  } else if (warp < 2 + NUM_EPI) {
+  } else if (warp < 2 + NEPI) {
     // ===================== epilogue =====================
     const int quarter = warp & 3;
+    const int c_first = (SAMPLE && warp >= 6) ? 1 : 0;   // SAMPLE: warps 2..5 take the even chunks, 6..9 the odd ones
+    constexpr int c_step = SAMPLE ? 2 : 1;
     uint8_t* slab = smem_epi + (size_t)(warp - 2) * 4096;
     const int cr = lane >> 3, cc = lane & 7;
     int it = 0;
@@ -189,10 +201,11 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
           const Bilin b = bilin_setup(__fmul_rn(xy.x, p.scale_w), __fmul_rn(xy.y, p.scale_h), p.Wp, p.Hp);
           const float omx = __fsub_rn(1.f, b.wx), omy = __fsub_rn(1.f, b.wy);
           const int fb = t * p.Hp * p.Wp;
+          if (p.debug & 1) { w[0] = w[1] = w[2] = w[3] = 0; } else {
           w[0] = (uint32_t)((fb + b.y0 * p.Wp + b.x0) * p.W);
           w[1] = (uint32_t)((fb + b.y0 * p.Wp + b.x1) * p.W);
           w[2] = (uint32_t)((fb + b.y1 * p.Wp + b.x0) * p.W);
-          w[3] = (uint32_t)((fb + b.y1 * p.Wp + b.x1) * p.W);
+          w[3] = (uint32_t)((fb + b.y1 * p.Wp + b.x1) * p.W); }
           w[4] = __float_as_uint(omx * omy);
           w[5] = __float_as_uint(b.wx * omy);
           w[6] = __float_as_uint(omx * b.wy);
@@ -248,17 +261,18 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
           a.y += dq.x * w0.y + dq.y * w1.y + dq.z * w2.y;
           a.z += dq.x * w0.z + dq.y * w1.z + dq.z * w2.z;
           a.w += dq.x * w0.w + dq.y * w1.w + dq.z * w2.w;
-          if (orow[i] != nullptr) *reinterpret_cast<float4*>(orow[i] + col0) = a;
+          if (orow[i] != nullptr && !((p.debug & 2) && a.x != 12345.678f)) *reinterpret_cast<float4*>(orow[i] + col0) = a;
         }
       };
+      static_assert(!SAMPLE || NCH % 2 == 0, "SAMPLE splits the chunks between two warps per quarter");
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
+      for (int c = c_first; c < NCH; c += c_step) {
         uint2 ga[4][4], gb[4][4];
         if constexpr (SAMPLE) gather(c, 0, ga);
         uint32_t r[32];
         tmem_ld32(tbase + (uint32_t)(c * 32), r);
         tmem_ld_wait();
-        if (c == NCH - 1) {
+        if (c + c_step >= NCH) {   // this warp's last read of the accumulator
           tcgen05_fence_before();
           mbar_arrive(tempty_bar);
         }
@@ -292,8 +306,8 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
     // Software pipelined over the flat (tile, K-block) sequence: the 128-bit loads of item i+1 are
     // in flight while item i is converted and written to shared memory (two register buffers), so
     // every producer thread keeps 2 x 8 x 16 B of HBM reads outstanding.
-    const int ptid = threadIdx.x - (2 + NUM_EPI) * 32;   // 0..255
-    const int rsub = ptid >> 4, l16 = ptid & 15;         // 16 lanes per row segment, 16 rows per pass
+    const int ptid = threadIdx.x - (2 + NEPI) * 32;      // 0..PT-1
+    const int rsub = ptid >> 4, l16 = ptid & 15;         // 16 lanes per row segment, RPP rows per pass
     const int64_t my_tiles = blockIdx.x < m_tiles ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     // feature K-blocks: straight-line load / convert code with no data-dependent branch between the
@@ -305,7 +319,7 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
       const int64_t ld = is_dino ? p.Dd : p.Dz;
       const int col = (is_dino ? kb - kb_dino0 : kb - kb_depth0) * 64 + l16 * 4;
 #pragma unroll
-      for (int ps = 0; ps < 8; ++ps) {
+      for (int ps = 0; ps < 8; ++ps) {   // streaming variant: PASSES == 8
         const int64_t r_ = row_base + ps * 16 + rsub;
         const float* ptr = src + (r_ < p.R ? r_ : 0) * ld + col;      // clamped: always a valid address
         v[ps] = __ldcs(reinterpret_cast<const float4*>(ptr));
@@ -348,12 +362,13 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
       if constexpr (SAMPLE) {
         // frame-major tile: the 128 rows are 128 tracks at one frame, T*12 bytes apart
         const int64_t tile = blockIdx.x + tile_iter * gridDim.x;
-        const int tf = (int)(tile / nt_n), n = (int)(tile % nt_n) * BM + (ptid >> 1);
-        if (ptid < 2 * BM) {   // two threads per row: 8 + 4 bytes
-          float* dst = smem_trk + (tile_iter & 1) * (BM * 3) + (ptid >> 1) * 3;
+        const int tf = (int)(tile / nt_n), n = (int)(tile % nt_n) * BM + ptid;
+        if (ptid < BM) {   // one thread per row (PT == BM): three 4-byte copies
+          float* dst = smem_trk + (tile_iter & 1) * (BM * 3) + ptid * 3;
           const float* src = p.tracks + ((int64_t)(n < Ntrk ? n : 0) * p.T + tf) * 3;
-          if (ptid & 1) __pipeline_memcpy_async(dst + 2, src + 2, 4);
-          else { __pipeline_memcpy_async(dst, src, 4); __pipeline_memcpy_async(dst + 1, src + 1, 4); }
+          __pipeline_memcpy_async(dst, src, 4);
+          __pipeline_memcpy_async(dst + 1, src + 1, 4);
+          __pipeline_memcpy_async(dst + 2, src + 2, 4);
         }
         __pipeline_commit();
         return;
@@ -380,8 +395,8 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
       const float ph = l16 >= 8 ? 1.57079632679489661923f : 0.f;
       const float s0 = p.fs[f0], s1 = p.fs[f0 + 1], s2 = p.fs[f0 + 2], s3 = p.fs[f0 + 3];
 #pragma unroll
-      for (int ps = 0; ps < 8; ++ps) {
-        const int row = ps * 16 + rsub;
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int row = ps * RPP + rsub;
         int64_t r_ = row_base + row;
         float x;
         if constexpr (SAMPLE) {
@@ -430,7 +445,7 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       prefetch_tile(ti + 1);
       __pipeline_wait_prior(0);                              // this tile's coordinates have landed ...
-      asm volatile("bar.sync 2, 256;" ::: "memory");        // ... for every producer warp
+      asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");   // ... for every producer warp
       if (ti + 1 < my_tiles) load_tracks(ti + 1);           // other half of the double buffer
       for (int kb = 0; kb < 4; ++kb) fourier(ti, kb);
       for (int kb = 4; kb < num_kb; kb += 2) {
@@ -457,8 +472,9 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
 
 template <int NB, int BNH, bool ACAT, bool SAMPLE = false>
 static int launch_v(const CUtensorMap& tmB, const EmbedParams& p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + NB * BNH * BK * 2) + NUM_EPI * 4096 + NB * BNH * 4 + 2 * BM * 3 * 4 + 256 + 1024 +
-                       (SAMPLE ? 3 * NB * BNH * 4 + NUM_EPI * 32 * 12 * 4 : 0);
+  constexpr int NEPI = SAMPLE ? 8 : NUM_EPI;
+  constexpr int SMEM = (SAMPLE ? 2 : STAGES) * (BM * BK * 2 + NB * BNH * BK * 2) + NEPI * 4096 + NB * BNH * 4 + 2 * BM * 3 * 4 + 256 + 1024 +
+                       (SAMPLE ? 3 * NB * BNH * 4 + NEPI * 32 * 12 * 4 : 0);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(embed_fused_kernel<NB, BNH, ACAT, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -504,7 +520,7 @@ int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth
   EmbedParams p;
   p.tracks = tracks; p.dino = dino; p.depth = depth; p.bias = bias; p.out = out; p.ldo = ldo; p.R = rows;
   p.acat = reinterpret_cast<bf16*>(a_cat); p.lda = lda;
-  p.proj = nullptr; p.trk2d = nullptr; p.dfeat = nullptr; p.wdep = nullptr; p.Hp = p.Wp = 0; p.scale_w = p.scale_h = 0.f;
+  p.proj = nullptr; p.trk2d = nullptr; p.dfeat = nullptr; p.wdep = nullptr; p.Hp = p.Wp = 0; p.scale_w = p.scale_h = 0.f; p.debug = 0;
   SPA3D_REQUIRE(a_cat == nullptr || (lda % 4 == 0 && (reinterpret_cast<uintptr_t>(a_cat) & 7) == 0), "embed_fused: a_cat must be 8-byte aligned");
   p.T = T; p.Dd = dino_dim; p.Dz = depth_dim; p.W = W; p.inv_scale = (float)(1.0 / (double)track_scale_factor); p.inv_T = (float)(1.0 / (double)T);
   for (int i = 0; i < 32; ++i) p.fs[i] = (float)pow(2.0, (double)i / 3.0);
@@ -551,6 +567,7 @@ int spa3d_embed_sampled(const float* xyz, const float* tracks_2d, const float* d
   p.T = T; p.Dd = 0; p.Dz = 0; p.W = W; p.inv_scale = (float)(1.0 / (double)track_scale_factor); p.inv_T = (float)(1.0 / (double)T);
   for (int i = 0; i < 32; ++i) p.fs[i] = (float)pow(2.0, (double)i / 3.0);
   p.l2_prefetch = 0;
+  { const char* e = getenv("SPA3D_EMBED_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.proj = reinterpret_cast<const bf16*>(proj); p.trk2d = tracks_2d; p.dfeat = dfeat; p.wdep = wdep; p.Hp = Hp; p.Wp = Wp;
   p.scale_w = (float)((double)Wp / (double)video_W);
   p.scale_h = (float)((double)Hp / (double)video_H);

@@ -22,7 +22,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import ops, params as P
+from . import ops, params as P, rng
 
 
 @dataclass
@@ -81,6 +81,7 @@ class Engine:
         self.fused_embed = True     # bf16 path: fused Fourier + feature conversion + first projection (K1)
         self.stream_chunk = 256     # support tracks per host->device pipeline stage (0 = one-shot upload)
         self._copy_stream = None
+        self._noise_cache = None    # ((B, tokens, dim, layout), device tensor) of the default quantiser noise
         self._stage = {}            # (input key, slot) -> persistent device staging buffer
         self.dev = weights.f32["latents_init"].device
 
@@ -385,10 +386,12 @@ class Engine:
         B, nl, ld_ = latents.shape
         if discretize:
             if noise is None:
-                raise ValueError(
-                    "discretize=True needs the explicit `noise` tensor U[0,1) of shape [B,%d,%d]: the reference draws it "
-                    "from jax.random.uniform(PRNGKey(0)), which cannot be reproduced without JAX (DESIGN.md)" % (nl, ld_)
-                )
+                # the reference's own draw: jax.random.uniform(PRNGKey(0), latents.shape), the same tensor on every call
+                # (track_autoencoder_3d.py:254-257); Threefry restated in rng.py, counter layout chosen on the module
+                key = (B, nl, ld_, getattr(cfg, "noise_layout", "original"))
+                if self._noise_cache is None or self._noise_cache[0] != key:
+                    self._noise_cache = (key, torch.from_numpy(rng.jax_uniform(0, (B, nl, ld_), key[3])).to(dev))
+                noise = self._noise_cache[1]
             noise = _as_dev(noise, torch.float32, dev)
         zq = ops.quantize_fwd(latents.reshape(B * nl, ld_), noise.reshape(B * nl, ld_) if discretize else None, discretize)
         zc = zq if self.cdt == torch.float32 else ops.convert(zq, torch.empty_like(zq, dtype=self.cdt))

@@ -251,6 +251,51 @@ def run_lifting_leg(spa, dev):
             "points_per_s": N * T / (ms * 1e-3)}
 
 
+def run_pipeline_leg(spa, model, variables, dev):
+    """the inference pipeline's lift -> sample -> embed stage (inference.py:543-557 + track_autoencoder_3d.py:123-149)
+    as K0 + K1 with the per-track features in HBM, against the fused "project, then sample" form (no per-track features)."""
+    eng = model.bind(variables, "bf16", dev)
+    ops = spa.ops
+    H, W, Hp, Wp = 518, 518, 37, 37
+    g = torch.Generator(device=dev).manual_seed(5)
+    depth = torch.rand(T, H, W, 1, generator=g, device=dev) * 9.5 + 0.5
+    dino = torch.randn(T, Hp, Wp, 768, generator=g, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {"workload": "lift + DINO/depth sampling + track embedding for N tracks x 150 frames, 518x518 video, 37x37x768 patch map, bf16 path",
+           "l2": "flushed between repetitions"}
+    for N in (2048, 4096):
+        tracks = (torch.rand(N, T, 2, generator=g, device=dev) * (W + 12) - 6).contiguous()
+
+        def unfused():
+            xyz, df, zf = ops.lift_sample(tracks, depth=depth, dino=dino, video_hw=(H, W))
+            return eng.embed_tracks(xyz[None], df[None], zf[None], readout=True)
+
+        def fused():
+            return eng.embed_tracks_from_maps(tracks, depth, dino, (H, W))[0]
+
+        res = {}
+        for name, fn in (("unfused_ms", unfused), ("fused_ms", fused)):
+            for _ in range(2):
+                fn()
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                y = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+                del y
+            res[name] = sorted(ts)[len(ts) // 2]
+        a, b = unfused(), fused()
+        res["max_rel_diff"] = float((a - b).abs().max() / a.abs().max())
+        res["feature_bytes_not_moved"] = int(N * T * 1024 * 4 * 2)   # [N,T,768] + [N,T,256] fp32, written by K0 and read by K1
+        out[f"tracks_{N}"] = res
+        del a, b, tracks
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -414,13 +459,17 @@ def run_ours(args):
     if not args.no_train:
         torch.cuda.empty_cache()
         train = run_train_leg(args, spa, model, variables, world, rank, dev, barrier)
+    pipeline = None
     if rank == 0 and not args.no_train:
         lifting = run_lifting_leg(spa, dev)
+        pipeline = run_pipeline_leg(spa, model, variables, dev)
     if rank == 0:
         if train is not None:
             line["train"] = train
         if lifting is not None:
             line["lifting"] = lifting
+        if pipeline is not None:
+            line["pipeline_lift_embed"] = pipeline
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -101,3 +101,39 @@ def test_split_matches_reference_fixture(spa, golden_dir, seed):
     np.random.seed(seed)  # seed=None follows the global legacy stream exactly like the reference
     b2 = spa.data.prepare_3d_batch(ex, S, Q, T, seed=None)
     np.testing.assert_array_equal(b2["query_points"], b["query_points"])
+
+
+def test_default_quantiser_noise_is_the_jax_stream(spa):
+    """rng.jax_uniform == jax.random.uniform(PRNGKey(seed), shape): Random123 block vectors, the documented scalar draw and the
+    jax quickstart's random.normal(key(0), (10,)) (a function of the same uniform bits) for both counter layouts; the product
+    generator and the oracle restatement (written separately) agree bit for bit."""
+    import importlib
+
+    from scipy.special import erfinv
+
+    from oracle import threefry as tf
+
+    rng = importlib.import_module("3dspa_code_b200.rng")
+    kat = [((0, 0), (0, 0), (0x6B200159, 0x99BA4EFE)),
+           ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+           ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]
+    for key, ctr, want in kat:
+        a, b = rng.threefry2x32(key[0], key[1], np.uint32([ctr[0]]), np.uint32([ctr[1]]))
+        assert (int(a[0]), int(b[0])) == want
+        a, b = tf.threefry2x32(key, np.uint32([ctr[0]]), np.uint32([ctr[1]]))
+        assert (int(a[0]), int(b[0])) == want
+    assert rng.jax_uniform(0, ()) == np.float32(0.41845703)
+    quickstart = {
+        "original": [-0.3721109, 0.26423115, -0.18252768, -0.7368197, -0.44030377, -0.1521442, -0.67135346, -0.5908641, 0.73168886, 0.5673026],
+        "partitionable": [1.6226422, 2.0252647, -0.43359444, -0.07861735, 0.1760909, -0.97208923, -0.49529874, 0.4943786, 0.6643493, -0.9501635],
+    }
+    lo = np.nextafter(np.float32(-1), np.float32(0))
+    for layout, want in quickstart.items():
+        b = rng.bits(0, 10, layout)
+        f = ((b >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1)
+        u = np.maximum(lo, f * (np.float32(1) - lo) + lo)
+        np.testing.assert_allclose(np.sqrt(2.0) * erfinv(u.astype(np.float64)), want, rtol=2e-6, atol=2e-7)
+        for shape in ((), (3,), (2, 128, 96), (5, 7)):
+            np.testing.assert_array_equal(rng.jax_uniform(0, shape, layout), tf.uniform(0, shape, layout == "partitionable"))
+    u = rng.jax_uniform(0, (2, 128, 96))
+    assert u.dtype == np.float32 and 0.0 <= u.min() and u.max() < 1.0 and abs(float(u.mean()) - 0.5) < 0.01

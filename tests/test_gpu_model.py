@@ -281,3 +281,25 @@ def test_forward_from_maps_matches_feature_path_and_oracle(spa):
     assert rel_err(got.tracks, unf.tracks) < 2e-2, rel_err(got.tracks, unf.tracks)
     assert rel_err(got.tracks, ref.tracks) < 2e-2, rel_err(got.tracks, ref.tracks)
     assert rel_err(got.visible_logits, ref.visible_logits) < 2e-2, rel_err(got.visible_logits, ref.visible_logits)
+
+
+def test_default_noise_is_the_reference_draw(spa):
+    """apply() without ``noise`` regenerates jax.random.uniform(PRNGKey(0), [B,128,96]) (track_autoencoder_3d.py:254-257)."""
+    import importlib
+
+    rng = importlib.import_module("3dspa_code_b200.rng")
+    c = small_cfg()
+    model = spa.TrackAutoEncoder3D(**{k: getattr(c, k) for k in om.Config3D.__dataclass_fields__})
+    inp, _ = make_inputs(c, B=2, N=8, Q=5)
+    variables = model.init(2, inp, arch=SMALL_ARCH)
+    a = model.apply(variables, inp, precision="fp32")
+    for layout in ("original", "partitionable"):
+        model.noise_layout = layout
+        b = model.apply(variables, inp, precision="fp32")
+        n = rng.jax_uniform(0, (2, c.num_latent_tokens, c.latent_token_dim), layout)
+        e = model.apply(variables, inp, noise=n, precision="fp32")
+        assert torch.equal(b.tracks, e.tracks)
+        if layout == "original":
+            assert torch.equal(a.tracks, b.tracks)
+        else:
+            assert not torch.equal(a.tracks, b.tracks)
