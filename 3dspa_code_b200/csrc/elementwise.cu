@@ -866,6 +866,28 @@ int head_rmsnorm_fwd_impl(void* buf, int64_t ld, int dtype, const float* scale, 
   return check_launch("head_rmsnorm_fwd");
 }
 
+// evaluate_tapvid3d.py:39-59: predictions [Q,T,C] / logits [Q,T] -> TAPVid-3D order [T,Q,C], occluded = logit <= 0;
+// optional per-point reconstruction error |pred - target|_2 in the same [T,Q] order (the visualiser's coords_score).
+__global__ void to_tapvid3d_kernel(const float* __restrict__ tracks, const float* __restrict__ logits,
+                                   const float* __restrict__ target, float* __restrict__ out_tracks,
+                                   uint8_t* __restrict__ out_occ, float* __restrict__ out_score, int64_t Q, int T, int C) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // output order: t-major
+  if (idx >= Q * T) return;
+  const int64_t t = idx / Q, q = idx % Q;
+  const int64_t src = q * T + t;
+  float err = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = tracks[src * C + c];
+    out_tracks[idx * C + c] = v;
+    if (out_score != nullptr) {
+      const float d = v - target[src * C + c];
+      err = fmaf(d, d, err);
+    }
+  }
+  out_occ[idx] = logits[src] <= 0.f ? 1 : 0;
+  if (out_score != nullptr) out_score[idx] = sqrtf(err);
+}
+
 }  // namespace spa3d
 
 using namespace spa3d;
@@ -1093,6 +1115,17 @@ int spa3d_split_outputs(const float* head_out, float* tracks, float* visible_log
   SPA3D_REQUIRE(coords == 2 || coords == 3, "split_outputs: coords must be 2 or 3");
   split_outputs_kernel<<<blocks_for(rows * T, 256), 256, 0, (cudaStream_t)stream>>>(head_out, tracks, visible_logits, certain_logits, rows, T, coords);
   return check_launch("split_outputs");
+}
+
+int spa3d_to_tapvid3d(const float* tracks, const float* visible_logits, const float* target_tracks, float* out_tracks,
+                      uint8_t* out_occluded, float* out_score, int64_t Q, int T, int coords, void* stream) {
+  if (Q == 0 || T == 0) return 0;
+  SPA3D_REQUIRE(tracks && visible_logits && out_tracks && out_occluded, "to_tapvid3d: NULL operand");
+  SPA3D_REQUIRE(coords >= 1 && coords <= 4, "to_tapvid3d: coords must be 1..4");
+  SPA3D_REQUIRE((out_score == nullptr) || (target_tracks != nullptr), "to_tapvid3d: a score needs target tracks");
+  spa3d::to_tapvid3d_kernel<<<blocks_for(Q * T, 256), 256, 0, (cudaStream_t)stream>>>(tracks, visible_logits, target_tracks, out_tracks,
+                                                                                     out_occluded, out_score, Q, T, coords);
+  return check_launch("to_tapvid3d");
 }
 
 int spa3d_loss_fwd(const float* head_out, const float* target_tracks, const float* target_vis,

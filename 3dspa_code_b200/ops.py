@@ -304,6 +304,16 @@ def split_outputs(head_out, T, coords=3):
     return tracks, vis, cert
 
 
+def to_tapvid3d(tracks, visible_logits, target_tracks=None):
+    """[Q,T,C], [Q,T(,1)] -> ([T,Q,C] f32, [T,Q] bool occluded, [T,Q] f32 reconstruction error or None)."""
+    Q, T, C = tracks.shape
+    out_t = torch.empty(T, Q, C, device=tracks.device, dtype=torch.float32)
+    occ = torch.empty(T, Q, device=tracks.device, dtype=torch.uint8)
+    score = torch.empty(T, Q, device=tracks.device, dtype=torch.float32) if target_tracks is not None else None
+    _call("spa3d_to_tapvid3d", _p(tracks), _p(visible_logits), _p(target_tracks), _p(out_t), _p(occ), _p(score), int(Q), int(T), int(C), _stream())
+    return out_t, occ.bool(), score
+
+
 def loss_fwd(head_out, target_tracks, target_vis, sums, T):
     _call("spa3d_loss_fwd", _p(head_out), _p(target_tracks), _p(target_vis), _p(sums), head_out.shape[0], T, _stream())
     return sums

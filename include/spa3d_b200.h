@@ -253,6 +253,11 @@ int spa3d_decoder_tokens_bwd(const void* d_tokens, int tok_dtype, const int32_t*
  * head_out [rows, 4*T] f32 (x|y|z|vis blocks) -> tracks [rows,T,3], visible_logits [rows,T]. */
 int spa3d_split_outputs(const float* head_out, float* tracks, float* visible_logits,
                         int64_t rows, int T, int coords, float* certain_logits, void* stream);
+/* evaluate_tapvid3d.py:39-59 (convert_predictions_to_tapvid3d_format) for one clip: tracks [Q,T,coords], visible_logits [Q,T]
+ * -> out_tracks [T,Q,coords], out_occluded [T,Q] (1 where logit <= 0).  With target_tracks [Q,T,coords] and out_score [T,Q] non-NULL it
+ * also writes the per-point reconstruction error |pred - target|_2 (the coords_score array visualize.py:186 consumes). */
+int spa3d_to_tapvid3d(const float* tracks, const float* visible_logits, const float* target_tracks, float* out_tracks,
+                      uint8_t* out_occluded, float* out_score, int64_t Q, int T, int coords, void* stream);
 /* sums[0] += sum |pred-tgt|*vis, sums[1] += sum BCE(logit,vis), sums[2] += sum vis.
  * (sums must be zeroed by the caller; the three scalars of compute_loss_3d follow on host or
  * after an all-reduce of sums across ranks.) */

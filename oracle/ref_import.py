@@ -89,8 +89,15 @@ def _install_stubs():
         "chex": _stub_module("chex"),
         "wandb": _stub_module("wandb"),
         "transformers": _stub_module("transformers"),
+        "tapnet": _stub_module("tapnet"),
+        "tapnet.tapvid3d": _stub_module("tapnet.tapvid3d"),
+        "tapnet.tapvid3d.evaluation": _stub_module("tapnet.tapvid3d.evaluation"),
+        "tapnet.tapvid3d.splits": _stub_module("tapnet.tapvid3d.splits"),
     }
-    for opt in ("cv2", "einops", "absl"):
+    # absl: always inert - the reference scripts re-define the same flag names, which the real absl rejects
+    for name in ("absl", "absl.app", "absl.flags", "absl.logging"):
+        stubs[name] = _stub_module(name)
+    for opt in ("cv2", "einops"):
         try:
             __import__(opt)
         except Exception:  # pragma: no cover

@@ -9,6 +9,7 @@ input/output pairs:
   lifting_edges.npz   same, integer pixels, out-of-range points, 1x1 maps, custom intrinsics
   split_small.npz     data_loader.py:56-110 prepare_3d_batch after np.random.seed(seed)
   unflatten.npz       inference.py:450-461  _unflatten_params (stored as flat keys + expected paths)
+  tapvid3d_format.npz evaluate_tapvid3d.py:39-59  convert_predictions_to_tapvid3d_format
 """
 import os
 import sys
@@ -77,6 +78,22 @@ def main():
             out[f"seed{seed}/{k}"] = np.asarray(v)
     out["meta"] = np.array([ntot, S, Q, T])
     np.savez_compressed(os.path.join(HERE, "split_small.npz"), **out)
+
+    # evaluate_tapvid3d.py:39-59 convert_predictions_to_tapvid3d_format (pure NumPy)
+    ev = ref_import.load("evaluate_tapvid3d")
+
+    class Pred:
+        pass
+
+    pr = Pred()
+    pr.tracks = rs.standard_normal((2, 7, 5, 3)).astype(np.float32)
+    pr.visible_logits = rs.standard_normal((2, 7, 5, 1)).astype(np.float32)
+    pr.visible_logits[0, 1, 2, 0] = 0.0      # logit == 0 counts as occluded (<= 0)
+    pr.visible_logits[0, 3, 0, 0] = -0.0
+    qp = rs.standard_normal((2, 7, 4)).astype(np.float32)
+    tr, occ = ev.convert_predictions_to_tapvid3d_format(pr, qp)
+    np.savez_compressed(os.path.join(HERE, "tapvid3d_format.npz"), tracks=pr.tracks, visible_logits=pr.visible_logits, query_points=qp,
+                        pred_tracks=tr, pred_occluded=occ)
 
     flat = {"a/b/kernel": np.arange(6.0).reshape(2, 3), "a/b/bias": np.zeros(3), "a/c/scale": np.ones(2), "top": np.array(3.0)}
     nested = inf._unflatten_params(flat)

@@ -63,3 +63,13 @@ def test_split_is_a_partition():
     sup, qry, frames = split.split_indices(100, 60, 30, 17, seed=3)
     assert len(set(sup) | set(qry)) == 90 and not (set(sup) & set(qry))
     assert frames.min() >= 0 and frames.max() < 17
+
+
+def test_tapvid3d_format_bit_exact(golden_dir):
+    from oracle import evaluation as oe
+
+    g = np.load(os.path.join(golden_dir, "tapvid3d_format.npz"))
+    tr, occ = oe.convert_predictions_to_tapvid3d_format(g["tracks"], g["visible_logits"])
+    np.testing.assert_array_equal(tr, g["pred_tracks"])
+    np.testing.assert_array_equal(occ, g["pred_occluded"])
+    assert occ.dtype == bool and occ[2, 1] and occ[0, 3]          # logits 0.0 and -0.0 are occluded
