@@ -296,6 +296,44 @@ def run_pipeline_leg(spa, model, variables, dev):
     return out
 
 
+def run_sweep_leg(spa, model, variables, dev, world):
+    """cfg5: video-realism scoring sweep - 1024 clips of 4096 support / 1024 query tracks, clips sharded over the GPUs with no
+    collective.  Per clip: lift + sample + embed from the clip's depth / DINO maps (fused path), encode, decode the held-out
+    query tracks, per-point reconstruction error -> one realism score.  A bounded sample of clips is timed per rank."""
+    ev = importlib.import_module("3dspa_code_b200.evaluation")
+    lifting = importlib.import_module("3dspa_code_b200.lifting")
+    S5, Q5, H, W, Hp, Wp, clips = 4096, 1024, 518, 518, 37, 37, 3
+    g = torch.Generator(device=dev).manual_seed(6)
+    depth = torch.rand(T, H, W, 1, generator=g, device=dev) * 9.5 + 0.5
+    dino = torch.randn(T, Hp, Wp, 768, generator=g, device=dev)
+    scores = []
+
+    def one_clip(seed):
+        gg = torch.Generator(device=dev).manual_seed(seed)
+        tr2 = (torch.rand(S5 + Q5, T, 2, generator=gg, device=dev) * (W - 1)).contiguous()
+        vis = (torch.rand(S5, T, 1, generator=gg, device=dev) < 0.9).float()
+        q_xyz = lifting.lift_2d_to_3d(tr2[S5:], depth, as_numpy=False)                      # held-out query tracks, lifted
+        qt = torch.randint(0, T, (Q5,), generator=gg, device=dev)
+        qp = torch.cat([qt[:, None].float(), q_xyz[torch.arange(Q5, device=dev), qt]], -1)[None]
+        inputs = {"support_tracks_2d": tr2[:S5], "support_tracks_visible": vis, "depth": depth, "dino_map": dino,
+                  "video_shape": (T, H, W, 3), "query_points": qp}
+        pred = model.apply_from_maps(variables, inputs, precision="bf16")
+        score = ev.reconstruction_score(pred, {"query_tracks": q_xyz[None]}, as_numpy=False)
+        return float(score.mean().item())                                                   # the clip's score, read back
+
+    one_clip(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(clips):
+        scores.append(one_clip(100 + i))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / clips
+    return {"workload": "cfg5: realism-scoring sweep, 4096 support / 1024 query tracks per clip, maps in HBM, fused lift+embed, bf16",
+            "ms_per_clip": ms, "clips_per_s_per_gpu": 1e3 / ms, "clips_timed": clips,
+            "sweep_1024_clips_s": 1024 / world * ms * 1e-3, "n_gpus": world, "collective": "none", "mean_score": sum(scores) / len(scores)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -459,10 +497,11 @@ def run_ours(args):
     if not args.no_train:
         torch.cuda.empty_cache()
         train = run_train_leg(args, spa, model, variables, world, rank, dev, barrier)
-    pipeline = None
+    pipeline = sweep = None
     if rank == 0 and not args.no_train:
         lifting = run_lifting_leg(spa, dev)
         pipeline = run_pipeline_leg(spa, model, variables, dev)
+        sweep = run_sweep_leg(spa, model, variables, dev, world)
     if rank == 0:
         if train is not None:
             line["train"] = train
@@ -470,6 +509,8 @@ def run_ours(args):
             line["lifting"] = lifting
         if pipeline is not None:
             line["pipeline_lift_embed"] = pipeline
+        if sweep is not None:
+            line["sweep"] = sweep
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

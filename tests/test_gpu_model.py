@@ -326,3 +326,33 @@ def test_tapvid3d_adapter_matches_reference_fixture(spa, golden_dir):
     tgt = np.random.RandomState(0).standard_normal(g["tracks"].shape).astype(np.float32)
     sc = ev.reconstruction_score(Pred, {"query_tracks": tgt})
     np.testing.assert_allclose(sc, oe.reconstruction_score(g["tracks"], tgt), rtol=1e-6, atol=1e-7)
+
+
+def test_sweep_clip_shape_properties(spa):
+    """BASELINE config 5 clip shape (4096 support / 1024 query tracks, 518x518 video, 37x37 patch map) through the fused
+    maps path: finite, invariant to the order of the support tracks, and the realism score has the visualiser's layout."""
+    import importlib
+
+    ev = importlib.import_module("3dspa_code_b200.evaluation")
+    lifting = importlib.import_module("3dspa_code_b200.lifting")
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(3)
+    S5, Q5, T, H, W = 4096, 1024, 150, 518, 518
+    model = spa.TrackAutoEncoder3D()
+    variables = model.init(4, {"dino_features": 1, "depth_features": 1})
+    depth = torch.rand(T, H, W, 1, generator=g, device=dev) * 9.5 + 0.5
+    dino = torch.randn(T, 37, 37, 768, generator=g, device=dev)
+    tr2 = (torch.rand(S5 + Q5, T, 2, generator=g, device=dev) * (W - 1)).contiguous()
+    vis = (torch.rand(S5, T, 1, generator=g, device=dev) < 0.9).float()
+    q_xyz = lifting.lift_2d_to_3d(tr2[S5:], depth, as_numpy=False)
+    qp = torch.cat([torch.zeros(Q5, 1, device=dev), q_xyz[:, 0]], -1)[None]
+    inputs = {"support_tracks_2d": tr2[:S5], "support_tracks_visible": vis, "depth": depth, "dino_map": dino,
+              "video_shape": (T, H, W, 3), "query_points": qp}
+    a = model.apply_from_maps(variables, inputs)
+    assert a.tracks.shape == (1, Q5, T, 3) and torch.isfinite(a.tracks).all() and torch.isfinite(a.visible_logits).all()
+    perm = torch.randperm(S5, generator=g, device=dev)
+    inputs2 = dict(inputs, support_tracks_2d=tr2[:S5][perm].contiguous(), support_tracks_visible=vis[perm].contiguous())
+    b = model.apply_from_maps(variables, inputs2)
+    assert rel_err(b.tracks, a.tracks) < 2e-2, rel_err(b.tracks, a.tracks)
+    sc = ev.reconstruction_score(a, {"query_tracks": q_xyz[None]}, as_numpy=False)
+    assert sc.shape == (T, Q5, 1) and torch.isfinite(sc).all()
