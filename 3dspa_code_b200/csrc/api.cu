@@ -90,7 +90,7 @@ int spa3d_gemm_rmsnorm(const void* A, int64_t lda, const void* Wt, int64_t ldw, 
 
 int spa3d_gemm_gelu(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
                     const float* bias, void* Z, int64_t ldz, void* H, int64_t ldh, int64_t M, int N, int K,
-                    int impl, void* stream) {
+                    int save_grad, int impl, void* stream) {
   using namespace spa3d;
   cudaStream_t st = (cudaStream_t)stream;
   SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_gelu: bad shape");
@@ -98,9 +98,10 @@ int spa3d_gemm_gelu(const void* A, int64_t lda, const void* Wt, int64_t ldw, int
   bool tc_ok = (a_dtype == SPA3D_BF16) && gemm_tcgen05_applicable(A, lda, Wt, ldw, M, N, K) &&
                (reinterpret_cast<uintptr_t>(Z) & 15) == 0 && ldz % 8 == 0;
   if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_gelu: tcgen05 path not applicable");
+  if (save_grad) SPA3D_REQUIRE(tc_ok && impl != SPA3D_GEMM_SIMT, "gemm_gelu: the gelu'(z) side output exists on the tcgen05 path only");
   if (impl != SPA3D_GEMM_SIMT && tc_ok)
     return gemm_tcgen05(A, lda, Wt, ldw, bias, SPA3D_ACT_GELU_TANH, nullptr, 0, 0, H, ldh, a_dtype, M, N, K, nullptr, st,
-                        0, Z, ldz);
+                        0, Z, ldz, save_grad ? 2 : 1);
   int rc = spa3d_gemm(A, lda, Wt, ldw, a_dtype, bias, 0, nullptr, 0, 0, Z, ldz, a_dtype, M, N, K,
                       impl == SPA3D_GEMM_SIMT ? SPA3D_GEMM_SIMT : SPA3D_GEMM_AUTO, stream);
   if (rc) return rc;
@@ -109,7 +110,7 @@ int spa3d_gemm_gelu(const void* A, int64_t lda, const void* Wt, int64_t ldw, int
 
 int spa3d_gemm_gelu_bwd(const void* dH_in, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
                         const void* Z, int64_t ldz, void* dZ, int64_t lddz, int64_t M, int N, int K,
-                        int impl, void* stream) {
+                        int z_is_grad, int impl, void* stream) {
   using namespace spa3d;
   cudaStream_t st = (cudaStream_t)stream;
   SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_gelu_bwd: bad shape");
@@ -119,8 +120,9 @@ int spa3d_gemm_gelu_bwd(const void* dH_in, int64_t lda, const void* Wt, int64_t 
                (reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && lddz % 8 == 0;
   if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_gelu_bwd: tcgen05 path not applicable");
   if (impl != SPA3D_GEMM_SIMT && tc_ok)
-    return gemm_tcgen05(dH_in, lda, Wt, ldw, nullptr, 0, Z, ldz, a_dtype, dZ, lddz, a_dtype, M, N, K, nullptr, st, 1,
-                        nullptr, 0);
+    return gemm_tcgen05(dH_in, lda, Wt, ldw, nullptr, 0, Z, ldz, a_dtype, dZ, lddz, a_dtype, M, N, K, nullptr, st,
+                        z_is_grad ? 2 : 1, nullptr, 0);
+  SPA3D_REQUIRE(!z_is_grad, "gemm_gelu_bwd: the saved-derivative form exists on the tcgen05 path only");
   int rc = spa3d_gemm(dH_in, lda, Wt, ldw, a_dtype, nullptr, 0, nullptr, 0, 0, dZ, lddz, a_dtype, M, N, K,
                       impl == SPA3D_GEMM_SIMT ? SPA3D_GEMM_SIMT : SPA3D_GEMM_AUTO, stream);
   if (rc) return rc;

@@ -26,6 +26,8 @@
 // Fused per-head RMSNorm (attention.py:166-167): BN/2 is a multiple of the head width, so every
 // epilogue thread holds whole heads of its row in registers: q/k normalisation (+ q/sqrt(Dh)) is a
 // sum of squares and a scale on values already loaded from TMEM.
+#include <type_traits>
+
 #include "tc_ptx.cuh"
 
 namespace spa3d {
@@ -72,8 +74,9 @@ struct EpiParams {
   const float* scale_k;
   float q_mul;
   float* rstd_out;   // [M, (q_cols+k_cols)/DH] or null
-  int aux_pre;       // EPI_TMA + GELU: also store the pre-activation (bf16) through the aux tensor map
-  int res_op;        // EPI_DIRECT: 0 = C = f(acc) + residual; 1 = C = acc * gelu'(residual) (residual = saved pre-activation)
+  int aux_pre;       // EPI_TMA + GELU: second bf16 output through the aux tensor map: 1 = the pre-activation z, 2 = gelu'(z)
+  int res_op;        // EPI_DIRECT: 0 = C = f(acc) + residual; 1 = C = acc * gelu'(residual) (residual = saved pre-activation);
+                     //             2 = C = acc * residual (residual = gelu'(z) saved by the forward GEMM)
   int atomic_add;    // EPI_DIRECT, fp32 C: C += tile with red.global.add.v4.f32 (split-K weight gradients)
   int debug_skip;    // SPA3D_GEMM_SKIP_EPI=1: accumulators are drained but nothing is computed or stored
 };
@@ -365,10 +368,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           const int col0 = colbase + c * 32;
           if (col0 < N && !ep.debug_skip) {
-            uint8_t* srow = slab + lane * 128;
+            const uint32_t slab_s = smem_u32(slab);
+            const uint32_t srow_s = slab_s + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) sts128(srow_s + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
             __syncwarp();
             float4 bcur = bq[0];
 #pragma unroll
@@ -380,47 +383,100 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int64_t cstep = 4 * ep.ldc * esz_c;
             const int rows_ok = col < N ? (int)min((int64_t)32, M - row0) : 0;   // rows of this chunk inside the matrix
             // row 4i + cr sits at chunk cc ^ ((4i + cr) & 7) = cc ^ cr ^ 4(i & 1): odd passes flip 64 bytes
-            const uint8_t* sp = slab + cr * 128 + ((cc ^ cr) << 4);
+            const uint32_t sp = slab_s + cr * 128 + ((cc ^ cr) << 4);
             const int odd_off = (cc & 4) ? -64 : 64;
+            // The eight coalesced passes of a chunk as straight-line code specialised at compile time for the epilogue
+            // flavours the model uses (RM: residual 0 none / 1 fp32 / 2 bf16, OP: 0 add / 1 * gelu'(res) / 2 * res,
+            // OF: fp32 output, AT: atomic accumulate) - all loads of the chunk, then all the arithmetic, then all stores.
+            // With the flavour tested inside the loop every pass was a chain of branches (12 % of the samples resolving
+            // branches, one LDS latency exposed per pass).
+            auto passes = [&](auto rm_c, auto op_c, auto of_c, auto at_c) {
+              constexpr int RM = decltype(rm_c)::value, OP = decltype(op_c)::value;
+              constexpr bool OF = decltype(of_c)::value, AT = decltype(at_c)::value;
+              float4 a[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 a = *reinterpret_cast<const float4*>(sp + i * 512 + ((i & 1) ? odd_off : 0));
-              a.x += bcur.x; a.y += bcur.y; a.z += bcur.z; a.w += bcur.w;
-              if (ep.act == SPA3D_ACT_GELU_TANH) {
+              for (int i = 0; i < 8; ++i) a[i] = lds128(sp + i * 512 + ((i & 1) ? odd_off : 0));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                a[i].x += bcur.x; a[i].y += bcur.y; a[i].z += bcur.z; a[i].w += bcur.w;
+                if constexpr (RM != 0) {
+                  const uint4 q = res[i];
+                  float4 rv;
+                  if constexpr (RM == 1) {
+                    rv = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+                  } else {
+                    rv = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                                     __uint_as_float(q.y & 0xffff0000u));
+                  }
+                  if constexpr (OP == 0) {
+                    a[i].x += rv.x; a[i].y += rv.y; a[i].z += rv.z; a[i].w += rv.w;
+                  } else if constexpr (OP == 2) {
+                    a[i].x *= rv.x; a[i].y *= rv.y; a[i].z *= rv.z; a[i].w *= rv.w;
+                  } else {
+                    a[i].x *= gelu_grad_fast(rv.x); a[i].y *= gelu_grad_fast(rv.y);
+                    a[i].z *= gelu_grad_fast(rv.z); a[i].w *= gelu_grad_fast(rv.w);
+                  }
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                char* cpi = cp + i * cstep;
+                if (i * 4 + cr < rows_ok) {
+                  if constexpr (AT) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cpi), "f"(a[i].x), "f"(a[i].y), "f"(a[i].z),
+                                 "f"(a[i].w)
+                                 : "memory");
+                  } else if constexpr (OF) {
+                    *reinterpret_cast<float4*>(cpi) = a[i];
+                  } else {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(a[i].x, a[i].y), h1 = __floats2bfloat162_rn(a[i].z, a[i].w);
+                    *reinterpret_cast<uint2*>(cpi) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                  }
+                }
+              }
+            };
+            using std::integral_constant;
+            using I0 = integral_constant<int, 0>; using I1 = integral_constant<int, 1>; using I2 = integral_constant<int, 2>;
+            using BT = integral_constant<bool, true>; using BF = integral_constant<bool, false>;
+            const int rmode = ep.residual == nullptr ? 0 : (ep.r_dtype == SPA3D_F32 ? 1 : 2);
+            if (ep.act == SPA3D_ACT_GELU_TANH) {
+              // (not produced by the model path: api.cu routes fp32 + GELU to the SIMT kernel) generic form
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 a = lds128(sp + i * 512 + ((i & 1) ? odd_off : 0));
+                a.x += bcur.x; a.y += bcur.y; a.z += bcur.z; a.w += bcur.w;
                 uint64_t g0 = gelu2_fast(pk(a.x, a.y)), g1 = gelu2_fast(pk(a.z, a.w));
                 upk(g0, a.x, a.y);
                 upk(g1, a.z, a.w);
-              }
-              const uint4 q = res[i];
-              if (ep.residual) {
-                float4 rv;
-                if (ep.r_dtype == SPA3D_F32) {
-                  rv = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
-                } else {
-                  const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
-                  const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
-                  rv = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
-                }
-                if (ep.res_op == 0) {
+                if (rmode) {
+                  const uint4 q = res[i];
+                  float4 rv = rmode == 1 ? make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w))
+                                         : make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u),
+                                                       __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
                   a.x += rv.x; a.y += rv.y; a.z += rv.z; a.w += rv.w;
-                } else {   // dz = dh * gelu'(z)
-                  a.x *= gelu_grad_fast(rv.x); a.y *= gelu_grad_fast(rv.y);
-                  a.z *= gelu_grad_fast(rv.z); a.w *= gelu_grad_fast(rv.w);
+                }
+                char* cpi = cp + i * cstep;
+                if (i * 4 + cr < rows_ok) {
+                  if (out_f32) {
+                    *reinterpret_cast<float4*>(cpi) = a;
+                  } else {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+                    *reinterpret_cast<uint2*>(cpi) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                  }
                 }
               }
-              if (i * 4 + cr < rows_ok) {
-                if (ep.atomic_add) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(a.x), "f"(a.y), "f"(a.z),
-                               "f"(a.w)
-                               : "memory");
-                } else if (out_f32) {
-                  *reinterpret_cast<float4*>(cp) = a;
-                } else {
-                  __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-                  *reinterpret_cast<uint2*>(cp) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-                }
-              }
-              cp += cstep;
+            } else if (ep.atomic_add) {
+              passes(I0{}, I0{}, BT{}, BT{});
+            } else if (ep.res_op == 2) {
+              if (out_f32) passes(I2{}, I2{}, BT{}, BF{}); else passes(I2{}, I2{}, BF{}, BF{});
+            } else if (ep.res_op == 1) {
+              if (out_f32) passes(I2{}, I1{}, BT{}, BF{}); else passes(I2{}, I1{}, BF{}, BF{});
+            } else if (rmode == 1) {
+              if (out_f32) passes(I1{}, I0{}, BT{}, BF{}); else passes(I1{}, I0{}, BF{}, BF{});
+            } else if (rmode == 2) {
+              if (out_f32) passes(I2{}, I0{}, BT{}, BF{}); else passes(I2{}, I0{}, BF{}, BF{});
+            } else {
+              if (out_f32) passes(I0{}, I0{}, BT{}, BF{}); else passes(I0{}, I0{}, BF{}, BF{});
             }
             __syncwarp();   // slab is rewritten by the next chunk
           }
@@ -451,10 +507,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = pku(r[c & 1][2 * i], r[c & 1][2 * i + 1]);
             if (ep.bias) epi_bias(v, breg[c]);
-            if (ep.aux_pre) {   // pre-activation z (saved for the backward pass) leaves through its own map
+            if (ep.aux_pre) {   // what the backward pass needs leaves through its own map: z, or gelu'(z) (shares tanh(u) with the activation)
+              uint64_t vg[16];
+              const bool grad = ep.aux_pre == 2;
+              if (grad) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = gelu2_fast_grad(v[i], vg[i]);
+              }
               if (lane == 0) bulk_wait_read<1>();
               __syncwarp();
-              slab_store_bf16(slab + sbuf * 2048, lane, v);
+              if (grad) slab_store_bf16(slab + sbuf * 2048, lane, vg);
+              else slab_store_bf16(slab + sbuf * 2048, lane, v);
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
@@ -463,7 +526,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
               sbuf ^= 1;
             }
-            epi_act(ep, v);
+            if (ep.aux_pre != 2) epi_act(ep, v);
             if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago has left this buffer
             __syncwarp();
             slab_store_bf16(slab + sbuf * 2048, lane, v);
@@ -584,10 +647,11 @@ static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiPa
   if (EPI == EPI_DIRECT) tmC = tmA;  // unused
   else if (make_map_c(&tmC, ep.C, M, N, ep.ldc)) return 1;
   tmAux = tmC;
+  const int aux_kind = ep.aux_pre;   // requested by the caller: 0/1 = pre-activation, 2 = activation derivative
   ep.aux_pre = 0;
   if (EPI == EPI_TMA && aux != nullptr) {
     if (make_map_c(&tmAux, aux, M, N, ld_aux)) return 1;
-    ep.aux_pre = 1;
+    ep.aux_pre = aux_kind == 2 ? 2 : 1;
   }
   ep.debug_skip = debug_skip_epilogue();
   static bool attr_set = false;
@@ -655,7 +719,7 @@ bool gemm_tcgen05_rms_applicable(int N, int dh, int q_cols, int k_cols, int c_dt
 int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias, int act,
                  const void* residual, int64_t ldr, int r_dtype, void* C, int64_t ldc, int c_dtype,
                  int64_t M, int N, int K, const RmsEpilogue* rms, cudaStream_t st, int res_op, void* aux_pre,
-                 int64_t ld_aux) {
+                 int64_t ld_aux, int aux_kind) {
   using namespace tc;
   SPA3D_REQUIRE(c_dtype == SPA3D_F32 || c_dtype == SPA3D_BF16, "gemm_tcgen05: bad C dtype");
   SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % (c_dtype == SPA3D_F32 ? 4 : 8) == 0,
@@ -668,7 +732,9 @@ int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const 
   if (aux_pre)
     SPA3D_REQUIRE(c_dtype == SPA3D_BF16 && !residual && (reinterpret_cast<uintptr_t>(aux_pre) & 15) == 0 && ld_aux % 8 == 0,
                   "gemm_tcgen05: the pre-activation side output needs a bf16 C, no residual, 16-byte aligned rows");
-  if (res_op) SPA3D_REQUIRE(residual != nullptr, "gemm_tcgen05: res_op needs the saved pre-activation");
+  if (res_op) SPA3D_REQUIRE(residual != nullptr && r_dtype == SPA3D_BF16, "gemm_tcgen05: res_op needs the saved bf16 pre-activation / derivative");
+  ep.aux_pre = aux_kind;
+  if (aux_kind == 2) SPA3D_REQUIRE(aux_pre != nullptr && act == SPA3D_ACT_GELU_TANH, "gemm_tcgen05: gelu'(z) side output needs the GELU epilogue");
   if (rms && rms->dh > 0) {
     SPA3D_REQUIRE(c_dtype == SPA3D_BF16 && !bias && !residual && act == 0, "gemm_tcgen05: fused RMSNorm is bf16, no bias/act/residual");
     ep.q_cols = rms->q_cols; ep.k_cols = rms->k_cols;

@@ -184,6 +184,35 @@ __device__ __forceinline__ uint64_t gelu2_fast(uint64_t x) {
   return fma2(hx, th, hx);
 }
 
+// h = gelu_tanh(x) (returned) and g = d gelu_tanh / dx, two lanes at a time, one tanh per element for both:
+//   u = k x (1 + c x^2), t = tanh u, h = x/2 (1 + t), g = (1 + t)/2 + x/2 (1 - t^2) k (1 + 3 c x^2)
+__device__ __forceinline__ uint64_t gelu2_fast_grad(uint64_t x, uint64_t& g) {
+  constexpr float k = 0.7978845608028654f;
+  const uint64_t c1 = pk(k * 0.044715f, k * 0.044715f), c0 = pk(k, k), half = pk(0.5f, 0.5f);
+  const uint64_t c3 = pk(3.0f * k * 0.044715f, 3.0f * k * 0.044715f), one = pk(1.0f, 1.0f), mone = pk(-1.0f, -1.0f);
+  const uint64_t t2 = mul2(x, x);
+  const uint64_t u = mul2(fma2(t2, c1, c0), x);
+  float u0, u1;
+  upk(u, u0, u1);
+  const uint64_t th = pk(tanh_fast(u0), tanh_fast(u1));
+  const uint64_t hx = mul2(x, half);
+  const uint64_t du = fma2(t2, c3, c0);
+  const uint64_t s = fma2(mul2(th, mone), th, one);          // 1 - t^2
+  g = fma2(mul2(hx, s), du, fma2(half, th, half));
+  return fma2(hx, th, hx);
+}
+
+// explicit shared-space 128-bit accesses (a pointer rebuilt from an aligned integer loses its address space and the compiler
+// falls back to generic LD/ST, which wait on the long scoreboard)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                :

@@ -141,22 +141,25 @@ def gemm(a, wt, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=None
     return out
 
 
-def gemm_gelu(a, wt, bias, impl=GEMM_AUTO):
-    """(z, h): z = a @ wt^T + bias, h = gelu_tanh(z), both in a.dtype (one GEMM, two outputs)."""
+def gemm_gelu(a, wt, bias, impl=GEMM_AUTO, save_grad=False):
+    """(z, h): z = a @ wt^T + bias, h = gelu_tanh(z), both in a.dtype (one GEMM, two outputs).
+    save_grad (bf16 tensor-core path): the first output is gelu_tanh'(z) instead of z (pair it with gemm_gelu_bwd(z_is_grad=True))."""
     M, K = a.shape
     N = wt.shape[0]
     z = torch.empty(M, N, device=a.device, dtype=a.dtype)
     h = torch.empty(M, N, device=a.device, dtype=a.dtype)
-    _call("spa3d_gemm_gelu", _p(a), _ld(a), _p(wt), _ld(wt), dt(a), _p(bias), _p(z), _ld(z), _p(h), _ld(h), M, N, K, int(impl), _stream())
+    _call("spa3d_gemm_gelu", _p(a), _ld(a), _p(wt), _ld(wt), dt(a), _p(bias), _p(z), _ld(z), _p(h), _ld(h), M, N, K, int(bool(save_grad)),
+          int(impl), _stream())
     return z, h
 
 
-def gemm_gelu_bwd(dy, wt, z, impl=GEMM_AUTO):
-    """dz = (dy @ wt^T) * gelu_tanh'(z)."""
+def gemm_gelu_bwd(dy, wt, z, impl=GEMM_AUTO, z_is_grad=False):
+    """dz = (dy @ wt^T) * gelu_tanh'(z)   (z_is_grad: ``z`` already holds gelu_tanh'(z))."""
     M, K = dy.shape
     N = wt.shape[0]
     dz = torch.empty(M, N, device=dy.device, dtype=dy.dtype)
-    _call("spa3d_gemm_gelu_bwd", _p(dy), _ld(dy), _p(wt), _ld(wt), dt(dy), _p(z), _ld(z), _p(dz), _ld(dz), M, N, K, int(impl), _stream())
+    _call("spa3d_gemm_gelu_bwd", _p(dy), _ld(dy), _p(wt), _ld(wt), dt(dy), _p(z), _ld(z), _p(dz), _ld(dz), M, N, K,
+          int(bool(z_is_grad)), int(impl), _stream())
     return dz
 
 

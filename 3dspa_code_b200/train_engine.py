@@ -124,6 +124,13 @@ def _c(st, t):
     return ops.convert(t, torch.empty(t.shape, device=t.device, dtype=st.cdt))
 
 
+def _gelu_grad_form(st, a, wt):
+    """True when MLP_in can save gelu'(z) instead of z (tcgen05 epilogue: bf16, 16-byte rows) - the backward epilogue is then
+    one multiply instead of a second tanh evaluation per element."""
+    return (st.cdt == torch.bfloat16 and a.shape[1] % 8 == 0 and wt.shape[0] % 8 == 0 and a.stride(0) % 8 == 0
+            and wt.stride(0) % 8 == 0 and a.data_ptr() % 16 == 0 and wt.data_ptr() % 16 == 0)
+
+
 def _lowp_out(st, t):
     """bf16 side output for the fp32 gradient tensor ``t`` (consumed by the next block's ``_c``)."""
     if st.cdt == torch.float32:
@@ -214,9 +221,10 @@ class MlpBlockFn(torch.autograd.Function):
     def forward(ctx, a, anchor, st, pre):
         f, w, cdt = st.f32, st.c, st.cdt
         an, mean, rstd = ops.layernorm_fwd(a, f[pre + "norm_attn"], cdt, stats=True)
-        z, h = ops.gemm_gelu(an, w[pre + "W1_t"], f[pre + "b1"])
+        zg = _gelu_grad_form(st, an, w[pre + "W1_t"])
+        z, h = ops.gemm_gelu(an, w[pre + "W1_t"], f[pre + "b1"], save_grad=zg)   # z is gelu'(z) when zg
         y = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=a, out_dtype=torch.float32)
-        ctx.saved = dict(a=a, mean=mean, rstd=rstd, an=an, z=z, h=h)
+        ctx.saved = dict(a=a, mean=mean, rstd=rstd, an=an, z=z, h=h, zg=zg)
         ctx.args = (st, pre)
         return y
 
@@ -228,7 +236,7 @@ class MlpBlockFn(torch.autograd.Function):
         dyc = _c(st, dy)
         st.accum_bias(pre + "b2", dyc)
         st.accum_dw(pre + "W2_t", dyc, s["h"])
-        dz = ops.gemm_gelu_bwd(dyc, st.ct[pre + "W2_t"], s["z"])
+        dz = ops.gemm_gelu_bwd(dyc, st.ct[pre + "W2_t"], s["z"], z_is_grad=s["zg"])
         st.accum_bias(pre + "b1", dz)
         st.accum_dw(pre + "W1_t", dz, s["an"])
         dan = ops.gemm(dz, st.ct[pre + "W1_t"])
@@ -260,10 +268,11 @@ class LastLayerFn(torch.autograd.Function):
         stats = ops.attention_fwd(q0, kvp[:, :A], kvp[:, A:], o0, batch, H, 1, L, Dh, key_mask, save_stats=True)
         a0 = ops.gemm(o0, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x.view(batch, L * d)[:, :d], out_dtype=torch.float32)
         an0, mean2, rstd2 = ops.layernorm_fwd(a0, f[pre + "norm_attn"], cdt, stats=True)
-        z0, h0 = ops.gemm_gelu(an0, w[pre + "W1_t"], f[pre + "b1"])
+        zg = _gelu_grad_form(st, an0, w[pre + "W1_t"])
+        z0, h0 = ops.gemm_gelu(an0, w[pre + "W1_t"], f[pre + "b1"], save_grad=zg)
         y0 = ops.gemm(h0, w[pre + "W2_t"], f[pre + "b2"], residual=a0, out_dtype=torch.float32)
         ctx.saved = dict(x=x, xn=xn, mean=mean, rstd=rstd, kvp=kvp, rk=rk, q0=q0, rq=rq, o0=o0, stats=stats, a0=a0, an0=an0,
-                         mean2=mean2, rstd2=rstd2, z0=z0, h0=h0)
+                         mean2=mean2, rstd2=rstd2, z0=z0, h0=h0, zg=zg)
         ctx.args = (st, pre, m, batch, L, key_mask)
         return y0
 
@@ -279,7 +288,7 @@ class LastLayerFn(torch.autograd.Function):
         dyc = _c(st, dy0)
         st.accum_bias(pre + "b2", dyc)
         st.accum_dw(pre + "W2_t", dyc, s["h0"])
-        dz0 = ops.gemm_gelu_bwd(dyc, st.ct[pre + "W2_t"], s["z0"])
+        dz0 = ops.gemm_gelu_bwd(dyc, st.ct[pre + "W2_t"], s["z0"], z_is_grad=s["zg"])
         st.accum_bias(pre + "b1", dz0)
         st.accum_dw(pre + "W1_t", dz0, s["an0"])
         dan0 = ops.gemm(dz0, st.ct[pre + "W1_t"])

@@ -123,15 +123,18 @@ int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dt
                void* stream);
 
 /* MLP_in with its activation, training form (attention.py:106): Z = A . Wt^T + bias (saved for the
- * backward pass) and H = gelu_tanh(Z), both [M,N] in a_dtype, from one pass over the accumulator. */
+ * backward pass) and H = gelu_tanh(Z), both [M,N] in a_dtype, from one pass over the accumulator.
+ * save_grad = 1 (tcgen05 path only): Z receives gelu_tanh'(A . Wt^T + bias) instead - the derivative shares tanh(u) with
+ * the activation, and the backward epilogue becomes one multiply. */
 int spa3d_gemm_gelu(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
                     const float* bias, void* Z, int64_t ldz, void* H, int64_t ldh, int64_t M, int N,
-                    int K, int impl, void* stream);
+                    int K, int save_grad, int impl, void* stream);
 /* Backward through MLP_out and the activation: dZ = (dY . Wt^T) * gelu_tanh'(Z); dY [M,K], Wt [N,K]
- * (MLP_out's kernel [N,K] as stored by Flax), Z, dZ [M,N], all in a_dtype. */
+ * (MLP_out's kernel [N,K] as stored by Flax), Z, dZ [M,N], all in a_dtype.  z_is_grad = 1: Z already holds
+ * gelu_tanh'(z) (spa3d_gemm_gelu with save_grad = 1) and dZ = (dY . Wt^T) * Z. */
 int spa3d_gemm_gelu_bwd(const void* dY, int64_t lddy, const void* Wt, int64_t ldw, int a_dtype,
                         const void* Z, int64_t ldz, void* dZ, int64_t lddz, int64_t M, int N, int K,
-                        int impl, void* stream);
+                        int z_is_grad, int impl, void* stream);
 
 /* Weight gradient of a Dense layer (backward of attention.py:106-107,154-183 and
  * track_autoencoder_3d.py:73-115 under jax.value_and_grad, train.py:161-162):

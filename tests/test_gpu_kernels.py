@@ -535,6 +535,15 @@ def test_gemm_gelu_fused_forward_and_backward(spa, impl):
         zz = z.double().requires_grad_(True)
         torch.nn.functional.gelu(zz, approximate="tanh").backward(dy.double() @ w2.double().t())
         assert rel_err(dz, zz.grad) < (1e-2 if impl == "tcgen05" else 2e-5), (M, d, Mh, rel_err(dz, zz.grad))
+        if impl == "tcgen05":
+            # saved-derivative form: the forward writes gelu'(z) (sharing tanh(u) with the activation), the backward multiplies
+            g, h2 = ops.gemm_gelu(a, w1t, b1, impl=code, save_grad=True)
+            assert torch.equal(h2, h)
+            z64 = zref.clone().requires_grad_(True)
+            torch.nn.functional.gelu(z64, approximate="tanh").sum().backward()
+            assert rel_err(g, z64.grad) < 6e-3, rel_err(g, z64.grad)
+            dz2 = ops.gemm_gelu_bwd(dy, w2, g, impl=code, z_is_grad=True)
+            assert rel_err(dz2, z64.grad * (dy.double() @ w2.double().t())) < 1e-2
 
 
 @pytest.mark.parametrize("N,T,Dd,Dz,W", [(40, 7, 768, 256, 384), (3, 150, 768, 256, 384), (33, 12, 64, 0, 256), (9, 5, 0, 128, 192)])

@@ -37,6 +37,8 @@ def main():
         ("tra.out", Mr, 768, 1280, "res"),
         ("tra.mlp1", Mr, 1280, 1536, "gelu"),
         ("tra.mlp2", Mr, 1536, 1280, "res"),
+        ("itt.gbwd", Mi, 384, 1536, "gbwd"),
+        ("itt.gfwd", Mi, 384, 1536, "gfwd"),
         ("embed", 2048 * 150 * args.clips, 1280, 384, "bias"),
         ("tra.out.f32", Mr, 768, 1280, "f32"),
         ("tra.out.resbf", Mr, 768, 1280, "resbf"),
@@ -51,13 +53,17 @@ def main():
         a = torch.randn(M, K, device=dev).to(torch.bfloat16)
         wt = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
         bias = torch.randn(N, device=dev)
-        res = torch.randn(M, N, device=dev) if kind in ("res", "resbf") else None
-        if kind == "resbf":
+        res = torch.randn(M, N, device=dev) if kind in ("res", "resbf", "gbwd") else None
+        if kind in ("resbf", "gbwd"):
             res = res.to(torch.bfloat16)
         sq = torch.ones(96, device=dev)
         out = torch.empty(M, N, device=dev, dtype=torch.float32 if kind in ("res", "f32") else torch.bfloat16)
 
         def ours():
+            if kind == "gbwd":   # dz = (dy . W2^T) * g'  (saved-derivative backward through MLP_out + GELU)
+                return ops.gemm_gelu_bwd(a, wt, res, z_is_grad=True)
+            if kind == "gfwd":   # training forward: h and gelu'(z)
+                return ops.gemm_gelu(a, wt, bias, save_grad=True)
             if kind == "rms":
                 return ops.gemm_rmsnorm(a, wt, 96, 768, 768, sq, sq)
             if kind in ("res", "resbf"):
