@@ -110,7 +110,7 @@ int spa3d_gemm_gelu(const void* A, int64_t lda, const void* Wt, int64_t ldw, int
 
 int spa3d_gemm_gelu_bwd(const void* dH_in, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
                         const void* Z, int64_t ldz, void* dZ, int64_t lddz, int64_t M, int N, int K,
-                        int z_is_grad, int impl, void* stream) {
+                        int z_is_grad, float* dz_colsum, int impl, void* stream) {
   using namespace spa3d;
   cudaStream_t st = (cudaStream_t)stream;
   SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_gelu_bwd: bad shape");
@@ -121,8 +121,8 @@ int spa3d_gemm_gelu_bwd(const void* dH_in, int64_t lda, const void* Wt, int64_t 
   if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_gelu_bwd: tcgen05 path not applicable");
   if (impl != SPA3D_GEMM_SIMT && tc_ok)
     return gemm_tcgen05(dH_in, lda, Wt, ldw, nullptr, 0, Z, ldz, a_dtype, dZ, lddz, a_dtype, M, N, K, nullptr, st,
-                        z_is_grad ? 2 : 1, nullptr, 0);
-  SPA3D_REQUIRE(!z_is_grad, "gemm_gelu_bwd: the saved-derivative form exists on the tcgen05 path only");
+                        z_is_grad ? 2 : 1, nullptr, 0, 1, dz_colsum);
+  SPA3D_REQUIRE(!z_is_grad && !dz_colsum, "gemm_gelu_bwd: the saved-derivative form and the fused column sums exist on the tcgen05 path only");
   int rc = spa3d_gemm(dH_in, lda, Wt, ldw, a_dtype, nullptr, 0, nullptr, 0, 0, dZ, lddz, a_dtype, M, N, K,
                       impl == SPA3D_GEMM_SIMT ? SPA3D_GEMM_SIMT : SPA3D_GEMM_AUTO, stream);
   if (rc) return rc;

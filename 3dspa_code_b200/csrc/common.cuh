@@ -134,7 +134,7 @@ struct RmsEpilogue {  // fused per-head RMSNorm of the leading q_cols / k_cols o
 int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias,
                  int act, const void* residual, int64_t ldr, int r_dtype, void* C, int64_t ldc,
                  int c_dtype, int64_t M, int N, int K, const RmsEpilogue* rms, cudaStream_t st,
-                 int res_op = 0, void* aux_pre = nullptr, int64_t ld_aux = 0, int aux_kind = 1);
+                 int res_op = 0, void* aux_pre = nullptr, int64_t ld_aux = 0, int aux_kind = 1, float* colsum = nullptr);
 bool gemm_tcgen05_rms_applicable(int N, int dh, int q_cols, int k_cols, int c_dtype);
 int head_rmsnorm_fwd_impl(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
                           float* rstd_out, int64_t rstd_ld, int64_t rows, int heads, int Dh,

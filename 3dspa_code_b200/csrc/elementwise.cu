@@ -231,20 +231,26 @@ layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float*
                           const float* __restrict__ mean, const float* __restrict__ rstd,
                           const TDY* __restrict__ dy, int64_t lddy, float* __restrict__ dx, int64_t lddx,
                           int dx_accumulate, bf16* __restrict__ dx_lowp, int64_t ldl,
-                          float* __restrict__ dscale_partial, int ds_accum, int64_t rows) {
+                          float* __restrict__ dscale_partial, int ds_accum, float* __restrict__ dcol, int64_t rows) {
   constexpr int D = 128 * J;
   constexpr bool DYF = sizeof(TDY) == 4;
+  constexpr bool CS = J <= 4;   // column sums of the final dx (the bias gradient of the layer that produced x): narrow rows only
   __shared__ float s_ds[D];
+  __shared__ float s_cs[CS ? D : 1];
   __shared__ __align__(16) float s_sc[D];
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     s_ds[i] = 0.f;
+    if constexpr (CS) s_cs[i] = 0.f;
     s_sc[i] = scale[i];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   float4 acc[J];
+  float4 csum[CS ? J : 1];
 #pragma unroll
   for (int j = 0; j < J; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < (CS ? J : 1); ++j) csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   auto unpack = [](const uint4& w) -> float4 {   // dy chunk as loaded (fp32: 4 floats; bf16: 4 values in .x,.y)
     if constexpr (DYF) {
       return make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
@@ -305,6 +311,9 @@ layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float*
         v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
       }
       *reinterpret_cast<float4*>(dxr + c) = v;
+      if constexpr (CS) {
+        csum[j].x += v.x; csum[j].y += v.y; csum[j].z += v.z; csum[j].w += v.w;
+      }
       if (dx_lowp) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
         *reinterpret_cast<uint2*>(dx_lowp + row * ldl + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
@@ -318,11 +327,22 @@ layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float*
     atomicAdd(&s_ds[c + 1], acc[j].y);
     atomicAdd(&s_ds[c + 2], acc[j].z);
     atomicAdd(&s_ds[c + 3], acc[j].w);
+    if constexpr (CS) {
+      if (dcol != nullptr) {
+        atomicAdd(&s_cs[c], csum[j].x);
+        atomicAdd(&s_cs[c + 1], csum[j].y);
+        atomicAdd(&s_cs[c + 2], csum[j].z);
+        atomicAdd(&s_cs[c + 3], csum[j].w);
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     if (ds_accum) atomicAdd(&dscale_partial[i], s_ds[i]);   // straight into the gradient of the scale
     else dscale_partial[(int64_t)blockIdx.x * D + i] = s_ds[i];
+    if constexpr (CS) {
+      if (dcol != nullptr) atomicAdd(&dcol[i], s_cs[i]);      // sum over rows of the final dx (+= into the caller's buffer)
+    }
   }
 }
 
@@ -977,19 +997,21 @@ int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* sc
                         const float* mean, const float* rstd, const void* dy, int64_t lddy,
                         int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int dx_accumulate,
                         void* dx_lowp, int64_t ldl, float* dscale_partial, int num_partials, int accumulate_dscale,
-                        int64_t rows, int d, void* stream) {
+                        float* dx_colsum, int64_t rows, int d, void* stream) {
   SPA3D_REQUIRE(num_partials > 0, "layernorm_bwd: num_partials must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool fast = x_dtype == SPA3D_F32 && dx_dtype == SPA3D_F32 && d % 128 == 0 && d <= 1536 && ldx % 4 == 0 &&
                     lddx % 4 == 0 && lddy % 4 == 0 && al16(x) && al16(dx) && al16(dy) && al16(scale) &&
                     (!dx_lowp || (ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(dx_lowp) & 7) == 0));
+  SPA3D_REQUIRE(dx_colsum == nullptr || (fast && d <= 512), "layernorm_bwd: dx_colsum needs the fp32 fast path with d <= 512");
   if (fast) {
 #define SPA3D_LN_BWD_FAST(J)                                                                                   \
   case J:                                                                                                      \
     SPA3D_DISPATCH(dy_dtype, TDY, {                                                                            \
       layernorm_bwd_fast_kernel<J, TDY><<<num_partials, 256, 0, st>>>((const float*)x, ldx, scale, mean, rstd, \
-          (const TDY*)dy, lddy, (float*)dx, lddx, dx_accumulate, (bf16*)dx_lowp, ldl, dscale_partial, accumulate_dscale, rows); \
+          (const TDY*)dy, lddy, (float*)dx, lddx, dx_accumulate, (bf16*)dx_lowp, ldl, dscale_partial, accumulate_dscale,   \
+          dx_colsum, rows);                                                                                    \
     });                                                                                                        \
     return check_launch("layernorm_bwd_fast");
     switch (d / 128) {

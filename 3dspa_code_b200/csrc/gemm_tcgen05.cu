@@ -79,6 +79,7 @@ struct EpiParams {
                      //             2 = C = acc * residual (residual = gelu'(z) saved by the forward GEMM)
   int atomic_add;    // EPI_DIRECT, fp32 C: C += tile with red.global.add.v4.f32 (split-K weight gradients)
   int debug_skip;    // SPA3D_GEMM_SKIP_EPI=1: accumulators are drained but nothing is computed or stored
+  float* colsum;     // EPI_DIRECT: [N] f32, += column sums of the stored values (a bias gradient), or null
 };
 
 // bias on one 32-column chunk of an output row held in registers (v = packed pairs).  Lane i holds
@@ -390,9 +391,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // OF: fp32 output, AT: atomic accumulate) - all loads of the chunk, then all the arithmetic, then all stores.
             // With the flavour tested inside the loop every pass was a chain of branches (12 % of the samples resolving
             // branches, one LDS latency exposed per pass).
-            auto passes = [&](auto rm_c, auto op_c, auto of_c, auto at_c) {
+            auto passes = [&](auto rm_c, auto op_c, auto of_c, auto at_c, auto cs_c) {
               constexpr int RM = decltype(rm_c)::value, OP = decltype(op_c)::value;
-              constexpr bool OF = decltype(of_c)::value, AT = decltype(at_c)::value;
+              constexpr bool OF = decltype(of_c)::value, AT = decltype(at_c)::value, CSUM = decltype(cs_c)::value;
               float4 a[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) a[i] = lds128(sp + i * 512 + ((i & 1) ? odd_off : 0));
@@ -417,6 +418,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     a[i].z *= gelu_grad_fast(rv.z); a[i].w *= gelu_grad_fast(rv.w);
                   }
                 }
+              }
+              if constexpr (CSUM) {
+                // column sums of this chunk (bias gradient): 8 rows per lane in registers, the four row groups by shuffle,
+                // one vector reduction per 4 columns into the [N] buffer
+                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (i * 4 + cr < rows_ok) { cs.x += a[i].x; cs.y += a[i].y; cs.z += a[i].z; cs.w += a[i].w; }
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {
+                  cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+                  cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+                }
+                if (cr == 0 && col < N)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ep.colsum + col), "f"(cs.x), "f"(cs.y), "f"(cs.z), "f"(cs.w)
+                               : "memory");
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -466,17 +483,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
               }
             } else if (ep.atomic_add) {
-              passes(I0{}, I0{}, BT{}, BT{});
+              passes(I0{}, I0{}, BT{}, BT{}, BF{});
             } else if (ep.res_op == 2) {
-              if (out_f32) passes(I2{}, I2{}, BT{}, BF{}); else passes(I2{}, I2{}, BF{}, BF{});
+              if (ep.colsum != nullptr) passes(I2{}, I2{}, BF{}, BF{}, BT{});   // host side: bf16 output only
+              else if (out_f32) passes(I2{}, I2{}, BT{}, BF{}, BF{});
+              else passes(I2{}, I2{}, BF{}, BF{}, BF{});
             } else if (ep.res_op == 1) {
-              if (out_f32) passes(I2{}, I1{}, BT{}, BF{}); else passes(I2{}, I1{}, BF{}, BF{});
+              if (out_f32) passes(I2{}, I1{}, BT{}, BF{}, BF{}); else passes(I2{}, I1{}, BF{}, BF{}, BF{});
             } else if (rmode == 1) {
-              if (out_f32) passes(I1{}, I0{}, BT{}, BF{}); else passes(I1{}, I0{}, BF{}, BF{});
+              if (out_f32) passes(I1{}, I0{}, BT{}, BF{}, BF{}); else passes(I1{}, I0{}, BF{}, BF{}, BF{});
             } else if (rmode == 2) {
-              if (out_f32) passes(I2{}, I0{}, BT{}, BF{}); else passes(I2{}, I0{}, BF{}, BF{});
+              if (out_f32) passes(I2{}, I0{}, BT{}, BF{}, BF{}); else passes(I2{}, I0{}, BF{}, BF{}, BF{});
             } else {
-              if (out_f32) passes(I0{}, I0{}, BT{}, BF{}); else passes(I0{}, I0{}, BF{}, BF{});
+              if (out_f32) passes(I0{}, I0{}, BT{}, BF{}, BF{}); else passes(I0{}, I0{}, BF{}, BF{}, BF{});
             }
             __syncwarp();   // slab is rewritten by the next chunk
           }
@@ -719,7 +738,7 @@ bool gemm_tcgen05_rms_applicable(int N, int dh, int q_cols, int k_cols, int c_dt
 int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias, int act,
                  const void* residual, int64_t ldr, int r_dtype, void* C, int64_t ldc, int c_dtype,
                  int64_t M, int N, int K, const RmsEpilogue* rms, cudaStream_t st, int res_op, void* aux_pre,
-                 int64_t ld_aux, int aux_kind) {
+                 int64_t ld_aux, int aux_kind, float* colsum) {
   using namespace tc;
   SPA3D_REQUIRE(c_dtype == SPA3D_F32 || c_dtype == SPA3D_BF16, "gemm_tcgen05: bad C dtype");
   SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % (c_dtype == SPA3D_F32 ? 4 : 8) == 0,
@@ -734,6 +753,9 @@ int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const 
                   "gemm_tcgen05: the pre-activation side output needs a bf16 C, no residual, 16-byte aligned rows");
   if (res_op) SPA3D_REQUIRE(residual != nullptr && r_dtype == SPA3D_BF16, "gemm_tcgen05: res_op needs the saved bf16 pre-activation / derivative");
   ep.aux_pre = aux_kind;
+  ep.colsum = colsum;
+  if (colsum) SPA3D_REQUIRE(residual != nullptr && res_op == 2 && c_dtype == SPA3D_BF16 && (reinterpret_cast<uintptr_t>(colsum) & 15) == 0,
+                            "gemm_tcgen05: fused column sums exist for the saved-derivative backward epilogue (bf16 output) only");
   if (aux_kind == 2) SPA3D_REQUIRE(aux_pre != nullptr && act == SPA3D_ACT_GELU_TANH, "gemm_tcgen05: gelu'(z) side output needs the GELU epilogue");
   if (rms && rms->dh > 0) {
     SPA3D_REQUIRE(c_dtype == SPA3D_BF16 && !bias && !residual && act == 0, "gemm_tcgen05: fused RMSNorm is bf16, no bias/act/residual");

@@ -153,13 +153,14 @@ def gemm_gelu(a, wt, bias, impl=GEMM_AUTO, save_grad=False):
     return z, h
 
 
-def gemm_gelu_bwd(dy, wt, z, impl=GEMM_AUTO, z_is_grad=False):
-    """dz = (dy @ wt^T) * gelu_tanh'(z)   (z_is_grad: ``z`` already holds gelu_tanh'(z))."""
+def gemm_gelu_bwd(dy, wt, z, impl=GEMM_AUTO, z_is_grad=False, dz_colsum=None):
+    """dz = (dy @ wt^T) * gelu_tanh'(z)   (z_is_grad: ``z`` already holds gelu_tanh'(z)).
+    dz_colsum ([N] fp32, tensor-core path): += column sums of dz (the gradient of MLP_in's bias) from the GEMM epilogue."""
     M, K = dy.shape
     N = wt.shape[0]
     dz = torch.empty(M, N, device=dy.device, dtype=dy.dtype)
     _call("spa3d_gemm_gelu_bwd", _p(dy), _ld(dy), _p(wt), _ld(wt), dt(dy), _p(z), _ld(z), _p(dz), _ld(dz), M, N, K,
-          int(bool(z_is_grad)), int(impl), _stream())
+          int(bool(z_is_grad)), _p(dz_colsum), int(impl), _stream())
     return dz
 
 
@@ -193,9 +194,9 @@ def layernorm_fwd(x, scale, out_dtype, rows=None, ldx=None, d=None, stats=False,
 
 
 def layernorm_bwd(x, scale, mean, rstd, dy, dx, rows=None, ldx=None, lddx=None, d=None, accumulate=False, num_partials=296,
-                  dx_lowp=None, dscale_accum=None):
+                  dx_lowp=None, dscale_accum=None, dx_colsum=None):
     """dscale_accum: the [d] fp32 gradient of the scale; when given the kernel adds into it directly and
-    nothing is returned (no partial buffer, no reduction pass)."""
+    nothing is returned (no partial buffer, no reduction pass).  dx_colsum ([d] fp32, d <= 512): += sum over rows of the final dx."""
     rows = x.shape[0] if rows is None else rows
     d = x.shape[-1] if d is None else d
     ldx = _ld(x) if ldx is None else ldx
@@ -203,7 +204,7 @@ def layernorm_bwd(x, scale, mean, rstd, dy, dx, rows=None, ldx=None, lddx=None, 
     partial = dscale_accum if dscale_accum is not None else torch.empty(num_partials, d, device=x.device, dtype=torch.float32)
     _call("spa3d_layernorm_bwd", _p(x), int(ldx), dt(x), _p(scale), _p(mean), _p(rstd), _p(dy), _ld(dy), dt(dy), _p(dx), int(lddx),
           dt(dx), int(accumulate), _p(dx_lowp), _ld(dx_lowp) if dx_lowp is not None else 0, _p(partial), num_partials,
-          int(dscale_accum is not None), int(rows), int(d), _stream())
+          int(dscale_accum is not None), _p(dx_colsum), int(rows), int(d), _stream())
     if dscale_accum is not None:
         return None
     dscale = torch.empty(d, device=x.device, dtype=torch.float32)

@@ -131,6 +131,12 @@ def _gelu_grad_form(st, a, wt):
             and wt.stride(0) % 8 == 0 and a.data_ptr() % 16 == 0 and wt.data_ptr() % 16 == 0)
 
 
+def _colsum_fusable(st, d):
+    """Bias gradients that are column sums of a LayerNorm-backward output can be reduced inside that kernel (bf16 mode, fp32
+    rows of at most 512 columns): the per-track transformer (d = 384) and the latent transformer (d = 512)."""
+    return st.cdt == torch.bfloat16 and d % 128 == 0 and d <= 512
+
+
 def _lowp_out(st, t):
     """bf16 side output for the fp32 gradient tensor ``t`` (consumed by the next block's ``_c``)."""
     if st.cdt == torch.float32:
@@ -146,7 +152,7 @@ class AttnBlockFn(torch.autograd.Function):
     """a = x + SelfAttn(LN(x)) [+ CrossAttn(LN(x), kv)]   (attention.py:75-100)."""
 
     @staticmethod
-    def forward(ctx, x, kv, anchor, st, pre, m, batch, L, Lkv, key_mask):
+    def forward(ctx, x, kv, anchor, st, pre, m, batch, L, Lkv, key_mask, prev_b2=None, bo_done=False):
         f, w, cdt = st.f32, st.c, st.cdt
         H, Dh = m["heads"], m["Dh"]
         A = H * Dh
@@ -166,11 +172,13 @@ class AttnBlockFn(torch.autograd.Function):
             a = ops.gemm(oc, w[pre + "cross.Wo_t"], f[pre + "cross.bo"], residual=a, out_dtype=torch.float32)
             ctx.saved.update(kv=kv, qc=qc, kvp=kvp, rqc=rqc, rkc=rkc, oc=oc, stc=stc)
         ctx.args = (st, pre, m, batch, L, Lkv, key_mask, kv is not None and kv.requires_grad)
+        ctx.fuse = (prev_b2, bo_done)
         return a
 
     @staticmethod
     def backward(ctx, da):
         st, pre, m, batch, L, Lkv, key_mask, kv_grad = ctx.args
+        prev_b2, bo_done = ctx.fuse
         s = ctx.saved
         f, cdt = st.f32, st.cdt
         H, Dh = m["heads"], m["Dh"]
@@ -194,7 +202,8 @@ class AttnBlockFn(torch.autograd.Function):
             dxn = ops.gemm(dqc, st.ct[pre + "cross.Wq_t"])
             if kv_grad:
                 dkv = ops.gemm(dkvp, st.ct[pre + "cross.Wkv_t"])
-        st.accum_bias(pre + "self.bo", dac)
+        if not bo_done:   # otherwise already reduced by the norm_attn backward that produced da (MlpBlockFn)
+            st.accum_bias(pre + "self.bo", dac)
         st.accum_dw(pre + "self.Wo_t", dac, s["o"])
         d_o = ops.gemm(dac, st.ct[pre + "self.Wo_t"])
         qkv = s["qkv"]
@@ -206,19 +215,20 @@ class AttnBlockFn(torch.autograd.Function):
         st.accum_dw(pre + "self.Wqkv_t", dqkv, s["xn"])
         dxn = ops.gemm(dqkv, st.ct[pre + "self.Wqkv_t"], residual=dxn)
         # dx = da + LN'(dxn): accumulate into da's buffer (da has no other consumer)
+        # ... and its column sums are the gradient of the previous layer's MLP_out bias (da = d loss / d (that layer's output))
         ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, da, accumulate=True, dx_lowp=_lowp_out(st, da),
-                          dscale_accum=st.g[pre + "norm_q"])
+                          dscale_accum=st.g[pre + "norm_q"], dx_colsum=st.g[prev_b2] if prev_b2 else None)
         ctx.saved = None
         if st.progress_cb is not None:
             st.progress_cb(pre)   # every parameter of this layer (and of everything after it) now has its final gradient
-        return da, dkv, None, None, None, None, None, None, None, None
+        return da, dkv, None, None, None, None, None, None, None, None, None, None
 
 
 class MlpBlockFn(torch.autograd.Function):
     """y = a + MLP_out(gelu(MLP_in(LN(a))))   (attention.py:102-108)."""
 
     @staticmethod
-    def forward(ctx, a, anchor, st, pre):
+    def forward(ctx, a, anchor, st, pre, b2_done=False, fuse_bo=False):
         f, w, cdt = st.f32, st.c, st.cdt
         an, mean, rstd = ops.layernorm_fwd(a, f[pre + "norm_attn"], cdt, stats=True)
         zg = _gelu_grad_form(st, an, w[pre + "W1_t"])
@@ -226,24 +236,30 @@ class MlpBlockFn(torch.autograd.Function):
         y = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=a, out_dtype=torch.float32)
         ctx.saved = dict(a=a, mean=mean, rstd=rstd, an=an, z=z, h=h, zg=zg)
         ctx.args = (st, pre)
+        ctx.fuse = (b2_done, fuse_bo)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         st, pre = ctx.args
+        b2_done, fuse_bo = ctx.fuse
         s = ctx.saved
         dy = dy.contiguous()
         dyc = _c(st, dy)
-        st.accum_bias(pre + "b2", dyc)
+        if not b2_done:   # otherwise reduced by the next layer's norm_q backward, which produced dy
+            st.accum_bias(pre + "b2", dyc)
         st.accum_dw(pre + "W2_t", dyc, s["h"])
-        dz = ops.gemm_gelu_bwd(dyc, st.ct[pre + "W2_t"], s["z"], z_is_grad=s["zg"])
-        st.accum_bias(pre + "b1", dz)
+        gb1 = st.g[pre + "b1"]
+        b1_fused = s["zg"] and gb1.data_ptr() % 16 == 0   # column sums of dz from the GEMM epilogue
+        dz = ops.gemm_gelu_bwd(dyc, st.ct[pre + "W2_t"], s["z"], z_is_grad=s["zg"], dz_colsum=gb1 if b1_fused else None)
+        if not b1_fused:
+            st.accum_bias(pre + "b1", dz)
         st.accum_dw(pre + "W1_t", dz, s["an"])
         dan = ops.gemm(dz, st.ct[pre + "W1_t"])
         ops.layernorm_bwd(s["a"], st.f32[pre + "norm_attn"], s["mean"], s["rstd"], dan, dy, accumulate=True, dx_lowp=_lowp_out(st, dy),
-                          dscale_accum=st.g[pre + "norm_attn"])
+                          dscale_accum=st.g[pre + "norm_attn"], dx_colsum=st.g[pre + "self.bo"] if fuse_bo else None)
         ctx.saved = None
-        return dy, None, None, None
+        return dy, None, None, None, None, None
 
 
 class LastLayerFn(torch.autograd.Function):
@@ -254,7 +270,7 @@ class LastLayerFn(torch.autograd.Function):
     the reference's graph too (XLA eliminates them), so forward and gradients are unchanged."""
 
     @staticmethod
-    def forward(ctx, x, anchor, st, pre, m, batch, L, key_mask):
+    def forward(ctx, x, anchor, st, pre, m, batch, L, key_mask, prev_b2=None):
         f, w, cdt = st.f32, st.c, st.cdt
         H, Dh = m["heads"], m["Dh"]
         A, d = H * Dh, m["d"]
@@ -274,6 +290,7 @@ class LastLayerFn(torch.autograd.Function):
         ctx.saved = dict(x=x, xn=xn, mean=mean, rstd=rstd, kvp=kvp, rk=rk, q0=q0, rq=rq, o0=o0, stats=stats, a0=a0, an0=an0,
                          mean2=mean2, rstd2=rstd2, z0=z0, h0=h0, zg=zg)
         ctx.args = (st, pre, m, batch, L, key_mask)
+        ctx.prev_b2 = prev_b2
         return y0
 
     @staticmethod
@@ -317,11 +334,11 @@ class LastLayerFn(torch.autograd.Function):
         dx = torch.zeros_like(s["x"])
         dx.view(batch, L * d)[:, :d].copy_(da0)              # the residual path reaches token 0 only
         ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, dx, accumulate=True, dx_lowp=_lowp_out(st, dx),
-                          dscale_accum=st.g[pre + "norm_q"])
+                          dscale_accum=st.g[pre + "norm_q"], dx_colsum=st.g[ctx.prev_b2] if ctx.prev_b2 else None)
         ctx.saved = None
         if st.progress_cb is not None:
             st.progress_cb(pre)
-        return dx, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None
 
 
 class FinalNormFn(torch.autograd.Function):
@@ -486,10 +503,17 @@ class TrainEngine(Engine):
         for i in range(m["layers"]):
             pre = f"{short}.{i}."
             if first and self.prune_last and i == m["layers"] - 1 and kv is None and L > 1:
-                y0 = LastLayerFn.apply(x, self.anchor, self.st, pre, m, batch, L, key_mask)
+                prev_b2 = f"{short}.{i - 1}.b2" if (_colsum_fusable(self.st, m["d"]) and i > 0) else None
+                y0 = LastLayerFn.apply(x, self.anchor, self.st, pre, m, batch, L, key_mask, prev_b2)
                 return FinalNormFn.apply(y0, self.anchor, self.st, f"{short}.norm_encoder", batch, 1, False)
-            a = AttnBlockFn.apply(x, kv, self.anchor, self.st, pre, m, batch, L, Lkv, key_mask)
-            x = MlpBlockFn.apply(a, self.anchor, self.st, pre)
+            # bias gradients reduced inside the LayerNorm backward that produces the gradient they are column sums of:
+            # this layer's attention block hands MLP_out's bias of the PREVIOUS layer to its norm_q backward, this layer's
+            # MLP block hands the attention out-projection bias of the SAME layer to its norm_attn backward
+            fuse = _colsum_fusable(self.st, m["d"])
+            prev_b2 = f"{short}.{i - 1}.b2" if (fuse and i > 0) else None
+            nxt_does_b2 = fuse and i + 1 < m["layers"]
+            a = AttnBlockFn.apply(x, kv, self.anchor, self.st, pre, m, batch, L, Lkv, key_mask, prev_b2, fuse)
+            x = MlpBlockFn.apply(a, self.anchor, self.st, pre, nxt_does_b2, fuse)
         return FinalNormFn.apply(x, self.anchor, self.st, f"{short}.norm_encoder", batch, L, first)
 
     def forward_train(self, inputs, noise, discretize=True):

@@ -131,10 +131,11 @@ int spa3d_gemm_gelu(const void* A, int64_t lda, const void* Wt, int64_t ldw, int
                     int K, int save_grad, int impl, void* stream);
 /* Backward through MLP_out and the activation: dZ = (dY . Wt^T) * gelu_tanh'(Z); dY [M,K], Wt [N,K]
  * (MLP_out's kernel [N,K] as stored by Flax), Z, dZ [M,N], all in a_dtype.  z_is_grad = 1: Z already holds
- * gelu_tanh'(z) (spa3d_gemm_gelu with save_grad = 1) and dZ = (dY . Wt^T) * Z. */
+ * gelu_tanh'(z) (spa3d_gemm_gelu with save_grad = 1) and dZ = (dY . Wt^T) * Z.  dz_colsum ([N] f32, may be NULL; tcgen05 path
+ * only) += the column sums of dZ, i.e. the gradient of MLP_in's bias, reduced in the epilogue (no pass over dZ). */
 int spa3d_gemm_gelu_bwd(const void* dY, int64_t lddy, const void* Wt, int64_t ldw, int a_dtype,
                         const void* Z, int64_t ldz, void* dZ, int64_t lddz, int64_t M, int N, int K,
-                        int z_is_grad, int impl, void* stream);
+                        int z_is_grad, float* dz_colsum, int impl, void* stream);
 
 /* Weight gradient of a Dense layer (backward of attention.py:106-107,154-183 and
  * track_autoencoder_3d.py:73-115 under jax.value_and_grad, train.py:161-162):
@@ -163,12 +164,14 @@ int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* sc
  * [num_partials, d] receives per-block partial sums of dy*xhat.  dx_lowp (bf16 [rows,d], ldl) may be
  * NULL; otherwise it receives a bf16 copy of the final dx (the operand of the next backward GEMMs).
  * accumulate_dscale != 0: dscale_partial is the [d] gradient of the scale itself and every block adds
- * its partial sum into it atomically (no separate reduction pass). */
+ * its partial sum into it atomically (no separate reduction pass).  dx_colsum ([d] f32, may be NULL; fp32 fast path with
+ * d <= 512 only) += the sum over rows of the FINAL dx: that is the bias gradient of the Dense layer that produced x
+ * (attention.py:107,182), so no separate pass over dx is needed for it. */
 int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
                         const float* mean, const float* rstd, const void* dy, int64_t lddy,
                         int dy_dtype, void* dx, int64_t lddx, int dx_dtype, int dx_accumulate,
                         void* dx_lowp, int64_t ldl, float* dscale_partial, int num_partials,
-                        int accumulate_dscale, int64_t rows, int d, void* stream);
+                        int accumulate_dscale, float* dx_colsum, int64_t rows, int d, void* stream);
 
 /* ---- per-head RMSNorm of q and k (attention.py:166-167) + q/sqrt(Dh) (flax attention) ------
  * In place on a packed projection buffer: for every row and head h < heads,

@@ -185,9 +185,12 @@ def test_layernorm_fwd_bwd(spa, d):
     x.grad = None
     scale.grad = None
     om.layer_norm(x.double(), scale.double()).backward(dyb.double())
-    dscale2 = ops.layernorm_bwd(x.detach(), scale.detach(), mean, rstd, dyb, dx2, accumulate=True, dx_lowp=low)
+    cs = torch.full((d,), 2.0, device="cuda") if (d % 128 == 0 and d <= 512) else None   # fused column sums of the final dx (+=)
+    dscale2 = ops.layernorm_bwd(x.detach(), scale.detach(), mean, rstd, dyb, dx2, accumulate=True, dx_lowp=low, dx_colsum=cs)
     assert rel_err(dx2, x.grad + 1) < 1e-4 and rel_err(dscale2, scale.grad) < 1e-4
     assert rel_err(low, x.grad + 1) < 6e-3
+    if cs is not None:
+        assert rel_err(cs, (x.grad + 1).sum(0) + 2.0) < 1e-5, rel_err(cs, (x.grad + 1).sum(0) + 2.0)
     # bf16 output and "first token of each sequence" addressing
     yb = ops.layernorm_fwd(x.detach(), scale.detach(), torch.bfloat16, rows=rows // 7, ldx=7 * d, d=d)
     assert rel_err(yb, ref[::7]) < 6e-3
@@ -542,8 +545,11 @@ def test_gemm_gelu_fused_forward_and_backward(spa, impl):
             z64 = zref.clone().requires_grad_(True)
             torch.nn.functional.gelu(z64, approximate="tanh").sum().backward()
             assert rel_err(g, z64.grad) < 6e-3, rel_err(g, z64.grad)
-            dz2 = ops.gemm_gelu_bwd(dy, w2, g, impl=code, z_is_grad=True)
-            assert rel_err(dz2, z64.grad * (dy.double() @ w2.double().t())) < 1e-2
+            bsum = torch.full((Mh,), 0.5, device="cuda")
+            dz2 = ops.gemm_gelu_bwd(dy, w2, g, impl=code, z_is_grad=True, dz_colsum=bsum)
+            want = z64.grad * (dy.double() @ w2.double().t())
+            assert rel_err(dz2, want) < 1e-2
+            assert rel_err(bsum, want.sum(0) + 0.5) < 1e-2, rel_err(bsum, want.sum(0) + 0.5)   # bias gradient from the epilogue (+=)
 
 
 @pytest.mark.parametrize("N,T,Dd,Dz,W", [(40, 7, 768, 256, 384), (3, 150, 768, 256, 384), (33, 12, 64, 0, 256), (9, 5, 0, 128, 192)])
