@@ -167,7 +167,8 @@ def synth_train_batch(B, seed, dev):
 
 def run_train_leg(args, spa, model, variables, world, rank, dev, barrier):
     """cfg3: one optimiser step over a global batch of 64 clips, 64/N clips per rank in micro-batches of
-    --train-micro clips (default 4: 6 % faster than one-clip micro-batches, 82 GB of saved activations), gradients summed over NCCL (overlapped with the last backward), AdamW on every rank."""
+    --train-micro clips (default 2: 4 % faster than one-clip micro-batches; 44 GB of saved activations beside the 80 GB of
+    resident synthetic inputs when one GPU holds all 64 clips), gradients summed over NCCL (overlapped with the last backward), AdamW on every rank."""
     import torch.distributed as dist
 
     te = importlib.import_module("3dspa_code_b200.train_engine")
@@ -530,7 +531,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the cfg3 training leg and the cfg4 gather leg")
     ap.add_argument("--train-batch", type=int, default=TRAIN_GLOBAL_BATCH, help="global batch of the training leg (clips)")
     ap.add_argument("--train-steps", type=int, default=2)
-    ap.add_argument("--train-micro", type=int, default=4, help="clips per micro-batch of the training leg (4 clips save 82 GB of activations)")
+    ap.add_argument("--train-micro", type=int, default=2, help="clips per micro-batch of the training leg (2 clips: 44 GB of saved activations beside the 80 GB of resident fp32 inputs at N=1)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when the
     # box exports NCCL_DEBUG=VERSION), so file descriptor 1 points at stderr while the benchmark runs and the JSON line goes
