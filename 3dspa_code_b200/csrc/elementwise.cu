@@ -260,63 +260,89 @@ layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float*
       return make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
     }
   };
-  for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
-    const float* xr = x + row * ldx;
-    const TDY* dyr = dy + row * lddy;
-    const float mu = mean[row], rs = rstd[row];
-    // the row stays in registers as loaded (x fp32, dy packed) between the statistics and the output pass
-    float4 xv[J];
-    uint2 dp[J];
-    uint2 dq[DYF ? J : 1];
+  // Narrow rows (J <= 4: a row is 12-16 floats per lane) are processed two at a time and the old dx of an accumulating call
+  // is loaded together with x and dy: every warp then keeps two rows x three streams in flight instead of paying one HBM
+  // round trip for x / dy and a second, dependent one for dx per row.  Wide rows (J >= 8) stay at one row (register budget).
+  constexpr int R = CS ? 2 : 1;
+  constexpr bool KEEPX = true;
+  const int64_t stride = (int64_t)gridDim.x * nwarp;
+  for (int64_t row0 = (int64_t)blockIdx.x * nwarp + warp; row0 < rows; row0 += stride * R) {
+    float4 xv[R][KEEPX ? J : 1];
+    uint2 dp[R][J];
+    uint2 dq[R][DYF ? J : 1];
+    float4 ov[R][CS ? J : 1];
+    float mu[R], rs[R];
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int c = (lane + 32 * j) * 4;
-      xv[j] = *reinterpret_cast<const float4*>(xr + c);
-      if constexpr (DYF) {
-        const uint4 w = *reinterpret_cast<const uint4*>(dyr + c);
-        dp[j] = make_uint2(w.x, w.y);
-        dq[j] = make_uint2(w.z, w.w);
-      } else {
-        dp[j] = *reinterpret_cast<const uint2*>(dyr + c);
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r * stride;
+      const bool ok = row < rows;
+      const int64_t rr = ok ? row : row0;   // clamped: loads stay in bounds, results of a phantom row are discarded
+      const float* xr = x + rr * ldx;
+      const TDY* dyr = dy + rr * lddy;
+      mu[r] = mean[rr];
+      rs[r] = rstd[rr];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c = (lane + 32 * j) * 4;
+        if constexpr (KEEPX) xv[r][j] = *reinterpret_cast<const float4*>(xr + c);
+        if constexpr (DYF) {
+          const uint4 w = *reinterpret_cast<const uint4*>(dyr + c);
+          dp[r][j] = make_uint2(w.x, w.y);
+          dq[r][j] = make_uint2(w.z, w.w);
+        } else {
+          dp[r][j] = *reinterpret_cast<const uint2*>(dyr + c);
+        }
+        if constexpr (CS) {
+          ov[r][j] = dx_accumulate ? *reinterpret_cast<const float4*>(dx + rr * lddx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
-    float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int c = (lane + 32 * j) * 4;
-      const float4 dv = unpack(make_uint4(dp[j].x, dp[j].y, DYF ? dq[DYF ? j : 0].x : 0u, DYF ? dq[DYF ? j : 0].y : 0u));
-      const float4 sc = *reinterpret_cast<const float4*>(s_sc + c);
-      const float4 xh = make_float4((xv[j].x - mu) * rs, (xv[j].y - mu) * rs, (xv[j].z - mu) * rs, (xv[j].w - mu) * rs);
-      const float4 g = make_float4(dv.x * sc.x, dv.y * sc.y, dv.z * sc.z, dv.w * sc.w);
-      sg += (g.x + g.y) + (g.z + g.w);
-      sgx += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
-      acc[j].x = fmaf(dv.x, xh.x, acc[j].x);
-      acc[j].y = fmaf(dv.y, xh.y, acc[j].y);
-      acc[j].z = fmaf(dv.z, xh.z, acc[j].z);
-      acc[j].w = fmaf(dv.w, xh.w, acc[j].w);
-    }
-    sg = warp_sum(sg) * (1.f / D);
-    sgx = warp_sum(sgx) * (1.f / D);
-    float* dxr = dx + row * lddx;
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r * stride;
+      if (row >= rows) break;
+      float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int c = (lane + 32 * j) * 4;
-      const float4 dv = unpack(make_uint4(dp[j].x, dp[j].y, DYF ? dq[DYF ? j : 0].x : 0u, DYF ? dq[DYF ? j : 0].y : 0u));
-      const float4 sc = *reinterpret_cast<const float4*>(s_sc + c);
-      const float4 xh = make_float4((xv[j].x - mu) * rs, (xv[j].y - mu) * rs, (xv[j].z - mu) * rs, (xv[j].w - mu) * rs);
-      float4 v = make_float4(rs * (dv.x * sc.x - sg - xh.x * sgx), rs * (dv.y * sc.y - sg - xh.y * sgx),
-                             rs * (dv.z * sc.z - sg - xh.z * sgx), rs * (dv.w * sc.w - sg - xh.w * sgx));
-      if (dx_accumulate) {
-        const float4 o = *reinterpret_cast<const float4*>(dxr + c);
-        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      for (int j = 0; j < J; ++j) {
+        const int c = (lane + 32 * j) * 4;
+        const float4 dv = unpack(make_uint4(dp[r][j].x, dp[r][j].y, DYF ? dq[r][DYF ? j : 0].x : 0u, DYF ? dq[r][DYF ? j : 0].y : 0u));
+        const float4 sc = *reinterpret_cast<const float4*>(s_sc + c);
+        const float4 xq = KEEPX ? xv[r][KEEPX ? j : 0] : *reinterpret_cast<const float4*>(x + row * ldx + c);
+        const float4 xh = make_float4((xq.x - mu[r]) * rs[r], (xq.y - mu[r]) * rs[r], (xq.z - mu[r]) * rs[r], (xq.w - mu[r]) * rs[r]);
+        const float4 g = make_float4(dv.x * sc.x, dv.y * sc.y, dv.z * sc.z, dv.w * sc.w);
+        sg += (g.x + g.y) + (g.z + g.w);
+        sgx += (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+        acc[j].x = fmaf(dv.x, xh.x, acc[j].x);
+        acc[j].y = fmaf(dv.y, xh.y, acc[j].y);
+        acc[j].z = fmaf(dv.z, xh.z, acc[j].z);
+        acc[j].w = fmaf(dv.w, xh.w, acc[j].w);
       }
-      *reinterpret_cast<float4*>(dxr + c) = v;
-      if constexpr (CS) {
-        csum[j].x += v.x; csum[j].y += v.y; csum[j].z += v.z; csum[j].w += v.w;
-      }
-      if (dx_lowp) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-        *reinterpret_cast<uint2*>(dx_lowp + row * ldl + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      sg = warp_sum(sg) * (1.f / D);
+      sgx = warp_sum(sgx) * (1.f / D);
+      float* dxr = dx + row * lddx;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c = (lane + 32 * j) * 4;
+        const float4 dv = unpack(make_uint4(dp[r][j].x, dp[r][j].y, DYF ? dq[r][DYF ? j : 0].x : 0u, DYF ? dq[r][DYF ? j : 0].y : 0u));
+        const float4 sc = *reinterpret_cast<const float4*>(s_sc + c);
+        const float4 xq = KEEPX ? xv[r][KEEPX ? j : 0] : *reinterpret_cast<const float4*>(x + row * ldx + c);
+        const float4 xh = make_float4((xq.x - mu[r]) * rs[r], (xq.y - mu[r]) * rs[r], (xq.z - mu[r]) * rs[r], (xq.w - mu[r]) * rs[r]);
+        float4 v = make_float4(rs[r] * (dv.x * sc.x - sg - xh.x * sgx), rs[r] * (dv.y * sc.y - sg - xh.y * sgx),
+                               rs[r] * (dv.z * sc.z - sg - xh.z * sgx), rs[r] * (dv.w * sc.w - sg - xh.w * sgx));
+        if constexpr (CS) {
+          v.x += ov[r][j].x; v.y += ov[r][j].y; v.z += ov[r][j].z; v.w += ov[r][j].w;
+        } else if (dx_accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(dxr + c);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        *reinterpret_cast<float4*>(dxr + c) = v;
+        if constexpr (CS) {
+          csum[j].x += v.x; csum[j].y += v.y; csum[j].z += v.z; csum[j].w += v.w;
+        }
+        if (dx_lowp) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+          *reinterpret_cast<uint2*>(dx_lowp + row * ldl + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
       }
     }
   }
