@@ -306,6 +306,12 @@ class Engine:
         keys = ["support_tracks", "support_tracks_visible"] + (["dino_features"] if use_dino else []) + (["depth_features"] if use_depth else [])
         host = {k: (inputs[k] if inputs[k].dtype == torch.float32 else inputs[k].float()) for k in keys}
         pieces = [(b, n0, min(n0 + self.stream_chunk, N)) for b in range(B) for n0 in range(0, N, self.stream_chunk)]
+        # taper the tail: whatever is computed after the LAST upload has landed is not hidden by any copy, so the final
+        # chunk is split 1/2, 1/4, 1/4 (the last piece's transformer pass is then a quarter as long)
+        b_, n0_, n1_ = pieces[-1]
+        if n1_ - n0_ >= 128 and (n1_ - n0_) % 4 == 0:
+            q = (n1_ - n0_) // 4
+            pieces[-1:] = [(b_, n0_, n0_ + 2 * q), (b_, n0_ + 2 * q, n0_ + 3 * q), (b_, n0_ + 3 * q, n1_)]
 
         # two persistent staging slots per input (no allocator traffic across streams: a tensor
         # allocated on the copy stream and freed after use on the compute stream makes the caching
