@@ -372,6 +372,111 @@ layernorm_bwd_fast_kernel(const float* __restrict__ x, int64_t ldx, const float*
   }
 }
 
+// Wide rows (d = 256*JH: 1024, 1280, 1536): two warps per row, each owning one half of the columns, so a thread holds
+// 4*JH floats of x, dy, the old dx and the two column accumulators (no spills under 128 registers, two blocks per SM);
+// the two row statistics are exchanged through shared memory under a 64-thread named barrier per warp pair.
+template <int JH, typename TDY>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd_wide_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ scale,
+                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const TDY* __restrict__ dy, int64_t lddy, float* __restrict__ dx, int64_t lddx,
+                          int dx_accumulate, bf16* __restrict__ dx_lowp, int64_t ldl,
+                          float* __restrict__ dscale_partial, int ds_accum, float* __restrict__ dcol, int64_t rows) {
+  constexpr int D = 256 * JH, DH_ = 128 * JH;
+  constexpr bool DYF = sizeof(TDY) == 4;
+  __shared__ float s_ds[D];
+  __shared__ float s_cs[D];
+  __shared__ __align__(16) float s_sc[D];
+  __shared__ float s_red[2][8][2];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    s_ds[i] = 0.f;
+    s_cs[i] = 0.f;
+    s_sc[i] = scale[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1, col0 = (warp & 1) * DH_;
+  float4 acc[JH], csum[JH];
+#pragma unroll
+  for (int j = 0; j < JH; ++j) acc[j] = csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int it = 0;
+  for (int64_t row = (int64_t)blockIdx.x * 4 + pair; row < rows; row += (int64_t)gridDim.x * 4, ++it) {
+    const float* xr = x + row * ldx + col0;
+    const TDY* dyr = dy + row * lddy + col0;
+    float* dxr = dx + row * lddx + col0;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[JH], dv[JH], ov[JH];
+#pragma unroll
+    for (int j = 0; j < JH; ++j) {
+      const int c = (lane + 32 * j) * 4;
+      xh[j] = *reinterpret_cast<const float4*>(xr + c);
+      if constexpr (DYF) {
+        dv[j] = *reinterpret_cast<const float4*>(dyr + c);
+      } else {
+        const uint2 w = *reinterpret_cast<const uint2*>(dyr + c);
+        dv[j] = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                            __uint_as_float(w.y & 0xffff0000u));
+      }
+      ov[j] = dx_accumulate ? *reinterpret_cast<const float4*>(dxr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < JH; ++j) {
+      const int c = col0 + (lane + 32 * j) * 4;
+      const float4 sc = *reinterpret_cast<const float4*>(s_sc + c);
+      xh[j] = make_float4((xh[j].x - mu) * rs, (xh[j].y - mu) * rs, (xh[j].z - mu) * rs, (xh[j].w - mu) * rs);
+      acc[j].x = fmaf(dv[j].x, xh[j].x, acc[j].x);
+      acc[j].y = fmaf(dv[j].y, xh[j].y, acc[j].y);
+      acc[j].z = fmaf(dv[j].z, xh[j].z, acc[j].z);
+      acc[j].w = fmaf(dv[j].w, xh[j].w, acc[j].w);
+      dv[j] = make_float4(dv[j].x * sc.x, dv[j].y * sc.y, dv[j].z * sc.z, dv[j].w * sc.w);   // g = dy * scale
+      sg += (dv[j].x + dv[j].y) + (dv[j].z + dv[j].w);
+      sgx += (dv[j].x * xh[j].x + dv[j].y * xh[j].y) + (dv[j].z * xh[j].z + dv[j].w * xh[j].w);
+    }
+    sg = warp_sum(sg);
+    sgx = warp_sum(sgx);
+    if (lane == 0) {
+      s_red[it & 1][warp][0] = sg;
+      s_red[it & 1][warp][1] = sgx;
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+    sg = (sg + s_red[it & 1][warp ^ 1][0]) * (1.f / D);
+    sgx = (sgx + s_red[it & 1][warp ^ 1][1]) * (1.f / D);
+#pragma unroll
+    for (int j = 0; j < JH; ++j) {
+      const int c = (lane + 32 * j) * 4;
+      float4 v = make_float4(rs * (dv[j].x - sg - xh[j].x * sgx), rs * (dv[j].y - sg - xh[j].y * sgx),
+                             rs * (dv[j].z - sg - xh[j].z * sgx), rs * (dv[j].w - sg - xh[j].w * sgx));
+      v.x += ov[j].x; v.y += ov[j].y; v.z += ov[j].z; v.w += ov[j].w;
+      *reinterpret_cast<float4*>(dxr + c) = v;
+      csum[j].x += v.x; csum[j].y += v.y; csum[j].z += v.z; csum[j].w += v.w;
+      if (dx_lowp) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(dx_lowp + row * ldl + col0 + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < JH; ++j) {
+    const int c = col0 + (lane + 32 * j) * 4;
+    atomicAdd(&s_ds[c], acc[j].x);
+    atomicAdd(&s_ds[c + 1], acc[j].y);
+    atomicAdd(&s_ds[c + 2], acc[j].z);
+    atomicAdd(&s_ds[c + 3], acc[j].w);
+    if (dcol != nullptr) {
+      atomicAdd(&s_cs[c], csum[j].x);
+      atomicAdd(&s_cs[c + 1], csum[j].y);
+      atomicAdd(&s_cs[c + 2], csum[j].z);
+      atomicAdd(&s_cs[c + 3], csum[j].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (ds_accum) atomicAdd(&dscale_partial[i], s_ds[i]);
+    else dscale_partial[(int64_t)blockIdx.x * D + i] = s_ds[i];
+    if (dcol != nullptr) atomicAdd(&dcol[i], s_cs[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // per-head RMSNorm (attention.py:166-167), in place; one warp per (row, head)
 // ------------------------------------------------------------------------------------------
@@ -1030,7 +1135,23 @@ int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* sc
   const bool fast = x_dtype == SPA3D_F32 && dx_dtype == SPA3D_F32 && d % 128 == 0 && d <= 1536 && ldx % 4 == 0 &&
                     lddx % 4 == 0 && lddy % 4 == 0 && al16(x) && al16(dx) && al16(dy) && al16(scale) &&
                     (!dx_lowp || (ldl % 4 == 0 && (reinterpret_cast<uintptr_t>(dx_lowp) & 7) == 0));
-  SPA3D_REQUIRE(dx_colsum == nullptr || (fast && d <= 512), "layernorm_bwd: dx_colsum needs the fp32 fast path with d <= 512");
+  const bool wide = fast && (d == 1024 || d == 1280 || d == 1536);
+  SPA3D_REQUIRE(dx_colsum == nullptr || (fast && (d <= 512 || wide)), "layernorm_bwd: dx_colsum needs the fp32 fast path with d <= 512 or d in {1024, 1280, 1536}");
+  if (wide) {
+#define SPA3D_LN_BWD_WIDE(JH)                                                                                  \
+  case JH:                                                                                                     \
+    SPA3D_DISPATCH(dy_dtype, TDY, {                                                                            \
+      layernorm_bwd_wide_kernel<JH, TDY><<<num_partials, 256, 0, st>>>((const float*)x, ldx, scale, mean, rstd, \
+          (const TDY*)dy, lddy, (float*)dx, lddx, dx_accumulate, (bf16*)dx_lowp, ldl, dscale_partial, accumulate_dscale,   \
+          dx_colsum, rows);                                                                                    \
+    });                                                                                                        \
+    return check_launch("layernorm_bwd_wide");
+    switch (d / 256) {
+      SPA3D_LN_BWD_WIDE(4) SPA3D_LN_BWD_WIDE(5) SPA3D_LN_BWD_WIDE(6)
+      default: break;
+    }
+#undef SPA3D_LN_BWD_WIDE
+  }
   if (fast) {
 #define SPA3D_LN_BWD_FAST(J)                                                                                   \
   case J:                                                                                                      \

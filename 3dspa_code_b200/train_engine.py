@@ -133,8 +133,9 @@ def _gelu_grad_form(st, a, wt):
 
 def _colsum_fusable(st, d):
     """Bias gradients that are column sums of a LayerNorm-backward output can be reduced inside that kernel (bf16 mode, fp32
-    rows of at most 512 columns): the per-track transformer (d = 384) and the latent transformer (d = 512)."""
-    return st.cdt == torch.bfloat16 and d % 128 == 0 and d <= 512
+    rows of at most 512 columns, or the two-warps-per-row kernel for 1024 / 1280 / 1536): the per-track transformer (d = 384),
+    the latent transformer (d = 512) and the read-out transformer (d = 1280)."""
+    return st.cdt == torch.bfloat16 and ((d % 128 == 0 and d <= 512) or d in (1024, 1280, 1536))
 
 
 def _lowp_out(st, t):

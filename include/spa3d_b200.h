@@ -165,7 +165,7 @@ int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* sc
  * NULL; otherwise it receives a bf16 copy of the final dx (the operand of the next backward GEMMs).
  * accumulate_dscale != 0: dscale_partial is the [d] gradient of the scale itself and every block adds
  * its partial sum into it atomically (no separate reduction pass).  dx_colsum ([d] f32, may be NULL; fp32 fast path with
- * d <= 512 only) += the sum over rows of the FINAL dx: that is the bias gradient of the Dense layer that produced x
+ * d <= 512 or d in {1024, 1280, 1536} only) += the sum over rows of the FINAL dx: that is the bias gradient of the Dense layer that produced x
  * (attention.py:107,182), so no separate pass over dx is needed for it. */
 int spa3d_layernorm_bwd(const void* x, int64_t ldx, int x_dtype, const float* scale,
                         const float* mean, const float* rstd, const void* dy, int64_t lddy,

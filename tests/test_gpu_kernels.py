@@ -163,7 +163,7 @@ def test_gemm_strided_backward_layouts(spa):
 
 
 # ---- norms -----------------------------------------------------------------------------------
-@pytest.mark.parametrize("d", [48, 384, 512, 1152, 1280])
+@pytest.mark.parametrize("d", [48, 384, 512, 1024, 1152, 1280, 1536])
 def test_layernorm_fwd_bwd(spa, d):
     ops = spa.ops
     torch.manual_seed(3)
@@ -185,7 +185,7 @@ def test_layernorm_fwd_bwd(spa, d):
     x.grad = None
     scale.grad = None
     om.layer_norm(x.double(), scale.double()).backward(dyb.double())
-    cs = torch.full((d,), 2.0, device="cuda") if (d % 128 == 0 and d <= 512) else None   # fused column sums of the final dx (+=)
+    cs = torch.full((d,), 2.0, device="cuda") if ((d % 128 == 0 and d <= 512) or d in (1024, 1280, 1536)) else None   # fused column sums of the final dx (+=)
     dscale2 = ops.layernorm_bwd(x.detach(), scale.detach(), mean, rstd, dyb, dx2, accumulate=True, dx_lowp=low, dx_colsum=cs)
     assert rel_err(dx2, x.grad + 1) < 1e-4 and rel_err(dscale2, scale.grad) < 1e-4
     assert rel_err(low, x.grad + 1) < 6e-3
