@@ -233,7 +233,8 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
         const bf16* pj = p.proj + c * 32 + cc * 4;
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
-          const uint4 off = *reinterpret_cast<const uint4*>(smp + ((half * 4 + i4) * 4 + cr) * 12);
+          const float4 offf = lds128(smem_u32(smp) + (((half * 4 + i4) * 4 + cr) * 12) * 4);
+          const uint4 off = make_uint4(__float_as_uint(offf.x), __float_as_uint(offf.y), __float_as_uint(offf.z), __float_as_uint(offf.w));
           g[i4][0] = __ldg(reinterpret_cast<const uint2*>(pj + off.x));
           g[i4][1] = __ldg(reinterpret_cast<const uint2*>(pj + off.y));
           g[i4][2] = __ldg(reinterpret_cast<const uint2*>(pj + off.z));
@@ -250,9 +251,9 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const int i = half * 4 + i4, rr = i * 4 + cr;
-          const float4 wq = *reinterpret_cast<const float4*>(smp + rr * 12 + 4);
-          const float4 dq = *reinterpret_cast<const float4*>(smp + rr * 12 + 8);
-          float4 a = *reinterpret_cast<const float4*>(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          const float4 wq = lds128(smem_u32(smp) + (rr * 12 + 4) * 4);
+          const float4 dq = lds128(smem_u32(smp) + (rr * 12 + 8) * 4);
+          float4 a = lds128(smem_u32(slab) + rr * 128 + ((cc ^ (rr & 7)) << 4));
           a.x += b.x + lo(g[i4][0].x) * wq.x + lo(g[i4][1].x) * wq.y + lo(g[i4][2].x) * wq.z + lo(g[i4][3].x) * wq.w;
           a.y += b.y + hi(g[i4][0].x) * wq.x + hi(g[i4][1].x) * wq.y + hi(g[i4][2].x) * wq.z + hi(g[i4][3].x) * wq.w;
           a.z += b.z + lo(g[i4][0].y) * wq.x + lo(g[i4][1].y) * wq.y + lo(g[i4][2].y) * wq.z + lo(g[i4][3].y) * wq.w;
@@ -277,12 +278,11 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
           mbar_arrive(tempty_bar);
         }
         const int col0 = c * 32;
-        uint8_t* srow = slab + lane * 128;
+        const uint32_t srow = smem_u32(slab) + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        for (int j = 0; j < 8; ++j) sts128(srow + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
-        const float4 b = *reinterpret_cast<const float4*>(smem_bias + col0 + cc * 4);
+        const float4 b = lds128(smem_u32(smem_bias) + (col0 + cc * 4) * 4);
         if constexpr (SAMPLE) {
           gather(c, 1, gb);
           finish(c, 0, ga, b);
@@ -292,7 +292,7 @@ embed_fused_kernel(const __grid_constant__ CUtensorMap tmB, const EmbedParams p)
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + cr;
             if (orow[i] != nullptr) {
-              float4 a = *reinterpret_cast<const float4*>(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
+              float4 a = lds128(smem_u32(slab) + rr * 128 + ((cc ^ (rr & 7)) << 4));
               a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
               *reinterpret_cast<float4*>(orow[i] + col0) = a;
             }

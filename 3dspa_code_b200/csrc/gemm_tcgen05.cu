@@ -109,14 +109,11 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
 
 // 32 bf16 of this lane's row -> 64-byte row of a [32 x 64 B] slab laid out for a SWIZZLE_64B TMA store
 __device__ __forceinline__ void slab_store_bf16(uint8_t* slab, int lane, const uint64_t (&v)[16]) {
-  uint8_t* srow = slab + lane * 64;
+  const uint32_t srow = smem_u32(slab) + lane * 64;   // explicit shared-space stores (see sts128)
   const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 w = make_uint4(pack_bf16x2(v[4 * j]), pack_bf16x2(v[4 * j + 1]), pack_bf16x2(v[4 * j + 2]),
-                         pack_bf16x2(v[4 * j + 3]));
-    *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = w;
-  }
+  for (int j = 0; j < 4; ++j)
+    sts128(srow + ((j ^ sw) << 4), pack_bf16x2(v[4 * j]), pack_bf16x2(v[4 * j + 1]), pack_bf16x2(v[4 * j + 2]), pack_bf16x2(v[4 * j + 3]));
 }
 
 // TN = false: C[M,N] = A[M,K] . Wt[N,K]^T (both operands K-major, boxes of 64 K-elements).
