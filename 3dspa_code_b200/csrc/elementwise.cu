@@ -726,29 +726,36 @@ __global__ void decoder_tokens_fwd_kernel(const TL* __restrict__ lat, const TQ* 
 }
 
 // d_lat[b,n,c] = sum_q d_tok[b,q,1+n,c] + sum_q [0 <= c-5t_q < 128] d_tok[b,q,1+n,C + c-5t_q]
+// The sum over the Q queries is split QS ways across blocks (B*L alone is 128 blocks of strictly serial loads) and the
+// partial sums are added atomically into the zeroed d_lat.
 template <typename TT>
 __global__ void decoder_tokens_bwd_kernel(const TT* __restrict__ d_tok, const int32_t* __restrict__ qframe,
                                           float* __restrict__ d_lat, float* __restrict__ d_qe, int B,
-                                          int Q, int L, int C) {
+                                          int Q, int L, int C, int QS) {
   int D = C + 128;
-  int64_t bn = blockIdx.x;  // b*L + n   (blocks [0, B*L)) then query rows [B*L, B*L + B*Q)
-  if (bn >= (int64_t)B * L) {
-    int64_t bq = bn - (int64_t)B * L;
+  const int64_t lat_blocks = (int64_t)B * L * QS;
+  if ((int64_t)blockIdx.x >= lat_blocks) {   // query rows: d_qe[b,q,:] = d_tok[b,q,0,:]
+    int64_t bq = (int64_t)blockIdx.x - lat_blocks;
     const TT* src = d_tok + bq * (L + 1) * D;
     for (int c = threadIdx.x; c < D; c += blockDim.x) d_qe[bq * D + c] = ldf<TT>(src + c);
     return;
   }
+  const int64_t bn = blockIdx.x / QS;   // b*L + n
+  const int split = (int)(blockIdx.x % QS);
+  const int qper = (Q + QS - 1) / QS;
+  const int q0 = split * qper, q1 = min(Q, q0 + qper);
   int b = (int)(bn / L), n = (int)(bn % L);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int q = 0; q < Q; ++q) {
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+    for (int q = q0; q < q1; ++q) {
       int64_t bq = (int64_t)b * Q + q;
       const TT* src = d_tok + (bq * (L + 1) + 1 + n) * D;
-      acc += ldf<TT>(src + c);
+      acc0 += ldf<TT>(src + c);
       int w = c - qframe[bq] * 5;
-      if (w >= 0 && w < 128) acc += ldf<TT>(src + C + w);
+      if (w >= 0 && w < 128) acc1 += ldf<TT>(src + C + w);
     }
-    d_lat[bn * C + c] = acc;
+    atomicAdd(&d_lat[bn * C + c], acc0 + acc1);
   }
 }
 
@@ -1269,11 +1276,14 @@ int spa3d_decoder_tokens_fwd(const void* lat, int lat_dtype, const void* query_e
 int spa3d_decoder_tokens_bwd(const void* d_tokens, int tok_dtype, const int32_t* query_frame,
                              float* d_lat, float* d_query_emb, int B, int Q, int L, int C,
                              void* stream) {
-  int64_t blocks = (int64_t)B * L + (int64_t)B * Q;
+  const int QS = Q >= 64 ? 8 : 1;   // query-axis splits of the latent-gradient reduction
+  int64_t blocks = (int64_t)B * L * QS + (int64_t)B * Q;
   if (blocks == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t me = cudaMemsetAsync(d_lat, 0, (size_t)B * L * C * sizeof(float), st);
+  SPA3D_REQUIRE(me == cudaSuccess, "decoder_tokens_bwd: memset: %s", cudaGetErrorString(me));
   SPA3D_DISPATCH(tok_dtype, TT, {
-    decoder_tokens_bwd_kernel<TT><<<(unsigned)blocks, 256, 0, st>>>((const TT*)d_tokens, query_frame, d_lat, d_query_emb, B, Q, L, C);
+    decoder_tokens_bwd_kernel<TT><<<(unsigned)blocks, 256, 0, st>>>((const TT*)d_tokens, query_frame, d_lat, d_query_emb, B, Q, L, C, QS);
   });
   return check_launch("decoder_tokens_bwd");
 }

@@ -384,6 +384,18 @@ def test_decoder_tokens_fwd_bwd(spa):
     ref2 = torch.cat([qe_r.view(B, Q, 1, D), om.append_time_feat(lat_r[:, None].expand(B, Q, L, C), qf.cpu())], dim=2)
     ref2.backward(g.view(B, Q, L + 1, D).cpu().double())
     assert rel_err(d_lat, lat_r.grad) < 1e-5 and rel_err(d_qe, qe_r.grad) < 1e-6
+    # many queries: the reduction over queries is split across blocks (atomic partial sums into a zeroed buffer)
+    Q2 = 83
+    qf2 = torch.randint(0, 41, (B, Q2), dtype=torch.int32, device="cuda")
+    g2 = torch.randn(B * Q2 * (L + 1), D, device="cuda")
+    d_lat2 = torch.full((B, L, C), float("nan"), device="cuda")
+    d_qe2 = torch.empty(B * Q2, D, device="cuda")
+    ops.decoder_tokens_bwd(g2, qf2, d_lat2, d_qe2, B, Q2, L, C)
+    lat_r = lat.cpu().double().requires_grad_(True)
+    qe2_r = torch.zeros(B * Q2, D, dtype=torch.float64, requires_grad=True)
+    ref3 = torch.cat([qe2_r.view(B, Q2, 1, D), om.append_time_feat(lat_r[:, None].expand(B, Q2, L, C), qf2.cpu())], dim=2)
+    ref3.backward(g2.view(B, Q2, L + 1, D).cpu().double())
+    assert rel_err(d_lat2, lat_r.grad) < 1e-5 and rel_err(d_qe2, qe2_r.grad) < 1e-6
 
 
 def test_split_and_loss(spa):
