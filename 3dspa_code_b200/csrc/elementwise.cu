@@ -713,16 +713,19 @@ __global__ void decoder_tokens_fwd_kernel(const TL* __restrict__ lat, const TQ* 
   }
   const TL* l = lat + ((int64_t)b * L + (tkn - 1)) * C;
   int off = qframe[bq] * 5;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float v;
-    if (c < C) {
-      v = ldf<TL>(l + c);
-    } else {
-      int src = c - C + off;
-      v = (src >= 0 && src < C) ? ldf<TL>(l + src) : 0.f;
+  auto value = [&](int c) -> float {
+    if (c < C) return ldf<TL>(l + c);
+    const int src = c - C + off;
+    return (src >= 0 && src < C) ? ldf<TL>(l + src) : 0.f;
+  };
+  if constexpr (sizeof(TT) == 4) {
+    if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(tok) & 15) == 0) {   // 128-bit stores (the latents are small and cached)
+      for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4)
+        *reinterpret_cast<float4*>(o + c) = make_float4(value(c), value(c + 1), value(c + 2), value(c + 3));
+      return;
     }
-    stf<TT>(o + c, v);
   }
+  for (int c = threadIdx.x; c < D; c += blockDim.x) stf<TT>(o + c, value(c));
 }
 
 // d_lat[b,n,c] = sum_q d_tok[b,q,1+n,c] + sum_q [0 <= c-5t_q < 128] d_tok[b,q,1+n,C + c-5t_q]

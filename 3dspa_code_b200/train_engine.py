@@ -332,10 +332,19 @@ class LastLayerFn(torch.autograd.Function):
         dxn = ops.gemm(dkv, ct[:, A:])                       # every token, through keys and values
         dxn0 = dxn.view(batch, L * d)[:, :d]
         ops.gemm(dq0, ct[:, :A], residual=dxn0, out=dxn0)    # token 0 also through its query
-        dx = torch.zeros_like(s["x"])
-        dx.view(batch, L * d)[:, :d].copy_(da0)              # the residual path reaches token 0 only
-        ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, dx, accumulate=True, dx_lowp=_lowp_out(st, dx),
+        # dx = LN'(dxn) on every token, plus the residual path, which reaches token 0 only: the norm backward writes dx
+        # (no zero-filled buffer to accumulate into), then the batch x d token-0 rows are patched in dx, in its bf16 copy and
+        # in the column sums handed to the previous layer's MLP_out bias
+        dx = torch.empty_like(s["x"])
+        low = _lowp_out(st, dx)
+        ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, dx, accumulate=False, dx_lowp=low,
                           dscale_accum=st.g[pre + "norm_q"], dx_colsum=st.g[ctx.prev_b2] if ctx.prev_b2 else None)
+        dx0 = dx.view(batch, L * d)[:, :d]
+        dx0.add_(da0)
+        if low is not None:
+            low.view(batch, L * d)[:, :d].copy_(dx0)
+        if ctx.prev_b2:
+            ops.colsum(da0, st.g[ctx.prev_b2], accumulate=True)
         ctx.saved = None
         if st.progress_cb is not None:
             st.progress_cb(pre)
