@@ -225,8 +225,9 @@ def test_forward_matches_reference_executed_golden(spa, precision, golden_dir):
     assert rel_err(res.visible_logits, torch.from_numpy(g["dec/visible_logits"])) < TOL[precision]
 
 
-def test_trajan_matches_reference_executed_golden(spa, golden_dir):
-    """TRAJAN 2D end to end, as written (track_autoencoder.py executed on the flax stand-ins), fp32 path."""
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_trajan_matches_reference_executed_golden(spa, golden_dir, precision):
+    """TRAJAN 2D end to end, as written (track_autoencoder.py executed on the flax stand-ins), fp32 and bf16 paths."""
     import os
 
     g = np.load(os.path.join(golden_dir, "model_trajan.npz"))
@@ -234,12 +235,12 @@ def test_trajan_matches_reference_executed_golden(spa, golden_dir):
     model = spa.TrackAutoEncoder(num_output_frames=F)
     variables = {"params": om.init_params_2d(om.Config2D(num_output_frames=F), seed=int(g["seed"]), randomize_norms=True)}
     inp = {k[3:]: np.asarray(g[k], np.int32 if k.endswith("boundary_frame") else np.float32) for k in g.files if k.startswith("in/")}
-    got = model.apply(variables, inp, discretize=False, precision="fp32")   # quantiser off: no round(x*128) flips
+    got = model.apply(variables, inp, discretize=False, precision=precision)   # quantiser off: no round(x*128) flips
     for name in ("tracks", "visible_logits", "certain_logits"):
         e = rel_err(getattr(got, name), torch.from_numpy(g["nodisc/" + name]))
-        assert e < 1e-4, (name, e)
-    lat = model.apply(variables, inp, method="encode", precision="fp32")
-    assert rel_err(lat, torch.from_numpy(g["latents"])) < 1e-4
+        assert e < TOL[precision], (name, e)
+    lat = model.apply(variables, inp, method="encode", precision=precision)
+    assert rel_err(lat, torch.from_numpy(g["latents"])) < TOL[precision]
 
 
 def test_forward_from_maps_matches_feature_path_and_oracle(spa):
