@@ -72,16 +72,44 @@ class ParamStore(DeviceWeights):
         self.g = g
         self.ct: Dict[str, torch.Tensor] = {}
         self.step_count = 0
-        self.progress_cb = None   # called with a layer prefix when that layer's backward has finished (DP overlap)
+        self.progress_cb = None   # called with the final-gradient frontier (elements) whenever a backward block completes (DP overlap)
+        self._pending = None      # names whose gradient is not final yet in the backward pass being tracked (None: not tracking)
+        self._by_prefix: Dict[str, List[str]] = {}
         self.lowp: Dict[int, torch.Tensor] = {}   # fp32 gradient data_ptr -> bf16 copy written by the producer kernel
         self.refresh()
 
-    def frontier(self, prefix):
-        """End offset (elements) of the flat buffers up to and including the parameters of ``prefix``:
-        the buffers are laid out in backward-completion order, so everything below is final once the
-        backward of that layer has run."""
-        ends = [self.offsets[n] + (self.f32[n].numel() + 63) // 64 * 64 for n in self.names if n.startswith(prefix)]
-        return max(ends) if ends else 0
+    # -- which gradients are final (data-parallel overlap) --------------------------------------------------
+    # The flat buffers are laid out in the order the backward pass USUALLY completes them, but nothing in autograd
+    # guarantees that order (its ready queue is free to run independent branches - query_encoder vs the decompress
+    # transformer, latents_init vs the per-track transformer - either way round).  So completion is tracked explicitly:
+    # every backward block reports the parameters it has finished, and the all-reduce frontier is the lowest offset that
+    # is still pending.  An out-of-order completion only delays a bucket; it can never send one early.
+    def begin_tracking(self):
+        self._pending = set(self.names)
+
+    def end_tracking(self):
+        left, self._pending = self._pending, None
+        return left
+
+    def with_prefix(self, prefix):
+        hit = self._by_prefix.get(prefix)
+        if hit is None:
+            hit = self._by_prefix[prefix] = [n for n in self.names if n.startswith(prefix)]
+        return hit
+
+    def final_below(self):
+        """Offset (elements) below which every gradient in the flat buffer is final."""
+        if not self._pending:
+            return self.total
+        return min(self.offsets[n] for n in self._pending)
+
+    def finish(self, names):
+        """The backward block that just ran has enqueued the last kernel that writes the gradients of ``names``."""
+        if self._pending is None:
+            return
+        self._pending.difference_update(names)
+        if self.progress_cb is not None:
+            self.progress_cb(self.final_below())
 
     def is_matrix(self, k):
         return self.f32[k].dim() == 2 and (k.endswith("_t") or k.endswith(".Wt"))
@@ -149,6 +177,9 @@ def _lowp_out(st, t):
 
 
 # ---- residual sub-blocks ---------------------------------------------------------------------------
+_MLP_LEAVES = ("norm_attn", "W1_t", "b1", "W2_t", "b2")   # parameters of the MLP sub-block of a layer (MlpBlockFn reports them)
+
+
 class AttnBlockFn(torch.autograd.Function):
     """a = x + SelfAttn(LN(x)) [+ CrossAttn(LN(x), kv)]   (attention.py:75-100)."""
 
@@ -220,8 +251,9 @@ class AttnBlockFn(torch.autograd.Function):
         ops.layernorm_bwd(s["x"], f[pre + "norm_q"], s["mean"], s["rstd"], dxn, da, accumulate=True, dx_lowp=_lowp_out(st, da),
                           dscale_accum=st.g[pre + "norm_q"], dx_colsum=st.g[prev_b2] if prev_b2 else None)
         ctx.saved = None
-        if st.progress_cb is not None:
-            st.progress_cb(pre)   # every parameter of this layer (and of everything after it) now has its final gradient
+        # final now: this layer's attention parameters (self.bo unless the MLP block's norm backward reduced it - then that block
+        # reported it) and, when fused here, MLP_out's bias of the previous layer (reported by that layer's MLP block, later: safe)
+        st.finish([n for n in st.with_prefix(pre) if n[len(pre):] not in _MLP_LEAVES and not (bo_done and n == pre + "self.bo")])
         return da, dkv, None, None, None, None, None, None, None, None, None, None
 
 
@@ -260,6 +292,8 @@ class MlpBlockFn(torch.autograd.Function):
         ops.layernorm_bwd(s["a"], st.f32[pre + "norm_attn"], s["mean"], s["rstd"], dan, dy, accumulate=True, dx_lowp=_lowp_out(st, dy),
                           dscale_accum=st.g[pre + "norm_attn"], dx_colsum=st.g[pre + "self.bo"] if fuse_bo else None)
         ctx.saved = None
+        # b2 is final either way: reduced above, or by the next layer's norm_q backward, which ran before this block
+        st.finish([pre + n for n in _MLP_LEAVES] + ([pre + "self.bo"] if fuse_bo else []))
         return dy, None, None, None, None, None
 
 
@@ -346,8 +380,7 @@ class LastLayerFn(torch.autograd.Function):
         if ctx.prev_b2:
             ops.colsum(da0, st.g[ctx.prev_b2], accumulate=True)
         ctx.saved = None
-        if st.progress_cb is not None:
-            st.progress_cb(pre)
+        st.finish(st.with_prefix(pre))
         return dx, None, None, None, None, None, None, None, None
 
 
@@ -379,6 +412,7 @@ class FinalNormFn(torch.autograd.Function):
             ds = ops.layernorm_bwd(x, st.f32[name], mean, rstd, dy, dx)
         ops.axpy(st.g[name], ds)
         ctx.saved = None
+        st.finish([name])
         return dx, None, None, None, None, None, None
 
 
@@ -392,12 +426,12 @@ class EmbedFn(torch.autograd.Function):
         if ro:
             ops.set_rows(x, T + 1, st.f32["readout_token"].view(-1), seqs)
         ctx.saved = a_cat
-        ctx.args = (st, bias_names, seqs, T, ro, wt.shape[1] == st.c["embed.Wt"].shape[1])
+        ctx.args = (st, bias_names, seqs, T, ro)
         return x
 
     @staticmethod
     def backward(ctx, dx):
-        st, bias_names, seqs, T, ro, full_width = ctx.args
+        st, bias_names, seqs, T, ro = ctx.args
         a_cat = ctx.saved
         dx = dx.contiguous()
         W = dx.shape[1]
@@ -411,10 +445,11 @@ class EmbedFn(torch.autograd.Function):
         ops.colsum(dx, db)
         for n in bias_names:
             ops.axpy(st.g[n], db)
-        if not full_width:
-            raise NotImplementedError("training with a feature missing from the batch but present in the tree")
+        # a feature the tree has a projection for but the batch lacks (track_autoencoder_3d.py:140,145 skip it): its columns of
+        # a_cat are zero, so its kernel receives a zero gradient from the same GEMM, and its bias is not in bias_names
         st.accum_dw("embed.Wt", _c(st, dx), a_cat)
         ctx.saved = None
+        st.finish(st.with_prefix("embed.") + ["readout_token"])
         return (None,) * 10
 
 
@@ -432,6 +467,7 @@ class LatentInitFn(torch.autograd.Function):
         st, B = ctx.args
         g = st.g["latents_init"]
         ops.colsum(d.contiguous().view(B, g.numel()), g.view(-1), accumulate=True)
+        st.finish(["latents_init"])
         return None, None, None
 
 
@@ -455,6 +491,7 @@ class DenseFn(torch.autograd.Function):
         st.accum_dw(name + ".Wt", dyc, x)
         dx = ops.gemm(dyc, st.ct[name + ".Wt"], out_dtype=x.dtype) if need_dx else None
         ctx.saved = None
+        st.finish([name + ".Wt", name + ".b"])
         return dx, None, None, None, None
 
 
@@ -532,17 +569,35 @@ class TrainEngine(Engine):
         tracks = _as_dev(inputs["support_tracks"], torch.float32, dev)
         visible = _as_dev(inputs["support_tracks_visible"], torch.float32, dev)
         boundary = _as_dev(inputs["boundary_frame"], torch.int32, dev)
-        dino = _as_dev(inputs["dino_features"], torch.float32, dev) if meta["has_dino"] and cfg.use_dino else None
-        depth = _as_dev(inputs["depth_features"], torch.float32, dev) if meta["has_depth"] and cfg.use_depth else None
+        dino = depth = None
+        if meta["has_dino"] and cfg.use_dino and inputs.get("dino_features") is not None:
+            dino = _as_dev(inputs["dino_features"], torch.float32, dev)
+        if meta["has_depth"] and cfg.use_depth and inputs.get("depth_features") is not None:
+            depth = _as_dev(inputs["depth_features"], torch.float32, dev)
         B, N, T, C3 = tracks.shape
         rows = B * N * T
         K = st.c["embed.Wt"].shape[1]
         a_cat = torch.empty(B * N * (T + 1), K, device=dev, dtype=self.cdt)
         a_cat.view(B * N, T + 1, K)[:, 0].zero_()
         bias_names = ["embed.b_track"] + (["embed.b_dino"] if dino is not None else []) + (["embed.b_depth"] if depth is not None else [])
+        missing = (meta["has_dino"] and dino is None) or (meta["has_depth"] and depth is None)
+        embed_bias = st.embed_bias
+        if missing:
+            # the tree has a projection the batch has no feature for: that Dense is skipped (:140,145) - zero feature columns
+            # (so the concatenated GEMM adds nothing and its kernel gets a zero gradient) and no bias
+            embed_bias = st.f32["embed.b_track"].clone()
+            for n in bias_names[1:]:
+                ops.axpy(embed_bias, st.f32[n])
+            off = meta["fourier_in"]
+            if meta["has_dino"]:
+                if dino is None:
+                    a_cat[:, off : off + meta["dino_dim"]].zero_()
+                off += meta["dino_dim"]
+            if meta["has_depth"] and depth is None:
+                a_cat[:, off : off + meta["depth_dim"]].zero_()
         x0 = None
         W = st.c["embed.Wt"].shape[0]
-        if (self.cdt == torch.bfloat16 and self.fused_embed and cfg.num_frequencies == 32 and C3 == 3
+        if (not missing and self.cdt == torch.bfloat16 and self.fused_embed and cfg.num_frequencies == 32 and C3 == 3
                 and ops.embed_fused_applicable(W, K, dino.shape[-1] if dino is not None else 0, depth.shape[-1] if depth is not None else 0, C3)):
             # K1: one kernel produces the tokens AND the bf16 concatenated features the weight gradient needs
             x0 = torch.empty(B * N * (T + 1), W, device=dev, dtype=torch.float32)
@@ -555,10 +610,11 @@ class TrainEngine(Engine):
             off = meta["fourier_in"]
             if dino is not None:
                 ops.convert(dino.view(rows, -1), a_cat[:, off : off + meta["dino_dim"]], out_row_group=T)
+            if meta["has_dino"]:
                 off += meta["dino_dim"]
             if depth is not None:
                 ops.convert(depth.view(rows, -1), a_cat[:, off : off + meta["depth_dim"]], out_row_group=T)
-        x = EmbedFn.apply(self.anchor, st, a_cat, st.c["embed.Wt"], st.embed_bias, bias_names, B * N, T, True, x0)
+        x = EmbedFn.apply(self.anchor, st, a_cat, st.c["embed.Wt"], embed_bias, bias_names, B * N, T, True, x0)
         key_mask = ops.build_key_mask(visible, boundary, True)
         stok = self._transformer_t("itt", x, B * N, T + 1, key_mask, first=True)
         nl = meta["latent_tokens"]
@@ -572,6 +628,10 @@ class TrainEngine(Engine):
         ctx = self.get_decoder_context(inputs)
         Q = ctx.query_frame.shape[1]
         qfeat = torch.empty(B * Q, meta["query_in"], device=dev, dtype=self.cdt)
+        # tail_zero assumes query_frame // time_scale_factor == 0 (:268-269); Engine.decode raises in the same case
+        lo_hi = torch.stack([ctx.query_frame.min(), ctx.query_frame.max()]).tolist()
+        if lo_hi[0] < 0 or lo_hi[1] >= cfg.time_scale_factor:
+            raise ValueError("query frames outside [0, time_scale_factor) are not supported")
         ops.fourier_features(ctx.decoder_query.reshape(B * Q, -1), qfeat, cfg.num_frequencies, cfg.track_scale_factor,
                              tail_zero=True, exact=self.exact)
         qe = DenseFn.apply(qfeat, self.anchor, st, "query_encoder", torch.float32)
@@ -584,6 +644,7 @@ class TrainEngine(Engine):
         ``denom`` = max(global visible count, 1) (train.py:111-113 normalises over the whole batch)."""
         dev = self.dev
         T = self.cfg.num_output_frames
+        self.st.lowp.clear()   # no bf16 gradient copy of an earlier backward may be matched by address
         with torch.enable_grad():
             head = self.forward_train(inputs, noise, discretize)
         tt = _as_dev(inputs["query_tracks"], torch.float32, dev).reshape(-1, T, 3)
@@ -614,12 +675,14 @@ class Trainer:
     """
 
     def __init__(self, model, tree, precision="bf16", device="cuda", base_lr=1e-4, warmup_steps=10000, total_steps=1000000,
-                 weight_decay=0.01, clip_norm=1.0, micro_batch=2, bucket_mb=64, group=None):
+                 weight_decay=0.01, clip_norm=1.0, micro_batch=2, bucket_mb=64, group=None, l1_weight=5000.0, bce_weight=1e-8):
         self.model = model
         self.store = ParamStore(tree, precision, device)
         self.engine = TrainEngine(model, self.store)
         self.hp = dict(base_lr=base_lr, warmup_steps=warmup_steps, total_steps=total_steps)
         self.wd, self.clip, self.micro = weight_decay, clip_norm, micro_batch
+        self.l1_weight, self.bce_weight = l1_weight, bce_weight   # compute_loss_3d weights (train.py:96-129)
+        self.unfinished = []
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.bucket_elems = bucket_mb * (1 << 20) // 4
@@ -627,6 +690,7 @@ class Trainer:
         self.step_idx = 0
         self.overlap = True
         self._sent = 0
+        self.debug_frontier = None   # set to [] to record (lo, hi, snapshot) of every region declared final (tests)
 
     # -- gradient all-reduce -----------------------------------------------------------------------------
     def _reduce_upto(self, frontier):
@@ -644,8 +708,14 @@ class Trainer:
             dp.bucketed_allreduce(self.store.grad[self._sent : hi], self.bucket_elems, self.group)
         self._sent = hi
 
-    def _progress(self, prefix):
-        self._reduce_upto(self.store.frontier(prefix))
+    def _progress(self, frontier):
+        if self.debug_frontier is not None:
+            # test hook: keep a copy of everything declared final; nothing may write there afterwards
+            lo = self.debug_frontier[-1][1] if self.debug_frontier else 0
+            if frontier > lo:
+                self.debug_frontier.append((lo, frontier, self.store.grad[lo:frontier].clone()))
+        if self.world > 1 and self.overlap:
+            self._reduce_upto(frontier)
 
     def _allreduce_rest(self):
         if self.world == 1:
@@ -671,8 +741,14 @@ class Trainer:
             # gradients are final only in the last micro-batch: overlap the all-reduce with ITS backward,
             # bucket by bucket, as the layers complete (the flat buffer is in backward-completion order)
             last = s + self.micro >= Bl
-            st.progress_cb = self._progress if (last and self.world > 1 and self.overlap) else None
-            self.engine.loss_and_backward(mb, noise[s : s + self.micro], denom, sums=sums)
+            track = last and ((self.world > 1 and self.overlap) or self.debug_frontier is not None)
+            if track:
+                st.progress_cb = self._progress
+                st.begin_tracking()
+            self.engine.loss_and_backward(mb, noise[s : s + self.micro], denom, l1_weight=self.l1_weight, bce_weight=self.bce_weight,
+                                          sums=sums)
+            if track:
+                self.unfinished = sorted(st.end_tracking())   # parameters no backward block reported (reduced with the rest below)
         st.progress_cb = None
         self._allreduce_rest()
         if self.world > 1:
@@ -685,5 +761,5 @@ class Trainer:
         st.refresh()
         s_host = sums.cpu()
         pos, bce = float(s_host[0]) / denom, float(s_host[1]) / denom
-        return {"total_loss": 5000.0 * pos + 1e-8 * bce, "position_loss": pos, "visible_loss": bce, "learning_rate": lr,
+        return {"total_loss": self.l1_weight * pos + self.bce_weight * bce, "position_loss": pos, "visible_loss": bce, "learning_rate": lr,
                 "grad_norm": float(ss.sqrt().item())}

@@ -47,3 +47,26 @@ def rel_err(a, b):
 
 def product():
     return importlib.import_module("3dspa_code_b200")
+
+
+def quantiser_aware_reference(params, cfg, inputs, noise, z_gpu):
+    """Reference outputs for a forward with the quantiser ON (track_autoencoder_3d.py:251-260).
+
+    round(z * 128) is discontinuous: a bf16-sized difference in a latent that sits next to a rounding boundary flips the
+    decision and moves that latent by 1/128, which says nothing about kernel parity.  So the comparison is made in two parts:
+      (1) the latents themselves (continuous) are held to the tolerance by the caller (``z_ref`` is returned);
+      (2) the decoder is compared on identical rounding decisions: the oracle decodes ``where(flipped, z_gpu, z_ref)``,
+          i.e. its own latents everywhere the two paths round the same way and the device value at the flipped positions
+          (the forward value of the straight-through quantiser depends on the latent only through round()).
+    Returns (ref_plain, ref_aware, z_ref, flipped_fraction): ``ref_plain`` is the oracle with its own rounding everywhere."""
+    ci = om.cast_inputs(inputs, torch.float32)
+    p = om.to_torch(params)
+    nz = torch.as_tensor(np.asarray(noise)).float()
+    with torch.no_grad():
+        z_ref = om.encode_3d(p, cfg, ci)
+        ctx = om.get_decoder_context(cfg, ci)
+        ref_plain = om.decode_3d(p, cfg, z_ref, ctx, nz, True)
+        zg = z_gpu.detach().cpu().float()
+        flipped = torch.round(zg.clamp(-1, 1) * 128.0) != torch.round(z_ref.clamp(-1, 1) * 128.0)
+        ref_aware = om.decode_3d(p, cfg, torch.where(flipped, zg, z_ref), ctx, nz, True)
+    return ref_plain, ref_aware, z_ref, float(flipped.float().mean())

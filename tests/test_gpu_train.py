@@ -140,3 +140,48 @@ def test_train_step_matches_oracle_adamw(spa):
             assert all(np.array_equal(got[k], before[k].float().numpy()) for k in keys)
     moved = max(float(np.abs(got[k] - np.asarray(om.flatten(tree)[k])).max()) for k in keys)
     assert moved > 1e-5
+
+
+@pytest.mark.parametrize("precision,real_widths", [("fp32", False), ("bf16", False), ("bf16", True)])
+def test_gradient_regions_declared_final_are_never_written_again(spa, precision, real_widths):
+    """Data-parallel overlap sends a bucket as soon as every gradient below the frontier is final.  Completion is tracked per
+    backward block (ParamStore.finish); here, on one GPU, every region is snapshotted when it is declared final and must be
+    bit-identical at the end of the backward pass, every parameter must have been reported, and the frontier must reach the
+    end of the buffer.  Real widths: the bias-gradient reductions fused into LayerNorm backward kernels cross block borders."""
+    te = importlib.import_module("3dspa_code_b200.train_engine")
+    if real_widths:
+        c = om.Config3D()
+        inp, noise = make_inputs(c, B=2, N=6, Q=4, targets=True, seed=17)
+        model = spa.TrackAutoEncoder3D()
+        tree = model.init(17, inp)["params"]
+    else:
+        c, model, tree, inp, noise = _setup(spa, seed=13, B=2)
+    tr = te.Trainer(model, tree, precision=precision, micro_batch=1)
+    tr.debug_frontier = []
+    tr.train_step(inp, noise)
+    assert tr.unfinished == [], tr.unfinished
+    regions = tr.debug_frontier
+    assert len(regions) > 4 and regions[0][0] == 0 and regions[-1][1] == tr.store.total
+    for (lo, hi, snap), nxt in zip(regions, regions[1:] + [None]):
+        assert hi > lo and (nxt is None or nxt[0] == hi)
+        assert torch.equal(tr.store.grad[lo:hi], snap), (lo, hi)
+
+
+def test_training_with_a_feature_missing_from_the_batch(spa):
+    """The tree has dino and depth projections, the batch has no depth features: that Dense is skipped
+    (track_autoencoder_3d.py:140,145) - no bias, zero gradient for its kernel and bias; everything else as the oracle."""
+    te = importlib.import_module("3dspa_code_b200.train_engine")
+    c, model, tree, inp, noise = _setup(spa, seed=19)
+    inp = {k: v for k, v in inp.items() if k != "depth_features"}
+    loss_ref, gref = oracle_grads(c, tree, inp, noise)
+    store = te.ParamStore(tree, "fp32")
+    eng = te.TrainEngine(model, store)
+    denom = max(float(inp["query_tracks_visible"].sum()), 1.0)
+    sums = eng.loss_and_backward(inp, noise, denom)
+    assert abs(float(sums[0]) / denom - float(loss_ref["position_loss"])) < 1e-4 * float(loss_ref["position_loss"])
+    got = spa.params.flatten(store.grad_tree())
+    for k, g in gref.items():
+        if g is None:
+            assert k.startswith("depth_projection") and not np.asarray(got[k]).any(), k
+        else:
+            assert rel_err(got[k], g) < 2e-3, (k, rel_err(got[k], g))
