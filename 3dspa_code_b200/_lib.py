@@ -26,7 +26,7 @@ def parse_header(path=HEADER):
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"//[^\n]*", "", src)
     protos = {}
-    for m in re.finditer(r"(int|const char\*)\s+(spa3d_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"(int64_t|int|const char\*)\s+(spa3d_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         parsed = []
         if args and args != "void":
@@ -37,7 +37,7 @@ def parse_header(path=HEADER):
                 else:
                     ty, nm = a.rsplit(" ", 1)
                     parsed.append((_CTYPE[ty.replace("const ", "").strip()], nm))
-        protos[name] = (ctypes.c_char_p if "char" in ret else ctypes.c_int, parsed)
+        protos[name] = (ctypes.c_char_p if "char" in ret else (ctypes.c_int64 if ret == "int64_t" else ctypes.c_int), parsed)
     return protos
 
 

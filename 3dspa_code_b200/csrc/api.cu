@@ -15,6 +15,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_stats[ST_COUNT];
+static const char* const kStatNames[ST_COUNT] = {
+    "gemm_tcgen05", "gemm_simt", "gemm_bf16_fallback", "gemm_dw_tcgen05", "gemm_dw_simt", "gemm_dw_bf16_fallback",
+    "attention_tcgen05", "attention_cross_tcgen05", "attention_mma", "attention_q1", "attention_simt", "attention_bf16_fallback",
+    "embed_fused"};
+void stat_add(int id) { __atomic_fetch_add(&g_stats[id], 1ll, __ATOMIC_RELAXED); }
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -32,6 +39,23 @@ int spa3d_version(void) { return 100; }
 
 const char* spa3d_last_error(void) { return spa3d::g_err; }
 
+int spa3d_stats(int64_t* out, int n) {
+  for (int i = 0; i < n && i < spa3d::ST_COUNT; ++i) out[i] = (int64_t)__atomic_load_n(&spa3d::g_stats[i], __ATOMIC_RELAXED);
+  return spa3d::ST_COUNT;
+}
+int spa3d_stats_reset(void) {
+  for (int i = 0; i < spa3d::ST_COUNT; ++i) __atomic_store_n(&spa3d::g_stats[i], 0ll, __ATOMIC_RELAXED);
+  return 0;
+}
+const char* spa3d_stat_name(int i) { return (i >= 0 && i < spa3d::ST_COUNT) ? spa3d::kStatNames[i] : ""; }
+
+// scratch sizes: the library never allocates; these are the buffers a caller passes in
+int64_t spa3d_gemm_workspace_bytes(int64_t M, int N, int K) { (void)M; (void)N; (void)K; return 0; }   // split-K partials are added atomically into C
+int64_t spa3d_sumsq_workspace_bytes(void) { return (int64_t)SPA3D_SUMSQ_WORKSPACE * 4; }
+int64_t spa3d_attention_bwd_workspace_bytes(int64_t batch, int heads, int Lq) { return batch * heads * (int64_t)Lq * 4; }   // delta
+int64_t spa3d_attention_stats_bytes(int64_t batch, int heads, int Lq) { return batch * heads * (int64_t)Lq * 2 * 4; }      // (max, sum) per row
+int64_t spa3d_layernorm_bwd_workspace_bytes(int num_partials, int d) { return (int64_t)num_partials * d * 4; }             // d-scale partial rows
+
 int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dtype,
                const float* bias, int act, const void* residual, int64_t ldr, int r_dtype,
                void* C, int64_t ldc, int c_dtype, int64_t M, int N, int K, int impl,
@@ -48,10 +72,13 @@ int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dt
                   a_dtype, (long long)lda, (long long)ldw, K);
   }
   if (impl != SPA3D_GEMM_SIMT && tc_ok) {
+    stat_add(ST_GEMM_TCGEN05);
     return gemm_tcgen05(A, lda, Wt, ldw, bias, act, residual, ldr, r_dtype, C, ldc, c_dtype, M, N,
                         K, nullptr, st);
   }
   // SIMT fp32-accumulate path: B(k,n) = Wt[n*ldw + k]
+  stat_add(ST_GEMM_SIMT);
+  if (impl == SPA3D_GEMM_AUTO && a_dtype == SPA3D_BF16) stat_add(ST_GEMM_BF16_FALLBACK);   // bf16 operands that missed the tensor-core path
   return gemm_simt(A, lda, 1, a_dtype, Wt, 1, ldw, a_dtype, bias, act, residual, ldr, r_dtype, C,
                    ldc, c_dtype, M, N, K, 0, st);
 }
@@ -70,6 +97,7 @@ int spa3d_gemm_rmsnorm(const void* A, int64_t lda, const void* Wt, int64_t ldw, 
   if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_rmsnorm: tcgen05 path not applicable");
   if (impl != SPA3D_GEMM_SIMT && tc_ok) {
     RmsEpilogue rms{Dh, q_cols, k_cols, scale_q, scale_k, q_mul, rstd_out};
+    stat_add(ST_GEMM_TCGEN05);
     return gemm_tcgen05(A, lda, Wt, ldw, nullptr, 0, nullptr, 0, 0, C, ldc, c_dtype, M, N, K, &rms, st);
   }
   // unfused: contraction, then the in-place normalisation pass over the q and k column blocks
@@ -99,9 +127,11 @@ int spa3d_gemm_gelu(const void* A, int64_t lda, const void* Wt, int64_t ldw, int
                (reinterpret_cast<uintptr_t>(Z) & 15) == 0 && ldz % 8 == 0;
   if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_gelu: tcgen05 path not applicable");
   if (save_grad) SPA3D_REQUIRE(tc_ok && impl != SPA3D_GEMM_SIMT, "gemm_gelu: the gelu'(z) side output exists on the tcgen05 path only");
-  if (impl != SPA3D_GEMM_SIMT && tc_ok)
+  if (impl != SPA3D_GEMM_SIMT && tc_ok) {
+    stat_add(ST_GEMM_TCGEN05);
     return gemm_tcgen05(A, lda, Wt, ldw, bias, SPA3D_ACT_GELU_TANH, nullptr, 0, 0, H, ldh, a_dtype, M, N, K, nullptr, st,
                         0, Z, ldz, save_grad ? 2 : 1);
+  }
   int rc = spa3d_gemm(A, lda, Wt, ldw, a_dtype, bias, 0, nullptr, 0, 0, Z, ldz, a_dtype, M, N, K,
                       impl == SPA3D_GEMM_SIMT ? SPA3D_GEMM_SIMT : SPA3D_GEMM_AUTO, stream);
   if (rc) return rc;
@@ -119,9 +149,11 @@ int spa3d_gemm_gelu_bwd(const void* dH_in, int64_t lda, const void* Wt, int64_t 
                (reinterpret_cast<uintptr_t>(Z) & 15) == 0 && ldz % 8 == 0 &&
                (reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && lddz % 8 == 0;
   if (impl == SPA3D_GEMM_TCGEN05) SPA3D_REQUIRE(tc_ok, "gemm_gelu_bwd: tcgen05 path not applicable");
-  if (impl != SPA3D_GEMM_SIMT && tc_ok)
+  if (impl != SPA3D_GEMM_SIMT && tc_ok) {
+    stat_add(ST_GEMM_TCGEN05);
     return gemm_tcgen05(dH_in, lda, Wt, ldw, nullptr, 0, Z, ldz, a_dtype, dZ, lddz, a_dtype, M, N, K, nullptr, st,
                         z_is_grad ? 2 : 1, nullptr, 0, 1, dz_colsum);
+  }
   SPA3D_REQUIRE(!z_is_grad && !dz_colsum, "gemm_gelu_bwd: the saved-derivative form and the fused column sums exist on the tcgen05 path only");
   int rc = spa3d_gemm(dH_in, lda, Wt, ldw, a_dtype, nullptr, 0, nullptr, 0, 0, dZ, lddz, a_dtype, M, N, K,
                       impl == SPA3D_GEMM_SIMT ? SPA3D_GEMM_SIMT : SPA3D_GEMM_AUTO, stream);
@@ -141,7 +173,12 @@ int spa3d_gemm_dw(const void* dY, int64_t lddy, const void* X, int64_t ldx, int 
     SPA3D_REQUIRE(e == cudaSuccess, "gemm_dw: memset: %s", cudaGetErrorString(e));
   }
   if (M == 0) return 0;
-  if (impl != SPA3D_GEMM_SIMT && tc_ok) return gemm_tcgen05_dw(dY, lddy, X, ldx, dW, lddw, M, N, K, st);
+  if (impl != SPA3D_GEMM_SIMT && tc_ok) {
+    stat_add(ST_GEMM_DW_TCGEN05);
+    return gemm_tcgen05_dw(dY, lddy, X, ldx, dW, lddw, M, N, K, st);
+  }
+  stat_add(ST_GEMM_DW_SIMT);
+  if (impl == SPA3D_GEMM_AUTO && dtype == SPA3D_BF16) stat_add(ST_GEMM_DW_BF16_FALLBACK);
   // SIMT: A(n,m) = dY[m*lddy + n], B(m,k) = X[m*ldx + k]
   return gemm_simt(dY, 1, lddy, dtype, X, ldx, 1, dtype, nullptr, 0, nullptr, 0, 0, dW, lddw, SPA3D_F32, N,
                    K, M, 1, st);

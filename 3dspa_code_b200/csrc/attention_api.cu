@@ -56,13 +56,21 @@ int spa3d_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   if (batch == 0 || Lq == 0) return 0;
   SPA3D_REQUIRE(Lk > 0, "attention: Lk must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
-  if (attention_q1_applicable(dtype, Lq, Lk, Dh))   // one query per sequence: the pruned last layers
+  if (attention_q1_applicable(dtype, Lq, Lk, Dh)) {   // one query per sequence: the pruned last layers
+    stat_add(ST_ATTN_Q1);
     return attention_q1_fwd(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse_out, batch, heads, Lk, Dh, st);
-  if (attention_fwd_tc_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, ldo, q, k, v, o))
+  }
+  if (attention_fwd_tc_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, ldo, q, k, v, o)) {
+    stat_add(ST_ATTN_TCGEN05);
     return attention_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse_out, batch, heads, Lq, Dh, st);
-  if (attention_fwd_mma_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, ldo))
+  }
+  if (attention_fwd_mma_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, ldo)) {
+    stat_add(ST_ATTN_MMA);
     return attention_fwd_mma(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, lse_out, batch, heads, Lq, Lk,
                              Dh, st);
+  }
+  stat_add(ST_ATTN_SIMT);
+  if (dtype == SPA3D_BF16) stat_add(ST_ATTN_BF16_FALLBACK);
   return attention_fwd_simt(q, ldq, k, ldk, v, ldv, o, ldo, dtype, key_mask, lse_out, batch, heads,
                             Lq, Lk, Dh, st);
 }
@@ -75,20 +83,26 @@ int spa3d_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   using namespace spa3d;
   if (batch == 0 || Lq == 0) return 0;
   SPA3D_REQUIRE(lse != nullptr && delta_ws != nullptr, "attention_bwd: lse/delta_ws required");
-  if (attention_q1_applicable(dtype, Lq, Lk, Dh))   // recomputes the softmax: neither lse nor delta is read
+  if (attention_q1_applicable(dtype, Lq, Lk, Dh)) {   // recomputes the softmax: neither lse nor delta is read
+    stat_add(ST_ATTN_Q1);
     return attention_q1_bwd(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, batch, heads, Lk, Dh,
                             (cudaStream_t)stream);
+  }
   if (attention_bwd_tc_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, lddo, lddq, lddk, lddv)) {
+    stat_add(ST_ATTN_TCGEN05);
     // delta is computed inside the kernel from P and dP
     return attention_bwd_tc(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, lse, delta_ws,
                             batch, heads, Lq, Dh, (cudaStream_t)stream);
   }
   if (attention_bwd_mma_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, lddo, lddq, lddk, lddv)) {
+    stat_add(ST_ATTN_MMA);
     int rc = attention_delta(o, ldo, d_o, lddo, dtype, delta_ws, batch, heads, Lq, Dh, (cudaStream_t)stream);
     if (rc) return rc;
     return attention_bwd_mma(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, lse,
                              delta_ws, batch, heads, Lq, Lk, Dh, (cudaStream_t)stream);
   }
+  stat_add(ST_ATTN_SIMT);
+  if (dtype == SPA3D_BF16) stat_add(ST_ATTN_BF16_FALLBACK);
   return attention_bwd_simt(q, ldq, k, ldk, v, ldv, o, ldo, d_o, lddo, dq, lddq, dk, lddk, dv, lddv,
                             dtype, key_mask, lse, delta_ws, batch, heads, Lq, Lk, Dh,
                             (cudaStream_t)stream);

@@ -23,6 +23,17 @@ int check_launch(const char* what);
     }                                 \
   } while (0)
 
+// ---- dispatch counters (spa3d_stats): which implementation every contraction / attention call took ----
+// A bf16 operand that does not meet the tensor-core kernels' alignment rules is still computed (SIMT), but 10-100x
+// slower; the counters make that visible (bench.py asserts the *_bf16_fallback counters stay zero).
+enum StatId {
+  ST_GEMM_TCGEN05 = 0, ST_GEMM_SIMT, ST_GEMM_BF16_FALLBACK,
+  ST_GEMM_DW_TCGEN05, ST_GEMM_DW_SIMT, ST_GEMM_DW_BF16_FALLBACK,
+  ST_ATTN_TCGEN05, ST_ATTN_CROSS_TCGEN05, ST_ATTN_MMA, ST_ATTN_Q1, ST_ATTN_SIMT, ST_ATTN_BF16_FALLBACK,
+  ST_EMBED_FUSED, ST_COUNT
+};
+void stat_add(int id);
+
 // ---- dtype helpers ----
 using bf16 = __nv_bfloat16;
 

@@ -1015,6 +1015,34 @@ __global__ void gelu_fwd_kernel(const TX* __restrict__ x, int64_t ldx, TY* __res
   stf<TY>(y + r * ldy + c, gelu_tanh(ldf<TX>(x + r * ldx + c)));
 }
 
+// compute-dtype shadows of one fp32 master matrix in one pass: dst[r,c] = T(src[r,c]) and dst_t[c,r] = T(src[r,c])
+// (the [out,in] operand of the forward / weight-gradient GEMMs and the [in,out] operand of dX = dY . W); 32 x 32 tiles through
+// shared memory so both stores are coalesced.
+template <typename T>
+__global__ void shadow_weights_kernel(const float* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd,
+                                      T* __restrict__ dst_t, int64_t ldt, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = src[(int64_t)r * lds + c];
+      if (dst != nullptr) stf<T>(dst + (int64_t)r * ldd + c, v);
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+  if (dst_t == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;   // transposed: row index of dst_t = column of src
+    if (r < rows && c < cols) stf<T>(dst_t + (int64_t)c * ldt + r, tile[tx][ty + 8 * i]);
+  }
+}
+
 static inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 int head_rmsnorm_fwd_impl(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
@@ -1361,6 +1389,24 @@ int spa3d_colsum(const void* x, int64_t ldx, int dtype, float* out, int accumula
     colsum_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, out, rows, cols, rpb);
   });
   return check_launch("colsum");
+}
+
+int spa3d_shadow_weights(const float* src, int64_t lds, void* dst, int64_t ldd, void* dst_t, int64_t ldt, int dtype,
+                         int rows, int cols, void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  SPA3D_REQUIRE(src != nullptr && (dst != nullptr || dst_t != nullptr), "shadow_weights: NULL operand");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  SPA3D_DISPATCH(dtype, T, {
+    shadow_weights_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, (T*)dst, ldd, (T*)dst_t, ldt, rows, cols);
+  });
+  return check_launch("shadow_weights");
+}
+
+int spa3d_fill_zero(void* p, int64_t bytes, void* stream) {
+  if (bytes == 0) return 0;
+  cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream);
+  SPA3D_REQUIRE(e == cudaSuccess, "fill_zero: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int spa3d_axpy(float* y, const float* x, float alpha, int64_t n, void* stream) {

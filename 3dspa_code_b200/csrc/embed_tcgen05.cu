@@ -54,7 +54,7 @@ struct EmbedParams {
   const float* wdep;     // [3, W] rows 0..2 of the depth projection kernel (fp32), or null
   int Hp, Wp;
   float scale_w, scale_h;   // Wp / video_W, Hp / video_H (inference.py:367-368)
-  int debug;                // SPA3D_EMBED_DEBUG (timing experiments only): 1 = all gathers hit one patch row, 2 = no stores
+  int debug;                // -DSPA3D_EMBED_DEBUG=n builds only (timing experiments): 1 = all gathers hit one patch row, 2 = no stores; 0 in the product
 };
 
 template <int NB, int BNH, bool ACAT, bool SAMPLE>   // W = NB * BNH output columns, BNH <= 256; ACAT: also store the bf16 features
@@ -524,10 +524,8 @@ int spa3d_embed_fused(const float* tracks, const float* dino, const float* depth
   SPA3D_REQUIRE(a_cat == nullptr || (lda % 4 == 0 && (reinterpret_cast<uintptr_t>(a_cat) & 7) == 0), "embed_fused: a_cat must be 8-byte aligned");
   p.T = T; p.Dd = dino_dim; p.Dz = depth_dim; p.W = W; p.inv_scale = (float)(1.0 / (double)track_scale_factor); p.inv_T = (float)(1.0 / (double)T);
   for (int i = 0; i < 32; ++i) p.fs[i] = (float)pow(2.0, (double)i / 3.0);
-  {
-    const char* e = getenv("SPA3D_EMBED_L2_PREFETCH");
-    p.l2_prefetch = (e && atoi(e) == 1) ? 1 : 0;   // measured: 0.54 ms with, 0.48 ms without - off by default
-  }
+  p.l2_prefetch = 0;   // measured: 0.54 ms with the L2 prefetch of the next tile's features, 0.48 ms without
+  spa3d::stat_add(spa3d::ST_EMBED_FUSED);
   const int K = 256 + dino_dim + depth_dim;
   CUtensorMap tmB;
   const int bnh = W > 256 ? W / 2 : W;
@@ -567,7 +565,11 @@ int spa3d_embed_sampled(const float* xyz, const float* tracks_2d, const float* d
   p.T = T; p.Dd = 0; p.Dz = 0; p.W = W; p.inv_scale = (float)(1.0 / (double)track_scale_factor); p.inv_T = (float)(1.0 / (double)T);
   for (int i = 0; i < 32; ++i) p.fs[i] = (float)pow(2.0, (double)i / 3.0);
   p.l2_prefetch = 0;
-  { const char* e = getenv("SPA3D_EMBED_DEBUG"); p.debug = e ? atoi(e) : 0; }
+#ifdef SPA3D_EMBED_DEBUG
+  p.debug = SPA3D_EMBED_DEBUG;   // timing experiments only, compile-time (1 = all gathers hit one patch row, 2 = no stores)
+#else
+  p.debug = 0;
+#endif
   p.proj = reinterpret_cast<const bf16*>(proj); p.trk2d = tracks_2d; p.dfeat = dfeat; p.wdep = wdep; p.Hp = Hp; p.Wp = Wp;
   p.scale_w = (float)((double)Wp / (double)video_W);
   p.scale_h = (float)((double)Hp / (double)video_H);

@@ -44,6 +44,14 @@ constexpr int EPI_TMA = 0;     // bf16 output, no residual: swizzled slab -> TMA
 constexpr int EPI_DIRECT = 1;  // fp32 output and/or residual: slab transpose -> coalesced ld/st.global
 constexpr int EPI_RMS = 2;     // bf16 output with fused per-head RMSNorm of the q / k columns
 
+// timing experiment only (accumulators are drained, nothing is computed or stored): a compile-time switch so that no
+// environment variable can make a product GEMM store nothing
+#ifdef SPA3D_GEMM_SKIP_EPI
+constexpr bool kSkipEpilogue = true;
+#else
+constexpr bool kSkipEpilogue = false;
+#endif
+
 template <int BN>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -78,7 +86,7 @@ struct EpiParams {
   int res_op;        // EPI_DIRECT: 0 = C = f(acc) + residual; 1 = C = acc * gelu'(residual) (residual = saved pre-activation);
                      //             2 = C = acc * residual (residual = gelu'(z) saved by the forward GEMM)
   int atomic_add;    // EPI_DIRECT, fp32 C: C += tile with red.global.add.v4.f32 (split-K weight gradients)
-  int debug_skip;    // SPA3D_GEMM_SKIP_EPI=1: accumulators are drained but nothing is computed or stored
+  int reserved;      // (was a run-time debug switch; the skip-epilogue experiment is compile-time now: -DSPA3D_GEMM_SKIP_EPI)
   float* colsum;     // EPI_DIRECT: [N] f32, += column sums of the stored values (a bias gradient), or null
 };
 
@@ -338,7 +346,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int c = 0; c < NCH; ++c) bq[c] = bq_next[c];
         load_bias_direct(t + gridDim.x, bq_next);
-        if (!ep.debug_skip) {
+        if (!kSkipEpilogue) {
           load_res(0);   // in flight while the MMAs of this tile still run
           // pull the residual of this CTA's next tile into L2 (one prefetch per 128-byte line)
           const int64_t tn = item_tile(t + gridDim.x);
@@ -365,7 +373,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_arrive(&tempty_bar[as]);   // every value of this accumulator is in registers
           }
           const int col0 = colbase + c * 32;
-          if (col0 < N && !ep.debug_skip) {
+          if (col0 < N && !kSkipEpilogue) {
             const uint32_t slab_s = smem_u32(slab);
             const uint32_t srow_s = slab_s + lane * 128;
 #pragma unroll
@@ -496,7 +504,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             __syncwarp();   // slab is rewritten by the next chunk
           }
-          if (c + 1 < NCH && !ep.debug_skip) load_res(c + 1);
+          if (c + 1 < NCH && !kSkipEpilogue) load_res(c + 1);
         }
       } else if constexpr (EPI == EPI_TMA) {
         // ---- bf16 outputs: slab -> TMA store, two 2 KB buffers per warp --------------------------
@@ -518,7 +526,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_arrive(&tempty_bar[as]);
           }
           const int col0 = colbase + c * 32;
-          if (col0 < N && !ep.debug_skip) {
+          if (col0 < N && !kSkipEpilogue) {
             uint64_t v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = pku(r[c & 1][2 * i], r[c & 1][2 * i + 1]);
@@ -574,7 +582,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tcgen05_fence_before();
             mbar_arrive(&tempty_bar[as]);
           }
-          if (gcol >= N || ep.debug_skip) continue;
+          if (gcol >= N || kSkipEpilogue) continue;
           const int kind = gcol < ep.q_cols ? 0 : (gcol < nq ? 1 : 2);   // q / k / v columns (warp uniform)
           uint64_t rs2 = pk(1.f, 1.f);
           if (kind < 2) {
@@ -638,15 +646,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-static int debug_skip_epilogue() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SPA3D_GEMM_SKIP_EPI");
-    v = (e && atoi(e) == 1) ? 1 : 0;
-  }
-  return v;
-}
-
 template <int BN, int EPI, int DH, bool TN = false>
 static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiParams ep, int64_t M,
                   int N, int64_t K, cudaStream_t st, void* aux = nullptr, int64_t ld_aux = 0) {
@@ -669,7 +668,6 @@ static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiPa
     if (make_map_c(&tmAux, aux, M, N, ld_aux)) return 1;
     ep.aux_pre = aux_kind == 2 ? 2 : 1;
   }
-  ep.debug_skip = debug_skip_epilogue();
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, DH, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);

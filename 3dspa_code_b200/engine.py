@@ -57,6 +57,10 @@ class DeviceWeights:
                         dst = torch.empty_like(v, dtype=self.cdt)
                         self.c[k] = dst
                     ops.convert(v, dst)
+        self._refresh_embed_bias()
+
+    def _refresh_embed_bias(self):
+        """Sum of the three embedding biases (the concatenated-K GEMM adds them once)."""
         eb = self.f32["embed.b_track"].clone()
         for k in ("embed.b_dino", "embed.b_depth"):
             if k in self.f32:

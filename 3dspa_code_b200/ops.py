@@ -341,6 +341,32 @@ def colsum(x, out, accumulate=False):
     return out
 
 
+def shadow_weights(src, dst=None, dst_t=None):
+    """dst [N,K] = cdt(src), dst_t [K,N] = cdt(src)^T from the fp32 master src [N,K], one pass."""
+    N, K = src.shape
+    ref = dst if dst is not None else dst_t
+    _call("spa3d_shadow_weights", _p(src), _ld(src), _p(dst), _ld(dst) if dst is not None else 0, _p(dst_t),
+          _ld(dst_t) if dst_t is not None else 0, dt(ref), N, K, _stream())
+
+
+def fill_zero(t):
+    assert t.is_contiguous()
+    _call("spa3d_fill_zero", _p(t), t.numel() * t.element_size(), _stream())
+    return t
+
+
+def stats(reset=False):
+    """{counter name: count} of the library's dispatch counters (spa3d_stats)."""
+    lib = _lib.lib()
+    n = lib.spa3d_stats(None, 0)
+    buf = (ctypes.c_int64 * n)()
+    lib.spa3d_stats(ctypes.cast(buf, ctypes.c_void_p), n)
+    out = {lib.spa3d_stat_name(i).decode(): int(buf[i]) for i in range(n)}
+    if reset:
+        lib.spa3d_stats_reset()
+    return out
+
+
 def axpy(y, x, alpha=1.0):
     _call("spa3d_axpy", _p(y), _p(x), float(alpha), y.numel(), _stream())
     return y
@@ -359,3 +385,12 @@ def adamw_step(p, g, m, v, sumsq_t, clip_norm, lr, b1, b2, eps, wd, step):
 
 def inv_sqrt(d):
     return 1.0 / math.sqrt(d)
+
+
+# ---- dispatcher registration ---------------------------------------------------------------------------------
+# The functions above are the ctypes-level implementations.  torch_ops defines the ``spa3d::`` operator library
+# (schema + CUDA impl + fake impl + autograd formula) on top of them and rebinds the public names of this module to
+# ``torch.ops.spa3d.*``, so every caller - model, training engine, tests, bench.py - goes through the dispatcher.
+from . import torch_ops as _torch_ops  # noqa: E402
+
+_torch_ops.install(globals())

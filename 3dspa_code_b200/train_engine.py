@@ -115,16 +115,20 @@ class ParamStore(DeviceWeights):
         return self.f32[k].dim() == 2 and (k.endswith("_t") or k.endswith(".Wt"))
 
     def refresh(self):
-        super().refresh()
+        """Compute-dtype shadows of every matrix from its fp32 master, [N,K] and [K,N] (dX = dY . W) in ONE pass per matrix."""
         for k, v in self.f32.items():
             if self.is_matrix(k):
-                # [K,N] copy for dX = dY . W  (weight re-layout once per optimiser step)
-                src = self.c[k]
-                dst = self.ct.get(k)
-                if dst is None:
-                    dst = torch.empty(src.shape[1], src.shape[0], device=src.device, dtype=self.cdt)
-                    self.ct[k] = dst
-                dst.copy_(src.t())
+                dst, dst_t = self.c.get(k), self.ct.get(k)
+                if dst_t is None:
+                    dst_t = self.ct[k] = torch.empty(v.shape[1], v.shape[0], device=v.device, dtype=self.cdt)
+                if self.cdt == torch.float32:
+                    self.c[k] = v
+                    ops.shadow_weights(v, None, dst_t)
+                else:
+                    if dst is None:
+                        dst = self.c[k] = torch.empty_like(v, dtype=self.cdt)
+                    ops.shadow_weights(v, dst, dst_t)
+        self._refresh_embed_bias()
 
     def accum_dw(self, name, g, x):
         """grad[name] ([N,K], fp32) += g[M,N]^T x[M,K]  (reduction over tokens)."""
@@ -728,7 +732,7 @@ class Trainer:
         query_tracks_visible targets); noise: [B_local,128,96] slice of the global noise tensor.
         Returns dict(total_loss, position_loss, visible_loss, learning_rate, grad_norm)."""
         st, dev = self.store, self.engine.dev
-        st.grad.zero_()
+        ops.fill_zero(st.grad)
         Bl = batch["support_tracks"].shape[0]
         tv = _as_dev(batch["query_tracks_visible"], torch.float32, dev)
         cnt = torch.zeros(1, device=dev)

@@ -148,38 +148,68 @@ def cpu_oracle_rate(sample_s=1024, sample_q=256, threads=None):
     return sample_q / dt, dt, f"oracle fp32 forward on 1 clip of {sample_s} support / {sample_q} query tracks, T={T} (same 4:1 ratio as cfg2; rate = queries / wall time)"
 
 
-def synth_train_batch(B, seed, dev):
-    """cfg3 micro data on the device: B clips with targets (held-out query tracks + visibility)."""
-    g = torch.Generator(device=dev).manual_seed(seed)
-    r = lambda *sh: torch.rand(*sh, generator=g, device=dev)
+def synth_train_batch(clip_ids, dev):
+    """cfg3 data on the device: one clip per GLOBAL clip index (seed 1000 + index), with targets (held-out query tracks +
+    visibility).  Seeding by global index makes the batch - and therefore the loss - independent of how the clips are
+    sharded over ranks: train.loss_step0 must agree across --gpus 1/2/4/8."""
+    B = len(clip_ids)
     batch = {
-        "support_tracks": r(B, S, T, 3) * 2 - 1,
-        "support_tracks_visible": (r(B, S, T, 1) < 0.9).float(),
-        "query_points": torch.cat([torch.randint(0, T, (B, Q, 1), generator=g, device=dev).float(), r(B, Q, 3) * 2 - 1], -1),
-        "boundary_frame": torch.full((B,), T, dtype=torch.int32, device=dev),
-        "dino_features": torch.randn(B, S, T, 768, generator=g, device=dev),
-        "depth_features": torch.randn(B, S, T, 256, generator=g, device=dev),
-        "query_tracks": r(B, Q, T, 3) * 2 - 1,
-        "query_tracks_visible": (r(B, Q, T, 1) < 0.9).float(),
+        "support_tracks": torch.empty(B, S, T, 3, device=dev), "support_tracks_visible": torch.empty(B, S, T, 1, device=dev),
+        "query_points": torch.empty(B, Q, 4, device=dev), "boundary_frame": torch.full((B,), T, dtype=torch.int32, device=dev),
+        "dino_features": torch.empty(B, S, T, 768, device=dev), "depth_features": torch.empty(B, S, T, 256, device=dev),
+        "query_tracks": torch.empty(B, Q, T, 3, device=dev), "query_tracks_visible": torch.empty(B, Q, T, 1, device=dev),
     }
-    return batch, r(B, 128, 96)
+    noise = torch.empty(B, 128, 96, device=dev)
+    for i, cid in enumerate(clip_ids):
+        g = torch.Generator(device=dev).manual_seed(1000 + int(cid))
+        r = lambda *sh: torch.rand(*sh, generator=g, device=dev)
+        batch["support_tracks"][i] = r(S, T, 3) * 2 - 1
+        batch["support_tracks_visible"][i] = (r(S, T, 1) < 0.9).float()
+        batch["query_points"][i] = torch.cat([torch.randint(0, T, (Q, 1), generator=g, device=dev).float(), r(Q, 3) * 2 - 1], -1)
+        batch["dino_features"][i].normal_(generator=g)
+        batch["depth_features"][i].normal_(generator=g)
+        batch["query_tracks"][i] = r(Q, T, 3) * 2 - 1
+        batch["query_tracks_visible"][i] = (r(Q, T, 1) < 0.9).float()
+        noise[i] = r(128, 96)       # quantiser noise indexed by GLOBAL clip position (track_autoencoder_3d.py:254-258)
+    return batch, noise
+
+
+def cpu_train_rate(sample_s=512, sample_q=128, threads=None):
+    """Reference-side cost of a training step on the host cores: fp32 oracle forward + autograd backward of compute_loss_3d
+    on ONE clip of a bounded size (same 4:1 support:query ratio), reported as clips/s scaled to the full clip by token count."""
+    from oracle import model as om
+
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = om.Config3D()
+    tree = om.to_torch(om.init_params_3d(cfg, seed=0), requires_grad=True)
+    inp, noise = synth_clip(2, s=sample_s, q=sample_q)
+    g = torch.Generator().manual_seed(3)
+    inp["query_tracks"] = torch.rand(1, sample_q, T, 3, generator=g) * 2 - 1
+    inp["query_tracks_visible"] = (torch.rand(1, sample_q, T, 1, generator=g) < 0.9).float()
+    t0 = time.perf_counter()
+    res = om.forward_3d(tree, cfg, inp, noise, True)
+    om.compute_loss_3d(res, inp)["total_loss"].backward()
+    dt = time.perf_counter() - t0
+    scale = S / sample_s   # per-clip work is linear in the number of tracks at a fixed support:query ratio
+    return 1.0 / (dt * scale), dt, (f"oracle fp32 forward + autograd backward of compute_loss_3d on 1 clip of {sample_s} support / {sample_q} "
+                                    f"query tracks, T={T}; clips/s = 1 / (seconds x {scale:g}) (work is linear in tracks)")
 
 
 def run_train_leg(args, spa, model, variables, world, rank, dev, barrier):
-    """cfg3: one optimiser step over a global batch of 64 clips, 64/N clips per rank in micro-batches of
-    --train-micro clips (automatic: 2 when one GPU holds all 64 clips - 44 GB of saved activations beside 80 GB of resident
-    synthetic inputs - and 4 otherwise; 4 % / 6 % faster than one-clip micro-batches), gradients summed over NCCL (overlapped with the last backward), AdamW on every rank."""
+    """cfg3: one optimiser step over a global batch of 64 clips, 64/N clips per rank in micro-batches of --train-micro clips
+    (2 at every GPU count; 4-clip micro-batches are ~6 % faster but do not fit beside the 80 GB of resident synthetic inputs
+    when one GPU holds all 64 clips), gradients summed over NCCL (overlapped with the last backward), AdamW on every rank."""
     import torch.distributed as dist
 
     te = importlib.import_module("3dspa_code_b200.train_engine")
     dp = importlib.import_module("3dspa_code_b200.dp")
     lo, hi = dp.shard_range(args.train_batch, world, rank)
-    # clips per micro-batch: 4 when the rank's share of the batch leaves room for 82 GB of saved activations beside its
-    # resident synthetic inputs (1.25 GB per clip), else 2 (one GPU holding all 64 clips: 80 GB of inputs)
-    want = args.train_micro if args.train_micro > 0 else (4 if hi - lo <= 32 else 2)
-    micro = max(1, min(want, hi - lo))
+    # clips per micro-batch: the SAME at every GPU count (default 2, what one GPU holding all 64 clips has memory for beside
+    # its 80 GB of resident synthetic inputs), so the 1 -> 8 GPU curve compares like with like
+    micro = max(1, min(args.train_micro, hi - lo))
     trainer = te.Trainer(model, variables["params"], precision="bf16", device=dev, micro_batch=micro)
-    batch, noise = synth_train_batch(hi - lo, 1000 + rank, dev)
+    batch, noise = synth_train_batch(range(lo, hi), dev)
     # executed contraction FLOPs of one step (the last layer of both read-out transformers is pruned to token 0,
     # so this is less than the algorithmic 3 x 9.413 TFLOP per clip): counted from the launches of the warm-up step
     ops = spa.ops
@@ -196,7 +226,7 @@ def run_train_leg(args, spa, model, variables, world, rank, dev, barrier):
     for n in names:
         setattr(ops, n, _count(orig[n], dw=(n == "gemm_dw")))
     l0 = ops.launch_count
-    trainer.train_step(batch, noise)   # warm-up (allocator, NCCL communicator)
+    log0 = trainer.train_step(batch, noise)   # warm-up (allocator, NCCL communicator); lr(0) = 0, so it is the loss at the initial weights
     launches = ops.launch_count - l0
     for n in names:
         setattr(ops, n, orig[n])
@@ -205,8 +235,9 @@ def run_train_leg(args, spa, model, variables, world, rank, dev, barrier):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.start()
+    steps = args.train_steps if args.train_steps > 0 else (2 if world == 1 else 5)   # a 1-GPU step takes 2.4 s, an 8-GPU step 0.3 s
     e0.record()
-    for _ in range(args.train_steps):
+    for _ in range(steps):
         log = trainer.train_step(batch, noise)
     e1.record()
     barrier()
@@ -214,21 +245,39 @@ def run_train_leg(args, spa, model, variables, world, rank, dev, barrier):
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.train_steps
+    ms = float(t.item()) / steps
     peak_tf, _, _ = measured_peaks()
     tf = 3 * FWD_TFLOP_PER_CLIP * args.train_batch / (ms * 1e-3)   # algorithmic TFLOP/s, whole job (fwd + 2x bwd)
+    # replicas must hold bit-identical parameters after the same updates: compare a checksum of the flat fp32 buffer
+    flat = trainer.store.flat
+    chk = torch.stack([flat.view(torch.int32).to(torch.int64).sum(), (flat.double() * flat.double()).sum().reshape(1).view(torch.int64)[0]])
+    identical = True
+    if world > 1:
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        identical = all(torch.equal(c, allc[0]) for c in allc)
+    exec_tf = counted["flop"] / (ms * 1e-3) / 1e12
+    out = {"metric": "3dspa_train_clips_per_s", "value": args.train_batch / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms,
+           "global_batch": args.train_batch, "clips_per_gpu": hi - lo, "micro_batch": micro, "steps": steps, "warmup": 1,
+           "scaling": "strong", "dtype": "bf16",
+           "model_flop_throughput_tflops_per_gpu": tf / world, "model_flop_frac_of_sustained_peak": tf / world / peak_tf,
+           "executed_gemm_tflops_per_gpu": exec_tf, "executed_frac_of_sustained_peak": exec_tf / peak_tf,
+           "algorithmic_tflop_per_clip": 3 * FWD_TFLOP_PER_CLIP, "executed_gemm_tflop_per_clip": counted["flop"] / max(hi - lo, 1) / 1e12,
+           "note": "utilisation = executed contraction FLOPs / time (the last layer of both read-out transformers is pruned to token 0); "
+                   "model_flop_* divides the un-pruned 3 x 9.413 TFLOP per clip by the same time and is a throughput figure, not utilisation",
+           "gpu_launches_per_step": int(launches), "loss": log["total_loss"], "loss_step0": log0["total_loss"],
+           "data_seeding": "per global clip index (sharding-independent): loss_step0 must agree across GPU counts",
+           "replicas_identical": bool(identical), "clocks": clocks,
+           "config": "cfg3: fwd+bwd+AdamW, B=64 global, T=150, S=2048, Q=512, DINO+depth, NCCL gradient all-reduce overlapped with backward"}
     del trainer, batch
     torch.cuda.empty_cache()
-    return {"metric": "3dspa_train_clips_per_s", "value": args.train_batch / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms,
-            "global_batch": args.train_batch, "clips_per_gpu": hi - lo, "micro_batch": micro, "steps": args.train_steps, "warmup": 1,
-            "scaling": "strong", "dtype": "bf16", "model_tflops_per_gpu": tf / world, "frac_of_sustained_peak_per_gpu": tf / world / peak_tf,
-            "algorithmic_tflop_per_clip": 3 * FWD_TFLOP_PER_CLIP, "executed_gemm_tflop_per_clip": counted["flop"] / max(hi - lo, 1) / 1e12,
-            "executed_gemm_tflops_per_gpu": counted["flop"] / (ms * 1e-3) / 1e12,
-            "gpu_launches_per_step": int(launches), "loss": log["total_loss"], "clocks": clocks,
-            "config": "cfg3: fwd+bwd+AdamW, B=64 global, T=150, S=2048, Q=512, DINO+depth, NCCL gradient all-reduce overlapped with backward"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, dt, sample = cpu_train_rate()
+        out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample, "seconds": dt}
+    return out
 
 
-def run_lifting_leg(spa, dev):
+def run_lifting_leg(spa, dev, cpu=False):
     """cfg4 (K0): bilinear DINO / depth sampling + unprojection for a 64x64 track grid over 150 frames."""
     g = torch.Generator(device=dev).manual_seed(4)
     N, H, W, Hp, Wp = 4096, 518, 518, 37, 37
@@ -250,10 +299,24 @@ def run_lifting_leg(spa, dev):
     ms = e0.elapsed_time(e1) / 5
     nbytes = dino.numel() * 4 + depth.numel() * 4 + tracks.numel() * 4 + N * T * (3 + 768 + 256) * 4   # 3.32 GB
     _, peak_bw, src = measured_peaks()
-    return {"workload": "cfg4: lift + sample 4096 tracks x 150 frames, 518x518 video, DINO map 37x37x768 (fp32 out)", "ms": ms,
-            "bound": "hbm", "algorithmic_bytes": int(nbytes), "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak_bw, "unit": "GB/s",
-            "frac": nbytes / (ms * 1e-3) / 1e9 / peak_bw, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})",
-            "points_per_s": N * T / (ms * 1e-3)}
+    out = {"workload": "cfg4: lift + sample 4096 tracks x 150 frames, 518x518 video, DINO map 37x37x768 (fp32 out)", "ms": ms,
+           "bound": "hbm", "algorithmic_bytes": int(nbytes), "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak_bw, "unit": "GB/s",
+           "frac": nbytes / (ms * 1e-3) / 1e9 / peak_bw, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})",
+           "points_per_s": N * T / (ms * 1e-3)}
+    if cpu:
+        # the reference's own form of this stage (inference.py:287-447): Python loops over (track, frame) with NumPy scalars,
+        # one host core, on 64 of the 4096 tracks (oracle/lifting_loops.py, bit-equal to the reference's functions on the fixtures)
+        from oracle import lifting_loops as ll
+
+        tr_h, d_h, f_h = tracks[:64].cpu().numpy(), depth.cpu().numpy(), dino.cpu().numpy()
+        t0 = time.perf_counter()
+        ll.lift_2d_to_3d(tr_h, d_h)
+        ll.sample_dino_features_for_tracks(f_h, tr_h, (T, H, W, 3))
+        ll.sample_depth_features_for_tracks(d_h, tr_h)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 64 * T / dt, "unit": "points/s", "cores": 1, "kind": "port", "seconds": dt,
+                               "sample": "per-point NumPy loops of inference.py:287-447 (lift + DINO sample + depth features) on 64 tracks x 150 frames of the same clip"}
+    return out
 
 
 def run_pipeline_leg(spa, model, variables, dev):
@@ -298,6 +361,51 @@ def run_pipeline_leg(spa, model, variables, dev):
         res["feature_bytes_not_moved"] = int(N * T * 1024 * 4 * 2)   # [N,T,768] + [N,T,256] fp32, written by K0 and read by K1
         out[f"tracks_{N}"] = res
         del a, b, tracks
+    return out
+
+
+def run_trajan_leg(spa, dev, cpu=True):
+    """cfg1 (BASELINE.json configs[0]): TRAJAN 2D (track_autoencoder.py:117-390) forward, batch 1, 150 frames, 2048 support /
+    512 query tracks, random-init weights, synthetic tracks U(0,1)^2 - on the GPU through the same kernels (bf16), and on the
+    host cores through the oracle restatement (the configuration BASELINE.json says the reference itself runs on CPU)."""
+    from oracle import model as om
+
+    rs = np.random.RandomState(11)
+    inp = {"support_tracks": rs.uniform(0, 1, (1, S, T, 2)).astype(np.float32),
+           "support_tracks_visible": (rs.uniform(size=(1, S, T, 1)) < 0.9).astype(np.float32),
+           "query_points": np.concatenate([rs.randint(0, T, (1, Q, 1)).astype(np.float32), rs.uniform(0, 1, (1, Q, 2)).astype(np.float32)], -1),
+           "boundary_frame": np.array([T], np.int32)}
+    noise = rs.uniform(size=(1, 128, 64)).astype(np.float32)
+    model = spa.TrackAutoEncoder()
+    variables = model.init(0, inp)
+    dev_inp = {k: torch.from_numpy(v).to(dev) for k, v in inp.items()}
+    dev_noise = torch.from_numpy(noise).to(dev)
+    fn = lambda: model.apply(variables, dev_inp, noise=dev_noise, precision="bf16")
+    for _ in range(3):
+        res = fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        res = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out = {"workload": "cfg1: TRAJAN 2D forward, 1 clip, T=150, 2048 support / 512 query 2D tracks, bf16, device-resident inputs (5 eager steps)",
+           "ms_per_clip": ms, "query_tracks_per_s": Q / (ms * 1e-3), "algorithmic_tflop_per_clip": 3.823,
+           "model_tflops": 3.823 / (ms * 1e-3), "finite": bool(torch.isfinite(res.tracks).all())}
+    if cpu:
+        cfg = om.Config2D()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ref = om.forward_2d(om.to_torch(variables["params"]), cfg, om.cast_inputs(inp, torch.float32), torch.from_numpy(noise), True)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": Q / dt, "unit": "query-tracks/s", "cores": torch.get_num_threads(), "kind": "port", "seconds": dt,
+                               "sample": "oracle fp32 TRAJAN forward on the full cfg1 clip (2048 support / 512 query tracks), one pass"}
+        # same inputs, same weights: the two legs must also agree (quantiser on: latents away from rounding ties almost surely)
+        d = (res.tracks.float().cpu() - ref.tracks).abs().max() / ref.tracks.abs().max()
+        out["rel_err_vs_cpu_oracle_tracks"] = float(d)
+    del model, variables
+    torch.cuda.empty_cache()
     return out
 
 
@@ -351,7 +459,7 @@ def run_reference(args):
     rates, times = [], []
     sample = ""
     for i in range(args.warmup + args.steps):
-        r, dt, sample = cpu_oracle_rate(128, 32, threads)
+        r, dt, sample = cpu_oracle_rate(S, Q, threads)     # the full cfg2 clip, every step (~15-25 s on the box's host cores)
         if i >= args.warmup:
             rates.append(r)
             times.append(dt)
@@ -361,7 +469,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2: 3DSPA inference forward, 1 clip per GPU, T=150, S=2048 support, Q=512 query, DINO 768 + depth 256, bf16",
-                   "reference_arm": "fp32 torch-CPU oracle restatement on all host cores; each step = a bounded 128-support / 32-query sample of the same clip shape"},
+                   "reference_arm": "fp32 torch-CPU oracle restatement on all host cores; each step = one forward of the FULL cfg2 clip (2048 support / 512 query)",
+                   "same_config": True},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is JAX/Flax (not installable here); this arm is the torch-CPU oracle restatement",
@@ -505,9 +614,10 @@ def run_ours(args):
     if not args.no_train:
         torch.cuda.empty_cache()
         train = run_train_leg(args, spa, model, variables, world, rank, dev, barrier)
-    pipeline = sweep = None
+    pipeline = sweep = trajan = None
     if rank == 0 and not args.no_train:
-        lifting = run_lifting_leg(spa, dev)
+        lifting = run_lifting_leg(spa, dev, cpu=(world == 1 and not args.no_cpu))
+        trajan = run_trajan_leg(spa, dev, cpu=(world == 1 and not args.no_cpu))
         pipeline = run_pipeline_leg(spa, model, variables, dev)
         sweep = run_sweep_leg(spa, model, variables, dev, world)
     if rank == 0:
@@ -515,6 +625,8 @@ def run_ours(args):
             line["train"] = train
         if lifting is not None:
             line["lifting"] = lifting
+        if trajan is not None:
+            line["trajan"] = trajan
         if pipeline is not None:
             line["pipeline_lift_embed"] = pipeline
         if sweep is not None:
@@ -533,8 +645,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the cfg3 training leg and the cfg4 gather leg")
     ap.add_argument("--train-batch", type=int, default=TRAIN_GLOBAL_BATCH, help="global batch of the training leg (clips)")
-    ap.add_argument("--train-steps", type=int, default=2)
-    ap.add_argument("--train-micro", type=int, default=0, help="clips per micro-batch of the training leg (0 = automatic: 4 when a rank holds at most 32 clips, else 2)")
+    ap.add_argument("--train-steps", type=int, default=0, help="timed optimiser steps of the training leg (0 = 2 on one GPU, 5 otherwise)")
+    ap.add_argument("--train-micro", type=int, default=2, help="clips per micro-batch of the training leg (the same at every GPU count)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when the
     # box exports NCCL_DEBUG=VERSION), so file descriptor 1 points at stderr while the benchmark runs and the JSON line goes

@@ -41,6 +41,26 @@ extern "C" {
 int spa3d_version(void);
 const char* spa3d_last_error(void);
 
+/* ---- dispatch counters -----------------------------------------------------------------------
+ * Every contraction / attention entry point picks an implementation (tcgen05, mma.sync, SIMT) from the
+ * operand dtypes and alignments.  spa3d_stats copies up to n process-wide counters into out and returns
+ * how many exist; spa3d_stat_name(i) names counter i.  The "*_bf16_fallback" counters count bf16 calls that
+ * were computed on the fp32 SIMT kernels because an operand missed the tensor-core path's alignment rules
+ * (correct, but 10-100x slower): a deployment should see zeros there (bench.py asserts it).
+ * The counters are the only process-wide mutable state of the library (relaxed atomics). */
+int spa3d_stats(int64_t* out, int n);
+int spa3d_stats_reset(void);
+const char* spa3d_stat_name(int i);
+
+/* ---- scratch sizes ---------------------------------------------------------------------------
+ * The library never allocates: scratch is caller-owned (XLA FFI: a ScratchAllocator / extra result
+ * buffer; otherwise the host framework's allocator).  Pure functions of the shapes. */
+int64_t spa3d_gemm_workspace_bytes(int64_t M, int N, int K);                        /* 0: split-K partials are added atomically into C */
+int64_t spa3d_sumsq_workspace_bytes(void);                                           /* spa3d_sumsq `workspace` */
+int64_t spa3d_attention_bwd_workspace_bytes(int64_t batch, int heads, int Lq);      /* spa3d_attention_bwd `delta_ws` */
+int64_t spa3d_attention_stats_bytes(int64_t batch, int heads, int Lq);              /* spa3d_attention_fwd `lse_out` (max, sum per row) */
+int64_t spa3d_layernorm_bwd_workspace_bytes(int num_partials, int d);               /* spa3d_layernorm_bwd `dscale_partial` */
+
 /* ---- K0: feature lifting (inference.py:287-447) ------------------------------------------
  * One pass over N x T track points: bilinear depth sample + pinhole unprojection
  * (lift_2d_to_3d, :287-336), bilinear DINO patch sample (:339-395) and the 256-channel depth
@@ -281,6 +301,13 @@ int spa3d_gelu_bwd(const void* pre, int64_t ldp, int p_dtype, const void* dy, in
                    void* stream);
 int spa3d_colsum(const void* x, int64_t ldx, int dtype, float* out, int accumulate,
                  int64_t rows, int cols, void* stream);
+/* Compute-dtype shadows of one fp32 master matrix src [rows, cols] in one pass (after an optimiser step):
+ * dst [rows, cols] = T(src) - the [out,in] operand of the forward GEMMs - and dst_t [cols, rows] = T(src)^T - the
+ * [in,out] operand of dX = dY . W.  Either destination may be NULL.  dtype = SPA3D_BF16 | SPA3D_F32. */
+int spa3d_shadow_weights(const float* src, int64_t lds, void* dst, int64_t ldd, void* dst_t, int64_t ldt, int dtype,
+                         int rows, int cols, void* stream);
+/* bytes of zeros (gradient buffers before the first accumulation). */
+int spa3d_fill_zero(void* p, int64_t bytes, void* stream);
 /* y = a + b elementwise over n floats (y may alias a). */
 int spa3d_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
 

@@ -149,5 +149,9 @@ def test_bf16_gradients_at_reference_widths(spa):
     worst_cos = min(stats.items(), key=lambda kv: kv[1][0])
     worst_rel = max(stats.items(), key=lambda kv: kv[1][1])
     print(f"[grads bf16, real widths] worst cosine {worst_cos[1][0]:.5f} ({worst_cos[0]}), worst rel err {worst_rel[1][1]:.3e} ({worst_rel[0]})")
+    total = float(sum(float(g.double().pow(2).sum()) for g in gref.values()) ** 0.5)
+    share = {k: float(g.double().norm()) / total for k, g in gref.items()}
+    for k, v in sorted(stats.items(), key=lambda kv: kv[1][0])[:30]:
+        print(f"    {k:70s} cos {v[0]:.5f} rel {v[1]:.3e} share-of-gradient-norm {share[k]:.2e}")
     bad = {k: v for k, v in stats.items() if v[0] < 0.995 or v[1] > 5e-2}
     assert not bad, sorted(bad.items(), key=lambda kv: kv[1][0])[:10]

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import lifting, split
+from oracle import lifting, lifting_loops, split
 
 
 def _check_lift(g, prefix=""):
@@ -21,6 +21,19 @@ def _check_lift(g, prefix=""):
 
 def test_lifting_small_bit_exact(golden_dir):
     _check_lift(np.load(os.path.join(golden_dir, "lifting_small.npz")))
+
+
+@pytest.mark.parametrize("case", ["", "integer/", "far_out/", "one_px/", "intrinsics/"])
+def test_per_point_lifting_port_bit_exact(golden_dir, case):
+    """oracle/lifting_loops.py (the per-point form bench.py times as the CPU lifting baseline) against the fixtures produced
+    by the reference's own functions."""
+    g = np.load(os.path.join(golden_dir, "lifting_edges.npz" if case else "lifting_small.npz"))
+    depth, dino, tracks, intr = g[case + "depth"], g[case + "dino"], g[case + "tracks"][:6], g[case + "intrinsics"]
+    intr = None if np.isnan(intr).any() else tuple(float(v) for v in intr)
+    T, H, W = depth.shape[:3]
+    np.testing.assert_array_equal(lifting_loops.lift_2d_to_3d(tracks, depth, intr), g[case + "xyz"][:6])
+    np.testing.assert_array_equal(lifting_loops.sample_dino_features_for_tracks(dino, tracks, (T, H, W, 3)), g[case + "dino_feat"][:6])
+    np.testing.assert_array_equal(lifting_loops.sample_depth_features_for_tracks(depth, tracks), g[case + "depth_feat"][:6])
 
 
 @pytest.mark.parametrize("case", ["integer", "far_out", "one_px", "intrinsics"])
