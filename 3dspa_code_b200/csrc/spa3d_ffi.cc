@@ -1,0 +1,308 @@
+// spa3d_ffi.cc - XLA FFI binder for lib3dspa_b200.so.
+//
+// *** UNBUILT AND UNTESTED IN THIS REPOSITORY. ***  The reference (TheProParadox/3dspa_code) is JAX/Flax, so the custom-call
+// mechanism its own framework offers is XLA FFI; but neither jax/jaxlib nor the FFI headers (xla/ffi/api/ffi.h ship inside
+// jaxlib) exist in the build environment (decision D-1), so this file is NOT in build.py's source list, is never
+// compiled here, and nothing in the tests or the bench depends on it.  What IS built and tested is the torch registration of
+// the same entry points (3dspa_code_b200/torch_ops.py).  This file is the binder a maintainer compiles against THEIR jaxlib:
+//
+//   g++ -shared -fPIC -std=c++17 spa3d_ffi.cc -I$(python -c "import jax.ffi; print(jax.ffi.include_dir())") \
+//       -I../../include -I/usr/local/cuda/include -L.. -l3dspa_b200 -o libspa3d_ffi.so
+//
+// Every handler is a thin adapter: buffers -> raw device pointers, dimensions -> sizes / leading dimensions, attributes ->
+// scalars, PlatformStream -> the stream argument, the int status -> ffi::Error with spa3d_last_error().  Results are
+// preallocated by XLA (Ret<>), scratch is an extra Ret<> buffer sized by the spa3d_*_workspace_bytes queries on the Python
+// side, nothing is allocated or synchronised in here.  Python-side registration and the custom_vjp wiring are in
+// INTEGRATION.md section 2.  Reference call sites each handler replaces are cited beside it (paths into the reference).
+#include <cstdint>
+
+#include "spa3d_b200.h"
+#include "xla/ffi/api/ffi.h"
+
+#include <cuda_runtime_api.h>
+
+namespace ffi = xla::ffi;
+
+namespace {
+
+inline int Code(ffi::DataType t) { return t == ffi::DataType::BF16 ? SPA3D_BF16 : SPA3D_F32; }
+inline ffi::Error Status(int rc) {
+  return rc == 0 ? ffi::Error::Success() : ffi::Error(ffi::ErrorCode::kInternal, spa3d_last_error());
+}
+// [rows, cols] view of a buffer whose leading axes are flattened (the library works on row-major token matrices)
+inline int64_t Cols(const ffi::AnyBuffer& b) { return b.dimensions().back(); }
+inline int64_t Rows(const ffi::AnyBuffer& b) { return b.element_count() / b.dimensions().back(); }
+template <typename B>
+inline void* Ptr(B& b) { return b.untyped_data(); }
+// optional operands arrive as zero-element buffers
+inline const void* Opt(const ffi::AnyBuffer& b) { return b.element_count() == 0 ? nullptr : b.untyped_data(); }
+
+}  // namespace
+
+// ---- nn.Dense / nn.DenseGeneral (attention.py:106-107,154-183; track_autoencoder_3d.py:73-115) ------------------------
+static ffi::Error GemmImpl(cudaStream_t stream, ffi::AnyBuffer a, ffi::AnyBuffer wt, ffi::AnyBuffer bias, ffi::AnyBuffer residual,
+                           int32_t act, ffi::Result<ffi::AnyBuffer> out) {
+  const int64_t M = Rows(a), K = Cols(a), N = wt.dimensions()[0];
+  return Status(spa3d_gemm(a.untyped_data(), K, wt.untyped_data(), K, Code(a.element_type()),
+                           static_cast<const float*>(Opt(bias)), act, Opt(residual), N, Code(residual.element_type()),
+                           out->untyped_data(), N, Code(out->element_type()), M, (int)N, (int)K, SPA3D_GEMM_AUTO, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dGemm, GemmImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Attr<int32_t>("act").Ret<ffi::AnyBuffer>());
+
+// ---- q/k/v projection + per-head nn.RMSNorm + q / sqrt(Dh) (attention.py:154-173) ------------------------------------
+static ffi::Error GemmRmsNormImpl(cudaStream_t stream, ffi::AnyBuffer a, ffi::AnyBuffer wt, ffi::Buffer<ffi::DataType::F32> scale_q,
+                                  ffi::Buffer<ffi::DataType::F32> scale_k, int32_t head_dim, int32_t q_cols, int32_t k_cols, float q_mul,
+                                  ffi::Result<ffi::AnyBuffer> out, ffi::Result<ffi::Buffer<ffi::DataType::F32>> rstd) {
+  const int64_t M = Rows(a), K = Cols(a), N = wt.dimensions()[0];
+  return Status(spa3d_gemm_rmsnorm(a.untyped_data(), K, wt.untyped_data(), K, Code(a.element_type()), out->untyped_data(), N,
+                                   Code(out->element_type()), M, (int)N, (int)K, head_dim, q_cols, k_cols, scale_q.typed_data(),
+                                   scale_k.typed_data(), q_mul, rstd->element_count() ? rstd->typed_data() : nullptr, SPA3D_GEMM_AUTO, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dGemmRmsNorm, GemmRmsNormImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::Buffer<ffi::DataType::F32>>().Attr<int32_t>("head_dim")
+                                  .Attr<int32_t>("q_cols").Attr<int32_t>("k_cols").Attr<float>("q_mul").Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+// ---- MLP_in + nn.gelu (attention.py:106), training form: (z or gelu'(z), h) ----------------------------------------------
+static ffi::Error GemmGeluImpl(cudaStream_t stream, ffi::AnyBuffer a, ffi::AnyBuffer wt, ffi::Buffer<ffi::DataType::F32> bias, int32_t save_grad,
+                               ffi::Result<ffi::AnyBuffer> z, ffi::Result<ffi::AnyBuffer> h) {
+  const int64_t M = Rows(a), K = Cols(a), N = wt.dimensions()[0];
+  return Status(spa3d_gemm_gelu(a.untyped_data(), K, wt.untyped_data(), K, Code(a.element_type()), bias.typed_data(), z->untyped_data(), N,
+                                h->untyped_data(), N, M, (int)N, (int)K, save_grad, SPA3D_GEMM_AUTO, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dGemmGelu, GemmGeluImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Attr<int32_t>("save_grad").Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>());
+
+// backward through MLP_out and the activation: dz = (dy . W2^T) * gelu'(z); also the column sums of dz (MLP_in's bias gradient)
+static ffi::Error GemmGeluBwdImpl(cudaStream_t stream, ffi::AnyBuffer dy, ffi::AnyBuffer wt, ffi::AnyBuffer z, int32_t z_is_grad,
+                                  ffi::Result<ffi::AnyBuffer> dz, ffi::Result<ffi::Buffer<ffi::DataType::F32>> dz_colsum) {
+  const int64_t M = Rows(dy), K = Cols(dy), N = wt.dimensions()[0];
+  if (dz_colsum->element_count()) cudaMemsetAsync(dz_colsum->typed_data(), 0, dz_colsum->size_bytes(), stream);   // the kernel accumulates
+  return Status(spa3d_gemm_gelu_bwd(dy.untyped_data(), K, wt.untyped_data(), K, Code(dy.element_type()), z.untyped_data(), N, dz->untyped_data(),
+                                    N, M, (int)N, (int)K, z_is_grad, dz_colsum->element_count() ? dz_colsum->typed_data() : nullptr,
+                                    SPA3D_GEMM_AUTO, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dGemmGeluBwd, GemmGeluBwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>().Attr<int32_t>("z_is_grad").Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+// weight gradient dW[N,K] = dY^T X (the cotangent of every Dense kernel under jax.value_and_grad, train.py:161-162)
+static ffi::Error GemmDwImpl(cudaStream_t stream, ffi::AnyBuffer dy, ffi::AnyBuffer x, ffi::Result<ffi::Buffer<ffi::DataType::F32>> dw) {
+  const int64_t M = Rows(dy), N = Cols(dy), K = Cols(x);
+  return Status(spa3d_gemm_dw(dy.untyped_data(), N, x.untyped_data(), K, Code(dy.element_type()), dw->typed_data(), K, M, (int)N, (int)K,
+                              /*accumulate=*/0, SPA3D_GEMM_AUTO, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dGemmDw, GemmDwImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+// ---- nn.LayerNorm(use_bias=False) (attention.py:49,76,103) ----------------------------------------------------------------
+static ffi::Error LayerNormFwdImpl(cudaStream_t stream, ffi::AnyBuffer x, ffi::Buffer<ffi::DataType::F32> scale, ffi::Result<ffi::AnyBuffer> y,
+                                   ffi::Result<ffi::Buffer<ffi::DataType::F32>> mean, ffi::Result<ffi::Buffer<ffi::DataType::F32>> rstd) {
+  const int64_t rows = Rows(x), d = Cols(x);
+  return Status(spa3d_layernorm_fwd(x.untyped_data(), d, Code(x.element_type()), scale.typed_data(), y->untyped_data(), d,
+                                    Code(y->element_type()), mean->element_count() ? mean->typed_data() : nullptr,
+                                    rstd->element_count() ? rstd->typed_data() : nullptr, rows, (int)d, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dLayerNormFwd, LayerNormFwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::DataType::F32>>().Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+static ffi::Error LayerNormBwdImpl(cudaStream_t stream, ffi::AnyBuffer x, ffi::Buffer<ffi::DataType::F32> scale, ffi::Buffer<ffi::DataType::F32> mean,
+                                   ffi::Buffer<ffi::DataType::F32> rstd, ffi::AnyBuffer dy, ffi::Result<ffi::AnyBuffer> dx,
+                                   ffi::Result<ffi::Buffer<ffi::DataType::F32>> dscale) {
+  const int64_t rows = Rows(x), d = Cols(x);
+  cudaMemsetAsync(dscale->typed_data(), 0, dscale->size_bytes(), stream);   // accumulate_dscale = 1 adds block partial sums atomically
+  return Status(spa3d_layernorm_bwd(x.untyped_data(), d, Code(x.element_type()), scale.typed_data(), mean.typed_data(), rstd.typed_data(),
+                                    dy.untyped_data(), d, Code(dy.element_type()), dx->untyped_data(), d, Code(dx->element_type()),
+                                    /*dx_accumulate=*/0, nullptr, 0, dscale->typed_data(), 0, /*accumulate_dscale=*/1, nullptr, rows, (int)d, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dLayerNormBwd, LayerNormBwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+// backward of the per-head nn.RMSNorm (attention.py:166-167), in place on the gradient of the normalised projection
+static ffi::Error HeadRmsNormBwdImpl(cudaStream_t stream, ffi::AnyBuffer y, ffi::Buffer<ffi::DataType::F32> scale, ffi::Buffer<ffi::DataType::F32> rstd,
+                                     ffi::AnyBuffer dy, float out_mul, int32_t heads, int32_t head_dim, ffi::Result<ffi::AnyBuffer> dx,
+                                     ffi::Result<ffi::Buffer<ffi::DataType::F32>> dscale) {
+  const int64_t rows = Rows(y), ld = Cols(y);
+  cudaMemcpyAsync(dx->untyped_data(), dy.untyped_data(), dy.size_bytes(), cudaMemcpyDeviceToDevice, stream);   // or alias dy -> dx with input_output_aliases
+  cudaMemsetAsync(dscale->typed_data(), 0, dscale->size_bytes(), stream);
+  return Status(spa3d_head_rmsnorm_bwd(y.untyped_data(), ld, Code(y.element_type()), scale.typed_data(), out_mul, rstd.typed_data(), heads,
+                                       dx->untyped_data(), ld, Code(dx->element_type()), dscale->typed_data(), 0, 1, rows, heads, head_dim, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dHeadRmsNormBwd, HeadRmsNormBwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::AnyBuffer>().Attr<float>("out_mul").Attr<int32_t>("heads")
+                                  .Attr<int32_t>("head_dim").Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+// ---- nn.dot_product_attention (attention.py:175): q,k,v [batch*L, heads*Dh] (q already normalised and scaled) ----------------
+static ffi::Error AttentionFwdImpl(cudaStream_t stream, ffi::AnyBuffer q, ffi::AnyBuffer k, ffi::AnyBuffer v, ffi::Buffer<ffi::DataType::U8> key_mask,
+                                   int64_t batch, int32_t heads, int32_t lq, int32_t lk, int32_t head_dim, ffi::Result<ffi::AnyBuffer> o,
+                                   ffi::Result<ffi::Buffer<ffi::DataType::F32>> stats) {
+  const int64_t ld = (int64_t)heads * head_dim;
+  return Status(spa3d_attention_fwd(q.untyped_data(), ld, k.untyped_data(), ld, v.untyped_data(), ld, o->untyped_data(), ld, Code(q.element_type()),
+                                    key_mask.element_count() ? key_mask.typed_data() : nullptr,
+                                    stats->element_count() ? stats->typed_data() : nullptr, batch, heads, lq, lk, head_dim, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dAttentionFwd, AttentionFwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::DataType::U8>>().Attr<int64_t>("batch").Attr<int32_t>("heads").Attr<int32_t>("lq")
+                                  .Attr<int32_t>("lk").Attr<int32_t>("head_dim").Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+static ffi::Error AttentionBwdImpl(cudaStream_t stream, ffi::AnyBuffer q, ffi::AnyBuffer k, ffi::AnyBuffer v, ffi::AnyBuffer o, ffi::AnyBuffer d_o,
+                                   ffi::Buffer<ffi::DataType::U8> key_mask, ffi::Buffer<ffi::DataType::F32> stats, int64_t batch, int32_t heads,
+                                   int32_t lq, int32_t lk, int32_t head_dim, ffi::Result<ffi::AnyBuffer> dq, ffi::Result<ffi::AnyBuffer> dk,
+                                   ffi::Result<ffi::AnyBuffer> dv, ffi::Result<ffi::Buffer<ffi::DataType::F32>> delta_ws) {
+  const int64_t ld = (int64_t)heads * head_dim;   // delta_ws: spa3d_attention_bwd_workspace_bytes(batch, heads, lq) / 4 floats
+  return Status(spa3d_attention_bwd(q.untyped_data(), ld, k.untyped_data(), ld, v.untyped_data(), ld, o.untyped_data(), ld, d_o.untyped_data(), ld,
+                                    dq->untyped_data(), ld, dk->untyped_data(), ld, dv->untyped_data(), ld, Code(q.element_type()),
+                                    key_mask.element_count() ? key_mask.typed_data() : nullptr, stats.typed_data(), delta_ws->typed_data(), batch,
+                                    heads, lq, lk, head_dim, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dAttentionBwd, AttentionBwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::DataType::U8>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Attr<int64_t>("batch").Attr<int32_t>("heads").Attr<int32_t>("lq").Attr<int32_t>("lk").Attr<int32_t>("head_dim")
+                                  .Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+// ---- embed_track_pos_visible (track_autoencoder_3d.py:123-149) + read-out slot, fused --------------------------------------
+static ffi::Error EmbedFusedImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> tracks, ffi::Buffer<ffi::DataType::F32> dino,
+                                 ffi::Buffer<ffi::DataType::F32> depth, ffi::AnyBuffer wt, ffi::Buffer<ffi::DataType::F32> bias, int32_t frames,
+                                 float track_scale_factor, ffi::Result<ffi::Buffer<ffi::DataType::F32>> out, ffi::Result<ffi::AnyBuffer> a_cat) {
+  const int64_t rows = tracks.element_count() / 3, W = wt.dimensions()[0], K = wt.dimensions()[1];
+  const int dd = dino.element_count() ? (int)dino.dimensions().back() : 0, dz = depth.element_count() ? (int)depth.dimensions().back() : 0;
+  return Status(spa3d_embed_fused(tracks.typed_data(), dd ? dino.typed_data() : nullptr, dz ? depth.typed_data() : nullptr, wt.untyped_data(), K,
+                                  bias.typed_data(), out->typed_data(), W, a_cat->element_count() ? a_cat->untyped_data() : nullptr, K, rows,
+                                  frames, dd, dz, (int)W, 32, track_scale_factor, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dEmbedFused, EmbedFusedImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Attr<int32_t>("frames").Attr<float>("track_scale_factor")
+                                  .Ret<ffi::Buffer<ffi::DataType::F32>>().Ret<ffi::AnyBuffer>());
+
+// ---- SinusoidalEmbedding (track_autoencoder.py:18-38) ---------------------------------------------------------------------------
+static ffi::Error FourierImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> x, int32_t num_freq, float scale_factor, int32_t append_time,
+                              int32_t tail_zero, int32_t exact, ffi::Result<ffi::AnyBuffer> out) {
+  const int64_t C = x.dimensions().back(), rows = x.element_count() / C;
+  return Status(spa3d_fourier_features(x.typed_data(), C, out->untyped_data(), out->dimensions().back(), Code(out->element_type()), rows, (int)C,
+                                       num_freq, scale_factor, append_time, tail_zero, exact, 0, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dFourierFeatures, FourierImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>().Attr<int32_t>("num_freq")
+                                  .Attr<float>("scale_factor").Attr<int32_t>("append_time").Attr<int32_t>("tail_zero").Attr<int32_t>("exact")
+                                  .Ret<ffi::AnyBuffer>());
+
+// ---- lift_2d_to_3d + sample_dino_features_for_tracks + sample_depth_features_for_tracks (inference.py:287-447) ---------------
+static ffi::Error LiftSampleImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> tracks_2d, ffi::Buffer<ffi::DataType::F32> depth,
+                                 ffi::Buffer<ffi::DataType::F32> dino, ffi::Buffer<ffi::DataType::F32> intrinsics_host, int32_t video_h,
+                                 int32_t video_w, ffi::Result<ffi::Buffer<ffi::DataType::F32>> xyz, ffi::Result<ffi::AnyBuffer> dino_feat,
+                                 ffi::Result<ffi::AnyBuffer> depth_feat) {
+  auto td = tracks_2d.dimensions();                   // [N, T, 2]
+  auto dd = depth.dimensions();                       // [T, H, W, 1]
+  auto fd = dino.dimensions();                        // [T, Hp, Wp, D]
+  // intrinsics are HOST scalars of the C ABI: pass them as four float attributes in production; shown as a buffer for brevity
+  return Status(spa3d_lift_sample(tracks_2d.typed_data(), depth.typed_data(), dino.typed_data(), xyz->typed_data(), dino_feat->untyped_data(),
+                                  depth_feat->untyped_data(), Code(dino_feat->element_type()), (int)td[0], (int)td[1], (int)dd[1], (int)dd[2],
+                                  (int)fd[1], (int)fd[2], (int)fd[3], (int)depth_feat->dimensions().back(), video_h, video_w,
+                                  intrinsics_host.element_count() ? intrinsics_host.typed_data() : nullptr, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dLiftSample, LiftSampleImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Attr<int32_t>("video_h").Attr<int32_t>("video_w").Ret<ffi::Buffer<ffi::DataType::F32>>().Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>());
+
+// ---- R1 key mask, quantiser, decoder tokens (track_autoencoder_3d.py:167-184, 251-260, 235-246 + 276-284) -----------------------
+static ffi::Error KeyMaskImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> visible, ffi::Buffer<ffi::DataType::S32> boundary, int32_t has_readout,
+                              ffi::Result<ffi::Buffer<ffi::DataType::U8>> mask) {
+  auto d = visible.dimensions();                      // [B, N, T, 1]
+  return Status(spa3d_build_key_mask(visible.typed_data(), boundary.typed_data(), mask->typed_data(), (int)d[0], (int)d[1], (int)d[2], has_readout, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dBuildKeyMask, KeyMaskImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::S32>>().Attr<int32_t>("has_readout").Ret<ffi::Buffer<ffi::DataType::U8>>());
+
+static ffi::Error QuantizeFwdImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> x, ffi::Buffer<ffi::DataType::F32> noise, int32_t discretize,
+                                  ffi::Result<ffi::Buffer<ffi::DataType::F32>> y, ffi::Result<ffi::Buffer<ffi::DataType::U8>> pass_mask) {
+  return Status(spa3d_quantize_fwd(x.typed_data(), noise.element_count() ? noise.typed_data() : nullptr, y->typed_data(),
+                                   pass_mask->element_count() ? pass_mask->typed_data() : nullptr, (int64_t)x.element_count(), discretize, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dQuantizeFwd, QuantizeFwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Attr<int32_t>("discretize").Ret<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Ret<ffi::Buffer<ffi::DataType::U8>>());
+
+static ffi::Error QuantizeBwdImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> dy, ffi::Buffer<ffi::DataType::U8> pass_mask,
+                                  ffi::Result<ffi::Buffer<ffi::DataType::F32>> dx) {
+  return Status(spa3d_quantize_bwd(dy.typed_data(), pass_mask.typed_data(), dx->typed_data(), (int64_t)dy.element_count(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dQuantizeBwd, QuantizeBwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::U8>>().Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+static ffi::Error DecoderTokensFwdImpl(cudaStream_t stream, ffi::AnyBuffer lat, ffi::AnyBuffer query_emb, ffi::Buffer<ffi::DataType::S32> query_frame,
+                                       ffi::Result<ffi::AnyBuffer> tokens) {
+  auto ld = lat.dimensions();                         // [B, L, C]
+  auto qd = query_frame.dimensions();                 // [B, Q]
+  return Status(spa3d_decoder_tokens_fwd(lat.untyped_data(), Code(lat.element_type()), query_emb.untyped_data(), Code(query_emb.element_type()),
+                                         query_frame.typed_data(), tokens->untyped_data(), Code(tokens->element_type()), (int)ld[0], (int)qd[1],
+                                         (int)ld[1], (int)ld[2], stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dDecoderTokensFwd, DecoderTokensFwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::DataType::S32>>().Ret<ffi::AnyBuffer>());
+
+static ffi::Error DecoderTokensBwdImpl(cudaStream_t stream, ffi::AnyBuffer d_tokens, ffi::Buffer<ffi::DataType::S32> query_frame, int32_t latents,
+                                       ffi::Result<ffi::Buffer<ffi::DataType::F32>> d_lat, ffi::Result<ffi::Buffer<ffi::DataType::F32>> d_query_emb) {
+  auto qd = query_frame.dimensions();                 // [B, Q]
+  const int C = (int)d_lat->dimensions().back();
+  return Status(spa3d_decoder_tokens_bwd(d_tokens.untyped_data(), Code(d_tokens.element_type()), query_frame.typed_data(), d_lat->typed_data(),
+                                         d_query_emb->typed_data(), (int)qd[0], (int)qd[1], latents, C, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dDecoderTokensBwd, DecoderTokensBwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::DataType::S32>>()
+                                  .Attr<int32_t>("latents").Ret<ffi::Buffer<ffi::DataType::F32>>().Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+// ---- output split + compute_loss_3d (track_autoencoder_3d.py:289-301; train.py:96-129) -----------------------------------------
+static ffi::Error SplitOutputsImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> head_out, int32_t frames, int32_t coords,
+                                   ffi::Result<ffi::Buffer<ffi::DataType::F32>> tracks, ffi::Result<ffi::Buffer<ffi::DataType::F32>> visible_logits,
+                                   ffi::Result<ffi::Buffer<ffi::DataType::F32>> certain_logits) {
+  const int64_t rows = head_out.element_count() / head_out.dimensions().back();
+  return Status(spa3d_split_outputs(head_out.typed_data(), tracks->typed_data(), visible_logits->typed_data(), rows, frames, coords,
+                                    certain_logits->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dSplitOutputs, SplitOutputsImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>().Attr<int32_t>("frames")
+                                  .Attr<int32_t>("coords").Ret<ffi::Buffer<ffi::DataType::F32>>().Ret<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+static ffi::Error LossFwdImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> head_out, ffi::Buffer<ffi::DataType::F32> target_tracks,
+                              ffi::Buffer<ffi::DataType::F32> target_vis, int32_t frames, ffi::Result<ffi::Buffer<ffi::DataType::F32>> sums) {
+  const int64_t rows = head_out.element_count() / head_out.dimensions().back();
+  cudaMemsetAsync(sums->typed_data(), 0, sums->size_bytes(), stream);
+  return Status(spa3d_loss_fwd(head_out.typed_data(), target_tracks.typed_data(), target_vis.typed_data(), sums->typed_data(), rows, frames, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dLossFwd, LossFwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::Buffer<ffi::DataType::F32>>().Attr<int32_t>("frames")
+                                  .Ret<ffi::Buffer<ffi::DataType::F32>>());
+
+static ffi::Error LossBwdImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> head_out, ffi::Buffer<ffi::DataType::F32> target_tracks,
+                              ffi::Buffer<ffi::DataType::F32> target_vis, int32_t frames, float l1_weight, float bce_weight, float inv_denom,
+                              ffi::Result<ffi::Buffer<ffi::DataType::F32>> d_head_out) {
+  const int64_t rows = head_out.element_count() / head_out.dimensions().back();
+  return Status(spa3d_loss_bwd(head_out.typed_data(), target_tracks.typed_data(), target_vis.typed_data(), d_head_out->typed_data(), l1_weight,
+                               bce_weight, inv_denom, rows, frames, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dLossBwd, LossBwdImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
+                                  .Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::Buffer<ffi::DataType::F32>>().Attr<int32_t>("frames")
+                                  .Attr<float>("l1_weight").Attr<float>("bce_weight").Attr<float>("inv_denom")
+                                  .Ret<ffi::Buffer<ffi::DataType::F32>>());
