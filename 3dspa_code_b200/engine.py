@@ -68,6 +68,14 @@ class DeviceWeights:
         self.embed_bias = eb
 
 
+def _feat_dev(x, device):
+    """Per-track DINO / depth features on the device: float32 as in the reference's batch, or bfloat16 when the caller
+    already holds them in bfloat16 (a torch tensor; halves the host->device bytes - the bf16 path rounds them to bf16 anyway)."""
+    if isinstance(x, torch.Tensor) and x.dtype == torch.bfloat16:
+        return x.to(device=device, non_blocking=True).contiguous()
+    return _as_dev(x, torch.float32, device)
+
+
 def _as_dev(x, dtype, device):
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
@@ -169,7 +177,10 @@ class Engine:
                 cols += list(range(off, off + meta["depth_dim"]))
                 ops.axpy(bias, self.w.f32["embed.b_depth"])
             wt = wt[:, cols].contiguous()
-        if (ro and self.cdt == torch.bfloat16 and self.fused_embed and cfg.num_frequencies == 32 and C == 3
+        lowp_in = any(t is not None and t.dtype != torch.float32 for t in (dino, depth))   # bf16 features: converted / copied, then one GEMM
+        if lowp_in and self.cdt != torch.bfloat16:
+            raise ValueError("bfloat16 features need precision='bf16'")
+        if (ro and not lowp_in and self.cdt == torch.bfloat16 and self.fused_embed and cfg.num_frequencies == 32 and C == 3
                 and ops.embed_fused_applicable(wt.shape[0], K, dino.shape[-1] if dino is not None else 0,
                                                depth.shape[-1] if depth is not None else 0, C)):
             # K1: Fourier features + fp32->bf16 feature conversion inside the GEMM's operand producers
@@ -264,9 +275,9 @@ class Engine:
         B, N, T, _ = inputs["support_tracks"].shape
         # host-resident inputs: overlap the host->device copies (1.26 GB of fp32 features per clip,
         # PCIe-bound) with the per-track work, chunk by chunk - tracks are independent until pooling
+        stream_keys = ["support_tracks", "support_tracks_visible"] + [k for k in ("dino_features", "depth_features") if inputs.get(k) is not None]
         streamed = three_d and self.stream_chunk > 0 and N >= 2 * self.stream_chunk and all(
-            isinstance(inputs.get(k), torch.Tensor) and not inputs[k].is_cuda
-            for k in ("support_tracks", "support_tracks_visible"))
+            isinstance(inputs.get(k), torch.Tensor) and not inputs[k].is_cuda for k in stream_keys)   # NumPy inputs: one-shot upload
         tracks = visible = None
         if not streamed:
             tracks = _as_dev(inputs["support_tracks"], torch.float32, dev)
@@ -274,9 +285,9 @@ class Engine:
         dino = depth = None
         if three_d and not streamed:
             if self.cfg.use_dino and meta["has_dino"] and inputs.get("dino_features") is not None:
-                dino = _as_dev(inputs["dino_features"], torch.float32, dev)
+                dino = _feat_dev(inputs["dino_features"], dev)
             if self.cfg.use_depth and meta["has_depth"] and inputs.get("depth_features") is not None:
-                depth = _as_dev(inputs["depth_features"], torch.float32, dev)
+                depth = _feat_dev(inputs["depth_features"], dev)
         if streamed:
             st = self._encode_tracks_streamed(inputs, boundary, B, N, T)
         elif three_d:
@@ -308,7 +319,8 @@ class Engine:
         use_dino = cfg.use_dino and meta["has_dino"] and inputs.get("dino_features") is not None
         use_depth = cfg.use_depth and meta["has_depth"] and inputs.get("depth_features") is not None
         keys = ["support_tracks", "support_tracks_visible"] + (["dino_features"] if use_dino else []) + (["depth_features"] if use_depth else [])
-        host = {k: (inputs[k] if inputs[k].dtype == torch.float32 else inputs[k].float()) for k in keys}
+        keep = lambda k, t: t.dtype == torch.float32 or (t.dtype == torch.bfloat16 and k in ("dino_features", "depth_features"))
+        host = {k: (inputs[k] if keep(k, inputs[k]) else inputs[k].float()) for k in keys}
         pieces = [(b, n0, min(n0 + self.stream_chunk, N)) for b in range(B) for n0 in range(0, N, self.stream_chunk)]
         # taper the tail: whatever is computed after the LAST upload has landed is not hidden by any copy, so the final
         # chunk is split 1/2, 1/4, 1/4 (the last piece's transformer pass is then a quarter as long)
@@ -325,8 +337,8 @@ class Engine:
             for k in keys:
                 shp = (1, C) + tuple(host[k].shape[2:])
                 cur_buf = self._stage.get((k, slot))
-                if cur_buf is None or cur_buf.shape != shp:
-                    self._stage[(k, slot)] = torch.empty(shp, device=dev, dtype=torch.float32)
+                if cur_buf is None or cur_buf.shape != shp or cur_buf.dtype != host[k].dtype:
+                    self._stage[(k, slot)] = torch.empty(shp, device=dev, dtype=host[k].dtype)
         done = [None, None]   # compute-finished events per slot
 
         def upload(i):

@@ -69,6 +69,43 @@ def synth_clip(seed, device=None, pinned=False, s=S, q=Q, t=T):
     return out, (noise.to(device) if device is not None else (noise.pin_memory() if pinned else noise))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to GPU ``index`` BEFORE its pinned buffers are allocated, so
+    first-touch places them on the GPU's own NUMA node.  With eight ranks uploading at once, buffers that all sit on one socket
+    turn the inter-socket link into the bottleneck (round 1: 55 GB/s per GPU alone, 23 GB/s with eight ranks)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [i for i in range(n_cpu) if (int(mask[i // 64]) >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
+def synth_maps_clip(seed, spa, dev, s=S, q=Q, t=T, H=518, W=518, Hp=37, Wp=37):
+    """cfg2 at the reference's real inference boundary (inference.py:523-590): what the backbones hand over - 2-D tracks,
+    per-frame depth maps and DINOv2 patch maps - in pinned host memory (float32).  Query points are held-out tracks lifted with
+    the same depth (set-up, outside every timed region)."""
+    lifting = importlib.import_module("3dspa_code_b200.lifting")
+    g = torch.Generator().manual_seed(seed)
+    tr2 = torch.rand(s + q, t, 2, generator=g) * (W - 1)
+    depth = torch.rand(t, H, W, 1, generator=g) * 1.5 + 0.5
+    q_xyz = lifting.lift_2d_to_3d(tr2[s:].to(dev), depth.to(dev), as_numpy=False).cpu()
+    qt = torch.randint(0, t, (q,), generator=g)
+    host = {"support_tracks_2d": tr2[:s].contiguous().pin_memory(),
+            "support_tracks_visible": (torch.rand(s, t, 1, generator=g) < 0.9).float().pin_memory(),
+            "depth": depth.pin_memory(), "dino_map": torch.randn(t, Hp, Wp, 768, generator=g).pin_memory(),
+            "video_shape": (t, H, W, 3),
+            "query_points": torch.cat([qt[:, None].float(), q_xyz[torch.arange(q), qt]], -1)[None].contiguous().pin_memory()}
+    return host, torch.rand(1, 128, 96, generator=g).pin_memory()
+
+
 class ClockSampler(threading.Thread):
     """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML through
     nvidia_ml_py (a query takes ~1 ms, so a 130 ms timed region gets several samples); falls back to
@@ -486,6 +523,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None   # one GPU: all host cores stay available to the cpu_baseline legs
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     spa = importlib.import_module("3dspa_code_b200")
@@ -565,18 +603,54 @@ def run_ours(args):
     gemm_flop = sum(f for _, _, f in gemm_log)
     ms_eager = ms_eager_total / args.steps
 
-    # ---- end to end through the public API with host buffers -------------------------------------
+    # ---- end to end through the public API with HOST buffers --------------------------------------------------
+    # Every step uploads its clip from pinned host memory, runs the forward and reads tracks + visibility logits back, all inside
+    # the timed region.  model.apply_stream overlaps the upload of clip i+1 with the forward of clip i (two device buffer sets).
+    #   maps          the reference's real inference boundary (inference.py:523-590): 2-D tracks + depth maps + DINOv2 patch maps
+    #                 (float32, 0.80 GB per clip); lifting, sampling and the embedding run fused on the device        <- headline e2e
+    #   features_fp32 the model call's own batch dict (track_autoencoder_3d.py:23-40) with float32 per-track features (1.26 GB)
+    #   features_bf16 the same with the DINO / depth features held in bfloat16 on the host (0.63 GB; converted OUTSIDE the timed region)
+    #   single_call   one blocking model.apply per clip (no cross-clip overlap; uploads chunked under the per-track transformer)
+    K = args.steps
+    maps_host, maps_noise = synth_maps_clip(200 + rank, spa, dev)
+    lowp_inputs = dict(host_inputs, dino_features=host_inputs["dino_features"].to(torch.bfloat16).pin_memory(),
+                       depth_features=host_inputs["depth_features"].to(torch.bfloat16).pin_memory())
+    stream_model = spa.TrackAutoEncoder3D()
+    stream_model.cuda_graph = True
+
+    def nbytes(d, noise):
+        return int(sum(v.numel() * v.element_size() for v in d.values() if isinstance(v, torch.Tensor)) + noise.numel() * noise.element_size())
+
+    def run_stream(batch, noise, from_maps, n):
+        m = model if from_maps else stream_model
+        last = None
+        for res in m.apply_stream(variables, (batch for _ in range(n)), noises=(noise for _ in range(n)), precision="bf16", from_maps=from_maps):
+            last = res
+        return last
+
+    e2e_variants = {}
+    for name, batch, noise, from_maps in (("maps", maps_host, maps_noise, True), ("features_fp32", host_inputs, host_noise, False),
+                                          ("features_bf16", lowp_inputs, host_noise, False)):
+        run_stream(batch, noise, from_maps, max(2, args.warmup))
+        ms = timed(lambda: run_stream(batch, noise, from_maps, K), 1) / K
+        e2e_variants[name] = {"ms_per_step": ms, "value": world * Q / (ms * 1e-3), "h2d_bytes_per_step": nbytes(batch, noise)}
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
-    # the copy alone (same pinned buffers, no compute): the PCIe floor of the end-to-end number
+    ms_single = timed(step_e2e, K) / K
+    e2e_variants["single_call_features_fp32"] = {"ms_per_step": ms_single, "value": world * Q / (ms_single * 1e-3),
+                                                 "h2d_bytes_per_step": nbytes(host_inputs, host_noise)}
+    # the copy alone (same pinned buffers, no compute): the PCIe floor of the headline variant
     def copy_only():
-        return [v.to(dev, non_blocking=True) for v in host_inputs.values()]
+        return [v.to(dev, non_blocking=True) for v in maps_host.values() if isinstance(v, torch.Tensor)]
     copy_only()
-    ms_copy = timed(copy_only, args.steps) / args.steps
-    h2d = sum(v.numel() * v.element_size() for v in host_inputs.values()) + host_noise.numel() * 4
+    ms_copy = timed(copy_only, K) / K
+    h2d = e2e_variants["maps"]["h2d_bytes_per_step"]
     d2h = Q * T * 4 * 4
-    e2e_value = world * Q / (ms_e2e * 1e-3)
+    ms_e2e = e2e_variants["maps"]["ms_per_step"]
+    e2e_value = e2e_variants["maps"]["value"]
+    fallbacks = {k: v for k, v in ops.stats().items() if k.endswith("_fallback")}
+    del stream_model, lowp_inputs, maps_host
+    torch.cuda.empty_cache()
 
     if rank == 0:
         peak_tf, peak_bw, src = measured_peaks()
@@ -589,10 +663,14 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "cfg2: 3DSPA inference forward, 1 clip per GPU, T=150, S=2048 support, Q=512 query, DINO 768 + depth 256, bf16",
                        "l2": "inputs_exceed_l2 (1.26 GB of features per clip vs 126 MB L2)", "weights": "random-init (109.14 M params)",
-                       "launch": "value: the forward replayed as one CUDA graph (model.cuda_graph = True); e2e: eager launches, chunked uploads"},
+                       "launch": "value: the forward replayed as one CUDA graph (model.cuda_graph = True); e2e: model.apply_stream from host-resident maps"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
                     "h2d_copy_alone_ms": ms_copy, "h2d_copy_alone_gbs": h2d / (ms_copy * 1e-3) / 1e9,
-                    "note": "uploads are chunked and overlapped with the per-track transformer; the host->device copy is the floor"},
+                    "path": "model.apply_stream(from_maps=True): per step, one clip's 2-D tracks + depth maps + DINOv2 patch maps (float32, pinned host) "
+                            "are uploaded, lifted / sampled / embedded fused, encoded and decoded; tracks + visibility logits are read back. "
+                            "The upload of clip i+1 overlaps the forward of clip i; K clips are timed from before the first upload to after the last read-back",
+                    "variants": e2e_variants, "host_numa_cpus": numa_cpus},
+            "dispatch_fallbacks": fallbacks,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all bf16 dense contractions of the step)",

@@ -360,3 +360,54 @@ def test_sweep_clip_shape_properties(spa):
     assert rel_err(b.tracks, a.tracks) < 2e-2, rel_err(b.tracks, a.tracks)
     sc = ev.reconstruction_score(a, {"query_tracks": q_xyz[None]}, as_numpy=False)
     assert sc.shape == (T, Q5, 1) and torch.isfinite(sc).all()
+
+
+def test_apply_stream_equals_per_clip_apply(spa):
+    """model.apply_stream (uploads of clip i+1 under the forward of clip i, asynchronous read-back) yields, clip by clip, exactly
+    what apply() returns for that clip - eagerly and with CUDA-graph replay; bfloat16 host features agree within the bf16 budget."""
+    c = small_cfg()
+    fields = {k: getattr(c, k) for k in om.Config3D.__dataclass_fields__}
+    model = spa.TrackAutoEncoder3D(**fields)
+    clips = [make_inputs(c, B=1, N=9, Q=5, seed=40 + i) for i in range(5)]
+    variables = model.init(8, clips[0][0], arch=SMALL_ARCH)
+    randomize(variables["params"], 8)
+    pin = lambda d: {k: torch.as_tensor(v).pin_memory() for k, v in d.items()}
+    batches = [pin(b) for b, _ in clips]
+    noises = [torch.as_tensor(n).pin_memory() for _, n in clips]
+    refs = [model.apply(variables, b, noise=n, precision="bf16") for b, n in clips]
+    for graphed in (False, True):
+        m = spa.TrackAutoEncoder3D(**fields)
+        m.cuda_graph = graphed
+        got = list(m.apply_stream(variables, batches, noises=noises, precision="bf16"))
+        assert len(got) == len(refs)
+        for g, r in zip(got, refs):
+            assert not g.tracks.is_cuda
+            assert torch.equal(g.tracks, r.tracks.cpu()) and torch.equal(g.visible_logits, r.visible_logits.cpu())
+    # one clip, zero clips
+    assert len(list(model.apply_stream(variables, batches[:1], noises=noises[:1]))) == 1
+    assert list(model.apply_stream(variables, [], noises=[])) == []
+    # bfloat16 features on the host (half the upload): same result up to the rounding the bf16 path applies anyway
+    lowp = [dict(b, dino_features=b["dino_features"].to(torch.bfloat16).pin_memory(), depth_features=b["depth_features"].to(torch.bfloat16).pin_memory())
+            for b in batches]
+    got = list(model.apply_stream(variables, lowp, noises=noises, precision="bf16"))
+    for g, r in zip(got, refs):
+        assert rel_err(g.tracks, r.tracks) < 1e-2, rel_err(g.tracks, r.tracks)
+
+
+def test_apply_stream_from_maps_equals_apply_from_maps(spa):
+    rs = np.random.RandomState(13)
+    N, T, Q, H, W, Hp, Wp = 40, 150, 5, 20, 24, 5, 6
+    model = spa.TrackAutoEncoder3D()
+    variables = model.init(22, {"dino_features": 1, "depth_features": 1})
+    batches = []
+    for i in range(3):
+        batches.append({"support_tracks_2d": np.stack([rs.uniform(-2, W + 1, (N, T)), rs.uniform(-2, H + 1, (N, T))], -1).astype(np.float32),
+                        "support_tracks_visible": (rs.uniform(size=(N, T, 1)) < 0.85).astype(np.float32),
+                        "depth": rs.uniform(0.5, 4.0, (T, H, W, 1)).astype(np.float32), "dino_map": rs.standard_normal((T, Hp, Wp, 768)).astype(np.float32),
+                        "video_shape": (T, H, W, 3),
+                        "query_points": np.concatenate([rs.randint(0, T, (1, Q, 1)).astype(np.float32), rs.uniform(-1, 1, (1, Q, 3)).astype(np.float32)], -1)})
+    noise = rs.uniform(size=(1, 128, 96)).astype(np.float32)
+    refs = [model.apply_from_maps(variables, b, noise=noise) for b in batches]
+    got = list(model.apply_stream(variables, batches, noises=[noise] * 3, from_maps=True))
+    for g, r in zip(got, refs):
+        assert torch.equal(g.tracks, r.tracks.cpu()) and torch.equal(g.visible_logits, r.visible_logits.cpu())
