@@ -82,11 +82,27 @@ __device__ __forceinline__ float ex2_fast(float x) {
   return y;
 }
 
-template <int DH, int LPAD, int MT>   // head width, padded sequence length (multiple of 32), 128-row query tiles
+// CROSS = true: one 128-key chunk of a (sequence, head) of the latents<-tracks cross-attention (track_autoencoder_3d.py:200-201;
+// Lq <= 128 queries, Lk keys streamed as ceil(Lk / 128) chunks, one work item each, so every SM takes part): the item's
+// unnormalised O (fp32) and its row statistics (max, sum) go to a workspace and attn_cross_merge_kernel combines the chunks
+// (flash-style split-K: O = sum_c e^(m_c - M) O_c / sum_c e^(m_c - M) l_c).
+struct CrossArgs {
+  int Lk, nchunks;
+  float* part_o;    // [items][128][DH]
+  float* part_ml;   // [items][128][2]
+};
+
+template <int DH, int LPAD, int MT, bool CROSS = false>   // head width, padded sequence length (multiple of 32), 128-row query tiles
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
-                   const uint8_t* __restrict__ mask, float* __restrict__ stats, int64_t items, int heads, int L) {
+                   const uint8_t* __restrict__ mask, float* __restrict__ stats, int64_t items, int heads, int L, CrossArgs cx) {
+  static_assert(!CROSS || (MT == 1 && LPAD == 128), "cross-attention items are 128 queries x 128 keys");
+  // item -> (sequence b, head h, key chunk ck); self-attention has one chunk (ck = 0) that starts at key 0
+  auto item_b = [&](int64_t it) -> int { return CROSS ? (int)(it / ((int64_t)heads * cx.nchunks)) : (int)(it / heads); };
+  auto item_h = [&](int64_t it) -> int { return CROSS ? (int)((it / cx.nchunks) % heads) : (int)(it % heads); };
+  auto item_k0 = [&](int64_t it) -> int { return CROSS ? (int)(it % cx.nchunks) * 128 : 0; };
+  const int Lkeys = CROSS ? cx.Lk : L;
   constexpr int DA = DH / 32;          // 32-channel atoms per operand row
   constexpr int KA = LPAD / 32;        // 32-key atoms per P row
   constexpr int QROWS = MT * 128;
@@ -139,18 +155,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       uint32_t ph = 0;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
-        const int b = (int)(it / heads), h = (int)(it % heads);
+        const int b = item_b(it), h = item_h(it), k0 = item_k0(it);
         mbar_wait(qk_empty, ph ^ 1);
         mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * DA * LPAD * 64));
 #pragma unroll
         for (int a = 0; a < DA; ++a) {
           tma_load_3d(sQ + a * (QROWS * 64), &tmQ, h * DH + a * 32, 0, b, qk_full);
-          tma_load_3d(sK + a * (LPAD * 64), &tmK, h * DH + a * 32, 0, b, qk_full);
+          tma_load_3d(sK + a * (LPAD * 64), &tmK, h * DH + a * 32, k0, b, qk_full);
         }
         mbar_wait(v_empty, ph ^ 1);
         mbar_arrive_expect_tx(v_full, (uint32_t)(DA * LPAD * 64));
 #pragma unroll
-        for (int a = 0; a < DA; ++a) tma_load_3d(sV + a * (LPAD * 64), &tmV, h * DH + a * 32, 0, b, v_full);
+        for (int a = 0; a < DA; ++a) tma_load_3d(sV + a * (LPAD * 64), &tmV, h * DH + a * 32, k0, b, v_full);
       }
     }
   } else if (warp == 1) {
@@ -202,14 +218,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t NEG_INF = 0xFF80u;
     int n = 0;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const int b = (int)(it / heads);
+      const int b = item_b(it), k0 = item_k0(it);
       const int mb = n & 1;
       if (lane == 0) mbar_wait(&m_empty[mb], ((n >> 1) & 1) ^ 1);
       __syncwarp();
       uint8_t* dstb = sB + mb * (LPAD * 32);
       for (int j = lane; j < LPAD; j += 32) {
         uint32_t val = NEG_INF;                                              // key does not exist
-        if (j < L) val = (mask == nullptr || mask[(int64_t)b * L + j] != 0) ? 0u : NEG_BIG;
+        if (k0 + j < Lkeys) val = (mask == nullptr || mask[(int64_t)b * Lkeys + k0 + j] != 0) ? 0u : NEG_BIG;
         const int pc = (j >> 2) & 1;
         *reinterpret_cast<uint4*>(dstb + j * 32 + pc * 16) = make_uint4(val, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(dstb + j * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -232,7 +248,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr float LOG2E = 1.4426950408889634f;
     uint32_t ph = 0;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
-      const int b = (int)(it / heads), h = (int)(it % heads);
+      const int b = item_b(it), h = item_h(it);
       mbar_wait(s_full, ph);
       tcgen05_fence_after();
       float mx = -INFINITY, lsum = 0.f;
@@ -285,7 +301,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // Staging reuses this warp's own 32 P rows of the first DA atoms (free once P V has completed).
       mbar_wait(o_full, ph);
       tcgen05_fence_after();
-      if (warp_live) {
+      if constexpr (CROSS) {
+        // this chunk's unnormalised output row and (max, sum): 384 contiguous bytes per thread
+        if (warp_live) {
+          float* orow = cx.part_o + ((int64_t)it * 128 + quarter * 32 + lane) * DH;
+#pragma unroll
+          for (int c = 0; c < DA; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tO + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(orow + c * 32 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+          *reinterpret_cast<float2*>(cx.part_ml + ((int64_t)it * 128 + quarter * 32 + lane) * 2) = make_float2(mx, lsum);
+        }
+      } else if (warp_live) {
         const float inv = 1.f / lsum;
 #pragma unroll
         for (int c = 0; c < DA; ++c) {
@@ -366,8 +397,71 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   }
   const int64_t items = batch * heads;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  attn_fwd_tc_kernel<DH, LPAD, MT><<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, tmO, mask, stats, items, heads, L);
+  attn_fwd_tc_kernel<DH, LPAD, MT><<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, tmO, mask, stats, items, heads, L, CrossArgs{0, 1, nullptr, nullptr});
   return check_launch("attention_fwd_tc");
+}
+
+// combine the key chunks of the cross-attention: one warp per (sequence, head, query row)
+template <int DH>
+__global__ void attn_cross_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, bf16* __restrict__ o, int64_t ldo,
+                                        float* __restrict__ stats, int64_t rows_total, int heads, int Lq, int nchunks) {
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (b * heads + h) * Lq + row
+  const int lane = threadIdx.x & 31;
+  if (w >= rows_total) return;
+  const int row = (int)(w % Lq);
+  const int64_t bh = w / Lq;
+  const int h = (int)(bh % heads);
+  const int64_t b = bh / heads;
+  const int64_t item0 = bh * nchunks;
+  constexpr float LOG2E = 1.4426950408889634f;
+  float M = -INFINITY;
+  for (int c = 0; c < nchunks; ++c) M = fmaxf(M, part_ml[((item0 + c) * 128 + row) * 2]);
+  float lsum = 0.f, acc[DH / 32];
+#pragma unroll
+  for (int i = 0; i < DH / 32; ++i) acc[i] = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float2 ml = *reinterpret_cast<const float2*>(part_ml + ((item0 + c) * 128 + row) * 2);
+    const float wgt = exp2f((ml.x - M) * LOG2E);
+    lsum = fmaf(wgt, ml.y, lsum);
+    const float* src = part_o + ((item0 + c) * 128 + row) * DH;
+#pragma unroll
+    for (int i = 0; i < DH / 32; ++i) acc[i] = fmaf(wgt, src[i * 32 + lane], acc[i]);
+  }
+  const float inv = 1.f / lsum;
+  bf16* dst = o + (b * Lq + row) * ldo + h * DH;
+#pragma unroll
+  for (int i = 0; i < DH / 32; ++i) dst[i * 32 + lane] = __float2bfloat16_rn(acc[i] * inv);
+  if (stats != nullptr && lane == 0) {
+    stats[w * 2] = M;
+    stats[w * 2 + 1] = inv;
+  }
+}
+
+template <int DH>
+static int launch_cross(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                        const uint8_t* mask, float* stats, float* workspace, int64_t batch, int heads, int Lq, int Lk, cudaStream_t st) {
+  constexpr int DA = DH / 32, KA = 4;
+  constexpr int SMEM = DA * 128 * 64 + 2 * DA * 128 * 64 + KA * 128 * 64 + 128 * 32 + 2 * 128 * 32 + 128 + 1024;
+  CUtensorMap tmQ, tmK, tmV;
+  const int cols = heads * DH;
+  if (make_map3(&tmQ, q, cols, Lq, batch, ldq, 128)) return 1;
+  if (make_map3(&tmK, k, cols, Lk, batch, ldk, 128)) return 1;
+  if (make_map3(&tmV, v, cols, Lk, batch, ldv, 128)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, 128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    SPA3D_REQUIRE(e == cudaSuccess, "attention_cross_fwd: smem attribute (%d B): %s", SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int nchunks = (Lk + 127) / 128;
+  const int64_t items = batch * heads * nchunks;
+  CrossArgs cx{Lk, nchunks, workspace, workspace + items * 128 * DH};
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  attn_fwd_tc_kernel<DH, 128, 1, true><<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, tmQ, mask, nullptr, items, heads, Lq, cx);
+  if (int rc = check_launch("attention_cross_fwd")) return rc;
+  const int64_t rows_total = batch * heads * Lq;
+  attn_cross_merge_kernel<DH><<<(unsigned)((rows_total + 7) / 8), 256, 0, st>>>(cx.part_o, cx.part_ml, (bf16*)o, ldo, stats, rows_total, heads, Lq, nchunks);
+  return check_launch("attention_cross_merge");
 }
 
 }  // namespace ta
@@ -383,6 +477,33 @@ bool attention_fwd_tc_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq,
   if (Dh != 96 && Dh != 64) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   return al16(q) && al16(k) && al16(v) && al16(o) && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0;
+}
+
+// Cross-attention (Lq <= 128 queries over Lk keys): key chunks split across CTAs + merge.  workspace: attention_cross_workspace_bytes.
+bool attention_cross_tc_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo_or_grads) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("SPA3D_ATTN_CROSS_TC");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!enabled || dtype != SPA3D_BF16 || Lq < 2 || Lq > 128 || Lk < 1 || Lq == Lk) return false;
+  if (Dh != 96 && Dh != 64) return false;
+  return ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo_or_grads % 8 == 0;
+}
+
+int64_t attention_cross_workspace_floats(int64_t batch, int heads, int Lk, int Dh) {
+  const int64_t items = batch * heads * ((Lk + 127) / 128);
+  return items * 128 * (Dh + 2);
+}
+
+int attention_cross_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                           const uint8_t* key_mask, float* stats, float* workspace, int64_t batch, int heads, int Lq, int Lk, int Dh,
+                           cudaStream_t st) {
+  using namespace ta;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  SPA3D_REQUIRE(al16(q) && al16(k) && al16(v) && al16(workspace) && workspace != nullptr, "attention_cross_fwd: operands must be 16-byte aligned");
+  if (Dh == 96) return launch_cross<96>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, workspace, batch, heads, Lq, Lk, st);
+  return launch_cross<64>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, workspace, batch, heads, Lq, Lk, st);
 }
 
 int attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
