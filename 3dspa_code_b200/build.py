@@ -20,7 +20,6 @@ SOURCES = [
     "gemm_tcgen05.cu",
     "embed_tcgen05.cu",
     "attention_simt.cu",
-    "attention_mma.cu",
     "attention_tc.cu",
     "attention_tc_bwd.cu",
     "attention_q1.cu",

@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...) {
 static long long g_stats[ST_COUNT];
 static const char* const kStatNames[ST_COUNT] = {
     "gemm_tcgen05", "gemm_simt", "gemm_bf16_fallback", "gemm_dw_tcgen05", "gemm_dw_simt", "gemm_dw_bf16_fallback",
-    "attention_tcgen05", "attention_cross_tcgen05", "attention_mma", "attention_q1", "attention_simt", "attention_bf16_fallback",
+    "attention_tcgen05", "attention_cross_tcgen05", "attention_q1", "attention_simt", "attention_bf16_fallback",
     "embed_fused"};
 void stat_add(int id) { __atomic_fetch_add(&g_stats[id], 1ll, __ATOMIC_RELAXED); }
 

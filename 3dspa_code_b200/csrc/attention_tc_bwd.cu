@@ -81,10 +81,24 @@ struct Maps {
   CUtensorMap q, k, v, g, dq, dk, dv;
 };
 
-template <int DH, int LPAD, int MT>
+// CROSS = true: one 128-key chunk of a (sequence, head) of the latents<-tracks cross-attention backward (Lq <= 128 queries, Lk keys
+// as ceil(Lk / 128) chunks, one work item each).  dK / dV of the chunk's own keys are complete and leave as in the self case;
+// dQ is a partial sum over this chunk's keys: it goes to a workspace as fp32 and attn_cross_dq_merge_kernel adds the chunks.
+// delta_i = sum_d O_id dO_id spans ALL keys, so it is read from `delta` (attention_delta) instead of being formed in place.
+struct CrossBwdArgs {
+  int Lk, nchunks;
+  float* part_dq;   // [items][128][DH]
+};
+
+template <int DH, int LPAD, int MT, bool CROSS = false>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ mask, const float* __restrict__ stats,
-                   const float* __restrict__ delta, int64_t items, int heads, int L) {
+                   const float* __restrict__ delta, int64_t items, int heads, int L, CrossBwdArgs cx) {
+  static_assert(!CROSS || (MT == 1 && LPAD == 128), "cross-attention items are 128 queries x 128 keys");
+  auto item_b = [&](int64_t it) -> int { return CROSS ? (int)(it / ((int64_t)heads * cx.nchunks)) : (int)(it / heads); };
+  auto item_h = [&](int64_t it) -> int { return CROSS ? (int)((it / cx.nchunks) % heads) : (int)(it % heads); };
+  auto item_k0 = [&](int64_t it) -> int { return CROSS ? (int)(it % cx.nchunks) * 128 : 0; };
+  const int Lkeys = CROSS ? cx.Lk : L;
   constexpr int DA = DH / 32;            // 32-channel atoms per row
   constexpr int KA = LPAD / 32;          // 32-key atoms per P / dS row
   constexpr int OPA = LPAD * 64;         // bytes of one 32-channel atom region of Q / K / V / dO
@@ -139,15 +153,15 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
     if (lane == 0) {
       uint32_t ph = 0;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
-        const int b = (int)(it / heads), h = (int)(it % heads);
+        const int b = item_b(it), h = item_h(it), k0 = item_k0(it);
         mbar_wait(ld_empty, ph ^ 1);
         mbar_arrive_expect_tx(ld_full, (uint32_t)(4 * OP_BYTES));
 #pragma unroll
         for (int a = 0; a < DA; ++a) {
           tma_load_3d(sQ + a * OPA, &tm.q, h * DH + a * 32, 0, b, ld_full);
-          tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, 0, b, ld_full);
+          tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, k0, b, ld_full);
           tma_load_3d(sG + a * OPA, &tm.g, h * DH + a * 32, 0, b, ld_full);
-          tma_load_3d(sV + a * OPA, &tm.v, h * DH + a * 32, 0, b, ld_full);
+          tma_load_3d(sV + a * OPA, &tm.v, h * DH + a * 32, k0, b, ld_full);
         }
       }
     }
@@ -207,14 +221,14 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
     const uint32_t NEG_BIG = 0xF14Au, NEG_INF = 0xFF80u;   // bf16(-1e30), bf16(-inf)
     int n = 0;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const int b = (int)(it / heads);
+      const int b = item_b(it), k0 = item_k0(it);
       const int mb = n & 1;
       if (lane == 0) mbar_wait(&m_empty[mb], ((n >> 1) & 1) ^ 1);
       __syncwarp();
       uint8_t* dstb = sB + mb * (LPAD * 32);
       for (int j = lane; j < LPAD; j += 32) {
         uint32_t val = NEG_INF;
-        if (j < L) val = (mask == nullptr || mask[(int64_t)b * L + j] != 0) ? 0u : NEG_BIG;
+        if (k0 + j < Lkeys) val = (mask == nullptr || mask[(int64_t)b * Lkeys + k0 + j] != 0) ? 0u : NEG_BIG;
         const int pc = (j >> 2) & 1;
         *reinterpret_cast<uint4*>(dstb + j * 32 + pc * 16) = make_uint4(val, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(dstb + j * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -238,7 +252,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
     constexpr float LOG2E = 1.4426950408889634f;
     int tcount = 0;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-      const int b = (int)(it / heads), h = (int)(it % heads);
+      const int b = item_b(it), h = item_h(it), k0 = item_k0(it);
       const int64_t sbase = ((int64_t)b * heads + h) * L;
 #pragma unroll 1
       for (int t = 0; t < MT; ++t, ++tcount) {
@@ -274,6 +288,16 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
               *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
           }
         }
+        else {
+          // rows past the sequence end: dO / Q rows are zero there, but 0 x (stale shared memory) must not be NaN
+          for (int c = c_lo; c < c_hi; ++c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(pRow + c * (128 * 64) + (j << 4)) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(dRow + c * (128 * 64) + (j << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        }
         tcgen05_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(p_done);
@@ -283,27 +307,32 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
         if (tile_live) {
           // delta_i = sum_d O_id dO_id = sum_j P_ij dP_ij: a row sum over the keys, half of them in the
           // partner warp of this lane quarter -> exchange through shared memory
-          float part = 0.f;
+          float dl;
+          if constexpr (CROSS) {
+            dl = row < L ? delta[sbase + row] : 0.f;   // over all keys of the row, not only this chunk's
+          } else {
+            float part = 0.f;
 #pragma unroll 1
-          for (int c = c_lo; c < c_hi; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c * 32), r);
-            const uint8_t* src = pRow + c * (128 * 64);
-            uint4 pw[4];
+            for (int c = c_lo; c < c_hi; ++c) {
+              uint32_t r[32];
+              tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c * 32), r);
+              const uint8_t* src = pRow + c * (128 * 64);
+              uint4 pw[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) pw[j] = *reinterpret_cast<const uint4*>(src + ((j ^ sw64) << 4));
-            tmem_ld_wait();
-            const uint32_t* pwu = reinterpret_cast<const uint32_t*>(pw);
+              for (int j = 0; j < 4; ++j) pw[j] = *reinterpret_cast<const uint4*>(src + ((j ^ sw64) << 4));
+              tmem_ld_wait();
+              const uint32_t* pwu = reinterpret_cast<const uint32_t*>(pw);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
-              part = fmaf(__low2float(pb), __uint_as_float(r[2 * i]), part);
-              part = fmaf(__high2float(pb), __uint_as_float(r[2 * i + 1]), part);
+              for (int i = 0; i < 16; ++i) {
+                const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
+                part = fmaf(__low2float(pb), __uint_as_float(r[2 * i]), part);
+                part = fmaf(__high2float(pb), __uint_as_float(r[2 * i + 1]), part);
+              }
             }
+            dpart[half * 128 + rloc] = part;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            dl = part + dpart[(half ^ 1) * 128 + rloc];
           }
-          dpart[half * 128 + rloc] = part;
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-          const float dl = part + dpart[(half ^ 1) * 128 + rloc];
 #pragma unroll 1
           for (int c = c_lo; c < c_hi; ++c) {
             uint32_t r[32];
@@ -329,7 +358,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
           }
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // dpart is rewritten for the next tile
+          if constexpr (!CROSS) asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // dpart is rewritten for the next tile
         }
         tcgen05_fence_before();
         fence_proxy_async_smem();
@@ -344,6 +373,13 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
             uint32_t r[32];
             tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c * 32), r);
             tmem_ld_wait();
+            if constexpr (CROSS) {   // partial dQ of this key chunk, fp32, 128 contiguous bytes per thread and channel atom
+              float* drow = cx.part_dq + ((int64_t)it * 128 + rloc) * DH + c * 32;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(drow + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+              continue;
+            }
             if (lane == 0) bulk_wait_read<1>();
             __syncwarp();
             uint8_t* dst = slab + sb * 2048 + lane * 64;
@@ -372,7 +408,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
           const uint32_t cbase = half == 0 ? C_DV : C_DK;
           const CUtensorMap* omap = half == 0 ? &tm.dv : &tm.dk;
           for (int c = 0; c < KA; ++c) {
-            if (c * 32 >= L) break;
+            if (k0 + c * 32 >= Lkeys) break;
             uint32_t r[32];
             tmem_ld32(tmem_base + lane_off + cbase + (uint32_t)(c * 32), r);
             tmem_ld_wait();
@@ -387,7 +423,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(omap, dst, h * DH + quarter * 32, c * 32, b);
+              tma_store_3d(omap, dst, h * DH + quarter * 32, k0 + c * 32, b);
               bulk_commit();
             }
             sb ^= 1;
@@ -448,8 +484,63 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   }
   const int64_t items = batch * heads;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  attn_bwd_tc_kernel<DH, LPAD, MT><<<grid, THREADS, SMEM, st>>>(tm, mask, stats, delta, items, heads, L);
+  attn_bwd_tc_kernel<DH, LPAD, MT><<<grid, THREADS, SMEM, st>>>(tm, mask, stats, delta, items, heads, L, CrossBwdArgs{0, 1, nullptr});
   return check_launch("attention_bwd_tc");
+}
+
+// dq[b, row, h*DH + d] = sum over key chunks of the partial dQ tiles (fp32) -> bf16
+template <int DH>
+__global__ void attn_cross_dq_merge_kernel(const float* __restrict__ part_dq, bf16* __restrict__ dq, int64_t lddq, int64_t rows_total,
+                                           int heads, int Lq, int nchunks) {
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (b * heads + h) * Lq + row
+  const int lane = threadIdx.x & 31;
+  if (w >= rows_total) return;
+  const int row = (int)(w % Lq);
+  const int64_t bh = w / Lq;
+  const int h = (int)(bh % heads);
+  const int64_t b = bh / heads;
+  float acc[DH / 32];
+#pragma unroll
+  for (int i = 0; i < DH / 32; ++i) acc[i] = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* src = part_dq + ((bh * nchunks + c) * 128 + row) * DH;
+#pragma unroll
+    for (int i = 0; i < DH / 32; ++i) acc[i] += src[i * 32 + lane];
+  }
+  bf16* dst = dq + (b * Lq + row) * lddq + h * DH;
+#pragma unroll
+  for (int i = 0; i < DH / 32; ++i) dst[i * 32 + lane] = __float2bfloat16_rn(acc[i]);
+}
+
+template <int DH>
+static int launch_cross(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                        int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, const uint8_t* mask,
+                        const float* stats, const float* delta, float* workspace, int64_t batch, int heads, int Lq, int Lk, cudaStream_t st) {
+  constexpr int DA = DH / 32, KA = 4;
+  constexpr int SMEM = 4 * DA * 128 * 64 + 2 * KA * 128 * 64 + 128 * 32 + 2 * 128 * 32 + 128 + 1024 + 1024;
+  Maps tm;
+  const int cols = heads * DH;
+  if (make_map3(&tm.q, q, cols, Lq, batch, ldq, 128)) return 1;
+  if (make_map3(&tm.k, k, cols, Lk, batch, ldk, 128)) return 1;
+  if (make_map3(&tm.v, v, cols, Lk, batch, ldv, 128)) return 1;
+  if (make_map3(&tm.g, d_o, cols, Lq, batch, lddo, 128)) return 1;
+  tm.dq = tm.q;   // unused: dQ leaves through the workspace
+  if (make_map3(&tm.dk, dk, cols, Lk, batch, lddk, 32)) return 1;
+  if (make_map3(&tm.dv, dv, cols, Lk, batch, lddv, 32)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, 128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    SPA3D_REQUIRE(e == cudaSuccess, "attention_cross_bwd: smem attribute (%d B): %s", SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int nchunks = (Lk + 127) / 128;
+  const int64_t items = batch * heads * nchunks;
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  attn_bwd_tc_kernel<DH, 128, 1, true><<<grid, THREADS, SMEM, st>>>(tm, mask, stats, delta, items, heads, Lq, CrossBwdArgs{Lk, nchunks, workspace});
+  if (int rc = check_launch("attention_cross_bwd")) return rc;
+  const int64_t rows_total = batch * heads * Lq;
+  attn_cross_dq_merge_kernel<DH><<<(unsigned)((rows_total + 7) / 8), 256, 0, st>>>(workspace, (bf16*)dq, lddq, rows_total, heads, Lq, nchunks);
+  return check_launch("attention_cross_dq_merge");
 }
 
 }  // namespace tb
@@ -464,6 +555,18 @@ bool attention_bwd_tc_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq,
   if (!enabled || dtype != SPA3D_BF16 || Lq != Lk || Lq < 2 || Lq > 160) return false;
   if (Dh != 96 && Dh != 64) return false;
   return ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0;
+}
+
+int attention_cross_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o, int64_t lddo,
+                           void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, const uint8_t* key_mask, const float* stats,
+                           const float* delta, float* workspace, int64_t batch, int heads, int Lq, int Lk, int Dh, cudaStream_t st) {
+  using namespace tb;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  SPA3D_REQUIRE(al16(q) && al16(k) && al16(v) && al16(d_o) && al16(dk) && al16(dv) && al16(workspace) && workspace != nullptr,
+                "attention_cross_bwd: operands must be 16-byte aligned");
+  if (Dh == 96)
+    return launch_cross<96>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, workspace, batch, heads, Lq, Lk, st);
+  return launch_cross<64>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, workspace, batch, heads, Lq, Lk, st);
 }
 
 int attention_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,

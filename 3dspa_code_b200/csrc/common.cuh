@@ -29,7 +29,7 @@ int check_launch(const char* what);
 enum StatId {
   ST_GEMM_TCGEN05 = 0, ST_GEMM_SIMT, ST_GEMM_BF16_FALLBACK,
   ST_GEMM_DW_TCGEN05, ST_GEMM_DW_SIMT, ST_GEMM_DW_BF16_FALLBACK,
-  ST_ATTN_TCGEN05, ST_ATTN_CROSS_TCGEN05, ST_ATTN_MMA, ST_ATTN_Q1, ST_ATTN_SIMT, ST_ATTN_BF16_FALLBACK,
+  ST_ATTN_TCGEN05, ST_ATTN_CROSS_TCGEN05, ST_ATTN_Q1, ST_ATTN_SIMT, ST_ATTN_BF16_FALLBACK,
   ST_EMBED_FUSED, ST_COUNT
 };
 void stat_add(int id);

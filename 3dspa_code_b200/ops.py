@@ -244,8 +244,22 @@ def head_rmsnorm_bwd(y, scale, out_mul, rstd, d_io, heads, Dh, num_partials=296,
     return dscale
 
 
+def _cross_workspace(q, batch, heads, Lq, Lk, Dh):
+    """Scratch of the tcgen05 cross-attention (per-chunk partial tiles), or None when that kernel does not cover the shape."""
+    lib = _lib.lib()
+    if Lq == Lk or not lib.spa3d_attention_cross_applicable(dt(q), int(Lq), int(Lk), int(Dh)):
+        return None
+    return torch.empty(lib.spa3d_attention_cross_workspace_bytes(int(batch), int(heads), int(Lq), int(Lk), int(Dh)) // 4,
+                       device=q.device, dtype=torch.float32)
+
+
 def attention_fwd(q, k, v, out, batch, heads, Lq, Lk, Dh, key_mask=None, save_stats=False):
     stats = torch.empty(batch, heads, Lq, 2, device=q.device, dtype=torch.float32) if save_stats else None
+    ws = _cross_workspace(q, batch, heads, Lq, Lk, Dh)
+    if ws is not None:   # latents <- tracks cross-attention: key chunks across CTAs + merge
+        _call("spa3d_attention_cross_fwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(out), _ld(out), dt(q), _p(key_mask), _p(stats),
+              _p(ws), int(batch), heads, Lq, Lk, Dh, _stream())
+        return stats
     _call("spa3d_attention_fwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(out), _ld(out), dt(q), _p(key_mask), _p(stats),
           int(batch), heads, Lq, Lk, Dh, _stream())
     return stats
@@ -253,6 +267,11 @@ def attention_fwd(q, k, v, out, batch, heads, Lq, Lk, Dh, key_mask=None, save_st
 
 def attention_bwd(q, k, v, o, d_o, dq, dk, dv, stats, batch, heads, Lq, Lk, Dh, key_mask=None):
     delta = torch.empty(batch * heads * Lq, device=q.device, dtype=torch.float32)
+    ws = _cross_workspace(q, batch, heads, Lq, Lk, Dh)
+    if ws is not None:
+        _call("spa3d_attention_cross_bwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), _ld(o), _p(d_o), _ld(d_o), _p(dq), _ld(dq),
+              _p(dk), _ld(dk), _p(dv), _ld(dv), dt(q), _p(key_mask), _p(stats), _p(delta), _p(ws), int(batch), heads, Lq, Lk, Dh, _stream())
+        return
     _call("spa3d_attention_bwd", _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(o), _ld(o), _p(d_o), _ld(d_o), _p(dq), _ld(dq),
           _p(dk), _ld(dk), _p(dv), _ld(dv), dt(q), _p(key_mask), _p(stats), _p(delta), int(batch), heads, Lq, Lk, Dh, _stream())
 

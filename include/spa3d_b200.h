@@ -42,7 +42,7 @@ int spa3d_version(void);
 const char* spa3d_last_error(void);
 
 /* ---- dispatch counters -----------------------------------------------------------------------
- * Every contraction / attention entry point picks an implementation (tcgen05, mma.sync, SIMT) from the
+ * Every contraction / attention entry point picks an implementation (tcgen05, SIMT) from the
  * operand dtypes and alignments.  spa3d_stats copies up to n process-wide counters into out and returns
  * how many exist; spa3d_stat_name(i) names counter i.  The "*_bf16_fallback" counters count bf16 calls that
  * were computed on the fp32 SIMT kernels because an operand missed the tensor-core path's alignment rules
@@ -236,6 +236,23 @@ int spa3d_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
                         int dtype, const uint8_t* key_mask, const float* lse, float* delta_ws,
                         int64_t batch, int heads, int Lq, int Lk, int Dh, void* stream);
 /* delta_ws: caller-provided scratch, [batch*heads*Lq] f32. */
+
+/* K6 on the tensor cores: the latents<-tracks cross-attention (track_autoencoder_3d.py:200-201; attention.py:92-100), Lq <= 128
+ * queries over Lk keys (Lq != Lk), bf16.  The keys are split into 128-key chunks, one tcgen05 work item per (sequence, head,
+ * chunk) so that every SM takes part; the chunks' (max, sum, O) states are merged flash-style by a second small kernel, and
+ * in the backward the chunks' partial dQ tiles are summed the same way.  `workspace` is caller-owned scratch of
+ * spa3d_attention_cross_workspace_bytes bytes (NULL, or shapes the kernel does not cover, fall back to
+ * spa3d_attention_fwd / _bwd).  Arguments otherwise as spa3d_attention_fwd / spa3d_attention_bwd. */
+int spa3d_attention_cross_applicable(int dtype, int Lq, int Lk, int Dh);
+int64_t spa3d_attention_cross_workspace_bytes(int64_t batch, int heads, int Lq, int Lk, int Dh);
+int spa3d_attention_cross_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                              int64_t ldo, int dtype, const uint8_t* key_mask, float* lse_out, float* workspace,
+                              int64_t batch, int heads, int Lq, int Lk, int Dh, void* stream);
+int spa3d_attention_cross_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                              const void* o, int64_t ldo, const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk,
+                              int64_t lddk, void* dv, int64_t lddv, int dtype, const uint8_t* key_mask, const float* lse,
+                              float* delta_ws, float* workspace, int64_t batch, int heads, int Lq, int Lk, int Dh,
+                              void* stream);
 
 /* ---- R1 key mask (track_autoencoder_3d.py:167-184, repaired) -------------------------------
  * mask[b,n,0] = 1 (if has_readout); mask[b,n,j] = visible[b,n,t]!=0 && t < boundary[b]. */

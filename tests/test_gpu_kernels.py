@@ -599,3 +599,37 @@ def test_embed_fused_matches_unfused_math(spa, N, T, Dd, Dz, W):
     cat = torch.cat(parts, -1)
     assert rel_err(ac[:, 1:, :256].reshape(R, 256), cat[:, :256]) < 1e-2          # sin.approx + bf16 rounding
     assert torch.equal(ac[:, 1:, 256:].reshape(R, K - 256).double(), cat[:, 256:])   # features: the same bf16 rounding
+
+
+@pytest.mark.parametrize("Lq,Lk,Dh,batch", [(128, 2048, 96, 2), (128, 4096, 96, 1), (128, 24, 96, 3), (100, 130, 96, 2), (37, 300, 64, 2), (128, 129, 64, 1)])
+def test_cross_attention_tcgen05_fwd_bwd(spa, Lq, Lk, Dh, batch):
+    """Latents<-tracks cross-attention (track_autoencoder_3d.py:200-201) on tcgen05: key chunks split across CTAs, flash-style
+    merge of the chunks' (max, sum, O) states, dQ summed over the chunks; with and without a key mask (a fully masked sequence
+    is uniform, finfo.min semantics), ragged Lq / Lk; the dispatch counter shows the tensor-core kernel ran."""
+    ops = spa.ops
+    torch.manual_seed(31)
+    H = 4
+    A = H * Dh
+    for masked in (False, True):
+        q = (torch.randn(batch * Lq, A, device="cuda") / math.sqrt(Dh)).to(torch.bfloat16)
+        k = torch.randn(batch * Lk, A, device="cuda").to(torch.bfloat16)
+        v = torch.randn(batch * Lk, A, device="cuda").to(torch.bfloat16)
+        mask = None
+        if masked:
+            mask = (torch.rand(batch, Lk, device="cuda") < 0.7).to(torch.uint8)
+            mask[:, 0] = 1
+            mask[batch - 1] = 0
+        qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+        ref = _attn_ref(qd, kd, vd, mask, batch, H, Lq, Lk, Dh)
+        d_o = torch.randn(batch * Lq, A, device="cuda").to(torch.bfloat16)
+        ref.backward(d_o.double())
+        ops.stats(reset=True)
+        o = torch.empty(batch * Lq, A, device="cuda", dtype=torch.bfloat16)
+        stats = ops.attention_fwd(q, k, v, o, batch, H, Lq, Lk, Dh, mask, save_stats=True)
+        assert rel_err(o, ref) < 1e-2, rel_err(o, ref)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ops.attention_bwd(q, k, v, o, d_o, dq, dk, dv, stats, batch, H, Lq, Lk, Dh, mask)
+        st = ops.stats()
+        assert st["attention_cross_tcgen05"] == 2 and st["attention_simt"] == 0, st
+        for got, want in ((dq, qd.grad), (dk, kd.grad), (dv, vd.grad)):
+            assert rel_err(got, want) < 2e-2, (masked, rel_err(got, want))
