@@ -401,6 +401,23 @@ def run_pipeline_leg(spa, model, variables, dev):
     return out
 
 
+def run_fp32_leg(spa, model, variables, inputs, noise, dev):
+    """The accurate mode (precision="fp32": every contraction with fp32 operands and fp32 accumulation, north_star tolerance 1e-4)
+    on the same cfg2 clip: one timed forward.  A correctness mode, reported so that its cost is known."""
+    model.apply(variables, inputs, noise=noise, precision="fp32")      # upload + warm-up
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = model.apply(variables, inputs, noise=noise, precision="fp32")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = {"workload": "cfg2 clip, precision='fp32' (accurate mode), device-resident inputs, 1 eager forward", "ms_per_clip": ms,
+           "query_tracks_per_s": Q / (ms * 1e-3), "model_tflops": FWD_TFLOP_PER_CLIP / (ms * 1e-3), "finite": bool(torch.isfinite(res.tracks).all())}
+    model.invalidate()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_trajan_leg(spa, dev, cpu=True):
     """cfg1 (BASELINE.json configs[0]): TRAJAN 2D (track_autoencoder.py:117-390) forward, batch 1, 150 frames, 2048 support /
     512 query tracks, random-init weights, synthetic tracks U(0,1)^2 - on the GPU through the same kernels (bf16), and on the
@@ -692,10 +709,11 @@ def run_ours(args):
     if not args.no_train:
         torch.cuda.empty_cache()
         train = run_train_leg(args, spa, model, variables, world, rank, dev, barrier)
-    pipeline = sweep = trajan = None
+    pipeline = sweep = trajan = fp32_leg = None
     if rank == 0 and not args.no_train:
         lifting = run_lifting_leg(spa, dev, cpu=(world == 1 and not args.no_cpu))
         trajan = run_trajan_leg(spa, dev, cpu=(world == 1 and not args.no_cpu))
+        fp32_leg = run_fp32_leg(spa, spa.TrackAutoEncoder3D(), variables, inputs, noise, dev)
         pipeline = run_pipeline_leg(spa, model, variables, dev)
         sweep = run_sweep_leg(spa, model, variables, dev, world)
     if rank == 0:
@@ -705,6 +723,8 @@ def run_ours(args):
             line["lifting"] = lifting
         if trajan is not None:
             line["trajan"] = trajan
+        if fp32_leg is not None:
+            line["fp32_path"] = fp32_leg
         if pipeline is not None:
             line["pipeline_lift_embed"] = pipeline
         if sweep is not None:
