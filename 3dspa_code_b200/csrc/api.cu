@@ -17,7 +17,7 @@ void set_error(const char* fmt, ...) {
 
 static long long g_stats[ST_COUNT];
 static const char* const kStatNames[ST_COUNT] = {
-    "gemm_tcgen05", "gemm_simt", "gemm_bf16_fallback", "gemm_dw_tcgen05", "gemm_dw_simt", "gemm_dw_bf16_fallback",
+    "gemm_tcgen05", "gemm_x3", "gemm_simt", "gemm_bf16_fallback", "gemm_dw_tcgen05", "gemm_dw_simt", "gemm_dw_bf16_fallback",
     "attention_tcgen05", "attention_cross_tcgen05", "attention_q1", "attention_simt", "attention_bf16_fallback",
     "embed_fused"};
 void stat_add(int id) { __atomic_fetch_add(&g_stats[id], 1ll, __ATOMIC_RELAXED); }
@@ -81,6 +81,18 @@ int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dt
   if (impl == SPA3D_GEMM_AUTO && a_dtype == SPA3D_BF16) stat_add(ST_GEMM_BF16_FALLBACK);   // bf16 operands that missed the tensor-core path
   return gemm_simt(A, lda, 1, a_dtype, Wt, 1, ldw, a_dtype, bias, act, residual, ldr, r_dtype, C,
                    ldc, c_dtype, M, N, K, 0, st);
+}
+
+int spa3d_gemm_x3_applicable(int64_t M, int N, int K) { return (K % 64 == 0 && N % 8 == 0 && M > 0) ? 1 : 0; }
+
+int spa3d_gemm_x3(const void* A3, int64_t lda, const void* W3, int64_t ldw, const float* bias, const void* residual, int64_t ldr,
+                  int r_dtype, float* C, int64_t ldc, int64_t M, int N, int K, void* stream) {
+  using namespace spa3d;
+  SPA3D_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_x3: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  if (M == 0) return 0;
+  SPA3D_REQUIRE(gemm_tcgen05_x3_applicable(A3, lda, W3, ldw, M, N, K), "gemm_x3: needs K %% 64 == 0, N %% 8 == 0 and 16-byte aligned rows");
+  stat_add(ST_GEMM_X3);
+  return gemm_tcgen05_x3(A3, lda, W3, ldw, bias, residual, ldr, r_dtype, C, ldc, M, N, K, (cudaStream_t)stream);
 }
 
 int spa3d_gemm_rmsnorm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dtype, void* C,

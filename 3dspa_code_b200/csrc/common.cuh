@@ -27,7 +27,7 @@ int check_launch(const char* what);
 // A bf16 operand that does not meet the tensor-core kernels' alignment rules is still computed (SIMT), but 10-100x
 // slower; the counters make that visible (bench.py asserts the *_bf16_fallback counters stay zero).
 enum StatId {
-  ST_GEMM_TCGEN05 = 0, ST_GEMM_SIMT, ST_GEMM_BF16_FALLBACK,
+  ST_GEMM_TCGEN05 = 0, ST_GEMM_X3, ST_GEMM_SIMT, ST_GEMM_BF16_FALLBACK,
   ST_GEMM_DW_TCGEN05, ST_GEMM_DW_SIMT, ST_GEMM_DW_BF16_FALLBACK,
   ST_ATTN_TCGEN05, ST_ATTN_CROSS_TCGEN05, ST_ATTN_Q1, ST_ATTN_SIMT, ST_ATTN_BF16_FALLBACK,
   ST_EMBED_FUSED, ST_COUNT
@@ -154,6 +154,9 @@ bool gemm_tcgen05_dw_applicable(const void* dY, int64_t lddy, const void* X, int
                                 int N, int K, const void* dW, int64_t lddw);
 int gemm_tcgen05_dw(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
                     int64_t M, int N, int K, cudaStream_t st);
+bool gemm_tcgen05_x3_applicable(const void* A3, int64_t lda, const void* W3, int64_t ldw, int64_t M, int N, int K);
+int gemm_tcgen05_x3(const void* A3, int64_t lda, const void* W3, int64_t ldw, const float* bias, const void* residual, int64_t ldr,
+                    int r_dtype, float* C, int64_t ldc, int64_t M, int N, int K, cudaStream_t st);
 bool gemm_tcgen05_applicable(const void* A, int64_t lda, const void* Wt, int64_t ldw, int64_t M,
                              int N, int K);
 

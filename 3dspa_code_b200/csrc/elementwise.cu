@@ -1043,6 +1043,29 @@ __global__ void shadow_weights_kernel(const float* __restrict__ src, int64_t lds
   }
 }
 
+// x = hi + mid + lo with three bf16 terms (24 mantissa bits): dst[r, p*K + c] = part p of src[r, c]
+__global__ void split3_kernel(const float* __restrict__ src, int64_t lds, bf16* __restrict__ dst, int64_t ldd, int64_t rows, int K4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (row, group of 4 columns)
+  if (i >= rows * K4) return;
+  const int64_t r = i / K4;
+  const int c4 = (int)(i % K4);
+  const float4 x = *reinterpret_cast<const float4*>(src + r * lds + c4 * 4);
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+  __nv_bfloat16 part[3][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(xs[e]);
+    const float r1 = xs[e] - __bfloat162float(h);               // exact
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);                  // exact
+    part[0][e] = h; part[1][e] = m; part[2][e] = __float2bfloat16_rn(r2);
+  }
+  const int64_t K = (int64_t)K4 * 4;
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+    *reinterpret_cast<uint2*>(dst + r * ldd + p * K + c4 * 4) = *reinterpret_cast<const uint2*>(part[p]);
+}
+
 static inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 int head_rmsnorm_fwd_impl(void* buf, int64_t ld, int dtype, const float* scale, float out_mul,
@@ -1400,6 +1423,14 @@ int spa3d_shadow_weights(const float* src, int64_t lds, void* dst, int64_t ldd, 
     shadow_weights_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, (T*)dst, ldd, (T*)dst_t, ldt, rows, cols);
   });
   return check_launch("shadow_weights");
+}
+
+int spa3d_split3(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int K, void* stream) {
+  if (rows == 0 || K == 0) return 0;
+  SPA3D_REQUIRE(K % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+                "split3: K and the row pitches must be multiples of 4, src 16-byte and dst 8-byte aligned");
+  split3_kernel<<<blocks_for(rows * (K / 4), 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (bf16*)dst, ldd, rows, K / 4);
+  return check_launch("split3");
 }
 
 int spa3d_fill_zero(void* p, int64_t bytes, void* stream) {

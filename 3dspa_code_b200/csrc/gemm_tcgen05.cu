@@ -86,7 +86,9 @@ struct EpiParams {
   int res_op;        // EPI_DIRECT: 0 = C = f(acc) + residual; 1 = C = acc * gelu'(residual) (residual = saved pre-activation);
                      //             2 = C = acc * residual (residual = gelu'(z) saved by the forward GEMM)
   int atomic_add;    // EPI_DIRECT, fp32 C: C += tile with red.global.add.v4.f32 (split-K weight gradients)
-  int reserved;      // (was a run-time debug switch; the skip-epilogue experiment is compile-time now: -DSPA3D_GEMM_SKIP_EPI)
+  int x3;            // "bf16 x 3" accurate mode: A and Wt are [rows, 3K] bf16 split operands (hi | mid | lo, x = hi + mid + lo to 24 bits);
+                     // the K loop runs the six products hi.hi, hi.mid, mid.hi, hi.lo, mid.mid, lo.hi into ONE fp32 accumulator
+                     // (every bf16 x bf16 product is exact in fp32), smallest terms first
   float* colsum;     // EPI_DIRECT: [N] f32, += column sums of the stored values (a bias gradient), or null
 };
 
@@ -154,7 +156,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb_all = (int)((K + BK - 1) / BK);
+  const int nk1 = (int)((K + BK - 1) / BK);                // K-blocks of one operand pair
+  const int num_kb_all = ep.x3 ? 6 * nk1 : nk1;
   const int kb_per_split = (num_kb_all + splits - 1) / splits;
   const int n_tiles = (N + BN - 1) / BN;
   const int64_t m_tiles = (M + BM - 1) / BM;
@@ -212,8 +215,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if constexpr (!TN) {
-            tma_load_2d(smem_a + stage * L::A_BYTES, &tmA, kb * BK, m_blk * BM, &full_bar[stage]);
-            tma_load_2d(smem_b + stage * L::B_BYTES, &tmB, kb * BK, n_blk * BN, &full_bar[stage]);
+            int ka = kb * BK, kw = kb * BK;
+            if (ep.x3) {
+              // pair order (A part, W part): (0,2) (1,1) (2,0) (0,1) (1,0) (0,0) - the 2^-16-sized terms first
+              const int pr = kb / nk1, kk = (kb - pr * nk1) * BK;
+              const int ai = (0x012010 >> (4 * (5 - pr))) & 15, wi = (0x210100 >> (4 * (5 - pr))) & 15;
+              ka = ai * (int)K + kk;
+              kw = wi * (int)K + kk;
+            }
+            tma_load_2d(smem_a + stage * L::A_BYTES, &tmA, ka, m_blk * BM, &full_bar[stage]);
+            tma_load_2d(smem_b + stage * L::B_BYTES, &tmB, kw, n_blk * BN, &full_bar[stage]);
           } else {
             // 64 tokens x 64 columns per box; column chunk c lands 8 KB after chunk c-1 (= LBO)
 #pragma unroll
@@ -656,8 +667,9 @@ static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiPa
     if (make_map(&tmA, A, K, M, lda, 64)) return 1;
     if (make_map(&tmB, Wt, K, N, ldw, 64)) return 1;
   } else {
-    if (make_map(&tmA, A, M, K, lda, BM)) return 1;
-    if (make_map(&tmB, Wt, N, K, ldw, BN)) return 1;
+    const int64_t kcols = ep.x3 ? 3 * K : K;   // split operands are [rows, 3K]
+    if (make_map(&tmA, A, M, kcols, lda, BM)) return 1;
+    if (make_map(&tmB, Wt, N, kcols, ldw, BN)) return 1;
   }
   if (EPI == EPI_DIRECT) tmC = tmA;  // unused
   else if (make_map_c(&tmC, ep.C, M, N, ep.ldc)) return 1;
@@ -771,6 +783,26 @@ int gemm_tcgen05(const void* A, int64_t lda, const void* Wt, int64_t ldw, const 
   const int bn = pick_bn(N);
   if (c_dtype == SPA3D_BF16 && !residual) return launch_bn<EPI_TMA>(bn, A, lda, Wt, ldw, ep, M, N, K, st, aux_pre, ld_aux);
   return launch_bn<EPI_DIRECT>(bn, A, lda, Wt, ldw, ep, M, N, K, st);
+}
+
+// "bf16 x 3" accurate contraction: C[M,N] (fp32) = A[M,K] . W[N,K]^T + bias (+ residual) with A3 / W3 the [rows, 3K] bf16 splits
+// of fp32 operands (spa3d_split3).  Six tcgen05 products per K block into one fp32 accumulator reproduce the fp32 product
+// to ~2^-22: the tensor-core form of the "fp32-accumulate" mode (north_star tolerance 1e-4), 6x the MMA work of the bf16 path.
+bool gemm_tcgen05_x3_applicable(const void* A3, int64_t lda, const void* W3, int64_t ldw, int64_t M, int N, int K) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return al16(A3) && al16(W3) && lda % 8 == 0 && ldw % 8 == 0 && K % tc::BK == 0 && N % 8 == 0 && M > 0 && M < (1ll << 31);
+}
+
+int gemm_tcgen05_x3(const void* A3, int64_t lda, const void* W3, int64_t ldw, const float* bias, const void* residual, int64_t ldr,
+                    int r_dtype, float* C, int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
+  using namespace tc;
+  SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0, "gemm_x3: C must be 16-byte aligned with 16-byte row pitch");
+  if (residual)
+    SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(residual) & 15) == 0 && ldr % (r_dtype == SPA3D_F32 ? 4 : 8) == 0,
+                  "gemm_x3: residual must be 16-byte aligned with 16-byte row pitch");
+  if (bias) SPA3D_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm_x3: bias must be 16-byte aligned");
+  EpiParams ep{bias, residual, ldr, r_dtype, C, ldc, SPA3D_F32, 0, 0, 0, nullptr, nullptr, 1.f, nullptr, 0, 0, 0, 1};
+  return launch_bn<EPI_DIRECT>(pick_bn(N), A3, lda, W3, ldw, ep, M, N, K, st);
 }
 
 // Weight gradient on the tensor cores: dW[N,K] += dY[M,N]^T . X[M,K]  (fp32 accumulate into dW;

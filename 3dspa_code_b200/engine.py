@@ -34,6 +34,14 @@ class DeviceWeights:
     c: Dict[str, torch.Tensor]     # matrices in the compute dtype ([out, in], K contiguous)
     cdt: torch.dtype
     embed_bias: torch.Tensor = None
+    x3: bool = True                # fp32 mode: contractions on the tensor cores as "bf16 x 3" split products where the shape allows
+    c3: Dict[str, torch.Tensor] = None   # fp32 mode: [out, 3*in] bf16 splits (hi | mid | lo) of the matrices ops.gemm_x3 can take
+
+    def mats(self):
+        """Weight lookup for the forward GEMMs: the compute-dtype matrix, or - fp32 mode - its three-term bf16 split."""
+        if not self.c3:
+            return self.c
+        return _Prefer(self.c3, self.c)
 
     @staticmethod
     def from_tree(tree, precision="bf16", device="cuda"):
@@ -47,10 +55,14 @@ class DeviceWeights:
 
     def refresh(self):
         """(Re)derive compute-dtype shadows from the fp32 masters (after an optimiser step)."""
+        if self.c3 is None:
+            self.c3 = {}
         for k, v in self.f32.items():
             if v.dim() == 2 and (k.endswith("_t") or k.endswith(".Wt")):
                 if self.cdt == torch.float32:
                     self.c[k] = v
+                    if self.x3 and ops.gemm_x3_applicable(1, v.shape[0], v.shape[1]):
+                        self.c3[k] = ops.split3(v, self.c3.get(k))
                 else:
                     dst = self.c.get(k)
                     if dst is None:
@@ -66,6 +78,17 @@ class DeviceWeights:
             if k in self.f32:
                 ops.axpy(eb, self.f32[k], 1.0)
         self.embed_bias = eb
+
+
+class _Prefer:
+    """Read-only mapping: ``first[k]`` when present, else ``second[k]``."""
+
+    def __init__(self, first, second):
+        self.first, self.second = first, second
+
+    def __getitem__(self, k):
+        hit = self.first.get(k)
+        return hit if hit is not None else self.second[k]
 
 
 def _feat_dev(x, device):
@@ -112,7 +135,7 @@ class Engine:
         H, Dh = m["heads"], m["Dh"]
         A = H * Dh
         d = m["d"]
-        w, f = self.w.c, self.w.f32
+        w, f = self.w.mats(), self.w.f32
         for i in range(m["layers"]):
             pre = f"{short}.{i}."
             prune = out_rows == "first" and i == m["layers"] - 1 and kv is None and L > 1
@@ -202,6 +225,8 @@ class Engine:
             off += meta["dino_dim"]
         if depth is not None:
             ops.convert(depth.view(rows, -1), a[:, off : off + meta["depth_dim"]], out_row_group=grp)
+        if wt is self.w.c["embed.Wt"]:
+            wt = self.w.mats()["embed.Wt"]       # fp32 mode: the three-term split when the shape allows
         x = ops.gemm(a, wt, bias, out_dtype=torch.float32)
         if ro:
             ops.set_rows(x, T + 1, self.w.f32["readout_token"].view(-1), B * N)
@@ -263,7 +288,7 @@ class Engine:
         nl, E = meta["latent_tokens"], meta["E"]
         lat = self.w.f32["latents_init"].unsqueeze(0).reshape(nl, E).contiguous()
         lat = self.transformer("t2l", lat, 1, nl, kv=st, Lkv=N)
-        z = ops.gemm(lat, self.w.c["compressor.Wt"], self.w.f32["compressor.b"], out_dtype=torch.float32)
+        z = ops.gemm(lat, self.w.mats()["compressor.Wt"], self.w.f32["compressor.b"], out_dtype=torch.float32)
         return z.view(1, nl, meta["latent_dim"]), xyz
 
     def encode(self, inputs):
@@ -303,7 +328,7 @@ class Engine:
         nl, E = meta["latent_tokens"], meta["E"]
         lat = self.w.f32["latents_init"].unsqueeze(0).expand(B, nl, E).reshape(B * nl, E).contiguous()
         lat = self.transformer("t2l", lat, B, nl, kv=st, Lkv=N)
-        z = ops.gemm(lat, self.w.c["compressor.Wt"], self.w.f32["compressor.b"], out_dtype=torch.float32)
+        z = ops.gemm(lat, self.w.mats()["compressor.Wt"], self.w.f32["compressor.b"], out_dtype=torch.float32)
         return z.view(B, nl, meta["latent_dim"])
 
     def _encode_tracks_streamed(self, inputs, boundary, B, N, T):
@@ -403,7 +428,7 @@ class Engine:
     def decode(self, latents, ctx, noise=None, discretize=True):
         """decode (track_autoencoder_3d.py:248-307) -> head output [B*Q, 4T] f32."""
         cfg, meta, dev = self.cfg, self.w.meta, self.dev
-        w, f = self.w.c, self.w.f32
+        w, f = self.w.mats(), self.w.f32
         latents = _as_dev(latents, torch.float32, dev)
         B, nl, ld_ = latents.shape
         if discretize:

@@ -128,8 +128,46 @@ def set_rows(dst, row_stride, vec, rows):
     return dst
 
 
+def gemm_x3_applicable(M, N, K):
+    return bool(_lib.lib().spa3d_gemm_x3_applicable(int(M), int(N), int(K)))
+
+
+def split3(x, out=None):
+    """[rows, K] fp32 -> [rows, 3K] bf16 (hi | mid | lo): the operand form of gemm_x3."""
+    rows, K = x.shape
+    if out is None:
+        out = torch.empty(rows, 3 * K, device=x.device, dtype=torch.bfloat16)
+    _call("spa3d_split3", _p(x), _ld(x), _p(out), _ld(out), int(rows), int(K), _stream())
+    return out
+
+
+def _is_split(a, wt):
+    """fp32 activations against a three-term bf16 split weight [N, 3K]: the "bf16 x 3" tensor-core form of the accurate mode."""
+    return a.dtype == torch.float32 and wt.dtype == torch.bfloat16 and wt.shape[1] == 3 * a.shape[1]
+
+
+def _gemm_x3(a, w3, bias, act, residual, out):
+    M, K = a.shape
+    N = w3.shape[0]
+    a3 = split3(a)
+    z = out if (out is not None and act == ACT_NONE) else torch.empty(M, N, device=a.device, dtype=torch.float32)
+    assert z.dtype == torch.float32, "the bf16 x 3 contraction writes float32"
+    res = residual if act == ACT_NONE else None
+    _call("spa3d_gemm_x3", _p(a3), _ld(a3), _p(w3), _ld(w3), _p(bias), _p(res), _ld(res) if res is not None else 0,
+          dt(res) if res is not None else F32, _p(z), _ld(z), M, N, K, _stream())
+    if act == ACT_NONE:
+        return z
+    h = out if out is not None else torch.empty_like(z)     # exact tanh-GELU on the fp32 pre-activation, then the residual
+    gelu_fwd(z, h)
+    if residual is not None:
+        axpy(h, residual.contiguous())
+    return h
+
+
 def gemm(a, wt, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=None, impl=GEMM_AUTO):
-    """out[M,N] = act(a[M,K] @ wt[N,K]^T + bias) + residual."""
+    """out[M,N] = act(a[M,K] @ wt[N,K]^T + bias) + residual.  (fp32 ``a`` with a split3 weight: the bf16 x 3 contraction.)"""
+    if _is_split(a, wt):
+        return _gemm_x3(a, wt, bias, act, residual, out)
     M, K = a.shape
     N = wt.shape[0]
     assert wt.shape[1] == K and wt.dtype == a.dtype, (a.shape, wt.shape, a.dtype, wt.dtype)
@@ -223,6 +261,17 @@ def gemm_rmsnorm(a, wt, Dh, q_cols, k_cols, scale_q, scale_k, save_rstd=False, i
     """QKV projection with fused per-head RMSNorm (q also multiplied by 1/sqrt(Dh))."""
     M, K = a.shape
     N = wt.shape[0]
+    if _is_split(a, wt):     # accurate mode on the tensor cores: contraction, then the in-place normalisation of the q / k blocks
+        out = _gemm_x3(a, wt, None, ACT_NONE, None, None)
+        nh = (q_cols + k_cols) // Dh
+        rstd = torch.empty(M, nh, device=a.device, dtype=torch.float32) if save_rstd else None
+        lib_call = lambda view, scale, mul, rs, heads: _call(
+            "spa3d_head_rmsnorm_fwd", _p(view), _ld(out), dt(out), _p(scale), float(mul), _p(rs), nh, M, heads, Dh, _stream())
+        if q_cols:
+            lib_call(out, scale_q, 1.0 / math.sqrt(Dh), rstd, q_cols // Dh)
+        if k_cols:
+            lib_call(out[:, q_cols:], scale_k, 1.0, rstd[:, q_cols // Dh :] if rstd is not None else None, k_cols // Dh)
+        return (out, rstd) if save_rstd else out
     out = torch.empty(M, N, device=a.device, dtype=a.dtype)
     nh = (q_cols + k_cols) // Dh
     rstd = torch.empty(M, nh, device=a.device, dtype=torch.float32) if save_rstd else None

@@ -142,6 +142,16 @@ int spa3d_gemm(const void* A, int64_t lda, const void* Wt, int64_t ldw, int a_dt
                void* C, int64_t ldc, int c_dtype, int64_t M, int N, int K, int impl,
                void* stream);
 
+/* Tensor-core form of the accurate ("fp32-accumulate", 1e-4) mode: "bf16 x 3".  spa3d_split3 writes an fp32 matrix as three bf16
+ * terms side by side, dst[r, p*K + c] = part p of src[r, c] with x = hi + mid + lo to 24 bits (dst bf16 [rows, 3K]).
+ * spa3d_gemm_x3 contracts two split operands: C[M,N] (f32) = A . W^T + bias (+ residual), six tcgen05 products per K block
+ * (hi.hi, hi.mid, mid.hi, hi.lo, mid.mid, lo.hi; every bf16 x bf16 product is exact in fp32) accumulated in ONE fp32 TMEM
+ * accumulator, smallest terms first.  Needs K % 64 == 0, N % 8 == 0 (spa3d_gemm_x3_applicable); other shapes use the SIMT path. */
+int spa3d_split3(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int K, void* stream);
+int spa3d_gemm_x3_applicable(int64_t M, int N, int K);
+int spa3d_gemm_x3(const void* A3, int64_t lda, const void* W3, int64_t ldw, const float* bias, const void* residual,
+                  int64_t ldr, int r_dtype, float* C, int64_t ldc, int64_t M, int N, int K, void* stream);
+
 /* MLP_in with its activation, training form (attention.py:106): Z = A . Wt^T + bias (saved for the
  * backward pass) and H = gelu_tanh(Z), both [M,N] in a_dtype, from one pass over the accumulator.
  * save_grad = 1 (tcgen05 path only): Z receives gelu_tanh'(A . Wt^T + bias) instead - the derivative shares tanh(u) with

@@ -633,3 +633,40 @@ def test_cross_attention_tcgen05_fwd_bwd(spa, Lq, Lk, Dh, batch):
         assert st["attention_cross_tcgen05"] == 2 and st["attention_simt"] == 0, st
         for got, want in ((dq, qd.grad), (dk, kd.grad), (dv, vd.grad)):
             assert rel_err(got, want) < 2e-2, (masked, rel_err(got, want))
+
+
+def test_gemm_bf16x3_accurate_mode(spa):
+    """"bf16 x 3": fp32 operands split into three bf16 terms, six tcgen05 products per K block into one fp32 accumulator - the
+    tensor-core form of the accurate mode.  Against float64 of the SAME fp32 operands: ~1e-6, i.e. fp32-GEMM quality (the
+    north_star's 1e-4 path), with bias, residual, GELU, strided rows, ragged M / N."""
+    ops = spa.ops
+    torch.manual_seed(41)
+    for (M, K, N) in [(300, 384, 2304), (1000, 1280, 600), (129, 64, 8), (5000, 1536, 384), (77, 12352, 1280), (256, 512, 96)]:
+        big = torch.randn(M, K + 8, device="cuda")
+        a = big[:, 4 : 4 + K]                      # row pitch K + 8, 16-byte aligned start
+        w = torch.randn(N, K, device="cuda") / math.sqrt(K)
+        bias = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda")
+        w3 = ops.split3(w)
+        parts = w3.float().view(N, 3, K)
+        assert torch.equal(parts.sum(1), w) or float((parts.sum(1) - w).abs().max()) < 2e-7 * float(w.abs().max())
+        ops.stats(reset=True)
+        y = ops.gemm(a, w3, bias, residual=res, out_dtype=torch.float32)
+        assert ops.stats()["gemm_x3"] == 1
+        ref = a.double() @ w.double().t() + bias.double() + res.double()
+        assert rel_err(y, ref) < 3e-6, (M, K, N, rel_err(y, ref))
+        h = ops.gemm(a, w3, bias, act=ops.ACT_GELU)
+        z = a.double() @ w.double().t() + bias.double()
+        gref = 0.5 * z * (1 + torch.tanh(0.7978845608028654 * (z + 0.044715 * z ** 3)))
+        assert rel_err(h, gref) < 3e-6, (M, K, N, "gelu", rel_err(h, gref))
+    # fused-form projection + per-head RMSNorm on split weights
+    M, K, H, Dh = 200, 384, 8, 96
+    A = H * Dh
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(3 * A, K, device="cuda") / math.sqrt(K)
+    sq, sk = torch.rand(Dh, device="cuda") + 0.5, torch.rand(Dh, device="cuda") + 0.5
+    out, rstd = ops.gemm_rmsnorm(a, ops.split3(w), Dh, A, A, sq, sk, save_rstd=True)
+    z = (a.double() @ w.double().t()).view(M, 3, H, Dh)
+    rms = lambda t, s: t * torch.rsqrt((t * t).mean(-1, keepdim=True) + 1e-6) * s.double()
+    ref = torch.stack([rms(z[:, 0], sq) / math.sqrt(Dh), rms(z[:, 1], sk), z[:, 2]], 1).reshape(M, 3 * A)
+    assert rel_err(out, ref) < 3e-6 and rstd.shape == (M, 2 * H)

@@ -66,7 +66,11 @@ def test_reference_widths_forward(spa, precision):
     inp, noise = make_inputs(c, B=1, N=24, Q=8, seed=4)
     variables = model.init(5, inp)
     randomize(variables["params"], 5)
+    spa.ops.stats(reset=True)
     got = model.apply(variables, inp, noise=noise, discretize=False, precision=precision)
+    st = spa.ops.stats()
+    # the accurate mode runs its large contractions on the tensor cores too ("bf16 x 3"); the bf16 mode never leaves them
+    assert (st["gemm_x3"] > 40 and st["gemm_tcgen05"] == 0) if precision == "fp32" else (st["gemm_tcgen05"] > 40 and st["gemm_bf16_fallback"] == 0), st
     ref = oracle_fwd(model, variables["params"], inp, noise, False)
     assert got.tracks.shape == (1, 8, 150, 3) and got.visible_logits.shape == (1, 8, 150, 1)
     assert rel_err(got.tracks, ref.tracks) < TOL[precision], rel_err(got.tracks, ref.tracks)
