@@ -131,17 +131,26 @@ __device__ __forceinline__ void slab_store_bf16(uint8_t* slab, int lane, const u
 //             tokens, both operands are token-major = MN-major for the MMA; boxes of 64 tokens x
 //             64 columns).  The reduction is split over `splits` CTAs per tile which add their
 //             partial tiles into C with vector atomics.
-template <int BN, int EPI, int DH, bool TN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// EW = epilogue warps: 8 (two per TMEM lane quarter, each owning half of the tile's columns) or 16 (four per quarter, a quarter of
+// the columns each: twice the warps per scheduler to hide the fixed-latency chains of the GELU epilogue; bf16 TMA-store flavour only).
+template <int BN, int EPI, int DH, bool TN, int EW = NUM_EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
                     EpiParams ep, int64_t M, int N, int64_t K, int splits) {
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
   constexpr int TMEM_COLS = tmem_cols_for(BN);
-  constexpr int HC = BN / 2;     // columns per epilogue warp
-  constexpr int NCH = HC / 32;   // 32-column chunks per epilogue warp
-  static_assert(HC % 32 == 0, "tile halves must be whole 32-column chunks");
+  constexpr int NUM_THREADS = 64 + 32 * EW;
+  constexpr int PARTS = EW / 4;      // column parts of a tile (one epilogue warp per TMEM lane quarter and part)
+  constexpr int HC = BN / PARTS;     // columns per epilogue warp
+  constexpr int NCH = HC / 32;       // 32-column chunks per epilogue warp
+  constexpr int SLAB = EW == NUM_EPI_WARPS ? 4096 : 2048;   // staging bytes per epilogue warp (2 x 2 KB, or 1 x 2 KB with 16 warps)
+  constexpr int NBUF = SLAB / 2048;
+  static_assert(HC % 32 == 0, "tile parts must be whole 32-column chunks");
+  static_assert(EW == NUM_EPI_WARPS || (EW == 16 && EPI == EPI_TMA && !TN), "16 epilogue warps: bf16 TMA-store flavour only");
+  // (measured and not kept: a 12-warp variant of the head-width-96 RMSNorm epilogue - partial sums of squares exchanged between the
+  //  three warps of a lane quarter - ran the ITT QKV shape at 987 instead of 999 TFLOP/s; that epilogue is not latency-bound)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -179,7 +188,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], NUM_EPI_WARPS * 32);
+      mbar_init(&tempty_bar[i], EW * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -285,8 +294,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== epilogue (warps 2..9) =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = ew >> 2;      // which half of the tile's columns
-    uint8_t* slab = smem_epi + (size_t)ew * 4096;
+    const int half = ew >> 2;      // which part of the tile's columns (0 .. PARTS-1)
+    uint8_t* slab = smem_epi + (size_t)ew * SLAB;
     const bool out_f32 = ep.c_dtype == SPA3D_F32;
     int sbuf = 0;
     int it = 0;
@@ -525,31 +534,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         load_bias_tma(t + gridDim.x, breg_next);   // next tile's bias: its L2 latency hides under this tile
         mbar_wait(&tfull_bar[as], aphase);
         tcgen05_fence_after();
-        uint32_t r[2][32];
-        tmem_ld32(tbase, r[0]);
+        // 8 warps: the TMEM load of chunk c+1 is in flight while chunk c is processed (two register buffers); 16 warps: one
+        // buffer (112 registers per thread), the other three warps of the scheduler cover the load
+        constexpr bool PREFETCH = EW == NUM_EPI_WARPS;
+        const int aux_mode = EW == NUM_EPI_WARPS ? ep.aux_pre : 0;   // the training forward's side outputs stay on the 8-warp kernel
+        uint32_t r[PREFETCH ? 2 : 1][32];
+        if constexpr (PREFETCH) tmem_ld32(tbase, r[0]);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
+          if constexpr (!PREFETCH) tmem_ld32(tbase + (uint32_t)(c * 32), r[0]);
           tmem_ld_wait();
           if (c + 1 < NCH) {
-            tmem_ld32(tbase + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
-          } else {
+            if constexpr (PREFETCH) tmem_ld32(tbase + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+          } else {   // every value of this accumulator is in registers: hand it back to the MMA warp
             tcgen05_fence_before();
             mbar_arrive(&tempty_bar[as]);
           }
           const int col0 = colbase + c * 32;
           if (col0 < N && !kSkipEpilogue) {
             uint64_t v[16];
+            constexpr int RB = PREFETCH ? 1 : 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = pku(r[c & 1][2 * i], r[c & 1][2 * i + 1]);
+            for (int i = 0; i < 16; ++i) v[i] = pku(r[c & RB][2 * i], r[c & RB][2 * i + 1]);
             if (ep.bias) epi_bias(v, breg[c]);
-            if (ep.aux_pre) {   // what the backward pass needs leaves through its own map: z, or gelu'(z) (shares tanh(u) with the activation)
+            if (aux_mode) {   // what the backward pass needs leaves through its own map: z, or gelu'(z) (shares tanh(u) with the activation)
               uint64_t vg[16];
-              const bool grad = ep.aux_pre == 2;
+              const bool grad = aux_mode == 2;
               if (grad) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = gelu2_fast_grad(v[i], vg[i]);
               }
-              if (lane == 0) bulk_wait_read<1>();
+              if (lane == 0) bulk_wait_read<NBUF - 1>();
               __syncwarp();
               if (grad) slab_store_bf16(slab + sbuf * 2048, lane, vg);
               else slab_store_bf16(slab + sbuf * 2048, lane, v);
@@ -559,10 +574,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tma_store_2d(&tmAux, slab + sbuf * 2048, col0, row0);
                 bulk_commit();
               }
-              sbuf ^= 1;
+              sbuf = (sbuf + 1) % NBUF;
             }
-            if (ep.aux_pre != 2) epi_act(ep, v);
-            if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago has left this buffer
+            if (aux_mode != 2) epi_act(ep, v);
+            if (lane == 0) bulk_wait_read<NBUF - 1>();   // the store issued two chunks ago has left this buffer
             __syncwarp();
             slab_store_bf16(slab + sbuf * 2048, lane, v);
             fence_proxy_async_smem();
@@ -571,7 +586,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_store_2d(&tmC, slab + sbuf * 2048, col0, row0);
               bulk_commit();
             }
-            sbuf ^= 1;
+            sbuf = (sbuf + 1) % NBUF;
           }
         }
       } else {
@@ -657,7 +672,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int EPI, int DH, bool TN = false>
+template <int BN, int EPI, int DH, bool TN = false, int EW = NUM_EPI_WARPS>
 static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiParams ep, int64_t M,
                   int N, int64_t K, cudaStream_t st, void* aux = nullptr, int64_t ld_aux = 0) {
   using L = SmemLayout<BN>;
@@ -682,7 +697,7 @@ static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiPa
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, DH, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, DH, TN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     SPA3D_REQUIRE(e == cudaSuccess, "gemm_tcgen05: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -701,13 +716,30 @@ static int launch(const void* A, int64_t lda, const void* Wt, int64_t ldw, EpiPa
   }
   const int64_t items = tiles * splits;
   int grid = (int)(items < num_sms() ? items : num_sms());
-  gemm_tcgen05_kernel<BN, EPI, DH, TN><<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, tmC, tmAux, ep, M, N, K, splits);
+  gemm_tcgen05_kernel<BN, EPI, DH, TN, EW><<<grid, 64 + 32 * EW, L::TOTAL, st>>>(tmA, tmB, tmC, tmAux, ep, M, N, K, splits);
   return check_launch("gemm_tcgen05");
+}
+
+static bool epi_warps16() {   // A/B switch for measurements: SPA3D_GEMM_EW16=0 keeps the 8-warp epilogue (both are product kernels)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPA3D_GEMM_EW16");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 template <int EPI>
 static int launch_bn(int bn, const void* A, int64_t lda, const void* Wt, int64_t ldw, const EpiParams& ep,
                      int64_t M, int N, int K, cudaStream_t st, void* aux = nullptr, int64_t ld_aux = 0) {
+  if constexpr (EPI == EPI_TMA) {
+    // GELU / plain bf16 outputs on 256-wide tiles: four epilogue warps per scheduler (see the kernel's EW)
+    // (short K: the epilogue, not the main loop, sets the pace - measured on M=309248, K=384, N=1536 + GELU: 0.41 -> 0.35 ms;
+    //  at K=1280 the main loop dominates and the 8-warp kernel with its double-buffered TMEM loads is 3 % faster; the training
+    //  forward's two outputs through the single 2 KB slab of a 16-warp layout measured no faster, so they keep 8 warps.)
+    if (bn == 256 && aux == nullptr && K <= 768 && epi_warps16())
+      return launch<256, EPI, 32, false, 16>(A, lda, Wt, ldw, ep, M, N, K, st, aux, ld_aux);
+  }
   switch (bn) {
     case 256: return launch<256, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st, aux, ld_aux);
     case 192: return launch<192, EPI, 32>(A, lda, Wt, ldw, ep, M, N, K, st, aux, ld_aux);
