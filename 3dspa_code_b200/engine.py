@@ -254,7 +254,9 @@ class Engine:
         Tm, Hp, Wp, D = dino_map.shape
         if Tm != T or D != meta["dino_dim"]:
             raise ValueError(f"dino_map {tuple(dino_map.shape)} does not match T={T}, dino_dim={meta['dino_dim']}")
-        dm = ops.convert(dino_map.view(T * Hp * Wp, D), torch.empty(T * Hp * Wp, D, device=self.dev, dtype=self.cdt))
+        dm = dino_map.view(T * Hp * Wp, D)
+        if dm.dtype != self.cdt:
+            dm = ops.convert(dm, torch.empty(T * Hp * Wp, D, device=self.dev, dtype=self.cdt))
         proj = ops.gemm(dm, wt[:, off : off + D])           # [T*Hp*Wp, W] bf16, no bias (added once per token)
         del dm
         bias = self.w.f32["embed.b_track"].clone()
@@ -279,7 +281,7 @@ class Engine:
         N, T = tr2.shape[:2]
         vis = _as_dev(inputs["support_tracks_visible"], torch.float32, dev).reshape(1, N, T, 1)
         depth = _as_dev(inputs["depth"], torch.float32, dev)
-        dino = _as_dev(inputs["dino_map"], torch.float32, dev)
+        dino = _feat_dev(inputs["dino_map"], dev)      # float32 as the backbone delivers it, or bfloat16 when the caller holds it so
         _, H, Wv = inputs["video_shape"][:3]
         boundary = _as_dev(inputs.get("boundary_frame", np.array([T], np.int32)), torch.int32, dev)
         x, xyz = self.embed_tracks_from_maps(tr2, depth, dino, (H, Wv), inputs.get("intrinsics"))
