@@ -92,12 +92,24 @@ struct CrossArgs {
   float* part_ml;   // [items][128][2]
 };
 
-template <int DH, int LPAD, int MT, bool CROSS = false>   // head width, padded sequence length (multiple of 32), 128-row query tiles
-__global__ void __launch_bounds__(THREADS, 1)
+// NP = 2: TWO softmax warps per (query tile, TMEM lane quarter), each owning half of the key chunks of the same 32 rows (a TMEM
+// lane quarter is readable by every warp with the same warp % 4); row maxima and sums are exchanged through shared memory with
+// one 64-thread named barrier each.  The softmax is a chain of fixed-latency instructions per warp (ncu: one issue every ~6
+// cycles per warp), so halving the chain and doubling the warps per scheduler shortens the serial S -> softmax -> PV item.
+constexpr int threads_for(int MT, int NP) { return NP == 1 ? THREADS : (MT == 2 ? 544 : 384); }
+
+template <int DH, int LPAD, int MT, bool CROSS = false, int NP = 1>   // head width, padded sequence length (multiple of 32), 128-row query tiles
+__global__ void __launch_bounds__(threads_for(MT, NP), 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                    const uint8_t* __restrict__ mask, float* __restrict__ stats, int64_t items, int heads, int L, CrossArgs cx) {
-  static_assert(!CROSS || (MT == 1 && LPAD == 128), "cross-attention items are 128 queries x 128 keys");
+  static_assert(!CROSS || (MT == 1 && LPAD == 128 && NP == 1), "cross-attention items are 128 queries x 128 keys");
+  constexpr int NTHREADS = threads_for(MT, NP);
+  // warp roles.  NP = 1: warps 2..8 softmax (tile = (warp-2)/4, quarter = warp%4), warp 9 key-bias builder.
+  //             NP = 2: warp 2 builder; warps 4..11 tile 0 (part = (warp-4)/4); warps 12 and 16 tile 1, lane quarter 0 (the only
+  //             quarter of a second tile with live rows for L <= 160), parts 0 and 1; the other warps only take part in the set-up.
+  constexpr int BUILDER = NP == 1 ? 2 + SM_WARPS : 2;
+  constexpr int NCOMP = NP == 1 ? SM_WARPS * 32 : (8 + (MT == 2 ? 2 : 0)) * 32;   // threads arriving on s_empty / p_full
   // item -> (sequence b, head h, key chunk ck); self-attention has one chunk (ck = 0) that starts at key 0
   auto item_b = [&](int64_t it) -> int { return CROSS ? (int)(it / ((int64_t)heads * cx.nchunks)) : (int)(it / heads); };
   auto item_h = [&](int64_t it) -> int { return CROSS ? (int)((it / cx.nchunks) % heads) : (int)(it % heads); };
@@ -122,6 +134,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* s_full = bars + 4, *s_empty = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
   uint64_t* m_full = bars + 8, *m_empty = bars + 10;   // [2] each
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  float* xch = reinterpret_cast<float*>(bars + 16);    // NP = 2: [max | sum][part][QROWS] exchanged between the two warps of a row
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -130,7 +143,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
     mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(s_empty, SM_WARPS * 32); mbar_init(p_full, SM_WARPS * 32); mbar_init(o_full, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, NCOMP); mbar_init(p_full, NCOMP); mbar_init(o_full, 1);
     mbar_init(&m_full[0], 1); mbar_init(&m_full[1], 1); mbar_init(&m_empty[0], 1); mbar_init(&m_empty[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -139,7 +152,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // ones operand: element 0 of every row = 1.0 (logical chunk 0 sits at physical chunk (row >> 2) & 1)
-  for (int r = threadIdx.x; r < QROWS; r += THREADS) {
+  for (int r = threadIdx.x; r < QROWS; r += NTHREADS) {
     const int pc = (r >> 2) & 1;
     *reinterpret_cast<uint4*>(sE + r * 32 + pc * 16) = make_uint4(0x3F80u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(sE + r * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -212,7 +225,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(v_empty);
       }
     }
-  } else if (warp == 2 + SM_WARPS) {
+  } else if (warp == BUILDER) {
     // ===================== key-bias operand builder (one warp, runs one item ahead) =====================
     const uint32_t NEG_BIG = 0xF14Au;   // bf16(-1e30)
     const uint32_t NEG_INF = 0xFF80u;
@@ -233,6 +246,121 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&m_full[mb]);
+    }
+  } else if (NP == 2) {
+    // ===================== softmax + epilogue, two warps per (tile, lane quarter) =====================
+    const bool tile0 = warp >= 4 && warp < 12;
+    const bool is_compute = tile0 || (MT == 2 && (warp == 12 || warp == 16));
+    if (is_compute) {
+      const int mt = tile0 ? 0 : 1;
+      const int part = tile0 ? (warp - 4) >> 2 : (warp == 12 ? 0 : 1);
+      const int quarter = warp & 3;          // 0 for the tile-1 warps
+      const int rloc = quarter * 32 + lane;
+      const int row = mt * 128 + rloc;
+      const bool warp_live = mt * 128 + quarter * 32 < L;   // uniform over the pair of warps of this (tile, quarter)
+      constexpr int C_SPLIT = (KA + 1) / 2, O_SPLIT = (DA + 1) / 2;
+      const int c_lo = part == 0 ? 0 : C_SPLIT, c_hi = part == 0 ? C_SPLIT : KA;
+      const int o_lo = part == 0 ? 0 : O_SPLIT, o_hi = part == 0 ? O_SPLIT : DA;
+      float* x_max = xch + part * QROWS + row;
+      float* x_max_other = xch + (part ^ 1) * QROWS + row;
+      float* x_sum = xch + (2 + part) * QROWS + row;
+      float* x_sum_other = xch + (2 + (part ^ 1)) * QROWS + row;
+      const int bar_id = 1 + mt * 4 + quarter;
+      const uint32_t tS = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(S_COL + mt * LPAD);
+      const uint32_t tO = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(O_COL + mt * DH);
+      uint8_t* pRow = sP + mt * P_BYTES + rloc * 64;
+      const int sw64 = (lane >> 1) & 3;
+      constexpr float LOG2E = 1.4426950408889634f;
+      uint32_t ph = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
+        const int b = item_b(it), h = item_h(it);
+        mbar_wait(s_full, ph);
+        tcgen05_fence_after();
+        float mx = -INFINITY;
+        if (warp_live) {
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tS + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(r[i]));
+              m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+            }
+            mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          }
+          *x_max = mx;
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          mx = fmaxf(mx, *x_max_other);
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tS + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2_fast((__uint_as_float(r[2 * i]) - mx) * LOG2E);
+              const float p1 = ex2_fast((__uint_as_float(r[2 * i + 1]) - mx) * LOG2E);
+              l0 += p0;
+              l1 += p1;
+              __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+              w[i] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+            uint8_t* dst = pRow + c * (128 * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          }
+          *x_sum = l0 + l1;
+        }
+        tcgen05_fence_before();
+        mbar_arrive(s_empty);
+        fence_proxy_async_smem();
+        mbar_arrive(p_full);
+        mbar_wait(o_full, ph);
+        tcgen05_fence_after();
+        if (warp_live) {
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");   // the partner's partial sum is in shared memory
+          const float inv = 1.f / (*x_sum + *x_sum_other);
+          for (int c = o_lo; c < o_hi; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tO + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            uint8_t* dst = pRow + c * (128 * 64);    // staging: this warp's rows of P atom c (free once P V has completed)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * e]) * inv, __uint_as_float(r[j * 8 + 2 * e + 1]) * inv);
+                w[e] = *reinterpret_cast<uint32_t*>(&hb);
+              }
+              *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            for (int c = o_lo; c < o_hi; ++c)
+              tma_store_3d(&tmO, sP + mt * P_BYTES + c * (128 * 64) + quarter * 2048, h * DH + c * 32, mt * 128 + quarter * 32, b);
+            bulk_commit();
+          }
+          if (part == 0 && stats != nullptr && row < L) {
+            const int64_t base = (((int64_t)b * heads + h) * L + row) * 2;
+            stats[base] = mx;
+            stats[base + 1] = inv;
+          }
+          if (lane == 0) bulk_wait_read<0>();   // the staging rows are P rows of the next item
+          __syncwarp();
+        }
+        tcgen05_fence_before();
+      }
     }
   } else {
     // ===================== softmax + epilogue: thread = query row =====================
@@ -378,11 +506,12 @@ static int make_map3(CUtensorMap* map, const void* ptr, int cols, int L, int64_t
   return 0;
 }
 
-template <int DH, int LPAD, int MT>
+template <int DH, int LPAD, int MT, int NP = 2>
 static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                   const uint8_t* mask, float* stats, int64_t batch, int heads, int L, cudaStream_t st) {
   constexpr int DA = DH / 32, KA = LPAD / 32;
-  constexpr int SMEM = DA * MT * 128 * 64 + 2 * DA * LPAD * 64 + MT * KA * 128 * 64 + MT * 128 * 32 + 2 * LPAD * 32 + 128 + 1024;
+  constexpr int SMEM = DA * MT * 128 * 64 + 2 * DA * LPAD * 64 + MT * KA * 128 * 64 + MT * 128 * 32 + 2 * LPAD * 32 + 128 + 1024 +
+                       (NP == 2 ? 4 * MT * 128 * 4 : 0);
   CUtensorMap tmQ, tmK, tmV, tmO;
   const int cols = heads * DH;
   if (make_map3(&tmQ, q, cols, L, batch, ldq, LPAD)) return 1;
@@ -391,13 +520,13 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   if (make_map3(&tmO, o, cols, L, batch, ldo, 32)) return 1;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, LPAD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, LPAD, MT, false, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     SPA3D_REQUIRE(e == cudaSuccess, "attention_tc: smem attribute (%d B): %s", SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
   const int64_t items = batch * heads;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  attn_fwd_tc_kernel<DH, LPAD, MT><<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, tmO, mask, stats, items, heads, L, CrossArgs{0, 1, nullptr, nullptr});
+  attn_fwd_tc_kernel<DH, LPAD, MT, false, NP><<<grid, threads_for(MT, NP), SMEM, st>>>(tmQ, tmK, tmV, tmO, mask, stats, items, heads, L, CrossArgs{0, 1, nullptr, nullptr});
   return check_launch("attention_fwd_tc");
 }
 
@@ -510,6 +639,19 @@ int attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                      int64_t ldo, const uint8_t* key_mask, float* stats, int64_t batch, int heads, int L, int Dh,
                      cudaStream_t st) {
   using namespace ta;
+  static int np1 = -1;   // A/B switch for measurements: SPA3D_ATTN_NP=1 keeps one softmax warp per (tile, lane quarter)
+  if (np1 < 0) {
+    const char* e = getenv("SPA3D_ATTN_NP");
+    np1 = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  if (np1) {
+    if (Dh == 96) {
+      if (L <= 128) return launch<96, 128, 1, 1>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+      return launch<96, 160, 2, 1>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+    }
+    if (L <= 128) return launch<64, 128, 1, 1>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+    return launch<64, 160, 2, 1>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+  }
   if (Dh == 96) {
     if (L <= 128) return launch<96, 128, 1>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
     return launch<96, 160, 2>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
