@@ -118,23 +118,35 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr int DA = DH / 32;          // 32-channel atoms per operand row
   constexpr int KA = LPAD / 32;        // 32-key atoms per P row
   constexpr int QROWS = MT * 128;
-  constexpr int Q_BYTES = DA * QROWS * 64, K_BYTES = DA * LPAD * 64, P_BYTES = KA * 128 * 64;
+  // DB (two query tiles, NP = 2): K and V are DOUBLE buffered so the loads of item i+1 run under the whole of item i (the Q load
+  // already runs under the softmax).  The shared memory for it comes from the padding of the second query tile, which has at most
+  // LPAD - 128 = 32 live rows: the Q regions hold LPAD rows instead of 256 and the second tile's P atoms 32 rows instead of 128.  The
+  // 128-row MMAs of that tile then read rows that belong to the neighbouring region - harmless, every output row depends on its own
+  // operand row only, and the rows past the live ones are never stored - and every such over-read stays inside the allocation.
+  constexpr bool DB = NP == 2 && MT == 2;
+  constexpr int QR = DB ? LPAD : QROWS;             // rows of one 32-channel Q atom region
+  constexpr int NKV = DB ? 2 : 1;
+  constexpr int Q_BYTES = DA * QR * 64, K_BYTES = DA * LPAD * 64, P_BYTES = KA * 128 * 64;
+  constexpr int P1_ATOM = DB ? 32 * 64 : 128 * 64;  // bytes of one 32-key atom of the SECOND tile's P
+  constexpr int P_TOTAL = MT == 1 ? P_BYTES : P_BYTES + KA * P1_ATOM;
   constexpr int S_COL = 0, O_COL = MT * LPAD;
   static_assert(MT * (LPAD + DH) <= 512, "TMEM: S and O accumulators of every query tile");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;
-  uint8_t* sV = sK + K_BYTES;
-  uint8_t* sP = sV + K_BYTES;                      // [MT][KA][128 rows][64 B]
-  uint8_t* sE = sP + MT * P_BYTES;                 // ones operand [QROWS][32 B], 32B-swizzled, constant
+  uint8_t* sK = sQ + Q_BYTES;                      // [NKV] buffers
+  uint8_t* sV = sK + NKV * K_BYTES;                // [NKV] buffers
+  uint8_t* sP = sV + NKV * K_BYTES;                // tile 0: [KA][128 rows][64 B]; tile 1: [KA][P1_ATOM]
+  uint8_t* sE = sP + P_TOTAL;                      // ones operand [QROWS][32 B], 32B-swizzled, constant
   uint8_t* sB = sE + QROWS * 32;                   // [2][LPAD][32 B] per-item key bias operand
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * LPAD * 32);
-  uint64_t* qk_full = bars, *qk_empty = bars + 1, *v_full = bars + 2, *v_empty = bars + 3;
-  uint64_t* s_full = bars + 4, *s_empty = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
-  uint64_t* m_full = bars + 8, *m_empty = bars + 10;   // [2] each
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
-  float* xch = reinterpret_cast<float*>(bars + 16);    // NP = 2: [max | sum][part][QROWS] exchanged between the two warps of a row
+  uint64_t* q_full = bars, *q_empty = bars + 1, *k_full = bars + 2, *k_empty = bars + 4, *v_full = bars + 6, *v_empty = bars + 8;   // k / v: [2]
+  uint64_t* s_full = bars + 10, *s_empty = bars + 11, *p_full = bars + 12, *o_full = bars + 13;
+  uint64_t* m_full = bars + 14, *m_empty = bars + 16;   // [2] each
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+  float* xch = reinterpret_cast<float*>(bars + 20);    // NP = 2: [max | sum][part][QROWS] exchanged between the two warps of a row
+  auto p_tile = [&](int mt) -> uint8_t* { return sP + (mt == 0 ? 0 : P_BYTES); };
+  auto p_atom = [&](int mt) -> int { return mt == 0 ? 128 * 64 : P1_ATOM; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -142,7 +154,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
-    mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     mbar_init(s_full, 1); mbar_init(s_empty, NCOMP); mbar_init(p_full, NCOMP); mbar_init(o_full, 1);
     mbar_init(&m_full[0], 1); mbar_init(&m_full[1], 1); mbar_init(&m_empty[0], 1); mbar_init(&m_empty[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -167,19 +180,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ===================== TMA loads =====================
     if (lane == 0) {
       uint32_t ph = 0;
-      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
+      int n = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1, ++n) {
         const int b = item_b(it), h = item_h(it), k0 = item_k0(it);
-        mbar_wait(qk_empty, ph ^ 1);
-        mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * DA * LPAD * 64));
+        const int kb = DB ? (n & 1) : 0;                               // K / V buffer of this item
+        const uint32_t kph = DB ? (uint32_t)((n >> 1) & 1) : ph;      // ... and the phase of its barriers
+        mbar_wait(&k_empty[kb], kph ^ 1);
+        mbar_arrive_expect_tx(&k_full[kb], (uint32_t)(DA * LPAD * 64));
 #pragma unroll
-        for (int a = 0; a < DA; ++a) {
-          tma_load_3d(sQ + a * (QROWS * 64), &tmQ, h * DH + a * 32, 0, b, qk_full);
-          tma_load_3d(sK + a * (LPAD * 64), &tmK, h * DH + a * 32, k0, b, qk_full);
-        }
-        mbar_wait(v_empty, ph ^ 1);
-        mbar_arrive_expect_tx(v_full, (uint32_t)(DA * LPAD * 64));
+        for (int a = 0; a < DA; ++a) tma_load_3d(sK + kb * K_BYTES + a * (LPAD * 64), &tmK, h * DH + a * 32, k0, b, &k_full[kb]);
+        auto load_v = [&]() {
+          mbar_wait(&v_empty[kb], kph ^ 1);
+          mbar_arrive_expect_tx(&v_full[kb], (uint32_t)(DA * LPAD * 64));
 #pragma unroll
-        for (int a = 0; a < DA; ++a) tma_load_3d(sV + a * (LPAD * 64), &tmV, h * DH + a * 32, k0, b, v_full);
+          for (int a = 0; a < DA; ++a) tma_load_3d(sV + kb * K_BYTES + a * (LPAD * 64), &tmV, h * DH + a * 32, k0, b, &v_full[kb]);
+        };
+        // double-buffered: V's buffer was released two items ago, issue it before waiting for the Q region; single-buffered: the V
+        // region is released only by the previous item's P V, so Q (released earlier, by its S) must not queue behind it
+        if constexpr (DB) load_v();
+        mbar_wait(q_empty, ph ^ 1);
+        mbar_arrive_expect_tx(q_full, (uint32_t)(DA * LPAD * 64));
+#pragma unroll
+        for (int a = 0; a < DA; ++a) tma_load_3d(sQ + a * (QR * 64), &tmQ, h * DH + a * 32, 0, b, q_full);
+        if constexpr (!DB) load_v();
       }
     }
   } else if (warp == 1) {
@@ -190,7 +213,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       int n = 0;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1, ++n) {
         const int mb = n & 1;
-        mbar_wait(qk_full, ph);
+        const int kb = DB ? (n & 1) : 0;
+        const uint32_t kph = DB ? (uint32_t)((n >> 1) & 1) : ph;
+        mbar_wait(&k_full[kb], kph);
+        mbar_wait(q_full, ph);
         mbar_wait(&m_full[mb], (n >> 1) & 1);
         mbar_wait(s_empty, ph ^ 1);   // the softmax of the previous item has finished reading S
         tcgen05_fence_after();
@@ -198,8 +224,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk) {
-            const uint64_t da = desc_k64(smem_u32(sQ + (kk >> 1) * (QROWS * 64) + mt * (128 * 64) + (kk & 1) * 32));
-            const uint64_t db = desc_k64(smem_u32(sK + (kk >> 1) * (LPAD * 64) + (kk & 1) * 32));
+            const uint64_t da = desc_k64(smem_u32(sQ + (kk >> 1) * (QR * 64) + mt * (128 * 64) + (kk & 1) * 32));
+            const uint64_t db = desc_k64(smem_u32(sK + kb * K_BYTES + (kk >> 1) * (LPAD * 64) + (kk & 1) * 32));
             umma_bf16(tmem_base + (uint32_t)(S_COL + mt * LPAD), da, db, idS, kk > 0 ? 1u : 0u);
           }
           // S += ones[q] x bias[k]: the key mask as one more K-step
@@ -207,22 +233,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     desc_k32(smem_u32(sB + mb * (LPAD * 32))), idS, 1u);
         }
         umma_commit(s_full);
-        umma_commit(qk_empty);
+        umma_commit(q_empty);
+        umma_commit(&k_empty[kb]);
         umma_commit(&m_empty[mb]);
-        mbar_wait(v_full, ph);
+        mbar_wait(&v_full[kb], kph);
         mbar_wait(p_full, ph);        // P is in shared memory (and O of the previous item has been drained)
         tcgen05_fence_after();
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
           for (int ks = 0; ks < LPAD / 16; ++ks) {
-            const uint64_t da = desc_k64(smem_u32(sP + mt * P_BYTES + (ks >> 1) * (128 * 64) + (ks & 1) * 32));
-            const uint64_t db = desc_mn64(smem_u32(sV + ks * (16 * 64)), (uint32_t)(LPAD * 64));
+            const uint64_t da = desc_k64(smem_u32(p_tile(mt) + (ks >> 1) * p_atom(mt) + (ks & 1) * 32));
+            const uint64_t db = desc_mn64(smem_u32(sV + kb * K_BYTES + ks * (16 * 64)), (uint32_t)(LPAD * 64));
             umma_bf16(tmem_base + (uint32_t)(O_COL + mt * DH), da, db, idO, ks > 0 ? 1u : 0u);
           }
         }
         umma_commit(o_full);
-        umma_commit(v_empty);
+        umma_commit(&v_empty[kb]);
       }
     }
   } else if (warp == BUILDER) {
@@ -268,7 +295,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int bar_id = 1 + mt * 4 + quarter;
       const uint32_t tS = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(S_COL + mt * LPAD);
       const uint32_t tO = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(O_COL + mt * DH);
-      uint8_t* pRow = sP + mt * P_BYTES + rloc * 64;
+      uint8_t* pRow = p_tile(mt) + rloc * 64;     // this thread's 64 B in every 32-key atom (tile 1: rloc < 32)
+      const int pstride = p_atom(mt);
       const int sw64 = (lane >> 1) & 3;
       constexpr float LOG2E = 1.4426950408889634f;
       uint32_t ph = 0;
@@ -312,7 +340,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
               w[i] = *reinterpret_cast<uint32_t*>(&hb);
             }
-            uint8_t* dst = pRow + c * (128 * 64);
+            uint8_t* dst = pRow + c * pstride;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
@@ -332,7 +360,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             uint32_t r[32];
             tmem_ld32(tO + (uint32_t)(c * 32), r);
             tmem_ld_wait();
-            uint8_t* dst = pRow + c * (128 * 64);    // staging: this warp's rows of P atom c (free once P V has completed)
+            uint8_t* dst = pRow + c * pstride;    // staging: this warp's rows of P atom c (free once P V has completed)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t w[4];
@@ -348,7 +376,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           __syncwarp();
           if (lane == 0) {
             for (int c = o_lo; c < o_hi; ++c)
-              tma_store_3d(&tmO, sP + mt * P_BYTES + c * (128 * 64) + quarter * 2048, h * DH + c * 32, mt * 128 + quarter * 32, b);
+              tma_store_3d(&tmO, p_tile(mt) + c * pstride + quarter * 2048, h * DH + c * 32, mt * 128 + quarter * 32, b);
             bulk_commit();
           }
           if (part == 0 && stats != nullptr && row < L) {
@@ -510,8 +538,10 @@ template <int DH, int LPAD, int MT, int NP = 2>
 static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                   const uint8_t* mask, float* stats, int64_t batch, int heads, int L, cudaStream_t st) {
   constexpr int DA = DH / 32, KA = LPAD / 32;
-  constexpr int SMEM = DA * MT * 128 * 64 + 2 * DA * LPAD * 64 + MT * KA * 128 * 64 + MT * 128 * 32 + 2 * LPAD * 32 + 128 + 1024 +
-                       (NP == 2 ? 4 * MT * 128 * 4 : 0);
+  constexpr bool DB = NP == 2 && MT == 2;
+  constexpr int SMEM = DA * (DB ? LPAD : MT * 128) * 64 + (DB ? 4 : 2) * DA * LPAD * 64 + KA * 128 * 64 + (MT == 2 ? KA * (DB ? 32 : 128) * 64 : 0) +
+                       MT * 128 * 32 + 2 * LPAD * 32 + 256 + 1024 + (NP == 2 ? 4 * MT * 128 * 4 : 0);
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   CUtensorMap tmQ, tmK, tmV, tmO;
   const int cols = heads * DH;
   if (make_map3(&tmQ, q, cols, L, batch, ldq, LPAD)) return 1;
@@ -570,7 +600,7 @@ template <int DH>
 static int launch_cross(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                         const uint8_t* mask, float* stats, float* workspace, int64_t batch, int heads, int Lq, int Lk, cudaStream_t st) {
   constexpr int DA = DH / 32, KA = 4;
-  constexpr int SMEM = DA * 128 * 64 + 2 * DA * 128 * 64 + KA * 128 * 64 + 128 * 32 + 2 * 128 * 32 + 128 + 1024;
+  constexpr int SMEM = DA * 128 * 64 + 2 * DA * 128 * 64 + KA * 128 * 64 + 128 * 32 + 2 * 128 * 32 + 256 + 1024;
   CUtensorMap tmQ, tmK, tmV;
   const int cols = heads * DH;
   if (make_map3(&tmQ, q, cols, Lq, batch, ldq, 128)) return 1;
