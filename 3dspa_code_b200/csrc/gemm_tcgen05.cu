@@ -149,7 +149,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int NBUF = SLAB / 2048;
   static_assert(HC % 32 == 0, "tile parts must be whole 32-column chunks");
   static_assert(EW == NUM_EPI_WARPS || (EW == 16 && EPI == EPI_TMA && !TN), "16 epilogue warps: bf16 TMA-store flavour only");
-  // (measured and not kept: a 12-warp variant of the head-width-96 RMSNorm epilogue - partial sums of squares exchanged between the
+  // (measured and not kept: 12 / 16 epilogue warps for the fp32 / residual flavour - 4 KB slabs per warp cost a smem stage at 256-wide
+  //  tiles and the 112-register cap spills: N=384 out-projection 0.254 -> 0.307 ms, gelu-backward 0.556 -> 0.698 ms; and
+  //  a 12-warp variant of the head-width-96 RMSNorm epilogue - partial sums of squares exchanged between the
   //  three warps of a lane quarter - ran the ITT QKV shape at 987 instead of 999 TFLOP/s; that epilogue is not latency-bound)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
