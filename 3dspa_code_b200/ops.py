@@ -179,13 +179,14 @@ def gemm(a, wt, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=None
     return out
 
 
-def gemm_gelu(a, wt, bias, impl=GEMM_AUTO, save_grad=False):
+def gemm_gelu(a, wt, bias, impl=GEMM_AUTO, save_grad=False, z=None, h=None):
     """(z, h): z = a @ wt^T + bias, h = gelu_tanh(z), both in a.dtype (one GEMM, two outputs).
     save_grad (bf16 tensor-core path): the first output is gelu_tanh'(z) instead of z (pair it with gemm_gelu_bwd(z_is_grad=True))."""
     M, K = a.shape
     N = wt.shape[0]
-    z = torch.empty(M, N, device=a.device, dtype=a.dtype)
-    h = torch.empty(M, N, device=a.device, dtype=a.dtype)
+    if z is None:
+        z = torch.empty(M, N, device=a.device, dtype=a.dtype)
+        h = torch.empty(M, N, device=a.device, dtype=a.dtype)
     _call("spa3d_gemm_gelu", _p(a), _ld(a), _p(wt), _ld(wt), dt(a), _p(bias), _p(z), _ld(z), _p(h), _ld(h), M, N, K, int(bool(save_grad)),
           int(impl), _stream())
     return z, h
@@ -217,14 +218,13 @@ def gemm_strided(a, sam, sak, b, sbk, sbn, out, M, N, K, accumulate=False):
     return out
 
 
-def layernorm_fwd(x, scale, out_dtype, rows=None, ldx=None, d=None, stats=False, out=None):
+def layernorm_fwd(x, scale, out_dtype, rows=None, ldx=None, d=None, stats=False, out=None, mean=None, rstd=None):
     rows = x.shape[0] if rows is None else rows
     d = x.shape[-1] if d is None else d
     ldx = _ld(x) if ldx is None else ldx
     if out is None:
         out = torch.empty(rows, d, device=x.device, dtype=out_dtype)
-    mean = rstd = None
-    if stats:
+    if stats and mean is None:
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
     _call("spa3d_layernorm_fwd", _p(x), int(ldx), dt(x), _p(scale), _p(out), _ld(out), dt(out), _p(mean), _p(rstd), int(rows), int(d), _stream())
@@ -257,7 +257,7 @@ def head_rmsnorm_fwd(buf, scale, out_mul, heads, Dh, save_rstd=False):
     return rstd
 
 
-def gemm_rmsnorm(a, wt, Dh, q_cols, k_cols, scale_q, scale_k, save_rstd=False, impl=GEMM_AUTO):
+def gemm_rmsnorm(a, wt, Dh, q_cols, k_cols, scale_q, scale_k, save_rstd=False, impl=GEMM_AUTO, out=None, rstd=None):
     """QKV projection with fused per-head RMSNorm (q also multiplied by 1/sqrt(Dh))."""
     M, K = a.shape
     N = wt.shape[0]
@@ -272,9 +272,11 @@ def gemm_rmsnorm(a, wt, Dh, q_cols, k_cols, scale_q, scale_k, save_rstd=False, i
         if k_cols:
             lib_call(out[:, q_cols:], scale_k, 1.0, rstd[:, q_cols // Dh :] if rstd is not None else None, k_cols // Dh)
         return (out, rstd) if save_rstd else out
-    out = torch.empty(M, N, device=a.device, dtype=a.dtype)
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=a.dtype)
     nh = (q_cols + k_cols) // Dh
-    rstd = torch.empty(M, nh, device=a.device, dtype=torch.float32) if save_rstd else None
+    if save_rstd and rstd is None:
+        rstd = torch.empty(M, nh, device=a.device, dtype=torch.float32)
     _call("spa3d_gemm_rmsnorm", _p(a), _ld(a), _p(wt), _ld(wt), dt(a), _p(out), _ld(out), dt(out), M, N, K, Dh, q_cols, k_cols,
           _p(scale_q), _p(scale_k), 1.0 / math.sqrt(Dh), _p(rstd), int(impl), _stream())
     return (out, rstd) if save_rstd else out

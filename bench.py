@@ -448,6 +448,17 @@ def run_trajan_leg(spa, dev, cpu=True):
         return e0.elapsed_time(e1) / n, r
 
     ms_eager, _ = run(model)                 # ~190 launches of 5-500 us: sensitive to the host's launch rate
+    if os.environ.get("SPA3D_BENCH_PROFILE"):
+        import cProfile, pstats, io
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(5):
+            model.apply(variables, dev_inp, noise=dev_noise, precision="bf16")
+        torch.cuda.synchronize()
+        pr.disable()
+        st = io.StringIO()
+        pstats.Stats(pr, stream=st).sort_stats("tottime").print_stats(18)
+        sys.stderr.write("[profile] trajan eager %.2f ms\n%s\n" % (ms_eager, st.getvalue()))
     gm = spa.TrackAutoEncoder()
     gm.cuda_graph = True                     # like the headline leg: the forward replayed as one CUDA graph
     ms, res = run(gm)
@@ -649,7 +660,7 @@ def run_ours(args):
         return int(sum(v.numel() * v.element_size() for v in d.values() if isinstance(v, torch.Tensor)) + noise.numel() * noise.element_size())
 
     def run_stream(batch, noise, from_maps, n):
-        m = model if from_maps else stream_model
+        m = stream_model      # cuda_graph = True: one graph per device buffer set, for the feature path and the maps path alike
         last = None
         for res in m.apply_stream(variables, (batch for _ in range(n)), noises=(noise for _ in range(n)), precision="bf16", from_maps=from_maps):
             last = res
@@ -696,7 +707,8 @@ def run_ours(args):
                     "h2d_copy_alone_ms": ms_copy, "h2d_copy_alone_gbs": h2d / (ms_copy * 1e-3) / 1e9,
                     "path": "model.apply_stream(from_maps=True): per step, one clip's 2-D tracks + depth maps + DINOv2 patch maps (float32, pinned host) "
                             "are uploaded, lifted / sampled / embedded fused, encoded and decoded; tracks + visibility logits are read back. "
-                            "The upload of clip i+1 overlaps the forward of clip i; K clips are timed from before the first upload to after the last read-back",
+                            "The upload of clip i+1 overlaps the forward of clip i (each device buffer set replays its forward as one CUDA graph); "
+                            "K clips are timed from before the first upload to after the last read-back",
                     "variants": e2e_variants, "host_numa_cpus": numa_cpus},
             "dispatch_fallbacks": fallbacks,
             "gpu_launches": int(launches),

@@ -415,3 +415,9 @@ def test_apply_stream_from_maps_equals_apply_from_maps(spa):
     got = list(model.apply_stream(variables, batches, noises=[noise] * 3, from_maps=True))
     for g, r in zip(got, refs):
         assert torch.equal(g.tracks, r.tracks.cpu()) and torch.equal(g.visible_logits, r.visible_logits.cpu())
+    gm = spa.TrackAutoEncoder3D()
+    gm.cuda_graph = True          # the maps forward of each device buffer set replayed as one CUDA graph
+    got = list(gm.apply_stream(variables, batches + batches, noises=[noise] * 6, from_maps=True))
+    assert len(gm._graphs) == 2
+    for g, r in zip(got, refs + refs):
+        assert torch.equal(g.tracks, r.tracks.cpu()) and torch.equal(g.visible_logits, r.visible_logits.cpu())

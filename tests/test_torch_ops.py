@@ -193,8 +193,10 @@ def test_model_forward_goes_through_the_dispatcher(spa):
     with Log():
         got = model.apply(variables, inp, noise=noise, precision="bf16")
     assert torch.equal(got.tracks, ref.tracks)
-    for name in ("spa3d.gemm.default", "spa3d.gemm_rmsnorm.default", "spa3d.attention_fwd.default", "spa3d.layernorm_fwd.default"):
-        assert seen.get(name, 0) > 0, (name, seen)
+    # under no_grad the engine takes the out-variants (no autograd key to cross); with grad mode on, the functional operators
+    for base in ("gemm", "gemm_rmsnorm", "layernorm_fwd"):
+        assert seen.get(f"spa3d.{base}_out.default", 0) + seen.get(f"spa3d.{base}.default", 0) > 0, (base, seen)
+    assert seen.get("spa3d.attention_fwd.default", 0) > 0, seen
 
 
 @pytest.mark.gpu
