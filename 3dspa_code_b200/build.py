@@ -19,6 +19,7 @@ SOURCES = [
     "gemm_simt.cu",
     "gemm_tcgen05.cu",
     "embed_tcgen05.cu",
+    "mlp_fused_tcgen05.cu",
     "attention_simt.cu",
     "attention_tc.cu",
     "attention_tc_bwd.cu",

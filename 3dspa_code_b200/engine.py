@@ -114,6 +114,10 @@ class Engine:
         self.cdt = weights.cdt
         self.exact = (weights.cdt == torch.float32) if exact_sin is None else exact_sin
         self.fused_embed = True     # bf16 path: fused Fourier + feature conversion + first projection (K1)
+        # bf16 path, d = 384: MLP_in -> GELU -> MLP_out as one kernel (spa3d_mlp_fused: the hidden activation stays on the SM).  Correct
+        # (tests/test_gpu_kernels.py) but OFF by default: measured 0.805 ms against 0.783 ms for the two GEMMs on the per-track shape -
+        # with the 96 KB token tile resident, shared memory leaves a 96 KB weight ring, about one L2 latency of look-ahead
+        self.fused_mlp = False
         self.stream_chunk = 256     # support tracks per host->device pipeline stage (0 = one-shot upload)
         self._copy_stream = None
         self._noise_cache = None    # ((B, tokens, dim, layout), device tensor) of the default quantiser noise
@@ -167,6 +171,12 @@ class Engine:
                 a = ops.gemm(oc, w[pre + "cross.Wo_t"], f[pre + "cross.bo"], residual=a, out_dtype=torch.float32)
                 del qc, kvp, oc
             an = ops.layernorm_fwd(a, f[pre + "norm_attn"], self.cdt)
+            if (self.fused_mlp and self.cdt == torch.bfloat16 and a.shape[0] >= 4096
+                    and ops.mlp_fused_applicable(d, w[pre + "W1_t"].shape[0])):
+                # MLP_in -> GELU -> MLP_out in one kernel: the hidden activation never reaches HBM (per-track transformer, d = 384)
+                x = ops.mlp_fused(an, w[pre + "W1_t"], f[pre + "b1"], w[pre + "W2_t"], f[pre + "b2"], a)
+                del xn, an, a
+                continue
             h = ops.gemm(an, w[pre + "W1_t"], f[pre + "b1"], act=ops.ACT_GELU)
             x = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=a, out_dtype=torch.float32)
             del xn, an, h, a

@@ -179,6 +179,21 @@ def gemm(a, wt, bias=None, act=ACT_NONE, residual=None, out=None, out_dtype=None
     return out
 
 
+def mlp_fused_applicable(D, Hd):
+    return bool(_lib.lib().spa3d_mlp_fused_applicable(int(D), int(Hd)))
+
+
+def mlp_fused(a, w1t, b1, w2t, b2, residual, out=None):
+    """out = residual + gelu_tanh(a @ w1t^T + b1) @ w2t^T + b2 in one kernel (bf16 a / weights, fp32 residual and out)."""
+    M, D = a.shape
+    Hd = w1t.shape[0]
+    if out is None:
+        out = torch.empty(M, D, device=a.device, dtype=torch.float32)
+    _call("spa3d_mlp_fused", _p(a), _ld(a), _p(w1t), _ld(w1t), _p(b1), _p(w2t), _ld(w2t), _p(b2), _p(residual), _ld(residual), _p(out), _ld(out),
+          int(M), int(D), int(Hd), _stream())
+    return out
+
+
 def gemm_gelu(a, wt, bias, impl=GEMM_AUTO, save_grad=False, z=None, h=None):
     """(z, h): z = a @ wt^T + bias, h = gelu_tanh(z), both in a.dtype (one GEMM, two outputs).
     save_grad (bf16 tensor-core path): the first output is gelu_tanh'(z) instead of z (pair it with gemm_gelu_bwd(z_is_grad=True))."""

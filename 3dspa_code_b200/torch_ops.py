@@ -47,6 +47,7 @@ _lib.define("gemm_rmsnorm_out(Tensor a, Tensor wt, int Dh, int q_cols, int k_col
 _lib.define("gemm_gelu(Tensor a, Tensor wt, Tensor bias, int impl, bool save_grad) -> (Tensor, Tensor)")
 _lib.define("gemm_gelu_out(Tensor a, Tensor wt, Tensor bias, Tensor(a!) z, Tensor(b!) h, int impl, bool save_grad) -> ()")
 _lib.define("layernorm_fwd_out(Tensor x, Tensor scale, Tensor(a!) out, Tensor(b!)? mean, Tensor(c!)? rstd, int rows, int ldx, int d) -> ()")
+_lib.define("mlp_fused(Tensor a, Tensor w1t, Tensor b1, Tensor w2t, Tensor b2, Tensor residual) -> Tensor")
 _lib.define("gemm_gelu_bwd(Tensor dy, Tensor wt, Tensor z, int impl, bool z_is_grad, Tensor(a!)? dz_colsum) -> Tensor")
 _lib.define("gemm_dw(Tensor dy, Tensor x, Tensor(a!) dw, bool accumulate, int impl) -> ()")
 _lib.define("attention_fwd(Tensor q, Tensor k, Tensor v, Tensor(a!) out, int batch, int heads, int Lq, int Lk, int Dh, Tensor? key_mask,"
@@ -67,7 +68,7 @@ _lib.define("loss_fwd(Tensor head_out, Tensor target_tracks, Tensor target_vis, 
 _lib.define("loss_bwd(Tensor head_out, Tensor target_tracks, Tensor target_vis, float l1_w, float bce_w, float inv_denom, int T) -> Tensor")
 _lib.define("loss_sums(Tensor head_out, Tensor target_tracks, Tensor target_vis, int T) -> Tensor")
 
-REGISTERED = ["gemm", "gemm_out", "gemm_rmsnorm", "gemm_rmsnorm_out", "gemm_gelu", "gemm_gelu_out", "layernorm_fwd_out", "gemm_gelu_bwd", "gemm_dw", "attention_fwd", "attention", "attention_bwd",
+REGISTERED = ["mlp_fused", "gemm", "gemm_out", "gemm_rmsnorm", "gemm_rmsnorm_out", "gemm_gelu", "gemm_gelu_out", "layernorm_fwd_out", "gemm_gelu_bwd", "gemm_dw", "attention_fwd", "attention", "attention_bwd",
               "layernorm_fwd", "layernorm_bwd", "embed_fused_out", "embed_fused", "lift_sample", "loss_fwd", "loss_bwd", "loss_sums"]
 
 
@@ -101,6 +102,10 @@ def _gemm_gelu_out(a, wt, bias, z, h, impl, save_grad):
 def _layernorm_fwd_out(x, scale, out, mean, rstd, rows, ldx, d):
     _raw["layernorm_fwd"](x, scale, out.dtype, None if rows < 0 else rows, None if ldx < 0 else ldx, None if d < 0 else d, mean is not None, out,
                           mean, rstd)
+
+
+def _mlp_fused(a, w1t, b1, w2t, b2, residual):
+    return _raw["mlp_fused"](a, w1t, b1, w2t, b2, residual)
 
 
 def _gemm_gelu_bwd(dy, wt, z, impl, z_is_grad, dz_colsum):
@@ -211,6 +216,11 @@ def _(a, wt, bias, z, h, impl, save_grad):
 @register_fake("spa3d::layernorm_fwd_out")
 def _(x, scale, out, mean, rstd, rows, ldx, d):
     return None
+
+
+@register_fake("spa3d::mlp_fused")
+def _(a, w1t, b1, w2t, b2, residual):
+    return torch.empty_like(residual)
 
 
 @register_fake("spa3d::gemm_gelu")
@@ -484,7 +494,7 @@ def install(ns):
     """Capture the ctypes-level implementations of ops.py and rebind its public names to ``torch.ops.spa3d.*``."""
     for n in ("gemm", "gemm_rmsnorm", "gemm_gelu", "gemm_gelu_bwd", "gemm_dw", "attention_fwd", "attention_bwd", "layernorm_fwd",
               "layernorm_bwd", "embed_fused", "lift_sample", "loss_fwd", "loss_bwd", "colsum", "set_rows", "gelu_bwd", "head_rmsnorm_bwd",
-              "shadow_weights"):
+              "shadow_weights", "mlp_fused"):
         _raw[n] = ns[n]
     o = torch.ops.spa3d
 
@@ -518,6 +528,9 @@ def install(ns):
 
     def gemm_gelu_bwd(dy, wt, z, impl=0, z_is_grad=False, dz_colsum=None):
         return o.gemm_gelu_bwd(dy, wt, z, int(impl), bool(z_is_grad), dz_colsum)
+
+    def mlp_fused(a, w1t, b1, w2t, b2, residual):
+        return o.mlp_fused(a, w1t, b1, w2t, b2, residual)
 
     def gemm_dw(dy, x, dw, accumulate=True, impl=0):
         o.gemm_dw(dy, x, dw, bool(accumulate), int(impl))
@@ -570,7 +583,7 @@ def install(ns):
     def loss_bwd(head_out, target_tracks, target_vis, l1_w, bce_w, inv_denom, T):
         return o.loss_bwd(head_out, target_tracks, target_vis, float(l1_w), float(bce_w), float(inv_denom), int(T))
 
-    for fn in (gemm, gemm_rmsnorm, gemm_gelu, gemm_gelu_bwd, gemm_dw, attention_fwd, attention_bwd, layernorm_fwd, layernorm_bwd,
+    for fn in (mlp_fused, gemm, gemm_rmsnorm, gemm_gelu, gemm_gelu_bwd, gemm_dw, attention_fwd, attention_bwd, layernorm_fwd, layernorm_bwd,
                embed_fused, lift_sample, loss_fwd, loss_bwd):
         fn.__doc__ = (_raw[fn.__name__].__doc__ or "") + "\n    (dispatched through torch.ops.spa3d." + fn.__name__ + ")"
         ns[fn.__name__] = fn

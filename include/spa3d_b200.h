@@ -167,6 +167,17 @@ int spa3d_gemm_gelu_bwd(const void* dY, int64_t lddy, const void* Wt, int64_t ld
                         const void* Z, int64_t ldz, void* dZ, int64_t lddz, int64_t M, int N, int K,
                         int z_is_grad, float* dz_colsum, int impl, void* stream);
 
+/* Fused MLP sub-block, inference form (attention.py:102-108): out = residual + gelu_tanh(A . W1 + b1) . W2 + b2 in ONE kernel - the
+ * hidden activation [M, Hd] never reaches HBM (unfused it is written by MLP_in and re-read by MLP_out: 2 x M x Hd x 2 bytes).
+ * A [M, D] bf16 = LayerNorm(a) (lda); W1t [Hd, D] bf16 and W2t [D, Hd] bf16 are the Flax kernels transposed (K contiguous); b1 [Hd],
+ * b2 [D] f32; residual, out [M, D] f32.  D = 384 and Hd % 128 == 0 (spa3d_mlp_fused_applicable): 128 TMEM columns for a hidden
+ * chunk plus D columns for the output tile are all 512.  Measured no faster than the two GEMMs on the per-track shape (its weight
+ * ring is one L2 latency deep; see the kernel header), so the model does not use it by default. */
+int spa3d_mlp_fused_applicable(int D, int Hd);
+int spa3d_mlp_fused(const void* A, int64_t lda, const void* W1t, int64_t ldw1, const float* b1, const void* W2t, int64_t ldw2,
+                    const float* b2, const float* residual, int64_t ldr, float* out, int64_t ldo, int64_t M, int D, int Hd,
+                    void* stream);
+
 /* Weight gradient of a Dense layer (backward of attention.py:106-107,154-183 and
  * track_autoencoder_3d.py:73-115 under jax.value_and_grad, train.py:161-162):
  *   dW[N,K] (+)= dY[M,N]^T . X[M,K]     dY, X in `dtype` (row-major, lddy / ldx), dW f32 (lddw),

@@ -671,3 +671,30 @@ def test_gemm_bf16x3_accurate_mode(spa):
     rms = lambda t, s: t * torch.rsqrt((t * t).mean(-1, keepdim=True) + 1e-6) * s.double()
     ref = torch.stack([rms(z[:, 0], sq) / math.sqrt(Dh), rms(z[:, 1], sk), z[:, 2]], 1).reshape(M, 3 * A)
     assert rel_err(out, ref) < 3e-6 and rstd.shape == (M, 2 * H)
+
+
+@pytest.mark.parametrize("M,Hd", [(128, 128), (1000, 256), (4531, 1536), (128 * 150 + 77, 1536)])
+def test_mlp_fused_matches_unfused_and_fp64(spa, M, Hd):
+    """out = residual + gelu_tanh(a W1 + b1) W2 + b2 in one kernel (hidden activation never in HBM) against float64 of the same bf16
+    operands (with the hidden activation rounded to bf16, as both CUDA paths do) and against the two-GEMM path; ragged M."""
+    ops = spa.ops
+    torch.manual_seed(51)
+    D = 384
+    a = torch.randn(M, D, device="cuda").to(torch.bfloat16)
+    w1 = (torch.randn(Hd, D, device="cuda") / math.sqrt(D)).to(torch.bfloat16)
+    w2 = (torch.randn(D, Hd, device="cuda") / math.sqrt(Hd)).to(torch.bfloat16)
+    b1, b2 = torch.randn(Hd, device="cuda") * 0.3, torch.randn(D, device="cuda") * 0.3
+    res = torch.randn(M, D, device="cuda")
+    guard = torch.full((M + 2, D), 7.0, device="cuda")
+    out = guard[1 : M + 1]
+    ops._torch_ops._raw["mlp_fused"](a, w1, b1, w2, b2, res, out)
+    assert float(guard[0].min()) == 7.0 and float(guard[M + 1].min()) == 7.0        # neighbours untouched
+    z = a.double() @ w1.double().t() + b1.double()
+    h = (0.5 * z * (1 + torch.tanh(0.7978845608028654 * (z + 0.044715 * z ** 3)))).to(torch.bfloat16).double()
+    ref = h @ w2.double().t() + b2.double() + res.double()
+    assert rel_err(out, ref) < 4e-3, rel_err(out, ref)
+    hh = ops.gemm(a, w1, b1, act=ops.ACT_GELU)
+    two = ops.gemm(hh, w2, b2, residual=res, out_dtype=torch.float32)
+    assert rel_err(out, two) < 4e-3, rel_err(out, two)
+    y = ops.mlp_fused(a, w1, b1, w2, b2, res)                                            # through the dispatcher
+    assert torch.equal(y, out)

@@ -98,6 +98,40 @@ def main():
         rows.append(res_row)
         print(json.dumps(res_row), flush=True)
         del a, wt, res, out
+    if not args.only or "fused" in args.only:
+        # the fused MLP sub-block against MLP_in (GELU) + MLP_out (residual) as two kernels
+        M, D, Hd = Mi, 384, 1536
+        a = torch.randn(M, D, device=dev).to(torch.bfloat16)
+        w1 = (torch.randn(Hd, D, device=dev) / D ** 0.5).to(torch.bfloat16)
+        w2 = (torch.randn(D, Hd, device=dev) / Hd ** 0.5).to(torch.bfloat16)
+        b1, b2 = torch.randn(Hd, device=dev), torch.randn(D, device=dev)
+        res = torch.randn(M, D, device=dev)
+        out = torch.empty(M, D, device=dev)
+
+        def two():
+            h = ops.gemm(a, w1, b1, act=ops.ACT_GELU)
+            return ops.gemm(h, w2, b2, residual=res, out=out)
+
+        def fused():
+            return ops.mlp_fused(a, w1, b1, w2, b2, res)
+
+        row = {"name": "itt.mlp.fused", "M": M, "D": D, "Hd": Hd}
+        for label, fn in (("two_kernels", two), ("fused", fused)):
+            for _ in range(2):
+                fn()
+            ts = []
+            for _ in range(args.reps):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                fn()
+                e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+            ms = sorted(ts)[len(ts) // 2]
+            row[label + "_ms"] = round(ms, 4)
+            row[label + "_tflops"] = round(4.0 * M * D * Hd / ms / 1e9, 1)
+        print(json.dumps(row), flush=True)
     tot_o = sum(r["ours_ms"] for r in rows)
     tot_c = sum(r["cublas_ms"] for r in rows)
     print(json.dumps({"total_ours_ms": tot_o, "total_cublas_ms": tot_c}))
