@@ -448,17 +448,6 @@ def run_trajan_leg(spa, dev, cpu=True):
         return e0.elapsed_time(e1) / n, r
 
     ms_eager, _ = run(model)                 # ~190 launches of 5-500 us: sensitive to the host's launch rate
-    if os.environ.get("SPA3D_BENCH_PROFILE"):
-        import cProfile, pstats, io
-        pr = cProfile.Profile()
-        pr.enable()
-        for _ in range(5):
-            model.apply(variables, dev_inp, noise=dev_noise, precision="bf16")
-        torch.cuda.synchronize()
-        pr.disable()
-        st = io.StringIO()
-        pstats.Stats(pr, stream=st).sort_stats("tottime").print_stats(18)
-        sys.stderr.write("[profile] trajan eager %.2f ms\n%s\n" % (ms_eager, st.getvalue()))
     gm = spa.TrackAutoEncoder()
     gm.cuda_graph = True                     # like the headline leg: the forward replayed as one CUDA graph
     ms, res = run(gm)
