@@ -20,7 +20,7 @@ int attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                      cudaStream_t st);
 bool attention_bwd_tc_applicable(int dtype, int Lq, int Lk, int Dh, int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddo,
                                  int64_t lddq, int64_t lddk, int64_t lddv);
-int attention_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+int attention_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo, const void* d_o,
                      int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                      const uint8_t* key_mask, const float* stats, const float* delta, int64_t batch, int heads, int L,
                      int Dh, cudaStream_t st);
@@ -125,7 +125,7 @@ int spa3d_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   if (attention_bwd_tc_applicable(dtype, Lq, Lk, Dh, ldq, ldk, ldv, lddo, lddq, lddk, lddv)) {
     stat_add(ST_ATTN_TCGEN05);
     // delta is computed inside the kernel from P and dP
-    return attention_bwd_tc(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, lse, delta_ws,
+    return attention_bwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, lse, delta_ws,
                             batch, heads, Lq, Dh, (cudaStream_t)stream);
   }
   stat_add(ST_ATTN_SIMT);

@@ -13,9 +13,13 @@
 //
 //   warp 0      TMA loads (Q, K, V, dO as 32-channel x L-row boxes, 3-D maps)
 //   warp 1      MMA issuer
-//   warps 2..9  element-wise phases and epilogues: two warps per TMEM lane quarter, each owning
-//               half of the 32-key chunks (no row reductions are needed in the backward)
-//   warp 10     builds the key-bias operand of the next item (mask as a rank-1 MMA K-step)
+//   warps 2..   element-wise phases and epilogues: HW warps per TMEM lane quarter (4 for the two-tile self-attention shapes,
+//               2 otherwise), each owning a share of the 32-key chunks; the only cross-warp value is the row sum delta.
+//               These phases are latency-bound chains (tcgen05.ld -> ex2 / fma -> st.shared) that sit between dependent MMAs,
+//               so their length is set by the chunks ONE warp walks: 4 warps per quarter cut it from 3 chunks to 2.
+//   last warp   builds the key-bias operand of the next item (mask as a rank-1 MMA K-step)
+// Loads are released in two groups: V and dO are last read by the dP / dV products of the last query tile, so the next
+// item's V / dO stream in under the rest of the item (phase B, dQ / dK products, all epilogues); Q and K follow at the end.
 #include "tc_ptx.cuh"
 
 namespace spa3d {
@@ -23,8 +27,7 @@ namespace tb {
 
 using namespace tc;
 
-constexpr int THREADS = 352;
-constexpr int CW = 8;   // compute warps
+__host__ __device__ constexpr int threads_for(int hw) { return (3 + 4 * hw) * 32; }
 
 __device__ __forceinline__ uint64_t desc_k64(uint32_t addr) {
   uint64_t d = 0;
@@ -90,8 +93,8 @@ struct CrossBwdArgs {
   float* part_dq;   // [items][128][DH]
 };
 
-template <int DH, int LPAD, int MT, bool CROSS = false>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int DH, int LPAD, int MT, bool CROSS = false, int HW = 2>
+__global__ void __launch_bounds__(threads_for(HW), 1)
 attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ mask, const float* __restrict__ stats,
                    const float* __restrict__ delta, int64_t items, int heads, int L, CrossBwdArgs cx) {
   static_assert(!CROSS || (MT == 1 && LPAD == 128), "cross-attention items are 128 queries x 128 keys");
@@ -99,6 +102,8 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
   auto item_h = [&](int64_t it) -> int { return CROSS ? (int)((it / cx.nchunks) % heads) : (int)(it % heads); };
   auto item_k0 = [&](int64_t it) -> int { return CROSS ? (int)(it % cx.nchunks) * 128 : 0; };
   const int Lkeys = CROSS ? cx.Lk : L;
+  constexpr int THREADS = threads_for(HW);
+  constexpr int CW = 4 * HW;             // compute warps
   constexpr int DA = DH / 32;            // 32-channel atoms per row
   constexpr int KA = LPAD / 32;          // 32-key atoms per P / dS row
   constexpr int OPA = LPAD * 64;         // bytes of one 32-channel atom region of Q / K / V / dO
@@ -117,10 +122,11 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
   uint8_t* sE = sD + PT_BYTES;             // ones operand [MT*128][32 B]
   uint8_t* sB = sE + MT * 128 * 32;        // [2][LPAD][32 B] key bias operand
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * LPAD * 32);
-  uint64_t* ld_full = bars, *ld_empty = bars + 1, *s_full = bars + 2, *p_done = bars + 3, *dp_full = bars + 4;
+  uint64_t* qk_full = bars, *qk_empty = bars + 1, *s_full = bars + 2, *p_done = bars + 3, *dp_full = bars + 4;
   uint64_t* ds_done = bars + 5, *dq_full = bars + 6, *dq_read = bars + 7, *m_full = bars + 8, *m_empty = bars + 10;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
-  float* dpart = reinterpret_cast<float*>(bars + 16);   // [2 halves][128 rows] partial row sums of P o dP
+  uint64_t* vg_full = bars + 12, *vg_empty = bars + 13;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+  float* dpart = reinterpret_cast<float*>(bars + 16);   // [HW parts][128 rows] partial row sums of P o dP
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -128,7 +134,8 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.k)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.v)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.g)) : "memory");
-    mbar_init(ld_full, 1); mbar_init(ld_empty, 1); mbar_init(s_full, 1); mbar_init(p_done, CW * 32);
+    mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(vg_full, 1); mbar_init(vg_empty, 1);
+    mbar_init(s_full, 1); mbar_init(p_done, CW * 32);
     mbar_init(dp_full, 1); mbar_init(ds_done, CW * 32); mbar_init(dq_full, 1); mbar_init(dq_read, CW * 32);
     mbar_init(&m_full[0], 1); mbar_init(&m_full[1], 1); mbar_init(&m_empty[0], 1); mbar_init(&m_empty[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -151,17 +158,33 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
   if (warp == 0) {
     // ===================== TMA loads =====================
     if (lane == 0) {
+      // V / dO of an item are released before its Q / K, so per item the wait order is (V, dO) then (Q, K)
       uint32_t ph = 0;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
         const int b = item_b(it), h = item_h(it), k0 = item_k0(it);
-        mbar_wait(ld_empty, ph ^ 1);
-        mbar_arrive_expect_tx(ld_full, (uint32_t)(4 * OP_BYTES));
+        if (it == (int64_t)blockIdx.x) {   // first item: Q / K first, the S product needs them first
+          mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * OP_BYTES));
+#pragma unroll
+          for (int a = 0; a < DA; ++a) {
+            tma_load_3d(sQ + a * OPA, &tm.q, h * DH + a * 32, 0, b, qk_full);
+            tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, k0, b, qk_full);
+          }
+        }
+        mbar_wait(vg_empty, ph ^ 1);
+        mbar_arrive_expect_tx(vg_full, (uint32_t)(2 * OP_BYTES));
 #pragma unroll
         for (int a = 0; a < DA; ++a) {
-          tma_load_3d(sQ + a * OPA, &tm.q, h * DH + a * 32, 0, b, ld_full);
-          tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, k0, b, ld_full);
-          tma_load_3d(sG + a * OPA, &tm.g, h * DH + a * 32, 0, b, ld_full);
-          tma_load_3d(sV + a * OPA, &tm.v, h * DH + a * 32, k0, b, ld_full);
+          tma_load_3d(sG + a * OPA, &tm.g, h * DH + a * 32, 0, b, vg_full);
+          tma_load_3d(sV + a * OPA, &tm.v, h * DH + a * 32, k0, b, vg_full);
+        }
+        if (it != (int64_t)blockIdx.x) {
+          mbar_wait(qk_empty, ph ^ 1);
+          mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * OP_BYTES));
+#pragma unroll
+          for (int a = 0; a < DA; ++a) {
+            tma_load_3d(sQ + a * OPA, &tm.q, h * DH + a * 32, 0, b, qk_full);
+            tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, k0, b, qk_full);
+          }
         }
       }
     }
@@ -173,7 +196,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
       int n = 0, tcount = 0;   // tcount = query tiles processed so far (phase of the per-tile barriers)
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1, ++n) {
         const int mb = n & 1;
-        mbar_wait(ld_full, ph);
+        mbar_wait(qk_full, ph);
         mbar_wait(&m_full[mb], (n >> 1) & 1);
 #pragma unroll 1
         for (int t = 0; t < MT; ++t, ++tcount) {
@@ -190,6 +213,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
           umma_commit(s_full);
           if (t == MT - 1) umma_commit(&m_empty[mb]);
           // dP_t = dO_t V^T (same columns, once the threads have turned S into P)
+          if (t == 0) mbar_wait(vg_full, ph);
           mbar_wait(p_done, tp);
           tcgen05_fence_after();
 #pragma unroll
@@ -197,23 +221,24 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
             umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sG + (kk >> 1) * OPA + t * (128 * 64) + (kk & 1) * 32)),
                       desc_k64(smem_u32(sV + (kk >> 1) * OPA + (kk & 1) * 32)), idS, kk > 0 ? 1u : 0u);
           umma_commit(dp_full);
-          // dQ_t = dS_t K ;  dV^T += dO_t^T P_t ;  dK^T += Q_t^T dS_t
+          // dV^T += dO_t^T P_t needs only P: it runs under phase B, and after the last tile V and dO are free
+          for (int j = 0; j < qk; ++j)
+            umma_bf16(tmem_base + C_DV, desc_mn64(smem_u32(sG + (t * 128 + j * 16) * 64), OPA),
+                      desc_mn64(smem_u32(sP + j * 1024), 128 * 64), idT, (t > 0 || j > 0) ? 1u : 0u);
+          if (t == MT - 1) umma_commit(vg_empty);
+          // dQ_t = dS_t K ;  dK^T += Q_t^T dS_t
           mbar_wait(ds_done, tp);
           tcgen05_fence_after();
 #pragma unroll
           for (int ks = 0; ks < LPAD / 16; ++ks)
             umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sD + (ks >> 1) * (128 * 64) + (ks & 1) * 32)),
                       desc_mn64(smem_u32(sK + ks * 1024), OPA), idQ, ks > 0 ? 1u : 0u);
-          for (int j = 0; j < qk; ++j) {
-            const uint32_t acc = (t > 0 || j > 0) ? 1u : 0u;
-            umma_bf16(tmem_base + C_DV, desc_mn64(smem_u32(sG + (t * 128 + j * 16) * 64), OPA),
-                      desc_mn64(smem_u32(sP + j * 1024), 128 * 64), idT, acc);
+          for (int j = 0; j < qk; ++j)
             umma_bf16(tmem_base + C_DK, desc_mn64(smem_u32(sQ + (t * 128 + j * 16) * 64), OPA),
-                      desc_mn64(smem_u32(sD + j * 1024), 128 * 64), idT, acc);
-          }
+                      desc_mn64(smem_u32(sD + j * 1024), 128 * 64), idT, (t > 0 || j > 0) ? 1u : 0u);
           umma_commit(dq_full);
         }
-        umma_commit(ld_empty);
+        umma_commit(qk_empty);
       }
     }
   } else if (warp == 2 + CW) {
@@ -241,8 +266,8 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
     // ===================== element-wise phases + epilogues =====================
     const int cw = warp - 2;
     const int quarter = warp & 3;          // TMEM lane quarter
-    const int half = cw >> 2;              // which half of the key chunks / output chunks
-    const int c_lo = half == 0 ? 0 : (KA + 1) / 2, c_hi = half == 0 ? (KA + 1) / 2 : KA;
+    const int part = cw >> 2;              // which share of the key chunks / output chunks
+    const int c_lo = part * KA / HW, c_hi = (part + 1) * KA / HW;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int rloc = quarter * 32 + lane;  // row inside the 128-row tile
     const int sw64 = (lane >> 1) & 3;
@@ -311,7 +336,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
           if constexpr (CROSS) {
             dl = row < L ? delta[sbase + row] : 0.f;   // over all keys of the row, not only this chunk's
           } else {
-            float part = 0.f;
+            float psum = 0.f;
 #pragma unroll 1
             for (int c = c_lo; c < c_hi; ++c) {
               uint32_t r[32];
@@ -325,13 +350,15 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
-                part = fmaf(__low2float(pb), __uint_as_float(r[2 * i]), part);
-                part = fmaf(__high2float(pb), __uint_as_float(r[2 * i + 1]), part);
+                psum = fmaf(__low2float(pb), __uint_as_float(r[2 * i]), psum);
+                psum = fmaf(__high2float(pb), __uint_as_float(r[2 * i + 1]), psum);
               }
             }
-            dpart[half * 128 + rloc] = part;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-            dl = part + dpart[(half ^ 1) * 128 + rloc];
+            dpart[part * 128 + rloc] = psum;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(HW * 32) : "memory");
+            dl = 0.f;
+#pragma unroll
+            for (int hp = 0; hp < HW; ++hp) dl += dpart[hp * 128 + rloc];   // same order in every warp of the quarter
           }
 #pragma unroll 1
           for (int c = c_lo; c < c_hi; ++c) {
@@ -358,7 +385,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
           }
-          if constexpr (!CROSS) asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // dpart is rewritten for the next tile
+          if constexpr (!CROSS) asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(HW * 32) : "memory");   // dpart is rewritten for the next tile
         }
         tcgen05_fence_before();
         fence_proxy_async_smem();
@@ -368,7 +395,7 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
         tcgen05_fence_after();
         int sb = 0;
         if (tile_live) {
-          const int o_lo = half == 0 ? 0 : (DA + 1) / 2, o_hi = half == 0 ? (DA + 1) / 2 : DA;
+          const int o_lo = part * DA / HW, o_hi = (part + 1) * DA / HW;
           for (int c = o_lo; c < o_hi; ++c) {
             uint32_t r[32];
             tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c * 32), r);
@@ -403,12 +430,13 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
           }
         }
         if (t == MT - 1 && quarter * 32 < DH) {
-          // transposed accumulators: lane = head channel quarter*32 + lane, column = key.
-          // half 0 stores dV, half 1 stores dK; each 32-key chunk goes out as a [32 keys][32 channels] box.
-          const uint32_t cbase = half == 0 ? C_DV : C_DK;
-          const CUtensorMap* omap = half == 0 ? &tm.dv : &tm.dk;
-          for (int c = 0; c < KA; ++c) {
-            if (k0 + c * 32 >= Lkeys) break;
+          // transposed accumulators: lane = head channel quarter*32 + lane, column = key.  The 2 * KA units (dV chunks, then
+          // dK chunks) are shared out over the HW warps of the quarter; each 32-key chunk goes out as a [32 keys][32 channels] box.
+          for (int u = part * 2 * KA / HW; u < (part + 1) * 2 * KA / HW; ++u) {
+            const int c = u < KA ? u : u - KA;
+            const uint32_t cbase = u < KA ? C_DV : C_DK;
+            const CUtensorMap* omap = u < KA ? &tm.dv : &tm.dk;
+            if (k0 + c * 32 >= Lkeys) continue;
             uint32_t r[32];
             tmem_ld32(tmem_base + lane_off + cbase + (uint32_t)(c * 32), r);
             tmem_ld_wait();
@@ -445,6 +473,561 @@ attn_bwd_tc_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 128 < L <= 152 (the track transformers: L = 151 and L = 129): "transposed tail".
+//
+// tcgen05.ld moves 16 B per clock per TMEM lane quarter whatever the number of useful lanes, so in the two-tile kernel above
+// the 23-row (or 1-row) second query tile costs as many TMEM read clocks as the full first tile (all of its 160 key columns are
+// read through lane quarter 0), and its S -> P -> dP -> dS -> dQ chain runs after the first tile's chain.  Here the tail queries
+// sit on the N (column) side instead: S^T = K Q_tail^T is [keys x 24 queries], two M tiles (keys 0..127, keys 128..159) of 24
+// columns each, as are dP^T = V dO_tail^T and dQ_tail^T = K^T dS_tail^T [channels x 24].  The tail then costs 24-column reads,
+// has its own TMEM columns (so its chain runs inside the waits of the main tile's chain), and its P^T / dS^T tile
+// ([key][query], 10 KB) feeds the transposed dV^T / dK^T accumulators as a K-major B operand.
+//   TMEM columns: [0,160) S / dP / dQ of the main tile, [160,312) dV^T, [312,464) dK^T (152 key columns), [464,512) the tail.
+//   The softmax denominators and delta of the tail rows are per COLUMN here; the key-bias warp stages them in shared memory one
+//   item ahead (delta_j = sum_d O_jd dO_jd from global memory: 24 rows x DH channels).
+//   dS overwrites P in place (after the dV^T product has read P); the freed 40 KB hold the tail tile and per-warp store staging.
+struct TailArgs {
+  const bf16* o;
+  int64_t ldo;
+  const bf16* d_o;
+  int64_t lddo;
+};
+
+constexpr int TT_THREADS = threads_for(4);
+constexpr int NT = 24;    // tail query columns (L - 128 <= 24)
+constexpr int NV = 152;   // key columns of the dV^T / dK^T accumulators
+
+template <int DH>
+constexpr int tt_smem_bytes() {
+  return 4 * (DH / 32) * 160 * 64 + 5 * 128 * 64 + 16 * 2048 + 160 * 64 + 128 * 32 + 2 * 160 * 32 + 640 + 2048 + 256 + 1024;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(TT_THREADS, 1)
+attn_bwd_tt_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ mask, const float* __restrict__ stats, TailArgs ta,
+                   int64_t items, int heads, int L) {
+  constexpr int LPAD = 160, DA = DH / 32, KA = 5, HW = 4, CW = 16;
+  constexpr int OPA = LPAD * 64, OP_BYTES = DA * OPA, PT_BYTES = KA * 128 * 64;
+  constexpr int C_S = 0, C_DV = 160, C_DK = 312, C_T = 464;
+  static_assert(C_T + 2 * NT == 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + OP_BYTES;
+  uint8_t* sV = sK + OP_BYTES;
+  uint8_t* sG = sV + OP_BYTES;             // dO
+  uint8_t* sP = sG + OP_BYTES;             // P, then dS, of the main query tile [query][key]
+  uint8_t* sX = sP + PT_BYTES;             // 16 x 2 KB store staging, one per element-wise warp
+  uint8_t* sT = sX + 16 * 2048;            // P^T, then dS^T, of the tail [key][query], 64 B rows
+  uint8_t* sE = sT + 160 * 64;             // ones operand [128][32 B]
+  uint8_t* sB = sE + 128 * 32;             // [2][160][32 B] key bias operand
+  float* side = reinterpret_cast<float*>(sB + 2 * LPAD * 32);   // [2][3][NT]: row maximum, 1 / denominator, delta of the tail rows
+  float* dpart = side + 160;               // [4][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dpart + 4 * 128);
+  uint64_t* qk_full = bars, *qk_empty = bars + 1, *vg_full = bars + 2, *vg_empty = bars + 3, *m_full = bars + 4, *m_empty = bars + 6;
+  uint64_t* s_full = bars + 8, *st_full = bars + 9, *p_done = bars + 10, *pt_done = bars + 11, *dp_full = bars + 12, *dv_done = bars + 13;
+  uint64_t* dpt_full = bars + 14, *dvt_done = bars + 15, *ds_done = bars + 16, *dst_done = bars + 17, *dq_full = bars + 18;
+  uint64_t* fin_full = bars + 19, *c_free = bars + 20, *t_free = bars + 21, *acc_free = bars + 22;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.k)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.v)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.g)) : "memory");
+    mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(vg_full, 1); mbar_init(vg_empty, 1);
+    mbar_init(&m_full[0], 1); mbar_init(&m_full[1], 1); mbar_init(&m_empty[0], 1); mbar_init(&m_empty[1], 1);
+    mbar_init(s_full, 1); mbar_init(st_full, 1); mbar_init(p_done, CW); mbar_init(pt_done, 5); mbar_init(dp_full, 1);
+    mbar_init(dv_done, 1); mbar_init(dpt_full, 1); mbar_init(dvt_done, 1); mbar_init(ds_done, CW); mbar_init(dst_done, 5);
+    mbar_init(dq_full, 1); mbar_init(fin_full, 1); mbar_init(c_free, CW); mbar_init(t_free, DA); mbar_init(acc_free, 4 * DA);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int r = threadIdx.x; r < 128; r += TT_THREADS) {   // ones operand: element 0 of every row = 1.0
+    const int pc = (r >> 2) & 1;
+    *reinterpret_cast<uint4*>(sE + r * 32 + pc * 16) = make_uint4(0x3F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sE + r * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA loads: (Q, K) and (V, dO) are released separately =====================
+    if (lane == 0) {
+      uint32_t ph = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
+        const int b = (int)(it / heads), h = (int)(it % heads);
+        if (it == (int64_t)blockIdx.x) {
+          mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * OP_BYTES));
+#pragma unroll
+          for (int a = 0; a < DA; ++a) {
+            tma_load_3d(sQ + a * OPA, &tm.q, h * DH + a * 32, 0, b, qk_full);
+            tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, 0, b, qk_full);
+          }
+        }
+        mbar_wait(vg_empty, ph ^ 1);
+        mbar_arrive_expect_tx(vg_full, (uint32_t)(2 * OP_BYTES));
+#pragma unroll
+        for (int a = 0; a < DA; ++a) {
+          tma_load_3d(sG + a * OPA, &tm.g, h * DH + a * 32, 0, b, vg_full);
+          tma_load_3d(sV + a * OPA, &tm.v, h * DH + a * 32, 0, b, vg_full);
+        }
+        if (it != (int64_t)blockIdx.x) {   // V / dO of an item are released before its Q / K: this is the order the buffers free up
+          mbar_wait(qk_empty, ph ^ 1);
+          mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * OP_BYTES));
+#pragma unroll
+          for (int a = 0; a < DA; ++a) {
+            tma_load_3d(sQ + a * OPA, &tm.q, h * DH + a * 32, 0, b, qk_full);
+            tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, 0, b, qk_full);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idS = idesc(LPAD, false, false), idQ = idesc(DH, false, true), idV = idesc(NV, true, true);
+      constexpr uint32_t idTs = idesc(NT, false, false), idTq = idesc(NT, true, true), idTv = idesc(NV, true, false);
+      int n = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const uint32_t ph = n & 1;
+        const int mb = n & 1;
+        const uint8_t* bias = sB + mb * (LPAD * 32);
+        mbar_wait(qk_full, ph);
+        mbar_wait(&m_full[mb], (n >> 1) & 1);
+        // S = Q K^T + ones x bias (main tile: queries 0..127)
+        mbar_wait(c_free, ph ^ 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sQ + (kk >> 1) * OPA + (kk & 1) * 32)),
+                    desc_k64(smem_u32(sK + (kk >> 1) * OPA + (kk & 1) * 32)), idS, kk > 0 ? 1u : 0u);
+        umma_bf16(tmem_base + C_S, desc_k32(smem_u32(sE)), desc_k32(smem_u32(bias)), idS, 1u);
+        umma_commit(s_full);
+        // tail: S^T = K Q_tail^T + bias x ones, key tiles 0..127 and 128..159
+        mbar_wait(t_free, ph ^ 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16(tmem_base + C_T + kt * NT, desc_k64(smem_u32(sK + (kk >> 1) * OPA + kt * (128 * 64) + (kk & 1) * 32)),
+                      desc_k64(smem_u32(sQ + (kk >> 1) * OPA + 128 * 64 + (kk & 1) * 32)), idTs, kk > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + C_T + kt * NT, desc_k32(smem_u32(bias + kt * (128 * 32))), desc_k32(smem_u32(sE)), idTs, 1u);
+        }
+        umma_commit(st_full);
+        // dP = dO V^T ; dV^T = dO^T P (main tile)
+        mbar_wait(vg_full, ph);
+        mbar_wait(p_done, ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sG + (kk >> 1) * OPA + (kk & 1) * 32)),
+                    desc_k64(smem_u32(sV + (kk >> 1) * OPA + (kk & 1) * 32)), idS, kk > 0 ? 1u : 0u);
+        umma_commit(dp_full);
+        mbar_wait(acc_free, ph ^ 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16(tmem_base + C_DV, desc_mn64(smem_u32(sG + (j * 16) * 64), OPA), desc_mn64(smem_u32(sP + j * 1024), 128 * 64), idV,
+                    j > 0 ? 1u : 0u);
+        umma_commit(dv_done);   // P may now be overwritten by dS
+        // tail: dP^T = V dO_tail^T ; dV^T += dO_tail^T P_tail
+        mbar_wait(pt_done, ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16(tmem_base + C_T + kt * NT, desc_k64(smem_u32(sV + (kk >> 1) * OPA + kt * (128 * 64) + (kk & 1) * 32)),
+                      desc_k64(smem_u32(sG + (kk >> 1) * OPA + 128 * 64 + (kk & 1) * 32)), idTs, kk > 0 ? 1u : 0u);
+        umma_commit(dpt_full);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          umma_bf16(tmem_base + C_DV, desc_mn64(smem_u32(sG + (128 + ks * 16) * 64), OPA), desc_k64(smem_u32(sT + ks * 32)), idTv, 1u);
+        umma_commit(dvt_done);  // P^T may now be overwritten by dS^T
+        umma_commit(vg_empty);  // V and dO are free
+        // dQ = dS K ; dK^T = Q^T dS (main tile)
+        mbar_wait(ds_done, ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < LPAD / 16; ++ks)
+          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sP + (ks >> 1) * (128 * 64) + (ks & 1) * 32)),
+                    desc_mn64(smem_u32(sK + ks * 1024), OPA), idQ, ks > 0 ? 1u : 0u);
+        umma_commit(dq_full);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16(tmem_base + C_DK, desc_mn64(smem_u32(sQ + (j * 16) * 64), OPA), desc_mn64(smem_u32(sP + j * 1024), 128 * 64), idV,
+                    j > 0 ? 1u : 0u);
+        // tail: dQ_tail^T = K^T dS_tail^T ; dK^T += Q_tail^T dS_tail
+        mbar_wait(dst_done, ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < LPAD / 16; ++ks)
+          umma_bf16(tmem_base + C_T, desc_mn64(smem_u32(sK + ks * 1024), OPA), desc_mn64(smem_u32(sT + ks * 1024), 1024), idTq,
+                    ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          umma_bf16(tmem_base + C_DK, desc_mn64(smem_u32(sQ + (128 + ks * 16) * 64), OPA), desc_k64(smem_u32(sT + ks * 32)), idTv, 1u);
+        umma_commit(fin_full);
+        umma_commit(qk_empty);
+        umma_commit(&m_empty[mb]);
+      }
+    }
+  } else if (warp == 2 + CW) {
+    // ===================== per-item side data, one item ahead: key bias operand, tail row statistics and delta =====================
+    const uint32_t NEG_BIG = 0xF14Au, NEG_INF = 0xFF80u;   // bf16(-1e30), bf16(-inf)
+    int n = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int b = (int)(it / heads), h = (int)(it % heads);
+      const int mb = n & 1;
+      uint8_t mk[KA];
+#pragma unroll
+      for (int jj = 0; jj < KA; ++jj) {
+        const int j = jj * 32 + lane;
+        mk[jj] = (mask != nullptr && j < L) ? mask[(int64_t)b * L + j] : (uint8_t)1;
+      }
+      float tm_ = 0.f, til = 0.f, tdl = 0.f;
+      const int trow = 128 + lane;
+      if (lane < NT && trow < L) {
+        const float2 st2 = *reinterpret_cast<const float2*>(stats + (((int64_t)b * heads + h) * L + trow) * 2);
+        tm_ = st2.x;
+        til = st2.y;
+        const uint4* po = reinterpret_cast<const uint4*>(ta.o + ((int64_t)b * L + trow) * ta.ldo + h * DH);
+        const uint4* pg = reinterpret_cast<const uint4*>(ta.d_o + ((int64_t)b * L + trow) * ta.lddo + h * DH);
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+          const uint4 a = po[c], g = pg[c];
+          const uint32_t au[4] = {a.x, a.y, a.z, a.w}, gu[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 ab = *reinterpret_cast<const __nv_bfloat162*>(&au[e]);
+            const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&gu[e]);
+            tdl = fmaf(__low2float(ab), __low2float(gb), tdl);
+            tdl = fmaf(__high2float(ab), __high2float(gb), tdl);
+          }
+        }
+      }
+      if (lane == 0) mbar_wait(&m_empty[mb], ((n >> 1) & 1) ^ 1);
+      __syncwarp();
+      uint8_t* dstb = sB + mb * (LPAD * 32);
+#pragma unroll
+      for (int jj = 0; jj < KA; ++jj) {
+        const int j = jj * 32 + lane;
+        uint32_t val = NEG_INF;
+        if (j < L) val = mk[jj] != 0 ? 0u : NEG_BIG;
+        const int pc = (j >> 2) & 1;
+        *reinterpret_cast<uint4*>(dstb + j * 32 + pc * 16) = make_uint4(val, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dstb + j * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (lane < NT) {
+        float* sd = side + mb * (3 * NT);
+        sd[lane] = tm_;
+        sd[NT + lane] = til;
+        sd[2 * NT + lane] = tdl;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&m_full[mb]);
+    }
+  } else {
+    // ===================== element-wise phases + epilogues =====================
+    const int cw = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter
+    const int part = cw >> 2;              // share of the main tile's key chunks: 1, 1, 1, 2
+    const int c_lo = part * KA / HW, c_hi = (part + 1) * KA / HW;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int rloc = quarter * 32 + lane;  // query row of the main tile
+    const int sw64 = (lane >> 1) & 3;
+    uint8_t* pRow = sP + rloc * 64;
+    // the tail's [key x query] tiles: part 0 owns keys quarter*32 + lane, (part 1, quarter 0) keys 128 + lane
+    const bool tail_warp = part == 0 || (part == 1 && quarter == 0);
+    const int tkey = part == 0 ? rloc : 128 + lane;
+    const uint32_t tcol = (uint32_t)(C_T + (part == 0 ? 0 : NT));
+    uint8_t* tRow = sT + tkey * 64;
+    // store staging: this warp's own 2 KB slab and its own block of the P tile (32 rows x 64 B of chunk c_lo)
+    uint8_t* const stage0 = sX + cw * 2048;
+    uint8_t* const stage1 = sP + c_lo * (128 * 64) + quarter * 2048;
+    constexpr float LOG2E = 1.4426950408889634f;
+    int n = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int b = (int)(it / heads), h = (int)(it % heads);
+      const uint32_t ph = n & 1;
+      const float* sd = side + (n & 1) * (3 * NT);
+      const float2 st2 = *reinterpret_cast<const float2*>(stats + (((int64_t)b * heads + h) * L + rloc) * 2);
+      const float m = st2.x, il = st2.y;
+      const bool row_grad = m > -1e29f;    // a fully masked row: its logits are constants, dS = 0
+      // ---- phase A: P = exp(S - m) / l -> bf16, [query][key] tile ----
+      mbar_wait(s_full, ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c * 32), r);
+        tmem_ld_wait();
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_fast((__uint_as_float(r[2 * i]) - m) * LOG2E) * il;
+          const float p1 = ex2_fast((__uint_as_float(r[2 * i + 1]) - m) * LOG2E) * il;
+          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+          w[i] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        uint8_t* dst = pRow + c * (128 * 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_done);
+      // ---- tail phase A: P^T[key][j] = exp(S^T - m_j) / l_j ----
+      uint32_t tp[NT / 2];   // this key's P^T row, bf16 pairs (kept for phase B)
+      if (tail_warp) {
+        mbar_wait(st_full, ph);
+        tcgen05_fence_after();
+        uint32_t r[NT];
+        tmem_ld8(tmem_base + lane_off + tcol, r);
+        tmem_ld8(tmem_base + lane_off + tcol + 8, r + 8);
+        tmem_ld8(tmem_base + lane_off + tcol + 16, r + 16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < NT / 2; ++i) {
+          const float p0 = ex2_fast((__uint_as_float(r[2 * i]) - sd[2 * i]) * LOG2E) * sd[NT + 2 * i];
+          const float p1 = ex2_fast((__uint_as_float(r[2 * i + 1]) - sd[2 * i + 1]) * LOG2E) * sd[NT + 2 * i + 1];
+          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+          tp[i] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          *reinterpret_cast<uint4*>(tRow + ((j ^ sw64) << 4)) = make_uint4(tp[4 * j], tp[4 * j + 1], tp[4 * j + 2], tp[4 * j + 3]);
+        *reinterpret_cast<uint4*>(tRow + ((3 ^ sw64) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // query columns 24..31 of the K = 32 steps
+        tcgen05_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pt_done);
+      }
+      // ---- phase B: dS = P o (dP - delta), written over P ----
+      mbar_wait(dp_full, ph);
+      tcgen05_fence_after();
+      {
+        // delta_i = sum_j P_ij dP_ij over all keys: the four warps of the lane quarter add their shares through shared memory.
+        // dP of the first chunk stays in registers (each TMEM column costs read bandwidth once)
+        uint32_t r0[32];
+        float psum = 0.f;
+        tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c_lo * 32), r0);
+        {
+          const uint8_t* src = pRow + c_lo * (128 * 64);
+          uint4 pw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pw[j] = *reinterpret_cast<const uint4*>(src + ((j ^ sw64) << 4));
+          tmem_ld_wait();
+          const uint32_t* pwu = reinterpret_cast<const uint32_t*>(pw);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
+            psum = fmaf(__low2float(pb), __uint_as_float(r0[2 * i]), psum);
+            psum = fmaf(__high2float(pb), __uint_as_float(r0[2 * i + 1]), psum);
+          }
+        }
+        if (c_hi - c_lo == 2) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + (c_lo + 1) * 32), r);
+          const uint8_t* src = pRow + (c_lo + 1) * (128 * 64);
+          uint4 pw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pw[j] = *reinterpret_cast<const uint4*>(src + ((j ^ sw64) << 4));
+          tmem_ld_wait();
+          const uint32_t* pwu = reinterpret_cast<const uint32_t*>(pw);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
+            psum = fmaf(__low2float(pb), __uint_as_float(r[2 * i]), psum);
+            psum = fmaf(__high2float(pb), __uint_as_float(r[2 * i + 1]), psum);
+          }
+        }
+        dpart[part * 128 + rloc] = psum;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+        float dl = 0.f;
+#pragma unroll
+        for (int hp = 0; hp < HW; ++hp) dl += dpart[hp * 128 + rloc];   // same order in every warp of the quarter
+        mbar_wait(dv_done, ph);   // dV^T = dO^T P has read the P tile
+        auto emit = [&](int c, const uint32_t (&rr)[32]) {
+          uint8_t* src = pRow + c * (128 * 64);
+          uint4 pw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pw[j] = *reinterpret_cast<const uint4*>(src + ((j ^ sw64) << 4));
+          const uint32_t* pwu = reinterpret_cast<const uint32_t*>(pw);
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
+            float d0 = __low2float(pb) * (__uint_as_float(rr[2 * i]) - dl);
+            float d1 = __high2float(pb) * (__uint_as_float(rr[2 * i + 1]) - dl);
+            if (!row_grad) d0 = d1 = 0.f;
+            __nv_bfloat162 hb = __floats2bfloat162_rn(d0, d1);
+            w[i] = *reinterpret_cast<uint32_t*>(&hb);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(src + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        };
+        emit(c_lo, r0);
+        if (c_hi - c_lo == 2) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + (c_lo + 1) * 32), r);
+          tmem_ld_wait();
+          emit(c_lo + 1, r);
+        }
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_done);
+      // ---- tail phase B: dS^T[key][j] = P^T o (dP^T - delta_j), written over P^T ----
+      if (tail_warp) {
+        mbar_wait(dpt_full, ph);
+        tcgen05_fence_after();
+        uint32_t r[NT];
+        tmem_ld8(tmem_base + lane_off + tcol, r);
+        tmem_ld8(tmem_base + lane_off + tcol + 8, r + 8);
+        tmem_ld8(tmem_base + lane_off + tcol + 16, r + 16);
+        tmem_ld_wait();
+        uint32_t w[NT / 2];
+#pragma unroll
+        for (int i = 0; i < NT / 2; ++i) {
+          const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&tp[i]);
+          float d0 = __low2float(pb) * (__uint_as_float(r[2 * i]) - sd[2 * NT + 2 * i]);
+          float d1 = __high2float(pb) * (__uint_as_float(r[2 * i + 1]) - sd[2 * NT + 2 * i + 1]);
+          if (!(sd[2 * i] > -1e29f)) d0 = 0.f;
+          if (!(sd[2 * i + 1] > -1e29f)) d1 = 0.f;
+          __nv_bfloat162 hb = __floats2bfloat162_rn(d0, d1);
+          w[i] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        mbar_wait(dvt_done, ph);   // dV^T += dO_tail^T P_tail has read the P^T tile
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          *reinterpret_cast<uint4*>(tRow + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        tcgen05_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dst_done);
+      }
+      // ---- dQ epilogue of the main tile: parts 1.. take one 32-channel atom each ----
+      int sb = 0;
+      mbar_wait(dq_full, ph);
+      tcgen05_fence_after();
+      if (part >= 1 && part - 1 < DA) {
+        const int c = part - 1;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c * 32), r);
+        tmem_ld_wait();
+        uint8_t* dst = stage0 + lane * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1]));
+            w[e] = *reinterpret_cast<uint32_t*>(&hb);
+          }
+          *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tm.dq, stage0, h * DH + c * 32, quarter * 32, b);
+          bulk_commit();
+        }
+        sb = 1;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c_free);
+      // ---- after the item's last product: dQ_tail^T, dV^T, dK^T (lane = head channel, column = query / key) ----
+      mbar_wait(fin_full, ph);
+      tcgen05_fence_after();
+      if (quarter * 32 < DH) {
+        if (part == 0) {
+          uint32_t r[NT];
+          tmem_ld8(tmem_base + lane_off + (uint32_t)C_T, r);
+          tmem_ld8(tmem_base + lane_off + (uint32_t)C_T + 8, r + 8);
+          tmem_ld8(tmem_base + lane_off + (uint32_t)C_T + 16, r + 16);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(t_free);
+            bulk_wait_read<1>();
+          }
+          __syncwarp();
+          uint8_t* dst = sb ? stage1 : stage0;
+#pragma unroll
+          for (int i = 0; i < NT; ++i) {   // query 128 + i = row i of the box; this lane's channel = column lane
+            const __nv_bfloat16 hv = __float2bfloat16_rn(__uint_as_float(r[i]));
+            *reinterpret_cast<__nv_bfloat16*>(dst + i * 64 + ((((lane >> 3) ^ ((i >> 1) & 3))) << 4) + (lane & 7) * 2) = hv;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tm.dq, dst, h * DH + quarter * 32, 128, b);   // rows >= L are clipped
+            bulk_commit();
+          }
+          sb ^= 1;
+        }
+        const int u_lo = part * 2 * KA / HW, u_hi = (part + 1) * 2 * KA / HW;
+        for (int u = u_lo; u < u_hi; ++u) {
+          const int c = u < KA ? u : u - KA;
+          const uint32_t cbase = u < KA ? C_DV : C_DK;
+          const CUtensorMap* omap = u < KA ? &tm.dv : &tm.dk;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_off + cbase + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+          if (u == u_hi - 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);
+          }
+          if (c * 32 >= L) continue;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          uint8_t* dst = sb ? stage1 : stage0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {   // key i of the chunk = row i of the box; this lane's channel = column lane
+            const __nv_bfloat16 hv = __float2bfloat16_rn(__uint_as_float(r[i]));
+            *reinterpret_cast<__nv_bfloat16*>(dst + i * 64 + ((((lane >> 3) ^ ((i >> 1) & 3))) << 4) + (lane & 7) * 2) = hv;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(omap, dst, h * DH + quarter * 32, c * 32, b);
+            bulk_commit();
+          }
+          sb ^= 1;
+        }
+      }
+      if (lane == 0) bulk_wait_read<0>();   // the staging block inside the P tile is rewritten by the next item's phase A
+      __syncwarp();
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 static int make_map3(CUtensorMap* map, const void* ptr, int cols, int L, int64_t batch, int64_t ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   SPA3D_REQUIRE(fn != nullptr, "attention_tc_bwd: cuTensorMapEncodeTiled not available from the driver");
@@ -459,14 +1042,15 @@ static int make_map3(CUtensorMap* map, const void* ptr, int cols, int L, int64_t
   return 0;
 }
 
-template <int DH, int LPAD, int MT>
+template <int DH, int LPAD, int MT, int HW>
 static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
                   int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                   const uint8_t* mask, const float* stats, const float* delta, int64_t batch, int heads, int L,
                   cudaStream_t st) {
   constexpr int DA = DH / 32, KA = LPAD / 32;
-  constexpr int SMEM = 4 * DA * LPAD * 64 + 2 * KA * 128 * 64 + MT * 128 * 32 + 2 * LPAD * 32 + 128 + 1024 + 1024;
+  constexpr int SMEM = 4 * DA * LPAD * 64 + 2 * KA * 128 * 64 + MT * 128 * 32 + 2 * LPAD * 32 + 128 + HW * 512 + 1024;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(4 * HW * 4096 <= 2 * KA * 128 * 64, "epilogue staging lives in the P / dS tiles");
   Maps tm;
   const int cols = heads * DH;
   if (make_map3(&tm.q, q, cols, L, batch, ldq, LPAD)) return 1;
@@ -478,14 +1062,41 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   if (make_map3(&tm.dv, dv, cols, L, batch, lddv, 32)) return 1;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, LPAD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<DH, LPAD, MT, false, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     SPA3D_REQUIRE(e == cudaSuccess, "attention_tc_bwd: smem attribute (%d B): %s", SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
   const int64_t items = batch * heads;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  attn_bwd_tc_kernel<DH, LPAD, MT><<<grid, THREADS, SMEM, st>>>(tm, mask, stats, delta, items, heads, L, CrossBwdArgs{0, 1, nullptr});
+  attn_bwd_tc_kernel<DH, LPAD, MT, false, HW><<<grid, threads_for(HW), SMEM, st>>>(tm, mask, stats, delta, items, heads, L, CrossBwdArgs{0, 1, nullptr});
   return check_launch("attention_bwd_tc");
+}
+
+template <int DH>
+static int launch_tt(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                     const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                     const uint8_t* mask, const float* stats, int64_t batch, int heads, int L, cudaStream_t st) {
+  constexpr int SMEM = tt_smem_bytes<DH>();
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  Maps tm;
+  const int cols = heads * DH;
+  if (make_map3(&tm.q, q, cols, L, batch, ldq, 160)) return 1;
+  if (make_map3(&tm.k, k, cols, L, batch, ldk, 160)) return 1;
+  if (make_map3(&tm.v, v, cols, L, batch, ldv, 160)) return 1;
+  if (make_map3(&tm.g, d_o, cols, L, batch, lddo, 160)) return 1;
+  if (make_map3(&tm.dq, dq, cols, L, batch, lddq, 32)) return 1;
+  if (make_map3(&tm.dk, dk, cols, L, batch, lddk, 32)) return 1;
+  if (make_map3(&tm.dv, dv, cols, L, batch, lddv, 32)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tt_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    SPA3D_REQUIRE(e == cudaSuccess, "attention_tc_bwd (tail): smem attribute (%d B): %s", SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t items = batch * heads;
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  attn_bwd_tt_kernel<DH><<<grid, TT_THREADS, SMEM, st>>>(tm, mask, stats, TailArgs{(const bf16*)o, ldo, (const bf16*)d_o, lddo}, items, heads, L);
+  return check_launch("attention_bwd_tc_tail");
 }
 
 // dq[b, row, h*DH + d] = sum over key chunks of the partial dQ tiles (fp32) -> bf16
@@ -536,7 +1147,7 @@ static int launch_cross(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   const int nchunks = (Lk + 127) / 128;
   const int64_t items = batch * heads * nchunks;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  attn_bwd_tc_kernel<DH, 128, 1, true><<<grid, THREADS, SMEM, st>>>(tm, mask, stats, delta, items, heads, Lq, CrossBwdArgs{Lk, nchunks, workspace});
+  attn_bwd_tc_kernel<DH, 128, 1, true><<<grid, threads_for(2), SMEM, st>>>(tm, mask, stats, delta, items, heads, Lq, CrossBwdArgs{Lk, nchunks, workspace});
   if (int rc = check_launch("attention_cross_bwd")) return rc;
   const int64_t rows_total = batch * heads * Lq;
   attn_cross_dq_merge_kernel<DH><<<(unsigned)((rows_total + 7) / 8), 256, 0, st>>>(workspace, (bf16*)dq, lddq, rows_total, heads, Lq, nchunks);
@@ -569,19 +1180,38 @@ int attention_cross_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ld
   return launch_cross<64>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, workspace, batch, heads, Lq, Lk, st);
 }
 
-int attention_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
-                     int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+int attention_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                     const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                      const uint8_t* key_mask, const float* stats, const float* delta, int64_t batch, int heads, int L,
                      int Dh, cudaStream_t st) {
   using namespace tb;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   SPA3D_REQUIRE(al(q) && al(k) && al(v) && al(d_o) && al(dq) && al(dk) && al(dv), "attention_tc_bwd: operands must be 16-byte aligned");
-  if (Dh == 96) {
-    if (L <= 128) return launch<96, 128, 1>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, batch, heads, L, st);
-    return launch<96, 160, 2>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, batch, heads, L, st);
+  // 128 < L <= 152: the queries past 128 go through the transposed-tail kernel (SPA3D_ATTN_BWD_TT=0: two-tile kernel, for A/B runs)
+  static int tt = -1;
+  if (tt < 0) {
+    const char* e = getenv("SPA3D_ATTN_BWD_TT");
+    tt = (e && atoi(e) == 0) ? 0 : 1;
   }
-  if (L <= 128) return launch<64, 128, 1>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, batch, heads, L, st);
-  return launch<64, 160, 2>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, batch, heads, L, st);
+  if (tt && L > 128 && L <= 128 + NT && o != nullptr && al(o) && ldo % 8 == 0) {
+    if (Dh == 96) return launch_tt<96>(q, ldq, k, ldk, v, ldv, o, ldo, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, batch, heads, L, st);
+    return launch_tt<64>(q, ldq, k, ldk, v, ldv, o, ldo, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, batch, heads, L, st);
+  }
+  // SPA3D_ATTN_BWD_HW=2 keeps two element-wise warps per lane quarter everywhere (A/B switch for the 4-warp variant)
+  static int hw4 = -1;
+  if (hw4 < 0) {
+    const char* e = getenv("SPA3D_ATTN_BWD_HW");
+    hw4 = (e && atoi(e) == 2) ? 0 : 1;
+  }
+#define SPA3D_BWD_LAUNCH(DH_, LPAD_, MT_, HW_) \
+  launch<DH_, LPAD_, MT_, HW_>(q, ldq, k, ldk, v, ldv, d_o, lddo, dq, lddq, dk, lddk, dv, lddv, key_mask, stats, delta, batch, heads, L, st)
+  if (Dh == 96) {
+    if (L <= 128) return hw4 ? SPA3D_BWD_LAUNCH(96, 128, 1, 4) : SPA3D_BWD_LAUNCH(96, 128, 1, 2);
+    return hw4 ? SPA3D_BWD_LAUNCH(96, 160, 2, 4) : SPA3D_BWD_LAUNCH(96, 160, 2, 2);
+  }
+  if (L <= 128) return hw4 ? SPA3D_BWD_LAUNCH(64, 128, 1, 4) : SPA3D_BWD_LAUNCH(64, 128, 1, 2);
+  return hw4 ? SPA3D_BWD_LAUNCH(64, 160, 2, 4) : SPA3D_BWD_LAUNCH(64, 160, 2, 2);
+#undef SPA3D_BWD_LAUNCH
 }
 
 }  // namespace spa3d
