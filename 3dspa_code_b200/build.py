@@ -33,6 +33,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "--fmad=true",
 ]
+NVCC_FLAGS += os.environ.get("SPA3D_NVCC_EXTRA", "").split()   # development switches, e.g. -DSPA3D_ATTN_TRACE
 
 
 def _nvcc():

@@ -494,17 +494,46 @@ struct TailArgs {
   int64_t lddo;
 };
 
-constexpr int TT_THREADS = threads_for(4);
+constexpr int TT_THREADS = (2 + 16) * 32;   // TMA + side data, MMA, 16 element-wise warps
+
+// NV values of this lane (its head channel) become column `lane` of rows ROW0 .. ROW0 + NV - 1 of a 64B-swizzled
+// [32 rows][32 channels] bf16 box
+template <int ROW0, int NV_>
+__device__ __forceinline__ void stage_transposed(uint8_t* dst, const uint32_t* r, int lane) {
+#pragma unroll
+  for (int j = 0; j < NV_; ++j) {
+    const int i = ROW0 + j;
+    *reinterpret_cast<__nv_bfloat16*>(dst + i * 64 + ((((lane >> 3) ^ ((i >> 1) & 3))) << 4) + (lane & 7) * 2) =
+        __float2bfloat16_rn(__uint_as_float(r[j]));
+  }
+}
+
 constexpr int NT = 24;    // tail query columns (L - 128 <= 24)
 constexpr int NV = 152;   // key columns of the dV^T / dK^T accumulators
 
 template <int DH>
 constexpr int tt_smem_bytes() {
-  return 4 * (DH / 32) * 160 * 64 + 5 * 128 * 64 + 16 * 2048 + 160 * 64 + 128 * 32 + 2 * 160 * 32 + 640 + 2048 + 256 + 1024;
+  return 4 * (DH / 32) * 160 * 64 + 5 * 128 * 64 + 16 * 2048 + 160 * 64 + 128 * 32 + 2 * 160 * 32 + 1920 + 2048 + 256 + 1024;
 }
 
+// Development aid (-DSPA3D_ATTN_TRACE, e.g. SPA3D_NVCC_EXTRA=-DSPA3D_ATTN_TRACE python -m 3dspa_code_b200.build): clock64 stamps of the
+// fifth item of CTA 0 at every barrier of the MMA thread (slots 0..15) and of three element-wise warps (32.., 64.., 96..);
+// the launcher prints them after its third call.  This is how the phase costs quoted above were measured.
+#ifdef SPA3D_ATTN_TRACE
+__device__ long long g_attn_trace[128];
+#define TRM(slot) if (blockIdx.x == 0 && n == 4) g_attn_trace[slot] = clock64();
+#define TRC(slot) if (blockIdx.x == 0 && n == 4 && lane == 0 && (cw == 0 || cw == 14 || cw == 6)) g_attn_trace[(cw == 0 ? 32 : cw == 14 ? 64 : 96) + slot] = clock64();
+#else
+#define TRM(slot)
+#define TRC(slot)
+#endif
+#ifdef SPA3D_ATTN_TRACE_SERIAL   // additionally wait for each MMA group to finish (serialises the tensor pipe: group durations, not a timeline)
+#define PROBE(slot) { umma_commit(probe); mbar_wait(probe, pph); pph ^= 1; TRM(slot) }
+#else
+#define PROBE(slot)
+#endif
 template <int DH>
-__global__ void __launch_bounds__(TT_THREADS, 1)
+__global__ void __launch_bounds__(TT_THREADS, 1)   // 96 registers per thread at this CTA size
 attn_bwd_tt_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ mask, const float* __restrict__ stats, TailArgs ta,
                    int64_t items, int heads, int L) {
   constexpr int LPAD = 160, DA = DH / 32, KA = 5, HW = 4, CW = 16;
@@ -523,12 +552,14 @@ attn_bwd_tt_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
   uint8_t* sE = sT + 160 * 64;             // ones operand [128][32 B]
   uint8_t* sB = sE + 128 * 32;             // [2][160][32 B] key bias operand
   float* side = reinterpret_cast<float*>(sB + 2 * LPAD * 32);   // [2][3][NT]: row maximum, 1 / denominator, delta of the tail rows
-  float* dpart = side + 160;               // [4][128]
+  float* kbias = side + 160;               // [2][160]: 0, -1e30 (masked key) or -inf (past the sequence), for the tail's per-lane keys
+  float* dpart = kbias + 320;              // [4][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(dpart + 4 * 128);
-  uint64_t* qk_full = bars, *qk_empty = bars + 1, *vg_full = bars + 2, *vg_empty = bars + 3, *m_full = bars + 4, *m_empty = bars + 6;
+  uint64_t* qk_full = bars, *qk_empty = bars + 1, *vg_full = bars + 2, *vg_empty = bars + 3, *m_full = bars + 4;
   uint64_t* s_full = bars + 8, *st_full = bars + 9, *p_done = bars + 10, *pt_done = bars + 11, *dp_full = bars + 12, *dv_done = bars + 13;
   uint64_t* dpt_full = bars + 14, *dvt_done = bars + 15, *ds_done = bars + 16, *dst_done = bars + 17, *dq_full = bars + 18;
   uint64_t* fin_full = bars + 19, *c_free = bars + 20, *t_free = bars + 21, *acc_free = bars + 22;
+  uint64_t* probe = bars + 23;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -538,10 +569,10 @@ attn_bwd_tt_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.v)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm.g)) : "memory");
     mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(vg_full, 1); mbar_init(vg_empty, 1);
-    mbar_init(&m_full[0], 1); mbar_init(&m_full[1], 1); mbar_init(&m_empty[0], 1); mbar_init(&m_empty[1], 1);
-    mbar_init(s_full, 1); mbar_init(st_full, 1); mbar_init(p_done, CW); mbar_init(pt_done, 5); mbar_init(dp_full, 1);
-    mbar_init(dv_done, 1); mbar_init(dpt_full, 1); mbar_init(dvt_done, 1); mbar_init(ds_done, CW); mbar_init(dst_done, 5);
-    mbar_init(dq_full, 1); mbar_init(fin_full, 1); mbar_init(c_free, CW); mbar_init(t_free, DA); mbar_init(acc_free, 4 * DA);
+    mbar_init(&m_full[0], 1); mbar_init(&m_full[1], 1);
+    mbar_init(s_full, 1); mbar_init(st_full, 1); mbar_init(p_done, CW); mbar_init(pt_done, 12); mbar_init(dp_full, 1);
+    mbar_init(dv_done, 1); mbar_init(dpt_full, 1); mbar_init(dvt_done, 1); mbar_init(ds_done, CW); mbar_init(dst_done, 12);
+    mbar_init(dq_full, 1); mbar_init(fin_full, 1); mbar_init(c_free, CW); mbar_init(t_free, DA); mbar_init(acc_free, 4 * DA); mbar_init(probe, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -560,140 +591,24 @@ attn_bwd_tt_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================== TMA loads: (Q, K) and (V, dO) are released separately =====================
-    if (lane == 0) {
-      uint32_t ph = 0;
-      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1) {
-        const int b = (int)(it / heads), h = (int)(it % heads);
-        if (it == (int64_t)blockIdx.x) {
-          mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * OP_BYTES));
-#pragma unroll
-          for (int a = 0; a < DA; ++a) {
-            tma_load_3d(sQ + a * OPA, &tm.q, h * DH + a * 32, 0, b, qk_full);
-            tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, 0, b, qk_full);
-          }
-        }
-        mbar_wait(vg_empty, ph ^ 1);
-        mbar_arrive_expect_tx(vg_full, (uint32_t)(2 * OP_BYTES));
-#pragma unroll
-        for (int a = 0; a < DA; ++a) {
-          tma_load_3d(sG + a * OPA, &tm.g, h * DH + a * 32, 0, b, vg_full);
-          tma_load_3d(sV + a * OPA, &tm.v, h * DH + a * 32, 0, b, vg_full);
-        }
-        if (it != (int64_t)blockIdx.x) {   // V / dO of an item are released before its Q / K: this is the order the buffers free up
-          mbar_wait(qk_empty, ph ^ 1);
-          mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * OP_BYTES));
-#pragma unroll
-          for (int a = 0; a < DA; ++a) {
-            tma_load_3d(sQ + a * OPA, &tm.q, h * DH + a * 32, 0, b, qk_full);
-            tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, 0, b, qk_full);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idS = idesc(LPAD, false, false), idQ = idesc(DH, false, true), idV = idesc(NV, true, true);
-      constexpr uint32_t idTs = idesc(NT, false, false), idTq = idesc(NT, true, true), idTv = idesc(NV, true, false);
-      int n = 0;
-      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const uint32_t ph = n & 1;
-        const int mb = n & 1;
-        const uint8_t* bias = sB + mb * (LPAD * 32);
-        mbar_wait(qk_full, ph);
-        mbar_wait(&m_full[mb], (n >> 1) & 1);
-        // S = Q K^T + ones x bias (main tile: queries 0..127)
-        mbar_wait(c_free, ph ^ 1);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sQ + (kk >> 1) * OPA + (kk & 1) * 32)),
-                    desc_k64(smem_u32(sK + (kk >> 1) * OPA + (kk & 1) * 32)), idS, kk > 0 ? 1u : 0u);
-        umma_bf16(tmem_base + C_S, desc_k32(smem_u32(sE)), desc_k32(smem_u32(bias)), idS, 1u);
-        umma_commit(s_full);
-        // tail: S^T = K Q_tail^T + bias x ones, key tiles 0..127 and 128..159
-        mbar_wait(t_free, ph ^ 1);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int kt = 0; kt < 2; ++kt) {
-#pragma unroll
-          for (int kk = 0; kk < DH / 16; ++kk)
-            umma_bf16(tmem_base + C_T + kt * NT, desc_k64(smem_u32(sK + (kk >> 1) * OPA + kt * (128 * 64) + (kk & 1) * 32)),
-                      desc_k64(smem_u32(sQ + (kk >> 1) * OPA + 128 * 64 + (kk & 1) * 32)), idTs, kk > 0 ? 1u : 0u);
-          umma_bf16(tmem_base + C_T + kt * NT, desc_k32(smem_u32(bias + kt * (128 * 32))), desc_k32(smem_u32(sE)), idTs, 1u);
-        }
-        umma_commit(st_full);
-        // dP = dO V^T ; dV^T = dO^T P (main tile)
-        mbar_wait(vg_full, ph);
-        mbar_wait(p_done, ph);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sG + (kk >> 1) * OPA + (kk & 1) * 32)),
-                    desc_k64(smem_u32(sV + (kk >> 1) * OPA + (kk & 1) * 32)), idS, kk > 0 ? 1u : 0u);
-        umma_commit(dp_full);
-        mbar_wait(acc_free, ph ^ 1);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_bf16(tmem_base + C_DV, desc_mn64(smem_u32(sG + (j * 16) * 64), OPA), desc_mn64(smem_u32(sP + j * 1024), 128 * 64), idV,
-                    j > 0 ? 1u : 0u);
-        umma_commit(dv_done);   // P may now be overwritten by dS
-        // tail: dP^T = V dO_tail^T ; dV^T += dO_tail^T P_tail
-        mbar_wait(pt_done, ph);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int kt = 0; kt < 2; ++kt)
-#pragma unroll
-          for (int kk = 0; kk < DH / 16; ++kk)
-            umma_bf16(tmem_base + C_T + kt * NT, desc_k64(smem_u32(sV + (kk >> 1) * OPA + kt * (128 * 64) + (kk & 1) * 32)),
-                      desc_k64(smem_u32(sG + (kk >> 1) * OPA + 128 * 64 + (kk & 1) * 32)), idTs, kk > 0 ? 1u : 0u);
-        umma_commit(dpt_full);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          umma_bf16(tmem_base + C_DV, desc_mn64(smem_u32(sG + (128 + ks * 16) * 64), OPA), desc_k64(smem_u32(sT + ks * 32)), idTv, 1u);
-        umma_commit(dvt_done);  // P^T may now be overwritten by dS^T
-        umma_commit(vg_empty);  // V and dO are free
-        // dQ = dS K ; dK^T = Q^T dS (main tile)
-        mbar_wait(ds_done, ph);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < LPAD / 16; ++ks)
-          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sP + (ks >> 1) * (128 * 64) + (ks & 1) * 32)),
-                    desc_mn64(smem_u32(sK + ks * 1024), OPA), idQ, ks > 0 ? 1u : 0u);
-        umma_commit(dq_full);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_bf16(tmem_base + C_DK, desc_mn64(smem_u32(sQ + (j * 16) * 64), OPA), desc_mn64(smem_u32(sP + j * 1024), 128 * 64), idV,
-                    j > 0 ? 1u : 0u);
-        // tail: dQ_tail^T = K^T dS_tail^T ; dK^T += Q_tail^T dS_tail
-        mbar_wait(dst_done, ph);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < LPAD / 16; ++ks)
-          umma_bf16(tmem_base + C_T, desc_mn64(smem_u32(sK + ks * 1024), OPA), desc_mn64(smem_u32(sT + ks * 1024), 1024), idTq,
-                    ks > 0 ? 1u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          umma_bf16(tmem_base + C_DK, desc_mn64(smem_u32(sQ + (128 + ks * 16) * 64), OPA), desc_k64(smem_u32(sT + ks * 32)), idTv, 1u);
-        umma_commit(fin_full);
-        umma_commit(qk_empty);
-        umma_commit(&m_empty[mb]);
-      }
-    }
-  } else if (warp == 2 + CW) {
-    // ===================== per-item side data, one item ahead: key bias operand, tail row statistics and delta =====================
+    // ===================== TMA loads + per-item side data =====================
+    // (Q, K) and (V, dO) are released separately: V and dO are last read by the tail's dV^T product in the middle of an item.
+    // The same warp stages, one item ahead, the key-bias operand, the tail rows' softmax statistics and their delta
+    // (delta_j = sum_d O_jd dO_jd straight from global memory: 24 rows x DH channels); buffer (n + 1) & 1 is free once item n - 1
+    // has released Q / K, which is the wait this warp sits in anyway.
     const uint32_t NEG_BIG = 0xF14Au, NEG_INF = 0xFF80u;   // bf16(-1e30), bf16(-inf)
-    int n = 0;
-    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+    auto build_side = [&](int64_t it, int mb) {
       const int b = (int)(it / heads), h = (int)(it % heads);
-      const int mb = n & 1;
-      uint8_t mk[KA];
+      uint8_t* dstb = sB + mb * (LPAD * 32);
 #pragma unroll
       for (int jj = 0; jj < KA; ++jj) {
         const int j = jj * 32 + lane;
-        mk[jj] = (mask != nullptr && j < L) ? mask[(int64_t)b * L + j] : (uint8_t)1;
+        uint32_t val = NEG_INF;
+        if (j < L) val = (mask == nullptr || mask[(int64_t)b * L + j] != 0) ? 0u : NEG_BIG;
+        const int pc = (j >> 2) & 1;
+        *reinterpret_cast<uint4*>(dstb + j * 32 + pc * 16) = make_uint4(val, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dstb + j * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        kbias[mb * 160 + j] = __uint_as_float(val << 16);   // the same bf16 value the rank-1 product adds in the main tile
       }
       float tm_ = 0.f, til = 0.f, tdl = 0.f;
       const int trow = 128 + lane;
@@ -716,216 +631,376 @@ attn_bwd_tt_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
           }
         }
       }
-      if (lane == 0) mbar_wait(&m_empty[mb], ((n >> 1) & 1) ^ 1);
-      __syncwarp();
-      uint8_t* dstb = sB + mb * (LPAD * 32);
-#pragma unroll
-      for (int jj = 0; jj < KA; ++jj) {
-        const int j = jj * 32 + lane;
-        uint32_t val = NEG_INF;
-        if (j < L) val = mk[jj] != 0 ? 0u : NEG_BIG;
-        const int pc = (j >> 2) & 1;
-        *reinterpret_cast<uint4*>(dstb + j * 32 + pc * 16) = make_uint4(val, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(dstb + j * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
-      }
       if (lane < NT) {
-        float* sd = side + mb * (3 * NT);
-        sd[lane] = tm_;
-        sd[NT + lane] = til;
-        sd[2 * NT + lane] = tdl;
+        float* sdw = side + mb * (3 * NT);
+        sdw[lane] = tm_;
+        sdw[NT + lane] = til;
+        sdw[2 * NT + lane] = tdl;
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&m_full[mb]);
+    };
+    auto load_qk = [&](int64_t it) {
+      const int b = (int)(it / heads), h = (int)(it % heads);
+      mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * OP_BYTES));
+#pragma unroll
+      for (int a = 0; a < DA; ++a) {
+        tma_load_3d(sQ + a * OPA, &tm.q, h * DH + a * 32, 0, b, qk_full);
+        tma_load_3d(sK + a * OPA, &tm.k, h * DH + a * 32, 0, b, qk_full);
+      }
+    };
+    if (lane == 0) load_qk(blockIdx.x);
+    build_side(blockIdx.x, 0);
+    if ((int64_t)blockIdx.x + gridDim.x < items) build_side((int64_t)blockIdx.x + gridDim.x, 1);
+    int n = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const uint32_t ph = n & 1;
+      if (lane == 0) {
+        const int b = (int)(it / heads), h = (int)(it % heads);
+        mbar_wait(vg_empty, ph ^ 1);
+        mbar_arrive_expect_tx(vg_full, (uint32_t)(2 * OP_BYTES));
+#pragma unroll
+        for (int a = 0; a < DA; ++a) {
+          tma_load_3d(sG + a * OPA, &tm.g, h * DH + a * 32, 0, b, vg_full);
+          tma_load_3d(sV + a * OPA, &tm.v, h * DH + a * 32, 0, b, vg_full);
+        }
+        if (n > 0) {
+          mbar_wait(qk_empty, ph ^ 1);
+          load_qk(it);
+        }
+      }
+      __syncwarp();
+      if (n > 0 && it + gridDim.x < items) build_side(it + gridDim.x, (n + 1) & 1);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idS = idesc(LPAD, false, false), idQ = idesc(DH, false, true), idV = idesc(NV, true, true);
+      constexpr uint32_t idTs = idesc(NT, false, false), idTq = idesc(NT, true, true), idTv = idesc(NV, true, false);
+      int n = 0;
+      uint32_t pph = 0;
+      (void)pph;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const uint32_t ph = n & 1;
+        const int mb = n & 1;
+        const uint8_t* bias = sB + mb * (LPAD * 32);
+        mbar_wait(qk_full, ph);
+        mbar_wait(&m_full[mb], (n >> 1) & 1);
+        TRM(0)
+        // S = Q K^T + ones x bias (main tile: queries 0..127)
+        mbar_wait(c_free, ph ^ 1);
+        tcgen05_fence_after();
+        TRM(1)
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sQ + (kk >> 1) * OPA + (kk & 1) * 32)),
+                    desc_k64(smem_u32(sK + (kk >> 1) * OPA + (kk & 1) * 32)), idS, kk > 0 ? 1u : 0u);
+        umma_bf16(tmem_base + C_S, desc_k32(smem_u32(sE)), desc_k32(smem_u32(bias)), idS, 1u);
+        umma_commit(s_full);
+        PROBE(18)
+        TRM(2)
+        // tail: S^T = K Q_tail^T, key tiles 0..127 and 128..159 (a key is a TMEM lane there: its bias is added by the thread)
+        mbar_wait(t_free, ph ^ 1);
+        tcgen05_fence_after();
+        TRM(3)
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16(tmem_base + C_T + kt * NT, desc_k64(smem_u32(sK + (kk >> 1) * OPA + kt * (128 * 64) + (kk & 1) * 32)),
+                      desc_k64(smem_u32(sQ + (kk >> 1) * OPA + 128 * 64 + (kk & 1) * 32)), idTs, kk > 0 ? 1u : 0u);
+        umma_commit(st_full);
+        PROBE(20)
+        TRM(4)
+        // dP = dO V^T ; dV^T = dO^T P (main tile)
+        mbar_wait(vg_full, ph);
+        mbar_wait(p_done, ph);
+        tcgen05_fence_after();
+        TRM(5)
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sG + (kk >> 1) * OPA + (kk & 1) * 32)),
+                    desc_k64(smem_u32(sV + (kk >> 1) * OPA + (kk & 1) * 32)), idS, kk > 0 ? 1u : 0u);
+        umma_commit(dp_full);
+        PROBE(22)
+        TRM(6)
+        mbar_wait(acc_free, ph ^ 1);
+        tcgen05_fence_after();
+        TRM(7)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16(tmem_base + C_DV, desc_mn64(smem_u32(sG + (j * 16) * 64), OPA), desc_mn64(smem_u32(sP + j * 1024), 128 * 64), idV,
+                    j > 0 ? 1u : 0u);
+        umma_commit(dv_done);   // P may now be overwritten by dS
+        PROBE(24)
+        TRM(8)
+        // tail: dP^T = V dO_tail^T ; dV^T += dO_tail^T P_tail
+        mbar_wait(pt_done, ph);
+        tcgen05_fence_after();
+        TRM(9)
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16(tmem_base + C_T + kt * NT, desc_k64(smem_u32(sV + (kk >> 1) * OPA + kt * (128 * 64) + (kk & 1) * 32)),
+                      desc_k64(smem_u32(sG + (kk >> 1) * OPA + 128 * 64 + (kk & 1) * 32)), idTs, kk > 0 ? 1u : 0u);
+        umma_commit(dpt_full);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          umma_bf16(tmem_base + C_DV, desc_mn64(smem_u32(sG + (128 + ks * 16) * 64), OPA), desc_k64(smem_u32(sT + ks * 32)), idTv, 1u);
+        umma_commit(dvt_done);  // P^T may now be overwritten by dS^T
+        umma_commit(vg_empty);  // V and dO are free
+        PROBE(26)
+        TRM(10)
+        // dQ = dS K ; dK^T = Q^T dS (main tile)
+        mbar_wait(ds_done, ph);
+        tcgen05_fence_after();
+        TRM(11)
+#pragma unroll
+        for (int ks = 0; ks < LPAD / 16; ++ks)
+          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sP + (ks >> 1) * (128 * 64) + (ks & 1) * 32)),
+                    desc_mn64(smem_u32(sK + ks * 1024), OPA), idQ, ks > 0 ? 1u : 0u);
+        umma_commit(dq_full);
+        PROBE(28)
+        TRM(12)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16(tmem_base + C_DK, desc_mn64(smem_u32(sQ + (j * 16) * 64), OPA), desc_mn64(smem_u32(sP + j * 1024), 128 * 64), idV,
+                    j > 0 ? 1u : 0u);
+        // tail: dQ_tail^T = K^T dS_tail^T ; dK^T += Q_tail^T dS_tail
+        mbar_wait(dst_done, ph);
+        tcgen05_fence_after();
+        TRM(14)
+#pragma unroll
+        for (int ks = 0; ks < LPAD / 16; ++ks)
+          umma_bf16(tmem_base + C_T, desc_mn64(smem_u32(sK + ks * 1024), OPA), desc_mn64(smem_u32(sT + ks * 1024), 1024), idTq,
+                    ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          umma_bf16(tmem_base + C_DK, desc_mn64(smem_u32(sQ + (128 + ks * 16) * 64), OPA), desc_k64(smem_u32(sT + ks * 32)), idTv, 1u);
+        umma_commit(fin_full);
+        umma_commit(qk_empty);   // also frees this item's side-data buffer
+        TRM(15)
+        PROBE(31)
+      }
     }
   } else {
     // ===================== element-wise phases + epilogues =====================
+    // TMEM reads are the resource here (16 B per clock and lane quarter), so the 160 key columns of the main tile are shared
+    // out evenly: each of the four warps of a lane quarter owns 40 columns = five 8-key groups (16 B of a P / dS row each).
     const int cw = warp - 2;
     const int quarter = warp & 3;          // TMEM lane quarter
-    const int part = cw >> 2;              // share of the main tile's key chunks: 1, 1, 1, 2
-    const int c_lo = part * KA / HW, c_hi = (part + 1) * KA / HW;
+    const int part = cw >> 2;              // 0..3: key groups 5 * part .. 5 * part + 4
+    const int g0 = 5 * part;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int rloc = quarter * 32 + lane;  // query row of the main tile
     const int sw64 = (lane >> 1) & 3;
     uint8_t* pRow = sP + rloc * 64;
-    // the tail's [key x query] tiles: part 0 owns keys quarter*32 + lane, (part 1, quarter 0) keys 128 + lane
-    const bool tail_warp = part == 0 || (part == 1 && quarter == 0);
-    const int tkey = part == 0 ? rloc : 128 + lane;
-    const uint32_t tcol = (uint32_t)(C_T + (part == 0 ? 0 : NT));
-    uint8_t* tRow = sT + tkey * 64;
-    // store staging: this warp's own 2 KB slab and its own block of the P tile (32 rows x 64 B of chunk c_lo)
+    auto grp = [&](int g) -> uint8_t* { return pRow + (g >> 2) * (128 * 64) + (((g & 3) ^ sw64) << 4); };
+    // the tail's [key x query] tiles: parts 0..2 own query columns 8 * part .. + 7, of key quarter*32 + lane and, in lane quarter 0,
+    // also of key 128 + lane
+    const bool tail_warp = part < 3;
+    const bool tail_hi = tail_warp && quarter == 0;
+    uint8_t* tRow0 = sT + rloc * 64;
+    uint8_t* tRow1 = sT + (128 + lane) * 64;
+    // store staging: this warp's own 2 KB slab, and a 2 KB block of the P tile (rows of this lane quarter in key atom `part`; other
+    // warps of the quarter write there in phase A, hence the quarter-wide barrier that ends an item)
     uint8_t* const stage0 = sX + cw * 2048;
-    uint8_t* const stage1 = sP + c_lo * (128 * 64) + quarter * 2048;
+    uint8_t* const stage1 = sP + part * (128 * 64) + quarter * 2048;
     constexpr float LOG2E = 1.4426950408889634f;
     int n = 0;
-    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const int b = (int)(it / heads), h = (int)(it % heads);
+    const int nitems = (int)items;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
       const uint32_t ph = n & 1;
-      const float* sd = side + (n & 1) * (3 * NT);
-      const float2 st2 = *reinterpret_cast<const float2*>(stats + (((int64_t)b * heads + h) * L + rloc) * 2);
+      const float* sd = side + (n & 1) * (3 * NT) + 8 * part;   // this warp's 8 tail columns: [0] maximum, [NT] 1 / denominator, [2 NT] delta
+      const float* kb = kbias + (n & 1) * 160;
+      const float2 st2 = *reinterpret_cast<const float2*>(stats + ((int64_t)it * L + rloc) * 2);   // it = b * heads + h
       const float m = st2.x, il = st2.y;
       const bool row_grad = m > -1e29f;    // a fully masked row: its logits are constants, dS = 0
       // ---- phase A: P = exp(S - m) / l -> bf16, [query][key] tile ----
       mbar_wait(s_full, ph);
       tcgen05_fence_after();
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c * 32), r);
+      TRC(0)
+      {
+        uint32_t r[32], r4[8];
+        tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + g0 * 8), r);
         tmem_ld_wait();
-        uint32_t w[16];
+        tmem_ld8(tmem_base + lane_off + (uint32_t)(C_S + (g0 + 4) * 8), r4);   // in flight under the first four groups
+        auto put_p = [&](int g, const uint32_t* rr) {
+          uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_fast((__uint_as_float(r[2 * i]) - m) * LOG2E) * il;
-          const float p1 = ex2_fast((__uint_as_float(r[2 * i + 1]) - m) * LOG2E) * il;
-          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-          w[i] = *reinterpret_cast<uint32_t*>(&hb);
-        }
-        uint8_t* dst = pRow + c * (128 * 64);
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = ex2_fast((__uint_as_float(rr[2 * e]) - m) * LOG2E) * il;
+            const float p1 = ex2_fast((__uint_as_float(rr[2 * e + 1]) - m) * LOG2E) * il;
+            __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+            w[e] = *reinterpret_cast<uint32_t*>(&hb);
+          }
+          *reinterpret_cast<uint4*>(grp(g)) = make_uint4(w[0], w[1], w[2], w[3]);
+        };
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        for (int i = 0; i < 4; ++i) put_p(g0 + i, r + 8 * i);
+        tmem_ld_wait();
+        put_p(g0 + 4, r4);
       }
       tcgen05_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_done);
-      // ---- tail phase A: P^T[key][j] = exp(S^T - m_j) / l_j ----
-      uint32_t tp[NT / 2];   // this key's P^T row, bf16 pairs (kept for phase B)
+      TRC(1)
+      // ---- tail phase A: P^T[key][j] = exp(S^T + bias_key - m_j) / l_j ----
       if (tail_warp) {
+        uint32_t tp0[4], tp1[4];   // this key's 8 P^T values per key tile, bf16 pairs
         mbar_wait(st_full, ph);
         tcgen05_fence_after();
-        uint32_t r[NT];
-        tmem_ld8(tmem_base + lane_off + tcol, r);
-        tmem_ld8(tmem_base + lane_off + tcol + 8, r + 8);
-        tmem_ld8(tmem_base + lane_off + tcol + 16, r + 16);
+        TRC(2)
+        uint32_t r[16];
+        tmem_ld8(tmem_base + lane_off + (uint32_t)(C_T + 8 * part), r);
+        if (tail_hi) tmem_ld8(tmem_base + lane_off + (uint32_t)(C_T + NT + 8 * part), r + 8);
+        const float kb0 = kb[rloc], kb1 = kb[128 + lane];
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < NT / 2; ++i) {
-          const float p0 = ex2_fast((__uint_as_float(r[2 * i]) - sd[2 * i]) * LOG2E) * sd[NT + 2 * i];
-          const float p1 = ex2_fast((__uint_as_float(r[2 * i + 1]) - sd[2 * i + 1]) * LOG2E) * sd[NT + 2 * i + 1];
-          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-          tp[i] = *reinterpret_cast<uint32_t*>(&hb);
+        for (int e = 0; e < 4; ++e) {
+          const float m0 = sd[2 * e], m1 = sd[2 * e + 1], l0 = sd[NT + 2 * e], l1 = sd[NT + 2 * e + 1];
+          __nv_bfloat162 hb = __floats2bfloat162_rn(ex2_fast((__uint_as_float(r[2 * e]) + kb0 - m0) * LOG2E) * l0,
+                                                    ex2_fast((__uint_as_float(r[2 * e + 1]) + kb0 - m1) * LOG2E) * l1);
+          tp0[e] = *reinterpret_cast<uint32_t*>(&hb);
+          if (tail_hi) {
+            hb = __floats2bfloat162_rn(ex2_fast((__uint_as_float(r[8 + 2 * e]) + kb1 - m0) * LOG2E) * l0,
+                                       ex2_fast((__uint_as_float(r[8 + 2 * e + 1]) + kb1 - m1) * LOG2E) * l1);
+            tp1[e] = *reinterpret_cast<uint32_t*>(&hb);
+          }
         }
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          *reinterpret_cast<uint4*>(tRow + ((j ^ sw64) << 4)) = make_uint4(tp[4 * j], tp[4 * j + 1], tp[4 * j + 2], tp[4 * j + 3]);
-        *reinterpret_cast<uint4*>(tRow + ((3 ^ sw64) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // query columns 24..31 of the K = 32 steps
+        *reinterpret_cast<uint4*>(tRow0 + ((part ^ sw64) << 4)) = make_uint4(tp0[0], tp0[1], tp0[2], tp0[3]);
+        if (part == 2) *reinterpret_cast<uint4*>(tRow0 + ((3 ^ sw64) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // query columns 24..31 of the K = 32 steps
+        if (tail_hi) {
+          *reinterpret_cast<uint4*>(tRow1 + ((part ^ sw64) << 4)) = make_uint4(tp1[0], tp1[1], tp1[2], tp1[3]);
+          if (part == 2) *reinterpret_cast<uint4*>(tRow1 + ((3 ^ sw64) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
         tcgen05_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(pt_done);
+        TRC(3)
       }
       // ---- phase B: dS = P o (dP - delta), written over P ----
       mbar_wait(dp_full, ph);
       tcgen05_fence_after();
+      TRC(4)
       {
         // delta_i = sum_j P_ij dP_ij over all keys: the four warps of the lane quarter add their shares through shared memory.
-        // dP of the first chunk stays in registers (each TMEM column costs read bandwidth once)
+        // dP stays in registers between the two passes (each TMEM column costs read bandwidth once)
+        // (32 of the 40 columns: the register file allows 96 per thread at this CTA size, and a spill costs an L2 round trip)
         uint32_t r0[32];
         float psum = 0.f;
-        tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + c_lo * 32), r0);
+        auto dot_p = [&](int g, const uint32_t* rr) {
+          const uint4 pq = *reinterpret_cast<const uint4*>(grp(g));
+          const uint32_t pu[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pu[e]);
+            psum = fmaf(__low2float(pb), __uint_as_float(rr[2 * e]), psum);
+            psum = fmaf(__high2float(pb), __uint_as_float(rr[2 * e + 1]), psum);
+          }
+        };
         {
-          const uint8_t* src = pRow + c_lo * (128 * 64);
-          uint4 pw[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pw[j] = *reinterpret_cast<const uint4*>(src + ((j ^ sw64) << 4));
+          uint32_t r4[8];
+          tmem_ld8(tmem_base + lane_off + (uint32_t)(C_S + (g0 + 4) * 8), r4);
           tmem_ld_wait();
-          const uint32_t* pwu = reinterpret_cast<const uint32_t*>(pw);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
-            psum = fmaf(__low2float(pb), __uint_as_float(r0[2 * i]), psum);
-            psum = fmaf(__high2float(pb), __uint_as_float(r0[2 * i + 1]), psum);
-          }
-        }
-        if (c_hi - c_lo == 2) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + (c_lo + 1) * 32), r);
-          const uint8_t* src = pRow + (c_lo + 1) * (128 * 64);
-          uint4 pw[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pw[j] = *reinterpret_cast<const uint4*>(src + ((j ^ sw64) << 4));
+          tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + g0 * 8), r0);
+          dot_p(g0 + 4, r4);
           tmem_ld_wait();
-          const uint32_t* pwu = reinterpret_cast<const uint32_t*>(pw);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
-            psum = fmaf(__low2float(pb), __uint_as_float(r[2 * i]), psum);
-            psum = fmaf(__high2float(pb), __uint_as_float(r[2 * i + 1]), psum);
-          }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dot_p(g0 + i, r0 + 8 * i);
         dpart[part * 128 + rloc] = psum;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
         float dl = 0.f;
 #pragma unroll
-        for (int hp = 0; hp < HW; ++hp) dl += dpart[hp * 128 + rloc];   // same order in every warp of the quarter
+        for (int hp = 0; hp < 4; ++hp) dl += dpart[hp * 128 + rloc];   // same order in every warp of the quarter
+        TRC(5)
         mbar_wait(dv_done, ph);   // dV^T = dO^T P has read the P tile
-        auto emit = [&](int c, const uint32_t (&rr)[32]) {
-          uint8_t* src = pRow + c * (128 * 64);
-          uint4 pw[4];
+        TRC(6)
+        auto put_ds = [&](int g, const uint32_t* rr) {
+          uint8_t* addr = grp(g);
+          const uint4 pq = *reinterpret_cast<const uint4*>(addr);
+          const uint32_t pu[4] = {pq.x, pq.y, pq.z, pq.w};
+          uint32_t w[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) pw[j] = *reinterpret_cast<const uint4*>(src + ((j ^ sw64) << 4));
-          const uint32_t* pwu = reinterpret_cast<const uint32_t*>(pw);
-          uint32_t w[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pwu[i]);
-            float d0 = __low2float(pb) * (__uint_as_float(rr[2 * i]) - dl);
-            float d1 = __high2float(pb) * (__uint_as_float(rr[2 * i + 1]) - dl);
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&pu[e]);
+            float d0 = __low2float(pb) * (__uint_as_float(rr[2 * e]) - dl);
+            float d1 = __high2float(pb) * (__uint_as_float(rr[2 * e + 1]) - dl);
             if (!row_grad) d0 = d1 = 0.f;
             __nv_bfloat162 hb = __floats2bfloat162_rn(d0, d1);
-            w[i] = *reinterpret_cast<uint32_t*>(&hb);
+            w[e] = *reinterpret_cast<uint32_t*>(&hb);
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(src + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          *reinterpret_cast<uint4*>(addr) = make_uint4(w[0], w[1], w[2], w[3]);
         };
-        emit(c_lo, r0);
-        if (c_hi - c_lo == 2) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_off + (uint32_t)(C_S + (c_lo + 1) * 32), r);
+        {
+          uint32_t r4[8];
+          tmem_ld8(tmem_base + lane_off + (uint32_t)(C_S + (g0 + 4) * 8), r4);   // the one group that is read twice
+#pragma unroll
+          for (int i = 0; i < 4; ++i) put_ds(g0 + i, r0 + 8 * i);
           tmem_ld_wait();
-          emit(c_lo + 1, r);
+          put_ds(g0 + 4, r4);
         }
       }
       tcgen05_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_done);
+      TRC(7)
       // ---- tail phase B: dS^T[key][j] = P^T o (dP^T - delta_j), written over P^T ----
       if (tail_warp) {
         mbar_wait(dpt_full, ph);
         tcgen05_fence_after();
-        uint32_t r[NT];
-        tmem_ld8(tmem_base + lane_off + tcol, r);
-        tmem_ld8(tmem_base + lane_off + tcol + 8, r + 8);
-        tmem_ld8(tmem_base + lane_off + tcol + 16, r + 16);
+        TRC(8)
+        uint32_t r[16];
+        tmem_ld8(tmem_base + lane_off + (uint32_t)(C_T + 8 * part), r);
+        if (tail_hi) tmem_ld8(tmem_base + lane_off + (uint32_t)(C_T + NT + 8 * part), r + 8);
+        // P^T comes back from shared memory (holding it in registers across phase B costs spills, and a spill costs an L2 round trip)
+        const uint4 q0 = *reinterpret_cast<const uint4*>(tRow0 + ((part ^ sw64) << 4));
+        uint4 q1 = make_uint4(0u, 0u, 0u, 0u);
+        if (tail_hi) q1 = *reinterpret_cast<const uint4*>(tRow1 + ((part ^ sw64) << 4));
+        const uint32_t tp0[4] = {q0.x, q0.y, q0.z, q0.w}, tp1[4] = {q1.x, q1.y, q1.z, q1.w};
         tmem_ld_wait();
-        uint32_t w[NT / 2];
+        uint32_t w0[4], w1[4];
 #pragma unroll
-        for (int i = 0; i < NT / 2; ++i) {
-          const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&tp[i]);
-          float d0 = __low2float(pb) * (__uint_as_float(r[2 * i]) - sd[2 * NT + 2 * i]);
-          float d1 = __high2float(pb) * (__uint_as_float(r[2 * i + 1]) - sd[2 * NT + 2 * i + 1]);
-          if (!(sd[2 * i] > -1e29f)) d0 = 0.f;
-          if (!(sd[2 * i + 1] > -1e29f)) d1 = 0.f;
-          __nv_bfloat162 hb = __floats2bfloat162_rn(d0, d1);
-          w[i] = *reinterpret_cast<uint32_t*>(&hb);
+        for (int e = 0; e < 4; ++e) {
+          const float dl0 = sd[2 * NT + 2 * e], dl1 = sd[2 * NT + 2 * e + 1];
+          const bool g0_ = sd[2 * e] > -1e29f, g1_ = sd[2 * e + 1] > -1e29f;
+          {
+            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&tp0[e]);
+            const float d0 = g0_ ? __low2float(pb) * (__uint_as_float(r[2 * e]) - dl0) : 0.f;
+            const float d1 = g1_ ? __high2float(pb) * (__uint_as_float(r[2 * e + 1]) - dl1) : 0.f;
+            __nv_bfloat162 hb = __floats2bfloat162_rn(d0, d1);
+            w0[e] = *reinterpret_cast<uint32_t*>(&hb);
+          }
+          if (tail_hi) {
+            const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&tp1[e]);
+            const float d0 = g0_ ? __low2float(pb) * (__uint_as_float(r[8 + 2 * e]) - dl0) : 0.f;
+            const float d1 = g1_ ? __high2float(pb) * (__uint_as_float(r[8 + 2 * e + 1]) - dl1) : 0.f;
+            __nv_bfloat162 hb = __floats2bfloat162_rn(d0, d1);
+            w1[e] = *reinterpret_cast<uint32_t*>(&hb);
+          }
         }
+        TRC(9)
         mbar_wait(dvt_done, ph);   // dV^T += dO_tail^T P_tail has read the P^T tile
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          *reinterpret_cast<uint4*>(tRow + ((j ^ sw64) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        *reinterpret_cast<uint4*>(tRow0 + ((part ^ sw64) << 4)) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+        if (tail_hi) *reinterpret_cast<uint4*>(tRow1 + ((part ^ sw64) << 4)) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
         tcgen05_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(dst_done);
+        TRC(10)
       }
       // ---- dQ epilogue of the main tile: parts 1.. take one 32-channel atom each ----
       int sb = 0;
+      const int b = it / heads, h = it - b * heads;
       mbar_wait(dq_full, ph);
       tcgen05_fence_after();
+      TRC(11)
       if (part >= 1 && part - 1 < DA) {
         const int c = part - 1;
         uint32_t r[32];
@@ -953,16 +1028,31 @@ attn_bwd_tt_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(c_free);
+      TRC(12)
       // ---- after the item's last product: dQ_tail^T, dV^T, dK^T (lane = head channel, column = query / key) ----
       mbar_wait(fin_full, ph);
       tcgen05_fence_after();
+      TRC(13)
       if (quarter * 32 < DH) {
+        const int u_lo = part * 2 * KA / HW, u_hi = (part + 1) * 2 * KA / HW;   // 2 or 3 of the 10 units: dV chunks, then dK chunks
+        auto unit_addr = [&](int u) -> uint32_t { return tmem_base + lane_off + (uint32_t)((u < KA ? C_DV : C_DK) + (u < KA ? u : u - KA) * 32); };
+        auto send_box = [&](uint8_t* dst, const CUtensorMap* omap, int row0) {   // rows >= L are clipped by the store
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(omap, dst, h * DH + quarter * 32, row0, b);
+            bulk_commit();
+          }
+          sb ^= 1;
+        };
+        uint32_t ra[16], rb[16];
         if (part == 0) {
-          uint32_t r[NT];
-          tmem_ld8(tmem_base + lane_off + (uint32_t)C_T, r);
-          tmem_ld8(tmem_base + lane_off + (uint32_t)C_T + 8, r + 8);
-          tmem_ld8(tmem_base + lane_off + (uint32_t)C_T + 16, r + 16);
+          uint32_t rt[NT];
+          tmem_ld8(tmem_base + lane_off + (uint32_t)C_T, rt);
+          tmem_ld8(tmem_base + lane_off + (uint32_t)C_T + 8, rt + 8);
+          tmem_ld8(tmem_base + lane_off + (uint32_t)C_T + 16, rt + 16);
           tmem_ld_wait();
+          tmem_ld16(unit_addr(u_lo), ra);
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -971,52 +1061,42 @@ attn_bwd_tt_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
           }
           __syncwarp();
           uint8_t* dst = sb ? stage1 : stage0;
-#pragma unroll
-          for (int i = 0; i < NT; ++i) {   // query 128 + i = row i of the box; this lane's channel = column lane
-            const __nv_bfloat16 hv = __float2bfloat16_rn(__uint_as_float(r[i]));
-            *reinterpret_cast<__nv_bfloat16*>(dst + i * 64 + ((((lane >> 3) ^ ((i >> 1) & 3))) << 4) + (lane & 7) * 2) = hv;
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&tm.dq, dst, h * DH + quarter * 32, 128, b);   // rows >= L are clipped
-            bulk_commit();
-          }
-          sb ^= 1;
+          stage_transposed<0, NT>(dst, rt, lane);
+          send_box(dst, &tm.dq, 128);
+        } else {
+          tmem_ld16(unit_addr(u_lo), ra);
         }
-        const int u_lo = part * 2 * KA / HW, u_hi = (part + 1) * 2 * KA / HW;
+        TRC(14)
+        // each 32-key unit goes through two 16-column reads; one half is staged while the next read is in flight
+#pragma unroll 1
         for (int u = u_lo; u < u_hi; ++u) {
           const int c = u < KA ? u : u - KA;
-          const uint32_t cbase = u < KA ? C_DV : C_DK;
-          const CUtensorMap* omap = u < KA ? &tm.dv : &tm.dk;
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_off + cbase + (uint32_t)(c * 32), r);
-          tmem_ld_wait();
-          if (u == u_hi - 1) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_free);
-          }
-          if (c * 32 >= L) continue;
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
+          const bool live = c * 32 < L;
           uint8_t* dst = sb ? stage1 : stage0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {   // key i of the chunk = row i of the box; this lane's channel = column lane
-            const __nv_bfloat16 hv = __float2bfloat16_rn(__uint_as_float(r[i]));
-            *reinterpret_cast<__nv_bfloat16*>(dst + i * 64 + ((((lane >> 3) ^ ((i >> 1) & 3))) << 4) + (lane & 7) * 2) = hv;
+          tmem_ld_wait();
+          tmem_ld16(unit_addr(u) + 16, rb);
+          if (live) {
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            stage_transposed<0, 16>(dst, ra, lane);
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(omap, dst, h * DH + quarter * 32, c * 32, b);
-            bulk_commit();
+          tmem_ld_wait();
+          if (u + 1 < u_hi) tmem_ld16(unit_addr(u + 1), ra);
+          if (live) {
+            stage_transposed<16, 16>(dst, rb, lane);
+            send_box(dst, u < KA ? &tm.dv : &tm.dk, c * 32);
           }
-          sb ^= 1;
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);
       }
-      if (lane == 0) bulk_wait_read<0>();   // the staging block inside the P tile is rewritten by the next item's phase A
+      TRC(15)
+      if (lane == 0) bulk_wait_read<0>();
       __syncwarp();
+      // staging blocks inside the P tile are rewritten by the next item's phase A of OTHER warps of this lane quarter
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+      TRC(16)
     }
   }
 
@@ -1027,6 +1107,10 @@ attn_bwd_tt_kernel(const __grid_constant__ Maps tm, const uint8_t* __restrict__ 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
+
+#undef TRM
+#undef TRC
+#undef PROBE
 
 static int make_map3(CUtensorMap* map, const void* ptr, int cols, int L, int64_t batch, int64_t ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -1096,6 +1180,16 @@ static int launch_tt(const void* q, int64_t ldq, const void* k, int64_t ldk, con
   const int64_t items = batch * heads;
   const int grid = (int)(items < num_sms() ? items : num_sms());
   attn_bwd_tt_kernel<DH><<<grid, TT_THREADS, SMEM, st>>>(tm, mask, stats, TailArgs{(const bf16*)o, ldo, (const bf16*)d_o, lddo}, items, heads, L);
+#ifdef SPA3D_ATTN_TRACE
+  static int calls = 0;
+  if (++calls == 3) {
+    cudaDeviceSynchronize();
+    long long hbuf[128];
+    cudaMemcpyFromSymbol(hbuf, g_attn_trace, sizeof(hbuf));
+    for (int i = 0; i < 128; ++i) if (hbuf[i]) printf("TRACE %d %lld\n", i, hbuf[i] - hbuf[0]);
+    fflush(stdout);
+  }
+#endif
   return check_launch("attention_bwd_tc_tail");
 }
 
