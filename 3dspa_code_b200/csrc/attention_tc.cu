@@ -560,6 +560,509 @@ static int launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   return check_launch("attention_fwd_tc");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 128 < L <= 152 (the track transformers: L = 151 and L = 129): "transposed tail", one TMEM read of S.
+//
+// tcgen05.ld moves 16 B per clock per TMEM lane quarter whatever the number of useful lanes (measured with the clock64 trace of
+// attention_tc_bwd.cu), so in the two-tile kernel above the 23-row (or 1-row) second query tile costs lane quarter 0 as many read
+// clocks as a full tile, on top of its share of the first tile, and every S column is read twice (row maximum, then exp).  Here
+//   * the queries past 128 sit on the N side of their own products: S^T = K Q_tail^T is [keys x 24], two M tiles (keys 0..127 and
+//     128..159), and O_tail^T = V^T P_tail^T is [channels x 24].  The softmax of those 24 columns runs down the TMEM lanes: column
+//     maxima and sums are butterfly shuffles inside a warp plus one exchange through shared memory;
+//   * four warps per lane quarter own 40 key columns of the main tile each and keep them in registers between the maximum and the
+//     exponentials, so S is read from TMEM once.
+// TMEM columns: [0,160) S, [160,256) O, [256,304) S^T (two key tiles), [304,328) O_tail^T.
+constexpr int FT_THREADS = 18 * 32;   // TMA + side data, MMA, 16 softmax / epilogue warps
+constexpr int FNT = 24;               // tail query columns (L - 128 <= 24)
+
+// Reduce eight per-lane values over the 32 lanes of a warp with 9 shuffles instead of 40 (the shuffle unit issues one warp
+// instruction per clock per SM): each exchange step halves the values a lane is responsible for.  On return every lane holds the
+// reduction of value (lane >> 2).
+template <bool IS_MAX>
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+  auto op = [](float a, float b) { return IS_MAX ? fmaxf(a, b) : a + b; };
+  float a4[4], a2[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = h16 ? v[j] : v[j + 4], keep = h16 ? v[j + 4] : v[j];
+    a4[j] = op(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = h8 ? a4[j] : a4[j + 2], keep = h8 ? a4[j + 2] : a4[j];
+    a2[j] = op(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+  const float send = h4 ? a2[0] : a2[1], keep = h4 ? a2[1] : a2[0];
+  float c = op(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  c = op(c, __shfl_xor_sync(0xffffffffu, c, 2));
+  c = op(c, __shfl_xor_sync(0xffffffffu, c, 1));
+  return c;
+}
+
+template <int DH>
+constexpr int ft_smem_bytes() {
+  return 4 * (DH / 32) * 160 * 64 + 5 * 128 * 64 + 15 * 2048 + 160 * 64 + 128 * 32 + 2 * 160 * 32 + 10240 + 1024;
+}
+__host__ __device__ constexpr uint32_t idesc_tt(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+// Development aid (-DSPA3D_ATTN_TRACE): clock64 stamps of the fifth item of CTA 0, MMA thread (slots 0..) and two softmax warps (32.., 64..)
+#ifdef SPA3D_ATTN_TRACE
+__device__ long long g_fwd_trace[128];
+#define FTM(slot) if (blockIdx.x == 0 && n == 4) g_fwd_trace[slot] = clock64();
+#define FTC(slot) if (blockIdx.x == 0 && n == 4 && lane == 0 && (cw == 0 || cw == 14)) g_fwd_trace[(cw == 0 ? 32 : 64) + slot] = clock64();
+#else
+#define FTM(slot)
+#define FTC(slot)
+#endif
+template <int DH>
+__global__ void __launch_bounds__(FT_THREADS, 1)
+attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmO, const uint8_t* __restrict__ mask, float* __restrict__ stats, int64_t items,
+                   int heads, int L) {
+  constexpr int LPAD = 160, DA = DH / 32, KA = 5;
+  constexpr int OPA = LPAD * 64, OP_BYTES = DA * OPA, PT_BYTES = KA * 128 * 64;
+  constexpr int C_S = 0, C_O = 160, C_T = 256, C_OT = 304;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + OP_BYTES;
+  uint8_t* sV = sK + OP_BYTES;             // [2] buffers
+  uint8_t* sP = sV + 2 * OP_BYTES;         // P of the main tile [query][key], 64B-swizzled atoms of 32 keys
+  uint8_t* sX = sP + PT_BYTES;             // 15 x 2 KB store staging: one per warp that stores
+  uint8_t* sT = sX + 15 * 2048;            // P^T of the tail [key][query], 64 B rows
+  uint8_t* sE = sT + 160 * 64;             // ones operand [128][32 B]
+  uint8_t* sB = sE + 128 * 32;             // [2][160][32 B] key bias operand
+  float* kbias = reinterpret_cast<float*>(sB + 2 * LPAD * 32);   // [3][160] key bias per key, for the tail's per-lane keys
+  float* xmax = kbias + 480;               // [4][128] row maxima of the four column shares
+  float* xsum = xmax + 512;                // [2][4][128] row sums (by item parity: the epilogue of item n overlaps the softmax of item n+1)
+  float* tmax = xsum + 1024;               // [2][4][FNT] column maxima per key quarter
+  float* tsum = tmax + 192;                // [2][4][FNT] column sums per key quarter
+  float* tinv = tsum + 192;                // [4][32] 1 / column sum, private to each tail-epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tinv + 128);
+  uint64_t* qk_full = bars, *qk_empty = bars + 1, *v_full = bars + 2, *v_empty = bars + 4, *m_full = bars + 6;
+  uint64_t* s_full = bars + 8, *st_full = bars + 9, *p_done = bars + 10, *pt_done = bars + 11, *o_full = bars + 12, *ot_full = bars + 13;
+  uint64_t* s_free = bars + 14, *t_free = bars + 15, *o_free = bars + 16, *ot_free = bars + 17;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+    mbar_init(qk_full, 1); mbar_init(qk_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); mbar_init(&m_full[i], 1); }
+    mbar_init(s_full, 1); mbar_init(st_full, 1); mbar_init(p_done, 16); mbar_init(pt_done, 12); mbar_init(o_full, 1); mbar_init(ot_full, 1);
+    mbar_init(s_free, 16); mbar_init(t_free, 12); mbar_init(o_free, 16); mbar_init(ot_free, DA);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int r = threadIdx.x; r < 128; r += FT_THREADS) {   // ones operand: element 0 of every row = 1.0
+    const int pc = (r >> 2) & 1;
+    *reinterpret_cast<uint4*>(sE + r * 32 + pc * 16) = make_uint4(0x3F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sE + r * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA loads + per-item key bias (operand for the main tile, per-key floats for the tail) =====================
+    const uint32_t NEG_BIG = 0xF14Au, NEG_INF = 0xFF80u;   // bf16(-1e30), bf16(-inf)
+    auto build_side = [&](int64_t it, int n_of_it) {
+      const int b = (int)(it / heads), mb = n_of_it & 1;
+      uint8_t* dstb = sB + mb * (LPAD * 32);
+      float* kbd = kbias + (n_of_it % 3) * 160;
+#pragma unroll
+      for (int jj = 0; jj < KA; ++jj) {
+        const int j = jj * 32 + lane;
+        uint32_t val = NEG_INF;
+        if (j < L) val = (mask == nullptr || mask[(int64_t)b * L + j] != 0) ? 0u : NEG_BIG;
+        const int pc = (j >> 2) & 1;
+        *reinterpret_cast<uint4*>(dstb + j * 32 + pc * 16) = make_uint4(val, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dstb + j * 32 + (pc ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        kbd[j] = __uint_as_float(val << 16);   // the same bf16 value the rank-1 product adds in the main tile
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&m_full[mb]);
+    };
+    auto load_qk = [&](int64_t it) {
+      const int b = (int)(it / heads), h = (int)(it % heads);
+      mbar_arrive_expect_tx(qk_full, (uint32_t)(2 * OP_BYTES));
+#pragma unroll
+      for (int a = 0; a < DA; ++a) {
+        tma_load_3d(sK + a * OPA, &tmK, h * DH + a * 32, 0, b, qk_full);
+        tma_load_3d(sQ + a * OPA, &tmQ, h * DH + a * 32, 0, b, qk_full);
+      }
+    };
+    if (lane == 0) load_qk(blockIdx.x);
+    build_side(blockIdx.x, 0);
+    if ((int64_t)blockIdx.x + gridDim.x < items) build_side((int64_t)blockIdx.x + gridDim.x, 1);
+    int n = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int vb = n & 1;
+      if (lane == 0) {
+        const int b = (int)(it / heads), h = (int)(it % heads);
+        mbar_wait(&v_empty[vb], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[vb], (uint32_t)OP_BYTES);
+#pragma unroll
+        for (int a = 0; a < DA; ++a) tma_load_3d(sV + vb * OP_BYTES + a * OPA, &tmV, h * DH + a * 32, 0, b, &v_full[vb]);
+        if (it + gridDim.x < items) {
+          mbar_wait(qk_empty, n & 1);   // S and S^T of this item have read Q / K (and the key bias operand)
+          load_qk(it + gridDim.x);
+        }
+      }
+      __syncwarp();
+      if (it + 2 * (int64_t)gridDim.x < items) build_side(it + 2 * (int64_t)gridDim.x, n + 2);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idS = idesc_tt(LPAD, false, false), idO = idesc_tt(DH, false, true);
+      constexpr uint32_t idTs = idesc_tt(FNT, false, false), idTo = idesc_tt(FNT, true, true);
+      int n = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const uint32_t ph = n & 1;
+        const int mb = n & 1, vb = n & 1;
+        const uint8_t* vbuf = sV + vb * OP_BYTES;
+        mbar_wait(qk_full, ph);
+        mbar_wait(&m_full[mb], (n >> 1) & 1);
+        FTM(0)
+        mbar_wait(s_free, ph ^ 1);   // the softmax of the previous item has S in registers
+        tcgen05_fence_after();
+        FTM(1)
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sQ + (kk >> 1) * OPA + (kk & 1) * 32)),
+                    desc_k64(smem_u32(sK + (kk >> 1) * OPA + (kk & 1) * 32)), idS, kk > 0 ? 1u : 0u);
+        umma_bf16(tmem_base + C_S, desc_k32(smem_u32(sE)), desc_k32(smem_u32(sB + mb * (LPAD * 32))), idS, 1u);
+        umma_commit(s_full);
+        FTM(2)
+        // tail: S^T = K Q_tail^T, key tiles 0..127 and 128..159 (a key is a TMEM lane there: its bias is added by the thread)
+        mbar_wait(t_free, ph ^ 1);
+        tcgen05_fence_after();
+        FTM(3)
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16(tmem_base + C_T + kt * FNT, desc_k64(smem_u32(sK + (kk >> 1) * OPA + kt * (128 * 64) + (kk & 1) * 32)),
+                      desc_k64(smem_u32(sQ + (kk >> 1) * OPA + 128 * 64 + (kk & 1) * 32)), idTs, kk > 0 ? 1u : 0u);
+        umma_commit(st_full);
+        umma_commit(qk_empty);
+        FTM(4)
+        // O = P V (main tile)
+        mbar_wait(&v_full[vb], (n >> 1) & 1);
+        FTM(5)
+        mbar_wait(p_done, ph);
+        FTM(6)
+        mbar_wait(o_free, ph ^ 1);
+        tcgen05_fence_after();
+        FTM(7)
+#pragma unroll
+        for (int ks = 0; ks < LPAD / 16; ++ks)
+          umma_bf16(tmem_base + C_O, desc_k64(smem_u32(sP + (ks >> 1) * (128 * 64) + (ks & 1) * 32)),
+                    desc_mn64(smem_u32(vbuf + ks * 1024), OPA), idO, ks > 0 ? 1u : 0u);
+        umma_commit(o_full);
+        FTM(8)
+        // tail: O_tail^T = V^T P_tail^T
+        mbar_wait(pt_done, ph);
+        FTM(9)
+        mbar_wait(ot_free, ph ^ 1);
+        tcgen05_fence_after();
+        FTM(10)
+#pragma unroll
+        for (int ks = 0; ks < LPAD / 16; ++ks)
+          umma_bf16(tmem_base + C_OT, desc_mn64(smem_u32(vbuf + ks * 1024), OPA), desc_mn64(smem_u32(sT + ks * 1024), 1024), idTo,
+                    ks > 0 ? 1u : 0u);
+        umma_commit(ot_full);
+        umma_commit(&v_empty[vb]);
+        FTM(11)
+      }
+    }
+  } else {
+    // ===================== softmax + epilogues: four warps per TMEM lane quarter, 40 key columns of the main tile each =====================
+    const int cw = warp - 2;
+    const int quarter = warp & 3;
+    const int part = cw >> 2;              // 0..3: key groups 5 * part .. 5 * part + 4 (8 keys = 16 B of a P row each)
+    const int g0 = 5 * part;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int rloc = quarter * 32 + lane;  // query row of the main tile; key of the tail's first key tile
+    const int sw64 = (lane >> 1) & 3;
+    uint8_t* pRow = sP + rloc * 64;
+    auto grp = [&](int g) -> uint8_t* { return pRow + (g >> 2) * (128 * 64) + (((g & 3) ^ sw64) << 4); };
+    // the tail: parts 0..2 own query columns 8 * part .. + 7 of key rloc and, in lane quarter 0, of key 128 + lane as well
+    const bool tail_warp = part < 3;
+    const bool tail_hi = tail_warp && quarter == 0;
+    uint8_t* tRow0 = sT + rloc * 64;
+    uint8_t* tRow1 = sT + (128 + lane) * 64;
+    // staging slabs: parts 1..3 store one 32-channel atom of the main tile each; part 3 (which has no share of the tail's softmax)
+    // of quarters 0..2 also stores the tail
+    uint8_t* const slab = sX + ((part >= 1 ? part - 1 : 0) * 4 + quarter) * 2048;
+    uint8_t* const slab_t = sX + (12 + quarter) * 2048;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int nitems = (int)items;
+    int n = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+      const uint32_t ph = n & 1;
+      const int par = n & 1;
+      // ---- main tile: row maximum and exponentials from ONE read of this warp's 40 S columns ----
+      mbar_wait(s_full, ph);
+      tcgen05_fence_after();
+      FTC(0)
+      float mx, lsum;
+      {
+        uint32_t r[40];
+        tmem_ld32p(tmem_base + lane_off + (uint32_t)(C_S + g0 * 8), r);
+        tmem_ld8(tmem_base + lane_off + (uint32_t)(C_S + (g0 + 4) * 8), r + 32);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        FTC(1)
+        float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+        for (int i = 4; i < 40; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(r[i]));
+          m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
+          m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        xmax[part * 128 + rloc] = mx;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+        FTC(2)
+        mx = fmaxf(fmaxf(xmax[rloc], xmax[128 + rloc]), fmaxf(xmax[256 + rloc], xmax[384 + rloc]));
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = ex2_fast((__uint_as_float(r[8 * i + 2 * e]) - mx) * LOG2E);
+            const float p1 = ex2_fast((__uint_as_float(r[8 * i + 2 * e + 1]) - mx) * LOG2E);
+            l0 += p0;
+            l1 += p1;
+            __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+            w[e] = *reinterpret_cast<uint32_t*>(&hb);
+          }
+          *reinterpret_cast<uint4*>(grp(g0 + i)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        lsum = l0 + l1;
+        xsum[(par * 4 + part) * 128 + rloc] = lsum;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_done);
+      FTC(3)
+      // ---- tail: softmax down the lanes of S^T[key][query] ----
+      if (tail_warp) {
+        mbar_wait(st_full, ph);
+        tcgen05_fence_after();
+        FTC(4)
+        uint32_t r[16];
+        tmem_ld8(tmem_base + lane_off + (uint32_t)(C_T + 8 * part), r);
+        if (tail_hi) tmem_ld8(tmem_base + lane_off + (uint32_t)(C_T + FNT + 8 * part), r + 8);
+        const float* kb = kbias + (n % 3) * 160;
+        const float kb0 = kb[rloc], kb1 = kb[128 + lane];
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_free);
+        FTC(5)
+        float s0[8], s1[8], cm[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s0[i] = __uint_as_float(r[i]) + kb0;
+          s1[i] = tail_hi ? __uint_as_float(r[8 + i]) + kb1 : -INFINITY;
+          cm[i] = fmaxf(s0[i], s1[i]);
+        }
+        float* tmx = tmax + par * (4 * FNT);
+        {
+          const float cmax = warp_reduce8<true>(cm, lane);   // of column 8 * part + (lane >> 2)
+          if ((lane & 3) == 0) tmx[quarter * FNT + 8 * part + (lane >> 2)] = cmax;
+        }
+        asm volatile("bar.sync 5, 384;" ::: "memory");
+        FTC(6)
+        float cs[8];
+        uint32_t w0[4], w1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float pv[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = 2 * e + u, col = 8 * part + i;
+            const float mj = fmaxf(fmaxf(tmx[col], tmx[FNT + col]), fmaxf(tmx[2 * FNT + col], tmx[3 * FNT + col]));
+            pv[u] = ex2_fast((s0[i] - mj) * LOG2E);
+            pv[2 + u] = tail_hi ? ex2_fast((s1[i] - mj) * LOG2E) : 0.f;
+            cs[i] = pv[u] + pv[2 + u];
+          }
+          __nv_bfloat162 hb = __floats2bfloat162_rn(pv[0], pv[1]);
+          w0[e] = *reinterpret_cast<uint32_t*>(&hb);
+          hb = __floats2bfloat162_rn(pv[2], pv[3]);
+          w1[e] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        float* tsm = tsum + par * (4 * FNT);
+        {
+          const float csum = warp_reduce8<false>(cs, lane);
+          if ((lane & 3) == 0) tsm[quarter * FNT + 8 * part + (lane >> 2)] = csum;
+        }
+        *reinterpret_cast<uint4*>(tRow0 + ((part ^ sw64) << 4)) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+        if (part == 2) *reinterpret_cast<uint4*>(tRow0 + ((3 ^ sw64) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // query columns 24..31
+        if (tail_hi) {
+          *reinterpret_cast<uint4*>(tRow1 + ((part ^ sw64) << 4)) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+          if (part == 2) *reinterpret_cast<uint4*>(tRow1 + ((3 ^ sw64) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pt_done);
+        FTC(7)
+      }
+      // ---- main tile epilogue: O / l -> bf16 -> TMA store; parts 1.. take one 32-channel atom each, part 0 the row statistics ----
+      const int b = it / heads, h = it - b * heads;
+      mbar_wait(o_full, ph);
+      tcgen05_fence_after();
+      FTC(8)
+      {
+        const float* xs = xsum + par * 512 + rloc;
+        const float inv = 1.f / ((xs[0] + xs[128]) + (xs[256] + xs[384]));
+        if (part >= 1 && part - 1 < DA) {
+          const int c = part - 1;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_off + (uint32_t)(C_O + c * 32), r);
+          if (lane == 0) bulk_wait_read<0>();   // the previous item's store has read this slab
+          __syncwarp();
+          tmem_ld_wait();
+          uint8_t* dst = slab + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * e]) * inv, __uint_as_float(r[j * 8 + 2 * e + 1]) * inv);
+              w[e] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+            *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmO, slab, h * DH + c * 32, quarter * 32, b);
+            bulk_commit();
+          }
+        } else if (part == 0 && stats != nullptr) {
+          *reinterpret_cast<float2*>(stats + ((int64_t)it * L + rloc) * 2) = make_float2(mx, inv);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      FTC(9)
+      // ---- tail epilogue: O_tail^T[channel][query] / l_query, transposed into rows 128.. of O ----
+      if (part == 3 && quarter * 32 < DH) {
+        mbar_wait(ot_full, ph);
+        tcgen05_fence_after();
+        FTC(10)
+        uint32_t r[FNT];
+        tmem_ld8(tmem_base + lane_off + (uint32_t)C_OT, r);
+        tmem_ld8(tmem_base + lane_off + (uint32_t)C_OT + 8, r + 8);
+        tmem_ld8(tmem_base + lane_off + (uint32_t)C_OT + 16, r + 16);
+        const float* tsm = tsum + par * (4 * FNT);
+        const float* tmx = tmax + par * (4 * FNT);
+        // a lone warp issues about one instruction every five clocks, so every lane computes ONE reciprocal column sum and the
+        // warp shares them through shared memory
+        float* tiv = tinv + quarter * 32;
+        float my_inv = 0.f, my_max = 0.f;
+        if (lane < FNT) {
+          my_inv = 1.f / ((tsm[lane] + tsm[FNT + lane]) + (tsm[2 * FNT + lane] + tsm[3 * FNT + lane]));
+          my_max = fmaxf(fmaxf(tmx[lane], tmx[FNT + lane]), fmaxf(tmx[2 * FNT + lane], tmx[3 * FNT + lane]));
+          tiv[lane] = my_inv;
+        }
+        __syncwarp();
+        float invj[FNT];
+#pragma unroll
+        for (int i = 0; i < FNT; ++i) invj[i] = tiv[i];
+        if (lane == 0) bulk_wait_read<1>();   // the tail store of the previous item has read slab_t (this item's main-tile store may be pending)
+        __syncwarp();
+        FTC(12)
+        tmem_ld_wait();
+        FTC(13)
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ot_free);
+#pragma unroll
+        for (int i = 0; i < FNT; ++i)   // query 128 + i = row i of the box; this lane's channel = column lane
+          *reinterpret_cast<__nv_bfloat16*>(slab_t + i * 64 + ((((lane >> 3) ^ ((i >> 1) & 3))) << 4) + (lane & 7) * 2) =
+              __float2bfloat16_rn(__uint_as_float(r[i]) * invj[i]);
+        FTC(14)
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO, slab_t, h * DH + quarter * 32, 128, b);   // rows >= L are clipped
+          bulk_commit();
+        }
+        FTC(11)
+        if (quarter == 0 && stats != nullptr && lane < FNT && 128 + lane < L)
+          *reinterpret_cast<float2*>(stats + ((int64_t)it * L + 128 + lane) * 2) = make_float2(my_max, my_inv);
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+#undef FTM
+#undef FTC
+
+template <int DH>
+static int launch_tt(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                     const uint8_t* mask, float* stats, int64_t batch, int heads, int L, cudaStream_t st) {
+  constexpr int SMEM = ft_smem_bytes<DH>();
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  const int cols = heads * DH;
+  if (make_map3(&tmQ, q, cols, L, batch, ldq, 160)) return 1;
+  if (make_map3(&tmK, k, cols, L, batch, ldk, 160)) return 1;
+  if (make_map3(&tmV, v, cols, L, batch, ldv, 160)) return 1;
+  if (make_map3(&tmO, o, cols, L, batch, ldo, 32)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tt_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    SPA3D_REQUIRE(e == cudaSuccess, "attention_tc (tail): smem attribute (%d B): %s", SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t items = batch * heads;
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  attn_fwd_tt_kernel<DH><<<grid, FT_THREADS, SMEM, st>>>(tmQ, tmK, tmV, tmO, mask, stats, items, heads, L);
+#ifdef SPA3D_ATTN_TRACE
+  static int calls = 0;
+  if (++calls == 3) {
+    cudaDeviceSynchronize();
+    long long hbuf[128];
+    cudaMemcpyFromSymbol(hbuf, g_fwd_trace, sizeof(hbuf));
+    for (int i = 0; i < 128; ++i) if (hbuf[i]) printf("FTRACE %d %lld\n", i, hbuf[i] - hbuf[0]);
+    fflush(stdout);
+  }
+#endif
+  return check_launch("attention_fwd_tc_tail");
+}
+
 // combine the key chunks of the cross-attention: one warp per (sequence, head, query row)
 template <int DH>
 __global__ void attn_cross_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, bf16* __restrict__ o, int64_t ldo,
@@ -669,6 +1172,16 @@ int attention_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                      int64_t ldo, const uint8_t* key_mask, float* stats, int64_t batch, int heads, int L, int Dh,
                      cudaStream_t st) {
   using namespace ta;
+  // 128 < L <= 152: transposed-tail kernel (SPA3D_ATTN_FWD_TT=0: two-tile kernel, for A/B runs)
+  static int tt = -1;
+  if (tt < 0) {
+    const char* e = getenv("SPA3D_ATTN_FWD_TT");
+    tt = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (tt && L > 128 && L <= 128 + FNT) {
+    if (Dh == 96) return launch_tt<96>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+    return launch_tt<64>(q, ldq, k, ldk, v, ldv, o, ldo, key_mask, stats, batch, heads, L, st);
+  }
   static int np1 = -1;   // A/B switch for measurements: SPA3D_ATTN_NP=1 keeps one softmax warp per (tile, lane quarter)
   if (np1 < 0) {
     const char* e = getenv("SPA3D_ATTN_NP");
