@@ -602,7 +602,7 @@ __device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
 
 template <int DH>
 constexpr int ft_smem_bytes() {
-  return 4 * (DH / 32) * 160 * 64 + 5 * 128 * 64 + 15 * 2048 + 160 * 64 + 128 * 32 + 2 * 160 * 32 + 10240 + 1024;
+  return 4 * (DH / 32) * 160 * 64 + 5 * 128 * 64 + 15 * 2048 + 160 * 64 + 128 * 32 + 2 * 160 * 32 + 10752 + 1024;
 }
 __host__ __device__ constexpr uint32_t idesc_tt(int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) |
@@ -625,7 +625,7 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    int heads, int L) {
   constexpr int LPAD = 160, DA = DH / 32, KA = 5;
   constexpr int OPA = LPAD * 64, OP_BYTES = DA * OPA, PT_BYTES = KA * 128 * 64;
-  constexpr int C_S = 0, C_O = 160, C_T = 256, C_OT = 304;
+  constexpr int C_S = 0, C_O = 160, C_T = 352, C_OT = 400;   // O and O_tail^T are double-buffered: [160,352) and [400,448)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -639,14 +639,14 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float* kbias = reinterpret_cast<float*>(sB + 2 * LPAD * 32);   // [3][160] key bias per key, for the tail's per-lane keys
   float* xmax = kbias + 480;               // [4][128] row maxima of the four column shares
   float* xsum = xmax + 512;                // [2][4][128] row sums (by item parity: the epilogue of item n overlaps the softmax of item n+1)
-  float* tmax = xsum + 1024;               // [2][4][FNT] column maxima per key quarter
-  float* tsum = tmax + 192;                // [2][4][FNT] column sums per key quarter
+  float* tmax = xsum + 1024;               // [3][4][FNT] column maxima per key quarter (written before the tail's exchange barrier: three items deep)
+  float* tsum = tmax + 288;                // [2][4][FNT] column sums per key quarter
   float* tinv = tsum + 192;                // [4][32] 1 / column sum, private to each tail-epilogue warp
   uint64_t* bars = reinterpret_cast<uint64_t*>(tinv + 128);
   uint64_t* qk_full = bars, *qk_empty = bars + 1, *v_full = bars + 2, *v_empty = bars + 4, *m_full = bars + 6;
   uint64_t* s_full = bars + 8, *st_full = bars + 9, *p_done = bars + 10, *pt_done = bars + 11, *o_full = bars + 12, *ot_full = bars + 13;
-  uint64_t* s_free = bars + 14, *t_free = bars + 15, *o_free = bars + 16, *ot_free = bars + 17;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* s_free = bars + 14, *t_free = bars + 15, *o_free = bars + 16 /* [2], one per O buffer */, *ot_free = bars + 18;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -657,7 +657,7 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(qk_full, 1); mbar_init(qk_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); mbar_init(&m_full[i], 1); }
     mbar_init(s_full, 1); mbar_init(st_full, 1); mbar_init(p_done, 16); mbar_init(pt_done, 12); mbar_init(o_full, 1); mbar_init(ot_full, 1);
-    mbar_init(s_free, 16); mbar_init(t_free, 12); mbar_init(o_free, 16); mbar_init(ot_free, DA);
+    mbar_init(s_free, 16); mbar_init(t_free, 12); mbar_init(&o_free[0], 16); mbar_init(&o_free[1], 16); mbar_init(ot_free, DA);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -730,28 +730,24 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idS = idesc_tt(LPAD, false, false), idO = idesc_tt(DH, false, true);
       constexpr uint32_t idTs = idesc_tt(FNT, false, false), idTo = idesc_tt(FNT, true, true);
-      int n = 0;
-      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const uint32_t ph = n & 1;
-        const int mb = n & 1, vb = n & 1;
-        const uint8_t* vbuf = sV + vb * OP_BYTES;
+      // issue order: S(0) S^T(0) | P V(n), S(n+1) S^T(n+1), V^T P^T(n) | ...: the logits of the next item are ready before the softmax
+      // warps have finished with this one, and neither product of an item sits behind a wait that belongs to the other
+      auto issue_s = [&](int m) {   // S and S^T of the CTA's m-th item
+        const uint32_t ph = m & 1;
+        const int mb = m & 1;
         mbar_wait(qk_full, ph);
-        mbar_wait(&m_full[mb], (n >> 1) & 1);
-        FTM(0)
+        mbar_wait(&m_full[mb], (m >> 1) & 1);
         mbar_wait(s_free, ph ^ 1);   // the softmax of the previous item has S in registers
         tcgen05_fence_after();
-        FTM(1)
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
           umma_bf16(tmem_base + C_S, desc_k64(smem_u32(sQ + (kk >> 1) * OPA + (kk & 1) * 32)),
                     desc_k64(smem_u32(sK + (kk >> 1) * OPA + (kk & 1) * 32)), idS, kk > 0 ? 1u : 0u);
         umma_bf16(tmem_base + C_S, desc_k32(smem_u32(sE)), desc_k32(smem_u32(sB + mb * (LPAD * 32))), idS, 1u);
         umma_commit(s_full);
-        FTM(2)
         // tail: S^T = K Q_tail^T, key tiles 0..127 and 128..159 (a key is a TMEM lane there: its bias is added by the thread)
         mbar_wait(t_free, ph ^ 1);
         tcgen05_fence_after();
-        FTM(3)
 #pragma unroll
         for (int kt = 0; kt < 2; ++kt)
 #pragma unroll
@@ -760,30 +756,42 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                       desc_k64(smem_u32(sQ + (kk >> 1) * OPA + 128 * 64 + (kk & 1) * 32)), idTs, kk > 0 ? 1u : 0u);
         umma_commit(st_full);
         umma_commit(qk_empty);
-        FTM(4)
+      };
+      issue_s(0);
+      int n = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const uint32_t ph = n & 1;
+        const int vb = n & 1;
+        const uint8_t* vbuf = sV + vb * OP_BYTES;
+        FTM(0)
         // O = P V (main tile)
         mbar_wait(&v_full[vb], (n >> 1) & 1);
-        FTM(5)
         mbar_wait(p_done, ph);
         FTM(6)
-        mbar_wait(o_free, ph ^ 1);
+        // the epilogue of item n - 2 has read this O buffer.  One barrier per buffer: with a single one this wait (completion n - 2)
+        // could find the epilogue of item n - 1 complete as well and mistake the phase
+        mbar_wait(&o_free[n & 1], ((n >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         FTM(7)
 #pragma unroll
         for (int ks = 0; ks < LPAD / 16; ++ks)
-          umma_bf16(tmem_base + C_O, desc_k64(smem_u32(sP + (ks >> 1) * (128 * 64) + (ks & 1) * 32)),
+          umma_bf16(tmem_base + C_O + (n & 1) * DH, desc_k64(smem_u32(sP + (ks >> 1) * (128 * 64) + (ks & 1) * 32)),
                     desc_mn64(smem_u32(vbuf + ks * 1024), OPA), idO, ks > 0 ? 1u : 0u);
         umma_commit(o_full);
         FTM(8)
+        if (it + gridDim.x < items) issue_s(n + 1);
+        FTM(4)
         // tail: O_tail^T = V^T P_tail^T
         mbar_wait(pt_done, ph);
         FTM(9)
-        mbar_wait(ot_free, ph ^ 1);
+        // the tail epilogue of the PREVIOUS item has read its O_tail^T: not for the buffer (there are two) but so that the three warps
+        // that wait on ot_full only there have seen its previous phase before this product can complete the next one
+        if (n >= 1) mbar_wait(ot_free, ph ^ 1);
         tcgen05_fence_after();
         FTM(10)
 #pragma unroll
         for (int ks = 0; ks < LPAD / 16; ++ks)
-          umma_bf16(tmem_base + C_OT, desc_mn64(smem_u32(vbuf + ks * 1024), OPA), desc_mn64(smem_u32(sT + ks * 1024), 1024), idTo,
+          umma_bf16(tmem_base + C_OT + (n & 1) * FNT, desc_mn64(smem_u32(vbuf + ks * 1024), OPA), desc_mn64(smem_u32(sT + ks * 1024), 1024), idTo,
                     ks > 0 ? 1u : 0u);
         umma_commit(ot_full);
         umma_commit(&v_empty[vb]);
@@ -813,14 +821,20 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr float LOG2E = 1.4426950408889634f;
     const int nitems = (int)items;
     int n = 0;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+    // The epilogues lag one item behind the softmax: O (and O_tail^T) of item n are drained after the softmax of item n + 1, so the
+    // P V and V^T P^T products, and the TMEM reads they have to wait for, never sit between two phases of the same warp.
+    float mx_prev = 0.f;
+    for (int it = blockIdx.x;; it += gridDim.x, ++n) {
+      const bool have = it < nitems;
       const uint32_t ph = n & 1;
       const int par = n & 1;
+      float mx = 0.f;
+      if (have) {
       // ---- main tile: row maximum and exponentials from ONE read of this warp's 40 S columns ----
       mbar_wait(s_full, ph);
       tcgen05_fence_after();
       FTC(0)
-      float mx, lsum;
+      float lsum;
       {
         uint32_t r[40];
         tmem_ld32p(tmem_base + lane_off + (uint32_t)(C_S + g0 * 8), r);
@@ -843,6 +857,7 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
         FTC(2)
         mx = fmaxf(fmaxf(xmax[rloc], xmax[128 + rloc]), fmaxf(xmax[256 + rloc], xmax[384 + rloc]));
+        if (n > 0) mbar_wait(o_full, ph ^ 1);   // P V of the previous item has read the P tile
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -887,7 +902,7 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           s1[i] = tail_hi ? __uint_as_float(r[8 + i]) + kb1 : -INFINITY;
           cm[i] = fmaxf(s0[i], s1[i]);
         }
-        float* tmx = tmax + par * (4 * FNT);
+        float* tmx = tmax + (n % 3) * (4 * FNT);
         {
           const float cmax = warp_reduce8<true>(cm, lane);   // of column 8 * part + (lane >> 2)
           if ((lane & 3) == 0) tmx[quarter * FNT + 8 * part + (lane >> 2)] = cmax;
@@ -912,6 +927,7 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           hb = __floats2bfloat162_rn(pv[2], pv[3]);
           w1[e] = *reinterpret_cast<uint32_t*>(&hb);
         }
+        if (n > 0) mbar_wait(ot_full, ph ^ 1);   // V^T P^T of the previous item has read the P^T tile
         float* tsm = tsum + par * (4 * FNT);
         {
           const float csum = warp_reduce8<false>(cs, lane);
@@ -928,57 +944,23 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane == 0) mbar_arrive(pt_done);
         FTC(7)
       }
-      // ---- main tile epilogue: O / l -> bf16 -> TMA store; parts 1.. take one 32-channel atom each, part 0 the row statistics ----
-      const int b = it / heads, h = it - b * heads;
-      mbar_wait(o_full, ph);
-      tcgen05_fence_after();
-      FTC(8)
-      {
-        const float* xs = xsum + par * 512 + rloc;
-        const float inv = 1.f / ((xs[0] + xs[128]) + (xs[256] + xs[384]));
-        if (part >= 1 && part - 1 < DA) {
-          const int c = part - 1;
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_off + (uint32_t)(C_O + c * 32), r);
-          if (lane == 0) bulk_wait_read<0>();   // the previous item's store has read this slab
-          __syncwarp();
-          tmem_ld_wait();
-          uint8_t* dst = slab + lane * 64;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * e]) * inv, __uint_as_float(r[j * 8 + 2 * e + 1]) * inv);
-              w[e] = *reinterpret_cast<uint32_t*>(&hb);
-            }
-            *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&tmO, slab, h * DH + c * 32, quarter * 32, b);
-            bulk_commit();
-          }
-        } else if (part == 0 && stats != nullptr) {
-          *reinterpret_cast<float2*>(stats + ((int64_t)it * L + rloc) * 2) = make_float2(mx, inv);
-        }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
-      FTC(9)
+      }   // have
+      if (n > 0) {
+      const int itp = it - (int)gridDim.x;   // the item whose outputs are drained now
+      const uint32_t pph = (n - 1) & 1;
+      const int ppar = (n - 1) & 1;
+      const int b = itp / heads, h = itp - b * heads;
       // ---- tail epilogue: O_tail^T[channel][query] / l_query, transposed into rows 128.. of O ----
       if (part == 3 && quarter * 32 < DH) {
-        mbar_wait(ot_full, ph);
+        mbar_wait(ot_full, pph);
         tcgen05_fence_after();
         FTC(10)
         uint32_t r[FNT];
-        tmem_ld8(tmem_base + lane_off + (uint32_t)C_OT, r);
-        tmem_ld8(tmem_base + lane_off + (uint32_t)C_OT + 8, r + 8);
-        tmem_ld8(tmem_base + lane_off + (uint32_t)C_OT + 16, r + 16);
-        const float* tsm = tsum + par * (4 * FNT);
-        const float* tmx = tmax + par * (4 * FNT);
+        tmem_ld8(tmem_base + lane_off + (uint32_t)(C_OT + ppar * FNT), r);
+        tmem_ld8(tmem_base + lane_off + (uint32_t)(C_OT + ppar * FNT) + 8, r + 8);
+        tmem_ld8(tmem_base + lane_off + (uint32_t)(C_OT + ppar * FNT) + 16, r + 16);
+        const float* tsm = tsum + ppar * (4 * FNT);
+        const float* tmx = tmax + ((n - 1) % 3) * (4 * FNT);
         // a lone warp issues about one instruction every five clocks, so every lane computes ONE reciprocal column sum and the
         // warp shares them through shared memory
         float* tiv = tinv + quarter * 32;
@@ -992,7 +974,7 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float invj[FNT];
 #pragma unroll
         for (int i = 0; i < FNT; ++i) invj[i] = tiv[i];
-        if (lane == 0) bulk_wait_read<1>();   // the tail store of the previous item has read slab_t (this item's main-tile store may be pending)
+        if (lane == 0) bulk_wait_read<1>();   // the tail store of the previous item has read slab_t (its main-tile store may be pending)
         __syncwarp();
         FTC(12)
         tmem_ld_wait();
@@ -1013,8 +995,54 @@ attn_fwd_tt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         FTC(11)
         if (quarter == 0 && stats != nullptr && lane < FNT && 128 + lane < L)
-          *reinterpret_cast<float2*>(stats + ((int64_t)it * L + 128 + lane) * 2) = make_float2(my_max, my_inv);
+          *reinterpret_cast<float2*>(stats + ((int64_t)itp * L + 128 + lane) * 2) = make_float2(my_max, my_inv);
       }
+          // ---- main tile epilogue: O / l -> bf16 -> TMA store; parts 1.. take one 32-channel atom each, part 0 the row statistics ----
+      // o_full of that item was already waited for in this iteration's softmax (before P was overwritten); waiting again here could
+      // see the barrier two phases on (P V of the current item may have completed) and block for good
+      if (!have) mbar_wait(o_full, pph);
+      tcgen05_fence_after();
+      FTC(8)
+      {
+        const float* xs = xsum + ppar * 512 + rloc;
+        const float inv = 1.f / ((xs[0] + xs[128]) + (xs[256] + xs[384]));
+        if (part >= 1 && part - 1 < DA) {
+          const int c = part - 1;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_off + (uint32_t)(C_O + ppar * DH + c * 32), r);
+          if (lane == 0) {   // the previous item's store has read this slab (part 3 may have its tail store of this item pending)
+            if (part == 3 && quarter * 32 < DH) bulk_wait_read<1>(); else bulk_wait_read<0>();
+          }
+          __syncwarp();
+          tmem_ld_wait();
+          uint8_t* dst = slab + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * e]) * inv, __uint_as_float(r[j * 8 + 2 * e + 1]) * inv);
+              w[e] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+            *reinterpret_cast<uint4*>(dst + ((j ^ sw64) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmO, slab, h * DH + c * 32, quarter * 32, b);
+            bulk_commit();
+          }
+        } else if (part == 0 && stats != nullptr) {
+          *reinterpret_cast<float2*>(stats + ((int64_t)itp * L + rloc) * 2) = make_float2(mx_prev, inv);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[ppar]);
+      FTC(9)
+      }   // n > 0
+      mx_prev = mx;
+      if (!have) break;
     }
     if (lane == 0) bulk_wait_read<0>();
   }

@@ -309,6 +309,38 @@ def test_attention_bwd(spa, dtype, Lq, Lk, Dh):
         assert rel_err(got, want) < tol, rel_err(got, want)
 
 
+@pytest.mark.parametrize("L,Dh", [(151, 96), (129, 96), (145, 64), (128, 96), (160, 96)])
+def test_attention_many_items_per_cta(spa, L, Dh):
+    """Several (sequence, head) items per persistent CTA: the cross-item pipelines of the tcgen05 kernels (operand release, lagging
+    epilogues, double-buffered accumulators) only show up with more items than SMs."""
+    ops = spa.ops
+    torch.manual_seed(11)
+    batch, H = 160, 4   # 640 items over 148 CTAs
+    A = H * Dh
+    q = (torch.randn(batch * L, A, device="cuda") / math.sqrt(Dh)).to(torch.bfloat16)
+    k = torch.randn(batch * L, A, device="cuda").to(torch.bfloat16)
+    v = torch.randn(batch * L, A, device="cuda").to(torch.bfloat16)
+    mask = (torch.rand(batch, L, device="cuda") < 0.8).to(torch.uint8)
+    mask[:, 0] = 1
+    mask[5] = 0
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qd, kd, vd, mask, batch, H, L, L, Dh)
+    d_o = torch.randn(batch * L, A, device="cuda").to(torch.bfloat16)
+    ref.backward(d_o.double())
+    o = torch.empty(batch * L, A, device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):   # twice: the second launch must not depend on state the first one left behind
+        o.zero_()
+        stats = ops.attention_fwd(q, k, v, o, batch, H, L, L, Dh, mask, save_stats=True)
+        assert rel_err(o, ref.detach()) < 1e-2, rel_err(o, ref.detach())
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ops.attention_bwd(q, k, v, o, d_o, dq, dk, dv, stats, batch, H, L, L, Dh, mask)
+        for got, want in ((dq, qd.grad), (dk, kd.grad), (dv, vd.grad)):
+            assert rel_err(got, want) < 2e-2, rel_err(got, want)
+    # per-sequence check: an error confined to one item would be averaged away above
+    per_seq = ((o.float() - ref.detach().float()).reshape(batch, -1).norm(dim=1) / ref.detach().float().reshape(batch, -1).norm(dim=1)).max().item()
+    assert per_seq < 2e-2, per_seq
+
+
 @pytest.mark.parametrize("Lk,Dh", [(151, 96), (129, 96), (160, 64), (7, 64), (1, 96)])
 def test_attention_one_query(spa, Lk, Dh):
     """Lq = 1 (the pruned last layers): dedicated kernel, key mask incl. a fully masked sequence, forward + backward."""
