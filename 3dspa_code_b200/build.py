@@ -25,6 +25,7 @@ SOURCES = [
     "attention_tc_bwd.cu",
     "attention_q1.cu",
     "attention_api.cu",
+    "host_pack.cc",      # host-only (g++): float32 -> bfloat16 staging of the end-to-end path
 ]
 
 NVCC_FLAGS = [
@@ -55,15 +56,18 @@ def _digest(path, extra=""):
 
 
 def _compile(src, verbose):
-    obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+    obj = os.path.join(BUILD, os.path.splitext(src)[0] + ".o")
     stamp = obj + ".sha"
     dig = _digest(os.path.join(CSRC, src), " ".join(NVCC_FLAGS))
     if os.path.isfile(obj) and os.path.isfile(stamp) and open(stamp).read() == dig:
         return obj, False
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    if src.endswith(".cc"):
+        cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-Wall", "-pthread", "-c", os.path.join(CSRC, src), "-o", obj]
+    else:
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+        raise RuntimeError(f"compile failed for {src}:\n{res.stdout}\n{res.stderr}")
     if verbose:
         sys.stderr.write(res.stderr)
     with open(stamp, "w") as f:

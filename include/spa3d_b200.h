@@ -356,6 +356,13 @@ int spa3d_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, co
                      float clip_norm, float lr, float b1, float b2, float eps, float wd,
                      int step, void* stream);
 
+/* ---- host-side staging for the end-to-end path (csrc/host_pack.cc; no device work) ---------
+ * dst[i] = bf16(src[i]) for n float32 values in HOST memory, round to nearest even (bit-identical to the
+ * device-side conversion of the embedding producers), on `threads` host threads, streaming stores.
+ * Replaces nothing in the reference: it halves the PCIe bytes of the float32 DINOv2 maps / features the
+ * reference's pipeline hands over on the host (inference.py:523-590) before model.apply. */
+int spa3d_host_pack_bf16(const float* src, void* dst, int64_t n, int threads);
+
 #ifdef __cplusplus
 }
 #endif

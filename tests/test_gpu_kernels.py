@@ -309,7 +309,7 @@ def test_attention_bwd(spa, dtype, Lq, Lk, Dh):
         assert rel_err(got, want) < tol, rel_err(got, want)
 
 
-@pytest.mark.parametrize("L,Dh", [(151, 96), (129, 96), (145, 64), (128, 96), (160, 96)])
+@pytest.mark.parametrize("L,Dh", [(151, 96), (129, 96), (152, 96), (137, 96), (145, 64), (128, 96), (160, 96)])
 def test_attention_many_items_per_cta(spa, L, Dh):
     """Several (sequence, head) items per persistent CTA: the cross-item pipelines of the tcgen05 kernels (operand release, lagging
     epilogues, double-buffered accumulators) only show up with more items than SMs."""
