@@ -468,6 +468,18 @@ def adamw_step(p, g, m, v, sumsq_t, clip_norm, lr, b1, b2, eps, wd, step):
           float(eps), float(wd), int(step), _stream())
 
 
+def host_pack_bf16(src: torch.Tensor, dst: torch.Tensor, threads: int = 1):
+    """dst (host, bfloat16) = bf16(src) (host, float32), round to nearest even, on ``threads`` host threads (csrc/host_pack.cc).
+    No device work and no launch: the staging step of model.apply_stream(host_pack="bf16").  Releases the GIL while it runs."""
+    if src.is_cuda or dst.is_cuda or src.dtype != torch.float32 or dst.dtype != torch.bfloat16:
+        raise ValueError("host_pack_bf16: float32 host source, bfloat16 host destination")
+    if not (src.is_contiguous() and dst.is_contiguous()) or src.numel() != dst.numel():
+        raise ValueError("host_pack_bf16: contiguous tensors of equal size")
+    _lib.check(_lib.lib().spa3d_host_pack_bf16(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), src.numel(), int(threads)),
+               "spa3d_host_pack_bf16")
+    return dst
+
+
 def inv_sqrt(d):
     return 1.0 / math.sqrt(d)
 

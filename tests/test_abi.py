@@ -35,6 +35,30 @@ def test_ops_refuse_cpu_tensors(spa):
         spa.ops.convert(torch.zeros(2, 2), torch.zeros(2, 2))
 
 
+def test_host_pack_bf16_is_round_to_nearest_even(spa):
+    """spa3d_host_pack_bf16 (host-only code of the library): bit-identical to torch's float32 -> bfloat16 conversion, for every
+    thread count, ragged sizes, unaligned destinations, infinities, signed zeros, denormals and ties; NaN stays NaN."""
+    import torch
+    g = torch.Generator().manual_seed(3)
+    for n in (0, 1, 31, 32, 33, 1000, (1 << 16) + 17, 3 * (1 << 16) + 5):
+        src = torch.randn(n + 1, generator=g)[1:].contiguous() * 3
+        if n >= 31:
+            src[:7] = torch.tensor([float("inf"), -float("inf"), 0.0, -0.0, 1e-40, 3.3895314e38, float("nan")])
+            bits = torch.tensor([0x3F808000, 0x3F818000, 0x3F807FFF, 0x3F808001, 0x7F7FFFFF], dtype=torch.int32)   # ties and neighbours
+            src[7:12] = bits.view(torch.float32)
+        want = src.to(torch.bfloat16)
+        for threads in (1, 2, 5):
+            for off in (0, 1):      # 1: destination not 64-byte aligned (plain stores instead of streaming stores)
+                buf = torch.zeros(n + 8, dtype=torch.bfloat16)
+                dst = buf[off:off + n]
+                spa.ops.host_pack_bf16(src, dst, threads)
+                same = (dst.view(torch.int16) == want.view(torch.int16)) | (dst.isnan() & want.isnan())
+                assert bool(same.all()), (n, threads, off)
+                assert float(buf[off + n:].abs().sum()) == 0 and float(buf[:off].abs().sum()) == 0
+    with pytest.raises(ValueError):
+        spa.ops.host_pack_bf16(torch.zeros(4), torch.zeros(4), 1)
+
+
 def test_pack_unpack_roundtrip_and_counts(spa):
     model = spa.TrackAutoEncoder3D()
     tree = model.init(0, {"dino_features": 1, "depth_features": 1})["params"]

@@ -379,14 +379,24 @@ def test_apply_stream_equals_per_clip_apply(spa):
     batches = [pin(b) for b, _ in clips]
     noises = [torch.as_tensor(n).pin_memory() for _, n in clips]
     refs = [model.apply(variables, b, noise=n, precision="bf16") for b, n in clips]
-    for graphed in (False, True):
+    # host_pack="bf16": the float32 features are rounded to bfloat16 on host threads, one clip ahead, instead of on the device -
+    # the same rounding, so not a bit of the result changes (7 clips: the ring of three staging buffers wraps twice)
+    for graphed, pack in ((False, None), (True, None), (False, "bf16"), (True, "bf16")):
         m = spa.TrackAutoEncoder3D(**fields)
         m.cuda_graph = graphed
-        got = list(m.apply_stream(variables, batches, noises=noises, precision="bf16"))
-        assert len(got) == len(refs)
-        for g, r in zip(got, refs):
+        rep = 1 if pack is None else 2
+        got = list(m.apply_stream(variables, (batches * rep)[:7], noises=(noises * rep)[:7], precision="bf16", host_pack=pack, pack_threads=3))
+        assert len(got) == min(7, len(refs) * rep)
+        for g, r in zip(got, refs * rep):
             assert not g.tracks.is_cuda
             assert torch.equal(g.tracks, r.tracks.cpu()) and torch.equal(g.visible_logits, r.visible_logits.cpu())
+    # a consumer that stops early releases the staging thread
+    gen = model.apply_stream(variables, batches, noises=noises, host_pack="bf16")
+    next(gen)
+    gen.close()
+    import threading, time
+    time.sleep(0.3)
+    assert not any(t.name == "spa3d-host-pack" and t.is_alive() for t in threading.enumerate())
     # one clip, zero clips
     assert len(list(model.apply_stream(variables, batches[:1], noises=noises[:1]))) == 1
     assert list(model.apply_stream(variables, [], noises=[])) == []
@@ -412,12 +422,13 @@ def test_apply_stream_from_maps_equals_apply_from_maps(spa):
                         "query_points": np.concatenate([rs.randint(0, T, (1, Q, 1)).astype(np.float32), rs.uniform(-1, 1, (1, Q, 3)).astype(np.float32)], -1)})
     noise = rs.uniform(size=(1, 128, 96)).astype(np.float32)
     refs = [model.apply_from_maps(variables, b, noise=noise) for b in batches]
-    got = list(model.apply_stream(variables, batches, noises=[noise] * 3, from_maps=True))
+    got = list(model.apply_stream(variables, batches, noises=[noise] * 3, from_maps=True, host_pack=None))
     for g, r in zip(got, refs):
         assert torch.equal(g.tracks, r.tracks.cpu()) and torch.equal(g.visible_logits, r.visible_logits.cpu())
-    gm = spa.TrackAutoEncoder3D()
-    gm.cuda_graph = True          # the maps forward of each device buffer set replayed as one CUDA graph
-    got = list(gm.apply_stream(variables, batches + batches, noises=[noise] * 6, from_maps=True))
-    assert len(gm._graphs) == 2
-    for g, r in zip(got, refs + refs):
-        assert torch.equal(g.tracks, r.tracks.cpu()) and torch.equal(g.visible_logits, r.visible_logits.cpu())
+    for pack in (None, "bf16"):   # the DINO patch map rounded to bf16 on the host instead of on the device: bit-identical
+        gm = spa.TrackAutoEncoder3D()
+        gm.cuda_graph = True          # the maps forward of each device buffer set replayed as one CUDA graph
+        got = list(gm.apply_stream(variables, batches + batches, noises=[noise] * 6, from_maps=True, host_pack=pack, pack_threads=2))
+        assert len(gm._graphs) == 2
+        for g, r in zip(got, refs + refs):
+            assert torch.equal(g.tracks, r.tracks.cpu()) and torch.equal(g.visible_logits, r.visible_logits.cpu())
