@@ -95,7 +95,32 @@ lift_sample_kernel(const float* __restrict__ tracks, const float* __restrict__ d
     const float* f10 = base + ((int64_t)b.y1 * Wp + b.x0) * D;
     const float* f11 = base + ((int64_t)b.y1 * Wp + b.x1) * D;
     TO* o = dino_out + pt * D;
-    if ((D & 3) == 0) {
+    if ((D & 255) == 0) {
+      // two 128-channel groups per trip (768 channels = 3 trips): eight independent 16-byte gathers are in flight per lane before
+      // the first blend - the kernel is bound by the latency of these L2 gathers (ncu: 74 % of the samples on the long
+      // scoreboard with four in flight), not by the bytes it writes
+      for (int c = lane * 4; c < D; c += 256) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(f00 + c));
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(f01 + c));
+        const float4 cq = __ldg(reinterpret_cast<const float4*>(f10 + c));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(f11 + c));
+        const float4 a2 = __ldg(reinterpret_cast<const float4*>(f00 + c + 128));
+        const float4 bq2 = __ldg(reinterpret_cast<const float4*>(f01 + c + 128));
+        const float4 cq2 = __ldg(reinterpret_cast<const float4*>(f10 + c + 128));
+        const float4 d2 = __ldg(reinterpret_cast<const float4*>(f11 + c + 128));
+        float4 r, r2;
+        r.x = blend(a.x, bq.x, cq.x, d.x, b.wx, b.wy, omx, omy);
+        r.y = blend(a.y, bq.y, cq.y, d.y, b.wx, b.wy, omx, omy);
+        r.z = blend(a.z, bq.z, cq.z, d.z, b.wx, b.wy, omx, omy);
+        r.w = blend(a.w, bq.w, cq.w, d.w, b.wx, b.wy, omx, omy);
+        r2.x = blend(a2.x, bq2.x, cq2.x, d2.x, b.wx, b.wy, omx, omy);
+        r2.y = blend(a2.y, bq2.y, cq2.y, d2.y, b.wx, b.wy, omx, omy);
+        r2.z = blend(a2.z, bq2.z, cq2.z, d2.z, b.wx, b.wy, omx, omy);
+        r2.w = blend(a2.w, bq2.w, cq2.w, d2.w, b.wx, b.wy, omx, omy);
+        store4<TO>(o + c, r);
+        store4<TO>(o + c + 128, r2);
+      }
+    } else if ((D & 3) == 0) {
       for (int c = lane * 4; c < D; c += 128) {
         float4 a = __ldg(reinterpret_cast<const float4*>(f00 + c));
         float4 bq = __ldg(reinterpret_cast<const float4*>(f01 + c));
