@@ -11,7 +11,7 @@ import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(HERE, "..", "include", "spa3d_b200.h")
-LIB_PATH = os.path.join(HERE, "lib3dspa_b200.so")
+LIB_PATH = os.environ.get("SPA3D_LIB_PATH") or os.path.join(HERE, "lib3dspa_b200.so")   # override: A/B of development builds
 
 _CTYPE = {
     "int": ctypes.c_int,

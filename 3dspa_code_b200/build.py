@@ -9,8 +9,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "lib3dspa_b200.so")
+TAG = os.environ.get("SPA3D_BUILD_TAG", "")   # development: a second library next to the product one (A/B with SPA3D_LIB_PATH)
+BUILD = os.path.join(HERE, "_build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "lib3dspa_b200" + ("_" + TAG if TAG else "") + ".so")
 
 SOURCES = [
     "api.cu",

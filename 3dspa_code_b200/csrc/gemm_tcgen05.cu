@@ -52,6 +52,19 @@ constexpr bool kSkipEpilogue = true;
 constexpr bool kSkipEpilogue = false;
 #endif
 
+// Cache policy of the streams a GEMM moves (A/B of four builds in one run, profiles/r02_gemm_cache_policy_ab.txt): the fp32 residual
+// read and the fp32 output of the residual flavour are touched once per kernel (0.5 - 1 GB, several times the 126 MB L2) and use
+// streaming loads / stores, so they do not push the weight and activation tiles other CTAs are about to re-read out of the L2:
+// N=1280 out-projection 0.183 -> 0.168 ms, N=384 MLP_out 0.422 -> 0.412 ms.  NOT for the bf16 side inputs of the backward epilogues
+// (the gelu'(z) the forward just wrote is still L2-resident: streaming it measured 0.557 -> 0.613 ms).  An L2 evict_last policy on the
+// weight-tile TMA loads changed nothing (the weights never leave the L2 anyway) and is compiled out.
+#ifndef SPA3D_TMA_HINTS
+#define SPA3D_TMA_HINTS 0
+#endif
+#ifndef SPA3D_EPI_STREAM
+#define SPA3D_EPI_STREAM 1
+#endif
+
 template <int BN>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -217,6 +230,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+#if SPA3D_TMA_HINTS
+      const uint64_t pol_w = l2_policy_evict_last();
+#endif
       for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int64_t tile = item_tile(t);
         const int sp = item_split(t);
@@ -235,7 +251,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               kw = wi * (int)K + kk;
             }
             tma_load_2d(smem_a + stage * L::A_BYTES, &tmA, ka, m_blk * BM, &full_bar[stage]);
+#if SPA3D_TMA_HINTS
+            tma_load_2d_hint(smem_b + stage * L::B_BYTES, &tmB, kw, n_blk * BN, &full_bar[stage], pol_w);
+#else
             tma_load_2d(smem_b + stage * L::B_BYTES, &tmB, kw, n_blk * BN, &full_bar[stage]);
+#endif
           } else {
             // 64 tokens x 64 columns per box; column chunk c lands 8 KB after chunk c-1 (= LBO)
 #pragma unroll
@@ -351,7 +371,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             res[i] = make_uint4(0, 0, 0, 0);
             if (i * 4 + cr < rows_ok) {
               if (ep.r_dtype == SPA3D_F32) {
+#if SPA3D_EPI_STREAM
+                res[i] = __ldcs(reinterpret_cast<const uint4*>(rp));
+#else
                 res[i] = *reinterpret_cast<const uint4*>(rp);
+#endif
               } else {
                 const uint2 h = *reinterpret_cast<const uint2*>(rp);
                 res[i].x = h.x;
@@ -471,7 +495,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                  "f"(a[i].w)
                                  : "memory");
                   } else if constexpr (OF) {
+#if SPA3D_EPI_STREAM
+                    __stcs(reinterpret_cast<float4*>(cpi), a[i]);
+#else
                     *reinterpret_cast<float4*>(cpi) = a[i];
+#endif
                   } else {
                     __nv_bfloat162 h0 = __floats2bfloat162_rn(a[i].x, a[i].y), h1 = __floats2bfloat162_rn(a[i].z, a[i].w);
                     *reinterpret_cast<uint2*>(cpi) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
