@@ -8,6 +8,8 @@
 // Mapping: one warp per track point; points are enumerated frame-major (p = t*N + n) so the
 // CTAs in flight at any moment gather from the same frame's DINO map (37x37x768 f32 = 4.2 MB),
 // which therefore stays L2-resident; lanes stride over channels with 128-bit loads/stores.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace spa3d {
@@ -35,7 +37,11 @@ template <typename TO>
 __device__ __forceinline__ void store4(TO* p, float4 v);
 template <>
 __device__ __forceinline__ void store4<float>(float* p, float4 v) {
+#ifdef SPA3D_LIFT_PLAIN_STORES
+  *reinterpret_cast<float4*>(p) = v;
+#else
   __stcs(reinterpret_cast<float4*>(p), v);   // streaming: written once, keep the L2 for the DINO maps
+#endif
 }
 template <>
 __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
@@ -140,13 +146,171 @@ lift_sample_kernel(const float* __restrict__ tracks, const float* __restrict__ d
   }
 }
 
+// ---- cell-binned form of the same gather ----------------------------------------------------------------------
+// What bounds the kernel above is the 4x read amplification of bilinear sampling on the L2 -> SM path: every point pulls its
+// four corner rows (4 x D floats = 12 KB at D = 768) through the L1 for 3 KB of output - 9.4 GB of gathers per cfg4 clip, of
+// which the L1 absorbs a third (ncu: 4.5 GB L2 -> L1, 74 % of the samples waiting on those loads, L2 / DRAM at 38 % / 51 %).
+// Measured and not kept on the way here: a persistent grid (same 0.78 ms), eight gathers in flight per lane (0.77), one scalar
+// phase per 8 points (0.87) and a cp.async.bulk version staging the four rows of every point in shared memory, one point
+// ahead (1.58 ms: no L1 reuse at all, 7.4 GB through the L2).
+// All points of a frame whose sample falls into the same patch cell share the four corner rows.  A pre-pass bins the points
+// of every frame by cell (counting sort in shared memory, one CTA per frame); the gather then walks (frame, cell) items: a
+// warp loads the cell's four corner rows ONCE into registers and blends them for every point of the cell, so the corner rows
+// are read once per occupied cell instead of once per point.  Same per-point arithmetic, same bits.
+// Cell key: the UNclamped floor of the sample position clamped to [-1, Wp-1] x [-1, Hp-1] - every point with that key has the
+// same clamped corners (x0, x1, y0, y1) in bilin_setup.
+__device__ __forceinline__ int lift_cell(float x, float y, float scale_w, float scale_h, int Wp, int Hp) {
+  const int kx = min(max((int)floorf(__fmul_rn(x, scale_w)), -1), Wp - 1);
+  const int ky = min(max((int)floorf(__fmul_rn(y, scale_h)), -1), Hp - 1);
+  return (ky + 1) * (Wp + 1) + (kx + 1);
+}
+
+// one CTA per frame: order[t*N + i] = the frame's point indices sorted by cell, starts[t*(cells+1) + c] = first position of cell c
+__global__ void __launch_bounds__(256)
+lift_bin_kernel(const float* __restrict__ tracks, int* __restrict__ order, int* __restrict__ starts, int N, int T, int Hp, int Wp,
+                float scale_w, float scale_h) {
+  extern __shared__ int bin_smem[];
+  const int cells = (Wp + 1) * (Hp + 1);
+  int* hist = bin_smem;            // [cells]: counts, then running cursors
+  int* part = bin_smem + cells;    // [256]: per-thread chunk sums
+  const int t = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < cells; c += 256) hist[c] = 0;
+  __syncthreads();
+  for (int n = tid; n < N; n += 256) {
+    const int64_t pt = (int64_t)n * T + t;
+    atomicAdd(&hist[lift_cell(tracks[pt * 2], tracks[pt * 2 + 1], scale_w, scale_h, Wp, Hp)], 1);
+  }
+  __syncthreads();
+  // exclusive scan: every thread owns a run of consecutive cells
+  const int per = (cells + 255) / 256, c0 = min(tid * per, cells), c1 = min(c0 + per, cells);
+  int sum = 0;
+  for (int c = c0; c < c1; ++c) sum += hist[c];
+  part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < 256; ++i) { const int v = part[i]; part[i] = run; run += v; }
+  }
+  __syncthreads();
+  int run = part[tid];
+  int* st = starts + (int64_t)t * (cells + 1);
+  for (int c = c0; c < c1; ++c) {
+    const int v = hist[c];
+    hist[c] = run;
+    st[c] = run;
+    run += v;
+  }
+  if (tid == 0) st[cells] = N;
+  __syncthreads();
+  for (int n = tid; n < N; n += 256) {
+    const int64_t pt = (int64_t)n * T + t;
+    const int pos = atomicAdd(&hist[lift_cell(tracks[pt * 2], tracks[pt * 2 + 1], scale_w, scale_h, Wp, Hp)], 1);
+    order[(int64_t)t * N + pos] = n;
+  }
+}
+
+#ifndef LIFT_BINNED_CTAS
+#define LIFT_BINNED_CTAS 2
+#endif
+// NJ 128-channel groups per pass (D is walked in passes of 128 * NJ channels; 4 * NJ float4 of corner rows live in registers)
+template <typename TO, int NJ>
+__global__ void __launch_bounds__(256, LIFT_BINNED_CTAS)
+lift_sample_binned_kernel(const float* __restrict__ tracks, const float* __restrict__ depth, const float* __restrict__ dino,
+                          const int* __restrict__ order, const int* __restrict__ starts, float* __restrict__ xyz,
+                          TO* __restrict__ dino_out, TO* __restrict__ depth_out, int N, int T, int H, int W, int Hp, int Wp, int D,
+                          int Cd, float scale_w, float scale_h, float fx, float fy, float cx, float cy) {
+  const int lane = threadIdx.x & 31;
+  const int cells = (Wp + 1) * (Hp + 1);
+  const int64_t items = (int64_t)T * cells, nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t it = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < items; it += nw) {
+    const int t = (int)(it / cells), cell = (int)(it % cells);
+    const int* st = starts + (int64_t)t * (cells + 1) + cell;
+    const int s0 = __ldg(st), s1 = __ldg(st + 1);
+    if (s0 == s1) continue;
+    const int kx = cell % (Wp + 1) - 1, ky = cell / (Wp + 1) - 1;
+    const int x0 = min(max(kx, 0), Wp - 1), x1 = min(max(kx + 1, 0), Wp - 1), y0 = min(max(ky, 0), Hp - 1), y1 = min(max(ky + 1, 0), Hp - 1);
+    const float* base = dino + (int64_t)t * Hp * Wp * D;
+    const float* f00 = base + ((int64_t)y0 * Wp + x0) * D;
+    const float* f01 = base + ((int64_t)y0 * Wp + x1) * D;
+    const float* f10 = base + ((int64_t)y1 * Wp + x0) * D;
+    const float* f11 = base + ((int64_t)y1 * Wp + x1) * D;
+    // the corner rows of the first pass are requested before the scalar phase: its chain of dependent loads (order -> track
+    // coordinates -> depth gathers -> previous-frame gathers) and the row gathers are then in flight together
+    float4 a[NJ], bq[NJ], cq[NJ], d[NJ];
+    auto load_rows = [&](int cb) {
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        const int c = cb + jj * 128 + lane * 4;
+        a[jj] = __ldg(reinterpret_cast<const float4*>(f00 + c));
+        bq[jj] = __ldg(reinterpret_cast<const float4*>(f01 + c));
+        cq[jj] = __ldg(reinterpret_cast<const float4*>(f10 + c));
+        d[jj] = __ldg(reinterpret_cast<const float4*>(f11 + c));
+      }
+    };
+    load_rows(0);
+    for (int b0 = s0; b0 < s1; b0 += 32) {
+      // ---- scalar phase: lane j owns point b0 + j of the cell ----
+      const int m = min(32, s1 - b0);
+      int n = 0;
+      float x = 0.f, y = 0.f, z = 0.f, grad = 0.f, wx = 0.f, wy = 0.f;
+      if (lane < m) {
+        n = __ldg(order + (int64_t)t * N + b0 + lane);
+        const int64_t pt = (int64_t)n * T + t;
+        x = tracks[pt * 2];
+        y = tracks[pt * 2 + 1];
+        const Bilin b = bilin_setup(__fmul_rn(x, scale_w), __fmul_rn(y, scale_h), Wp, Hp);
+        wx = b.wx;
+        wy = b.wy;
+        if (depth != nullptr) {
+          z = sample_depth(depth, t, H, W, x, y);
+          if (xyz != nullptr) {
+            xyz[pt * 3 + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(x, cx), z), fx);
+            xyz[pt * 3 + 1] = __fdiv_rn(__fmul_rn(__fsub_rn(y, cy), z), fy);
+            xyz[pt * 3 + 2] = z;
+          }
+          if (depth_out != nullptr && t > 0) {
+            const float zp = sample_depth(depth, t - 1, H, W, tracks[(pt - 1) * 2], tracks[(pt - 1) * 2 + 1]);
+            grad = __fsub_rn(z, zp);
+          }
+        }
+      }
+      // ---- depth-feature rows: (z, z/10, dz, 0) then zeros (inference.py:437-443) ----
+      if (depth != nullptr && depth_out != nullptr) {
+        for (int j = 0; j < m; ++j) {
+          const float zj = __shfl_sync(0xffffffffu, z, j), gj = __shfl_sync(0xffffffffu, grad, j);
+          TO* o = depth_out + ((int64_t)__shfl_sync(0xffffffffu, n, j) * T + t) * Cd;
+          for (int c = lane * 4; c < Cd; c += 128)
+            store4<TO>(o + c, c == 0 ? make_float4(zj, __fdiv_rn(zj, 10.f), gj, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+      // ---- feature rows: the cell's corner rows are loaded once per pass and blended for each of its points ----
+      for (int cb = 0; cb < D; cb += 128 * NJ) {
+        if (cb != 0 || b0 != s0) load_rows(cb);
+        for (int j = 0; j < m; ++j) {
+          const float wxj = __shfl_sync(0xffffffffu, wx, j), wyj = __shfl_sync(0xffffffffu, wy, j);
+          const float omx = __fsub_rn(1.f, wxj), omy = __fsub_rn(1.f, wyj);
+          TO* o = dino_out + ((int64_t)__shfl_sync(0xffffffffu, n, j) * T + t) * D + cb + lane * 4;
+#pragma unroll
+          for (int jj = 0; jj < NJ; ++jj) {
+            float4 r;
+            r.x = blend(a[jj].x, bq[jj].x, cq[jj].x, d[jj].x, wxj, wyj, omx, omy);
+            r.y = blend(a[jj].y, bq[jj].y, cq[jj].y, d[jj].y, wxj, wyj, omx, omy);
+            r.z = blend(a[jj].z, bq[jj].z, cq[jj].z, d[jj].z, wxj, wyj, omx, omy);
+            r.w = blend(a[jj].w, bq[jj].w, cq[jj].w, d[jj].w, wxj, wyj, omx, omy);
+            store4<TO>(o + jj * 128, r);
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace spa3d
 
-extern "C" int spa3d_lift_sample(const float* tracks_2d, const float* depth, const float* dino,
-                                 float* xyz, void* dino_out, void* depth_out, int out_dtype, int N,
-                                 int T, int H, int W, int Hp, int Wp, int D, int Cd, int video_H,
-                                 int video_W, const float* intrinsics, void* stream) {
-  using namespace spa3d;
+namespace spa3d {
+static int lift_sample_impl(const float* tracks_2d, const float* depth, const float* dino, float* xyz, void* dino_out, void* depth_out,
+                            int out_dtype, int N, int T, int H, int W, int Hp, int Wp, int D, int Cd, int video_H, int video_W,
+                            const float* intrinsics, void* workspace, int64_t workspace_bytes, void* stream) {
   int64_t pts = (int64_t)N * T;
   if (pts == 0) return 0;
   SPA3D_REQUIRE(tracks_2d != nullptr, "lift_sample: tracks_2d is NULL");
@@ -165,10 +329,69 @@ extern "C" int spa3d_lift_sample(const float* tracks_2d, const float* depth, con
     cx = (float)((double)W / 2.0);
     cy = (float)((double)H / 2.0);
   }
-  unsigned blocks = (unsigned)((pts + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
+  // cell-binned form: needs the patch features, channel groups of 128, vector-aligned rows and the caller's workspace
+  static int use_binned = -1;   // A/B switch for measurements: SPA3D_LIFT_BINNED=0 keeps the per-point kernel (both are product kernels)
+  if (use_binned < 0) {
+    const char* e = getenv("SPA3D_LIFT_BINNED");
+    use_binned = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const int64_t cells = (int64_t)(Wp + 1) * (Hp + 1);
+  const bool binned = use_binned && dino && dino_out && D % 128 == 0 && (depth_out == nullptr || Cd % 4 == 0) && workspace != nullptr &&
+                      workspace_bytes >= spa3d_lift_workspace_bytes(N, T, Hp, Wp) && (cells + 256) * 4 <= 200 * 1024 &&
+                      (reinterpret_cast<uintptr_t>(workspace) & 3) == 0;
+  if (binned) {
+    int* order = reinterpret_cast<int*>(workspace);
+    int* starts = order + pts;
+    const size_t bin_smem = (size_t)(cells + 256) * 4;
+    static bool attr_set = false;
+    if (!attr_set && bin_smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(lift_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      SPA3D_REQUIRE(e == cudaSuccess, "lift_sample: smem attribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    lift_bin_kernel<<<T, 256, bin_smem, st>>>(tracks_2d, order, starts, N, T, Hp, Wp, scale_w, scale_h);
+    if (check_launch("lift_bin")) return 1;
+    const int sms = num_sms();
+    const int64_t items = (int64_t)T * cells;
+    const unsigned grid = (unsigned)std::min<int64_t>((items + 7) / 8, (int64_t)sms * LIFT_BINNED_CTAS);
+    // measured on the cfg4 shape (D = 768): 3 groups per pass at two CTAs per SM 0.624 ms; 2 groups 0.643; 1 group 0.71 - 0.84; all six
+    // groups in one pass (168 registers, 12 warps per SM) 0.633 - 0.645; three CTAs per SM (80 registers) 0.638 with 2 groups
+    const int nj = D % 384 == 0 ? 3 : (D % 256 == 0 ? 2 : 1);
+    SPA3D_DISPATCH(out_dtype, TO, {
+      if (nj == 3)
+        lift_sample_binned_kernel<TO, 3><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, order, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
+      else if (nj == 2)
+        lift_sample_binned_kernel<TO, 2><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, order, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
+      else
+        lift_sample_binned_kernel<TO, 1><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, order, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
+    });
+    return check_launch("lift_sample_binned");
+  }
+  unsigned blocks = (unsigned)((pts + 7) / 8);
   SPA3D_DISPATCH(out_dtype, TO, {
     lift_sample_kernel<TO><<<blocks, 256, 0, st>>>(tracks_2d, depth, dino, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
   });
   return check_launch("lift_sample");
+}
+}  // namespace spa3d
+
+extern "C" int64_t spa3d_lift_workspace_bytes(int N, int T, int Hp, int Wp) {
+  return 4 * ((int64_t)N * T + (int64_t)T * ((int64_t)(Wp + 1) * (Hp + 1) + 1));
+}
+
+extern "C" int spa3d_lift_sample(const float* tracks_2d, const float* depth, const float* dino,
+                                 float* xyz, void* dino_out, void* depth_out, int out_dtype, int N,
+                                 int T, int H, int W, int Hp, int Wp, int D, int Cd, int video_H,
+                                 int video_W, const float* intrinsics, void* stream) {
+  return spa3d::lift_sample_impl(tracks_2d, depth, dino, xyz, dino_out, depth_out, out_dtype, N, T, H, W, Hp, Wp, D, Cd, video_H, video_W,
+                                 intrinsics, nullptr, 0, stream);
+}
+
+extern "C" int spa3d_lift_sample_ws(const float* tracks_2d, const float* depth, const float* dino,
+                                    float* xyz, void* dino_out, void* depth_out, int out_dtype, int N,
+                                    int T, int H, int W, int Hp, int Wp, int D, int Cd, int video_H,
+                                    int video_W, const float* intrinsics, void* workspace, int64_t workspace_bytes, void* stream) {
+  return spa3d::lift_sample_impl(tracks_2d, depth, dino, xyz, dino_out, depth_out, out_dtype, N, T, H, W, Hp, Wp, D, Cd, video_H, video_W,
+                                 intrinsics, workspace, workspace_bytes, stream);
 }

@@ -81,8 +81,13 @@ def lift_sample(tracks_2d, depth=None, dino=None, video_hw=None, intrinsics=None
     intr = None
     if intrinsics is not None:
         intr = (ctypes.c_float * 4)(*[float(v) for v in intrinsics])
-    _call("spa3d_lift_sample", _p(tracks_2d), _p(depth), _p(dino), _p(xyz), _p(dfeat), _p(zfeat), _DT[out_dtype],
-          N, T, H, W, Hp, Wp, D, depth_feature_dim, vh, vw, ctypes.cast(intr, ctypes.c_void_p) if intr else None, _stream())
+    ws, ws_bytes = None, 0
+    if dfeat is not None and D % 128 == 0:   # cell-binned gather (corner rows read once per occupied patch cell): caller-owned scratch
+        ws_bytes = int(_lib.lib().spa3d_lift_workspace_bytes(N, T, Hp, Wp))
+        ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.int32)
+    _call("spa3d_lift_sample_ws", _p(tracks_2d), _p(depth), _p(dino), _p(xyz), _p(dfeat), _p(zfeat), _DT[out_dtype],
+          N, T, H, W, Hp, Wp, D, depth_feature_dim, vh, vw, ctypes.cast(intr, ctypes.c_void_p) if intr else None, _p(ws), ws_bytes,
+          _stream())
     return xyz, dfeat, zfeat
 
 

@@ -60,6 +60,7 @@ int64_t spa3d_sumsq_workspace_bytes(void);                                      
 int64_t spa3d_attention_bwd_workspace_bytes(int64_t batch, int heads, int Lq);      /* spa3d_attention_bwd `delta_ws` */
 int64_t spa3d_attention_stats_bytes(int64_t batch, int heads, int Lq);              /* spa3d_attention_fwd `lse_out` (max, sum per row) */
 int64_t spa3d_layernorm_bwd_workspace_bytes(int num_partials, int d);               /* spa3d_layernorm_bwd `dscale_partial` */
+int64_t spa3d_lift_workspace_bytes(int N, int T, int Hp, int Wp);                   /* spa3d_lift_sample_ws `workspace` */
 
 /* ---- K0: feature lifting (inference.py:287-447) ------------------------------------------
  * One pass over N x T track points: bilinear depth sample + pinhole unprojection
@@ -74,6 +75,16 @@ int spa3d_lift_sample(const float* tracks_2d, const float* depth, const float* d
                       float* xyz, void* dino_out, void* depth_out, int out_dtype,
                       int N, int T, int H, int W, int Hp, int Wp, int D, int Cd,
                       int video_H, int video_W, const float* intrinsics, void* stream);
+/* The same call with caller-owned scratch (spa3d_lift_workspace_bytes; int32 point order per frame + cell offsets): the
+ * points of every frame are first binned by DINO patch cell, and the four corner rows of a cell are then read ONCE for
+ * all of its points instead of once per point (bilinear sampling re-reads 4 bytes per byte written otherwise).  Used when
+ * dino / dino_out are given and D % 128 == 0; any other call (or workspace == NULL) takes the per-point kernel of
+ * spa3d_lift_sample.  Bit-identical results either way. */
+int spa3d_lift_sample_ws(const float* tracks_2d, const float* depth, const float* dino,
+                         float* xyz, void* dino_out, void* depth_out, int out_dtype,
+                         int N, int T, int H, int W, int Hp, int Wp, int D, int Cd,
+                         int video_H, int video_W, const float* intrinsics,
+                         void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- a1: SinusoidalEmbedding (track_autoencoder.py:18-38) --------------------------------
  * out[r, c*2F + f] = sin(x[r,c]/scale * 2^(f/3)),  out[r, c*2F + F + f] = sin(... + pi/2).

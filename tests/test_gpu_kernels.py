@@ -71,6 +71,47 @@ def test_lift_sample_config4_shape_vs_oracle(spa):
     assert torch.equal(dfb, df.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("D,Cd,out_dtype,with_depth", [(128, 256, torch.float32, True), (256, 4, torch.float32, True),
+                                                       (384, 8, torch.bfloat16, True), (768, 256, torch.float32, False)])
+def test_lift_sample_binned_equals_per_point_kernel_and_oracle(spa, D, Cd, out_dtype, with_depth):
+    """The cell-binned gather (corner rows read once per occupied patch cell; spa3d_lift_sample_ws) against the per-point
+    kernel (spa3d_lift_sample, no workspace) and the NumPy restatement, bit for bit: crowded cells (more than 32 points in one
+    cell: several batches), empty cells, points far outside the frame (clamped corners), both output dtypes, no depth."""
+    import ctypes
+    rs = np.random.RandomState(D + Cd)
+    N, T, H, W, Hp, Wp = 150, 5, 40, 56, 3, 4
+    tr = np.stack([rs.uniform(-30, W + 30, (N, T)), rs.uniform(-30, H + 30, (N, T))], -1).astype(np.float32)
+    tr[:70, :, 0] = rs.uniform(15, 27, (70, T))      # 70 points of every frame inside one cell (cell width 14 px)
+    tr[:70, :, 1] = rs.uniform(14, 26, (70, T))
+    tr[70:80] = np.float32([W - 1, H - 1])           # exactly on the last pixel
+    depth = rs.uniform(0.5, 10, (T, H, W, 1)).astype(np.float32)
+    dino = rs.standard_normal((T, Hp, Wp, D)).astype(np.float32)
+    dev = torch.device("cuda")
+    t_tr, t_dino = torch.as_tensor(tr, device=dev), torch.as_tensor(dino, device=dev)
+    t_depth = torch.as_tensor(depth, device=dev) if with_depth else None
+    xyz, df, zf = spa.ops.lift_sample(t_tr, t_depth, t_dino, (H, W), None, out_dtype, Cd)      # binned (D % 128 == 0)
+    # per-point kernel through the plain entry point
+    xyz2 = torch.full((N, T, 3), 7.0, device=dev) if with_depth else None
+    df2 = torch.empty(N, T, D, device=dev, dtype=out_dtype)
+    zf2 = torch.empty(N, T, Cd, device=dev, dtype=out_dtype) if with_depth else None
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    rc = spa._lib.lib().spa3d_lift_sample(P(t_tr), P(t_depth), P(t_dino), P(xyz2), P(df2), P(zf2), spa.ops.dt(df2), N, T,
+                                          H if with_depth else 0, W if with_depth else 0, Hp, Wp, D, Cd, H, W, None,
+                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(df, df2)
+    want = torch.as_tensor(olift.sample_dino_features_for_tracks(dino, tr, (T, H, W, 3)), device=dev)
+    assert torch.equal(df, want.to(out_dtype))
+    if with_depth:
+        assert torch.equal(xyz, xyz2) and torch.equal(zf, zf2)
+        np.testing.assert_array_equal(xyz.cpu().numpy(), olift.lift_2d_to_3d(tr, depth))
+        if Cd == 256:
+            np.testing.assert_array_equal(zf.float().cpu().numpy(), olift.sample_depth_features_for_tracks(depth, tr))
+    else:
+        assert xyz is None and zf is None
+
+
 # ---- Fourier features ---------------------------------------------------------------------
 def test_fourier_exact_matches_oracle(spa):
     rs = np.random.RandomState(1)
