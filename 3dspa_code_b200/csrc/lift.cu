@@ -165,9 +165,18 @@ __device__ __forceinline__ int lift_cell(float x, float y, float scale_w, float 
   return (ky + 1) * (Wp + 1) + (kx + 1);
 }
 
-// one CTA per frame: order[t*N + i] = the frame's point indices sorted by cell, starts[t*(cells+1) + c] = first position of cell c
+// one CTA per frame: rec[t*N + i] = the frame's points sorted by cell, one 32-byte record each - (n, x, y, x_prev, y_prev): what the
+// gather's scalar phase needs, so that it starts from ONE coalesced load instead of the chain order -> track coordinates ->
+// previous-frame coordinates; starts[t*(cells+1) + c] = first position of cell c
+struct __align__(16) LiftRec {
+  int n;
+  float x, y, xp, yp;
+  int pad[3];
+};
+static_assert(sizeof(LiftRec) == 32, "record size");
+
 __global__ void __launch_bounds__(256)
-lift_bin_kernel(const float* __restrict__ tracks, int* __restrict__ order, int* __restrict__ starts, int N, int T, int Hp, int Wp,
+lift_bin_kernel(const float* __restrict__ tracks, LiftRec* __restrict__ rec, int* __restrict__ starts, int N, int T, int Hp, int Wp,
                 float scale_w, float scale_h) {
   extern __shared__ int bin_smem[];
   const int cells = (Wp + 1) * (Hp + 1);
@@ -204,8 +213,17 @@ lift_bin_kernel(const float* __restrict__ tracks, int* __restrict__ order, int* 
   __syncthreads();
   for (int n = tid; n < N; n += 256) {
     const int64_t pt = (int64_t)n * T + t;
-    const int pos = atomicAdd(&hist[lift_cell(tracks[pt * 2], tracks[pt * 2 + 1], scale_w, scale_h, Wp, Hp)], 1);
-    order[(int64_t)t * N + pos] = n;
+    const float x = tracks[pt * 2], y = tracks[pt * 2 + 1];
+    const int pos = atomicAdd(&hist[lift_cell(x, y, scale_w, scale_h, Wp, Hp)], 1);
+    uint4 lo, hi = make_uint4(0, 0, 0, 0);
+    lo.x = (uint32_t)n;
+    lo.y = __float_as_uint(x);
+    lo.z = __float_as_uint(y);
+    lo.w = t > 0 ? __float_as_uint(tracks[(pt - 1) * 2]) : 0u;
+    hi.x = t > 0 ? __float_as_uint(tracks[(pt - 1) * 2 + 1]) : 0u;
+    uint4* dst = reinterpret_cast<uint4*>(rec + (int64_t)t * N + pos);
+    dst[0] = lo;
+    dst[1] = hi;
   }
 }
 
@@ -216,7 +234,7 @@ lift_bin_kernel(const float* __restrict__ tracks, int* __restrict__ order, int* 
 template <typename TO, int NJ>
 __global__ void __launch_bounds__(256, LIFT_BINNED_CTAS)
 lift_sample_binned_kernel(const float* __restrict__ tracks, const float* __restrict__ depth, const float* __restrict__ dino,
-                          const int* __restrict__ order, const int* __restrict__ starts, float* __restrict__ xyz,
+                          const LiftRec* __restrict__ rec, const int* __restrict__ starts, float* __restrict__ xyz,
                           TO* __restrict__ dino_out, TO* __restrict__ depth_out, int N, int T, int H, int W, int Hp, int Wp, int D,
                           int Cd, float scale_w, float scale_h, float fx, float fy, float cx, float cy) {
   const int lane = threadIdx.x & 31;
@@ -234,8 +252,8 @@ lift_sample_binned_kernel(const float* __restrict__ tracks, const float* __restr
     const float* f01 = base + ((int64_t)y0 * Wp + x1) * D;
     const float* f10 = base + ((int64_t)y1 * Wp + x0) * D;
     const float* f11 = base + ((int64_t)y1 * Wp + x1) * D;
-    // the corner rows of the first pass are requested before the scalar phase: its chain of dependent loads (order -> track
-    // coordinates -> depth gathers -> previous-frame gathers) and the row gathers are then in flight together
+    // the corner rows of the first pass are requested before the scalar phase: its chain of dependent loads (point record ->
+    // depth gathers of both frames) and the row gathers are then in flight together
     float4 a[NJ], bq[NJ], cq[NJ], d[NJ];
     auto load_rows = [&](int cb) {
 #pragma unroll
@@ -254,24 +272,27 @@ lift_sample_binned_kernel(const float* __restrict__ tracks, const float* __restr
       int n = 0;
       float x = 0.f, y = 0.f, z = 0.f, grad = 0.f, wx = 0.f, wy = 0.f;
       if (lane < m) {
-        n = __ldg(order + (int64_t)t * N + b0 + lane);
+        const uint4* rp = reinterpret_cast<const uint4*>(rec + (int64_t)t * N + b0 + lane);
+        const uint4 lo = __ldg(rp);
+        const uint32_t ypb = __ldg(reinterpret_cast<const uint32_t*>(rp + 1));
+        n = (int)lo.x;
+        x = __uint_as_float(lo.y);
+        y = __uint_as_float(lo.z);
         const int64_t pt = (int64_t)n * T + t;
-        x = tracks[pt * 2];
-        y = tracks[pt * 2 + 1];
         const Bilin b = bilin_setup(__fmul_rn(x, scale_w), __fmul_rn(y, scale_h), Wp, Hp);
         wx = b.wx;
         wy = b.wy;
         if (depth != nullptr) {
-          z = sample_depth(depth, t, H, W, x, y);
+          // both frames' gathers are independent of each other: issued together
+          const float zc = sample_depth(depth, t, H, W, x, y);
+          const float zp = (depth_out != nullptr && t > 0) ? sample_depth(depth, t - 1, H, W, __uint_as_float(lo.w), __uint_as_float(ypb)) : 0.f;
+          z = zc;
           if (xyz != nullptr) {
             xyz[pt * 3 + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(x, cx), z), fx);
             xyz[pt * 3 + 1] = __fdiv_rn(__fmul_rn(__fsub_rn(y, cy), z), fy);
             xyz[pt * 3 + 2] = z;
           }
-          if (depth_out != nullptr && t > 0) {
-            const float zp = sample_depth(depth, t - 1, H, W, tracks[(pt - 1) * 2], tracks[(pt - 1) * 2 + 1]);
-            grad = __fsub_rn(z, zp);
-          }
+          if (depth_out != nullptr && t > 0) grad = __fsub_rn(z, zp);
         }
       }
       // ---- depth-feature rows: (z, z/10, dz, 0) then zeros (inference.py:437-443) ----
@@ -339,10 +360,10 @@ static int lift_sample_impl(const float* tracks_2d, const float* depth, const fl
   const int64_t cells = (int64_t)(Wp + 1) * (Hp + 1);
   const bool binned = use_binned && dino && dino_out && D % 128 == 0 && (depth_out == nullptr || Cd % 4 == 0) && workspace != nullptr &&
                       workspace_bytes >= spa3d_lift_workspace_bytes(N, T, Hp, Wp) && (cells + 256) * 4 <= 200 * 1024 &&
-                      (reinterpret_cast<uintptr_t>(workspace) & 3) == 0;
+                      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
   if (binned) {
-    int* order = reinterpret_cast<int*>(workspace);
-    int* starts = order + pts;
+    LiftRec* rec = reinterpret_cast<LiftRec*>(workspace);
+    int* starts = reinterpret_cast<int*>(rec + pts);
     const size_t bin_smem = (size_t)(cells + 256) * 4;
     static bool attr_set = false;
     if (!attr_set && bin_smem > 48 * 1024) {
@@ -350,7 +371,7 @@ static int lift_sample_impl(const float* tracks_2d, const float* depth, const fl
       SPA3D_REQUIRE(e == cudaSuccess, "lift_sample: smem attribute: %s", cudaGetErrorString(e));
       attr_set = true;
     }
-    lift_bin_kernel<<<T, 256, bin_smem, st>>>(tracks_2d, order, starts, N, T, Hp, Wp, scale_w, scale_h);
+    lift_bin_kernel<<<T, 256, bin_smem, st>>>(tracks_2d, rec, starts, N, T, Hp, Wp, scale_w, scale_h);
     if (check_launch("lift_bin")) return 1;
     const int sms = num_sms();
     const int64_t items = (int64_t)T * cells;
@@ -360,11 +381,11 @@ static int lift_sample_impl(const float* tracks_2d, const float* depth, const fl
     const int nj = D % 384 == 0 ? 3 : (D % 256 == 0 ? 2 : 1);
     SPA3D_DISPATCH(out_dtype, TO, {
       if (nj == 3)
-        lift_sample_binned_kernel<TO, 3><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, order, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
+        lift_sample_binned_kernel<TO, 3><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, rec, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
       else if (nj == 2)
-        lift_sample_binned_kernel<TO, 2><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, order, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
+        lift_sample_binned_kernel<TO, 2><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, rec, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
       else
-        lift_sample_binned_kernel<TO, 1><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, order, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
+        lift_sample_binned_kernel<TO, 1><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, rec, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
     });
     return check_launch("lift_sample_binned");
   }
@@ -377,7 +398,7 @@ static int lift_sample_impl(const float* tracks_2d, const float* depth, const fl
 }  // namespace spa3d
 
 extern "C" int64_t spa3d_lift_workspace_bytes(int N, int T, int Hp, int Wp) {
-  return 4 * ((int64_t)N * T + (int64_t)T * ((int64_t)(Wp + 1) * (Hp + 1) + 1));
+  return 32 * (int64_t)N * T + 4 * (int64_t)T * ((int64_t)(Wp + 1) * (Hp + 1) + 1);   // point records + cell offsets per frame
 }
 
 extern "C" int spa3d_lift_sample(const float* tracks_2d, const float* depth, const float* dino,

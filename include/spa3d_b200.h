@@ -75,7 +75,7 @@ int spa3d_lift_sample(const float* tracks_2d, const float* depth, const float* d
                       float* xyz, void* dino_out, void* depth_out, int out_dtype,
                       int N, int T, int H, int W, int Hp, int Wp, int D, int Cd,
                       int video_H, int video_W, const float* intrinsics, void* stream);
-/* The same call with caller-owned scratch (spa3d_lift_workspace_bytes; int32 point order per frame + cell offsets): the
+/* The same call with caller-owned scratch (spa3d_lift_workspace_bytes; 32-byte point records sorted by cell per frame + cell offsets): the
  * points of every frame are first binned by DINO patch cell, and the four corner rows of a cell are then read ONCE for
  * all of its points instead of once per point (bilinear sampling re-reads 4 bytes per byte written otherwise).  Used when
  * dino / dino_out are given and D % 128 == 0; any other call (or workspace == NULL) takes the per-point kernel of
