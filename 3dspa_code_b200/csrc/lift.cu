@@ -5,9 +5,10 @@
 // round-to-nearest intrinsics (no FMA contraction), so results are bit-identical to the NumPy
 // code for float32 inputs.
 //
-// Mapping: one warp per track point; points are enumerated frame-major (p = t*N + n) so the
-// CTAs in flight at any moment gather from the same frame's DINO map (37x37x768 f32 = 4.2 MB),
-// which therefore stays L2-resident; lanes stride over channels with 128-bit loads/stores.
+// Two forms (same arithmetic, same bits): the per-point kernel - one warp per track point, points enumerated frame-major
+// (p = t*N + n) so the CTAs in flight gather from the same frame's DINO map (37x37x768 f32 = 4.2 MB, L2-resident), lanes stride
+// over channels with 128-bit loads / stores - and, below it, the cell-binned form the product uses when the patch features are
+// requested: the points of a frame are sorted by patch cell and a cell's four corner rows are read once for all of its points.
 #include <algorithm>
 
 #include "common.cuh"
