@@ -130,10 +130,20 @@ __global__ void layernorm_fwd_kernel(const TX* __restrict__ x, int64_t ldx,
   }
 }
 
-// Bandwidth-shaped forward: fp32 rows of d = 128*J floats, one warp per row, the whole row in registers (J float4 per
-// lane, read once with 128-bit loads), bf16 or fp32 output with 8 / 16-byte stores.
-template <int J, typename TY>
-__global__ void __launch_bounds__(256) layernorm_fwd_fast_kernel(const float* __restrict__ x, int64_t ldx,
+// Bandwidth-shaped forward: rows of d = 128*J values (fp32, or bf16 when the residual stream is kept in bf16), one warp per row, the
+// whole row in registers (J float4 per lane, read once with 128 / 64-bit loads), bf16 or fp32 output with 8 / 16-byte stores.
+template <typename TX>
+__device__ __forceinline__ float4 ln_load4(const TX* p);
+template <>
+__device__ __forceinline__ float4 ln_load4<float>(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+template <>
+__device__ __forceinline__ float4 ln_load4<bf16>(const bf16* p) {
+  const uint2 h = __ldcs(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u), __uint_as_float(h.y << 16), __uint_as_float(h.y & 0xffff0000u));
+}
+
+template <int J, typename TY, typename TX = float>
+__global__ void __launch_bounds__(256) layernorm_fwd_fast_kernel(const TX* __restrict__ x, int64_t ldx,
                                                                  const float* __restrict__ scale, TY* __restrict__ y,
                                                                  int64_t ldy, float* __restrict__ mean_out,
                                                                  float* __restrict__ rstd_out, int64_t rows) {
@@ -141,10 +151,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_fast_kernel(const float* __
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   constexpr int d = 128 * J;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const TX* xr = x + row * ldx;
   float4 v[J];
 #pragma unroll
-  for (int j = 0; j < J; ++j) v[j] = __ldcs(xr + j * 32 + lane);
+  for (int j = 0; j < J; ++j) v[j] = ln_load4<TX>(xr + (j * 32 + lane) * 4);
   float s = 0.f, ss = 0.f;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
@@ -1164,11 +1174,13 @@ int spa3d_layernorm_fwd(const void* x, int64_t ldx, int x_dtype, const float* sc
   {
     auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
     const bool ybf = y_dtype == SPA3D_BF16;
-    if (x_dtype == SPA3D_F32 && (ybf || y_dtype == SPA3D_F32) && d % 128 == 0 && d <= 1536 && ldx % 4 == 0 && ldy % 4 == 0 &&
-        al(x, 16) && al(scale, 16) && al(y, ybf ? 8 : 16)) {
+    const bool xbf = x_dtype == SPA3D_BF16;
+    if ((x_dtype == SPA3D_F32 || (xbf && ybf)) && (ybf || y_dtype == SPA3D_F32) && d % 128 == 0 && d <= 1536 && ldx % 4 == 0 && ldy % 4 == 0 &&
+        al(x, xbf ? 8 : 16) && al(scale, 16) && al(y, ybf ? 8 : 16)) {
 #define SPA3D_LN_FWD_FAST(J)                                                                                              \
   case J:                                                                                                                 \
-    if (ybf) layernorm_fwd_fast_kernel<J, bf16><<<blocks_for(rows, 8), 256, 0, st>>>((const float*)x, ldx, scale, (bf16*)y, ldy, mean_out, rstd_out, rows); \
+    if (xbf) layernorm_fwd_fast_kernel<J, bf16, bf16><<<blocks_for(rows, 8), 256, 0, st>>>((const bf16*)x, ldx, scale, (bf16*)y, ldy, mean_out, rstd_out, rows); \
+    else if (ybf) layernorm_fwd_fast_kernel<J, bf16><<<blocks_for(rows, 8), 256, 0, st>>>((const float*)x, ldx, scale, (bf16*)y, ldy, mean_out, rstd_out, rows); \
     else layernorm_fwd_fast_kernel<J, float><<<blocks_for(rows, 8), 256, 0, st>>>((const float*)x, ldx, scale, (float*)y, ldy, mean_out, rstd_out, rows);   \
     return check_launch("layernorm_fwd_fast");
       switch (d / 128) {

@@ -118,6 +118,10 @@ class Engine:
         # (tests/test_gpu_kernels.py) but OFF by default: measured 0.805 ms against 0.783 ms for the two GEMMs on the per-track shape -
         # with the 96 KB token tile resident, shared memory leaves a 96 KB weight ring, about one L2 latency of look-ahead
         self.fused_mlp = False
+        # dtype of the residual stream INSIDE the transformer stacks.  float32 (default) is the reference's; bfloat16 halves the bytes the
+        # residual GEMMs and the LayerNorms move (they are HBM-bound at 8 bytes per output element) at the price of one more
+        # bf16 rounding per residual add - an inference-only option (model.residual_dtype), measured in DESIGN 5, off by default
+        self.sdt = torch.float32
         self.stream_chunk = 256     # support tracks per host->device pipeline stage (0 = one-shot upload)
         self._copy_stream = None
         self._noise_cache = None    # ((B, tokens, dim, layout), device tensor) of the default quantiser noise
@@ -140,6 +144,7 @@ class Engine:
         A = H * Dh
         d = m["d"]
         w, f = self.w.mats(), self.w.f32
+        sdt = self.sdt if self.cdt == torch.bfloat16 else torch.float32
         for i in range(m["layers"]):
             pre = f"{short}.{i}."
             prune = out_rows == "first" and i == m["layers"] - 1 and kv is None and L > 1
@@ -151,16 +156,16 @@ class Engine:
                 q0 = ops.gemm_rmsnorm(xn.view(batch, L * d)[:, :d], wqkv[:A], Dh, A, 0, sq, sk)  # queries: token 0
                 o = torch.empty(batch, A, device=self.dev, dtype=self.cdt)
                 ops.attention_fwd(q0, kvp[:, :A], kvp[:, A:], o, batch, H, 1, L, Dh, key_mask)
-                x = ops.gemm(o, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x.view(batch, L * d)[:, :d], out_dtype=torch.float32)
+                x = ops.gemm(o, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x.view(batch, L * d)[:, :d], out_dtype=sdt)
                 del kvp, q0, o
                 an = ops.layernorm_fwd(x, f[pre + "norm_attn"], self.cdt)
                 h = ops.gemm(an, w[pre + "W1_t"], f[pre + "b1"], act=ops.ACT_GELU)
-                x = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=x, out_dtype=torch.float32)
+                x = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=x, out_dtype=sdt)
                 return ops.layernorm_fwd(x, f[f"{short}.norm_encoder"], self.cdt)
             qkv = ops.gemm_rmsnorm(xn, w[pre + "self.Wqkv_t"], Dh, A, A, sq, sk)
             o = torch.empty(x.shape[0], A, device=self.dev, dtype=self.cdt)
             ops.attention_fwd(qkv[:, :A], qkv[:, A : 2 * A], qkv[:, 2 * A :], o, batch, H, L, L, Dh, key_mask)
-            a = ops.gemm(o, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x, out_dtype=torch.float32)
+            a = ops.gemm(o, w[pre + "self.Wo_t"], f[pre + "self.bo"], residual=x, out_dtype=sdt)
             del qkv, o
             if kv is not None:
                 cq, ck = f[pre + "cross.norm_query"], f[pre + "cross.norm_key"]
@@ -168,7 +173,7 @@ class Engine:
                 kvp = ops.gemm_rmsnorm(kv, w[pre + "cross.Wkv_t"], Dh, 0, A, cq, ck)
                 oc = torch.empty(x.shape[0], A, device=self.dev, dtype=self.cdt)
                 ops.attention_fwd(qc, kvp[:, :A], kvp[:, A:], oc, batch, H, L, Lkv, Dh, None)
-                a = ops.gemm(oc, w[pre + "cross.Wo_t"], f[pre + "cross.bo"], residual=a, out_dtype=torch.float32)
+                a = ops.gemm(oc, w[pre + "cross.Wo_t"], f[pre + "cross.bo"], residual=a, out_dtype=sdt)
                 del qc, kvp, oc
             an = ops.layernorm_fwd(a, f[pre + "norm_attn"], self.cdt)
             if (self.fused_mlp and self.cdt == torch.bfloat16 and a.shape[0] >= 4096
@@ -178,7 +183,7 @@ class Engine:
                 del xn, an, a
                 continue
             h = ops.gemm(an, w[pre + "W1_t"], f[pre + "b1"], act=ops.ACT_GELU)
-            x = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=a, out_dtype=torch.float32)
+            x = ops.gemm(h, w[pre + "W2_t"], f[pre + "b2"], residual=a, out_dtype=sdt)
             del xn, an, h, a
         if out_rows == "first":
             return ops.layernorm_fwd(x, f[f"{short}.norm_encoder"], self.cdt, rows=batch, ldx=L * d, d=d)
