@@ -40,6 +40,9 @@ def main():
         ("itt.gbwd", Mi, 384, 1536, "gbwd"),
         ("itt.gfwd", Mi, 384, 1536, "gfwd"),
         ("embed", 2048 * 150 * args.clips, 1280, 384, "bias"),
+        ("itt.out.resbf", Mi, 768, 384, "resbf"),
+        ("itt.mlp2.resbf", Mi, 1536, 384, "resbf"),
+        ("tra.mlp2.resbf", Mr, 1536, 1280, "resbf"),
         ("tra.out.f32", Mr, 768, 1280, "f32"),
         ("tra.out.resbf", Mr, 768, 1280, "resbf"),
         ("tra.out.bf16", Mr, 768, 1280, "bias"),
