@@ -203,21 +203,24 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dFourierFeatures, FourierImpl,
 static ffi::Error LiftSampleImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> tracks_2d, ffi::Buffer<ffi::DataType::F32> depth,
                                  ffi::Buffer<ffi::DataType::F32> dino, ffi::Buffer<ffi::DataType::F32> intrinsics_host, int32_t video_h,
                                  int32_t video_w, ffi::Result<ffi::Buffer<ffi::DataType::F32>> xyz, ffi::Result<ffi::AnyBuffer> dino_feat,
-                                 ffi::Result<ffi::AnyBuffer> depth_feat) {
+                                 ffi::Result<ffi::AnyBuffer> depth_feat, ffi::Result<ffi::Buffer<ffi::DataType::S32>> scratch) {
   auto td = tracks_2d.dimensions();                   // [N, T, 2]
   auto dd = depth.dimensions();                       // [T, H, W, 1]
   auto fd = dino.dimensions();                        // [T, Hp, Wp, D]
   // intrinsics are HOST scalars of the C ABI: pass them as four float attributes in production; shown as a buffer for brevity
-  return Status(spa3d_lift_sample(tracks_2d.typed_data(), depth.typed_data(), dino.typed_data(), xyz->typed_data(), dino_feat->untyped_data(),
-                                  depth_feat->untyped_data(), Code(dino_feat->element_type()), (int)td[0], (int)td[1], (int)dd[1], (int)dd[2],
-                                  (int)fd[1], (int)fd[2], (int)fd[3], (int)depth_feat->dimensions().back(), video_h, video_w,
-                                  intrinsics_host.element_count() ? intrinsics_host.typed_data() : nullptr, stream));
+  // scratch: spa3d_lift_workspace_bytes(N, T, Hp, Wp) / 4 int32 elements, sized on the Python side (the cell-binned gather); a
+  // zero-sized buffer selects the per-point kernel
+  return Status(spa3d_lift_sample_ws(tracks_2d.typed_data(), depth.typed_data(), dino.typed_data(), xyz->typed_data(), dino_feat->untyped_data(),
+                                     depth_feat->untyped_data(), Code(dino_feat->element_type()), (int)td[0], (int)td[1], (int)dd[1], (int)dd[2],
+                                     (int)fd[1], (int)fd[2], (int)fd[3], (int)depth_feat->dimensions().back(), video_h, video_w,
+                                     intrinsics_host.element_count() ? intrinsics_host.typed_data() : nullptr,
+                                     scratch->element_count() ? scratch->untyped_data() : nullptr, (int64_t)scratch->element_count() * 4, stream));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(Spa3dLiftSample, LiftSampleImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
                                   .Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::Buffer<ffi::DataType::F32>>().Arg<ffi::Buffer<ffi::DataType::F32>>()
                                   .Attr<int32_t>("video_h").Attr<int32_t>("video_w").Ret<ffi::Buffer<ffi::DataType::F32>>().Ret<ffi::AnyBuffer>()
-                                  .Ret<ffi::AnyBuffer>());
+                                  .Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::DataType::S32>>());
 
 // ---- R1 key mask, quantiser, decoder tokens (track_autoencoder_3d.py:167-184, 251-260, 235-246 + 276-284) -----------------------
 static ffi::Error KeyMaskImpl(cudaStream_t stream, ffi::Buffer<ffi::DataType::F32> visible, ffi::Buffer<ffi::DataType::S32> boundary, int32_t has_readout,
