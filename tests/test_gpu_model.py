@@ -390,6 +390,27 @@ def test_apply_stream_equals_per_clip_apply(spa):
         for g, r in zip(got, refs * rep):
             assert not g.tracks.is_cuda
             assert torch.equal(g.tracks, r.tracks.cpu()) and torch.equal(g.visible_logits, r.visible_logits.cpu())
+    # the staging thread allocates pinned and device memory WHILE the consumer thread captures the forward (a fresh model captures inside the
+    # stream): the capture must not be invalidated by another thread's CUDA calls (the capture is begun in relaxed mode)
+    real_pack = spa.ops.host_pack_bf16
+    hoard = []
+
+    def noisy_pack(src, dst, threads):
+        hoard.append(torch.empty(1 << 20).pin_memory())                       # cudaHostAlloc
+        hoard.append(torch.empty((48 << 20) + len(hoard), device="cuda", dtype=torch.uint8))   # a fresh cudaMalloc
+        return real_pack(src, dst, threads)
+
+    spa.ops.host_pack_bf16 = noisy_pack
+    try:
+        for _ in range(3):
+            m = spa.TrackAutoEncoder3D(**fields)
+            m.cuda_graph = True
+            got = list(m.apply_stream(variables, batches, noises=noises, precision="bf16", host_pack="bf16", pack_threads=2))
+            for g, r in zip(got, refs):
+                assert torch.equal(g.tracks, r.tracks.cpu())
+    finally:
+        spa.ops.host_pack_bf16 = real_pack
+        del hoard
     # a consumer that stops early releases the staging thread
     gen = model.apply_stream(variables, batches, noises=noises, host_pack="bf16")
     next(gen)
