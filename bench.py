@@ -724,7 +724,7 @@ def run_ours(args):
                     "host_bytes_per_step": int(host_bytes), "host_pack_threads": int(pack_threads),
                     "h2d_copy_alone_ms": ms_copy, "h2d_copy_alone_gbs": host_bytes / (ms_copy * 1e-3) / 1e9,
                     "path": "model.apply_stream(from_maps=True) with its defaults: per step, one clip's 2-D tracks + depth maps + DINOv2 patch maps "
-                            "(float32, pinned host: host_bytes_per_step) are handed over; with >= 12 host cores per rank the DINOv2 patch map is rounded to "
+                            "(float32, pinned host: host_bytes_per_step) are handed over; on a single-rank host with >= 12 cores the DINOv2 patch map is rounded to "
                             "bf16 by host_pack_threads host threads INSIDE the timed region (the rounding the bf16 path applies on the device otherwise - "
                             "results are bit-identical) so h2d_bytes_per_step cross PCIe; lifted / sampled / embedded fused, encoded and decoded; tracks + "
                             "visibility logits are read back.  The rounding of clip i+2, the upload of clip i+1 and the forward of clip i overlap (each "
