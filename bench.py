@@ -684,9 +684,9 @@ def run_ours(args):
         saved = packed_bytes(batch) if pack == "auto" else 0
         e2e_variants[name] = {"ms_per_step": ms, "value": world * Q / (ms * 1e-3), "h2d_bytes_per_step": nbytes(batch, noise) - saved,
                               "host_bytes_per_step": nbytes(batch, noise), "host_pack_threads": pack_threads if pack == "auto" else 0}
-    for k in ("maps", "features_fp32"):
-        if k not in e2e_variants:
-            e2e_variants[k] = dict(e2e_variants[k + "_upload"])
+    for k, same in (("maps", "maps_fp32_upload"), ("features_fp32", "features_fp32_upload")):
+        if k not in e2e_variants:           # no host-side staging on this host: the default path IS the float32 upload
+            e2e_variants[k] = dict(e2e_variants[same])
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     ms_single = timed(step_e2e, K) / K
