@@ -59,6 +59,23 @@ def test_host_pack_bf16_is_round_to_nearest_even(spa):
         spa.ops.host_pack_bf16(torch.zeros(4), torch.zeros(4), 1)
 
 
+def test_host_pack_policy(spa, monkeypatch):
+    """apply_stream's host_pack="auto": on only for a single rank on a host with >= 12 cores, bf16 precision; explicit "bf16" always
+    packs; None / the fp32 precision never do."""
+    import os
+    f = spa.TrackAutoEncoder3D._pack_threads
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(16)))
+    assert f("auto", "bf16", None) == 10 and f("bf16", "bf16", 3) == 3 and f(None, "bf16", None) == 0 and f("auto", "fp32", None) == 0
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(8)))
+    assert f("auto", "bf16", None) == 0 and f("bf16", "bf16", None) == 4
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(64)))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+    assert f("auto", "bf16", None) == 0 and f("bf16", "bf16", None) == 10
+    with pytest.raises(ValueError):
+        f("fp8", "bf16", None)
+
+
 def test_pack_unpack_roundtrip_and_counts(spa):
     model = spa.TrackAutoEncoder3D()
     tree = model.init(0, {"dino_features": 1, "depth_features": 1})["params"]
