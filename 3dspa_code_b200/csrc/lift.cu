@@ -147,6 +147,36 @@ lift_sample_kernel(const float* __restrict__ tracks, const float* __restrict__ d
   }
 }
 
+// ---- geometry only: one THREAD per point -------------------------------------------------------------------------
+// The fused maps path (spa3d_embed_sampled) needs the lifted coordinates and the narrow depth feature (d, d/10, d_t - d_{t-1}, 0)
+// but no per-point patch features: a warp per point would spend its time on one lane's chain of dependent gathers.  Points are
+// enumerated frame-major like above; a thread writes its point's xyz and its Cd <= 8 feature values itself.
+template <typename TO>
+__global__ void __launch_bounds__(256)
+lift_points_kernel(const float* __restrict__ tracks, const float* __restrict__ depth, float* __restrict__ xyz, TO* __restrict__ depth_out,
+                   int N, int T, int H, int W, int Cd, float fx, float fy, float cx, float cy) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (int64_t)N * T) return;
+  const int t = (int)(p / N);
+  const int64_t pt = (int64_t)(p % N) * T + t;
+  const float x = tracks[pt * 2], y = tracks[pt * 2 + 1];
+  const float z = sample_depth(depth, t, H, W, x, y);
+  if (xyz != nullptr) {
+    xyz[pt * 3 + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(x, cx), z), fx);
+    xyz[pt * 3 + 1] = __fdiv_rn(__fmul_rn(__fsub_rn(y, cy), z), fy);
+    xyz[pt * 3 + 2] = z;
+  }
+  if (depth_out != nullptr) {
+    float grad = 0.f;
+    if (t > 0) grad = __fsub_rn(z, sample_depth(depth, t - 1, H, W, tracks[(pt - 1) * 2], tracks[(pt - 1) * 2 + 1]));
+    TO* o = depth_out + pt * Cd;
+    stf<TO>(o, z);
+    stf<TO>(o + 1, __fdiv_rn(z, 10.f));
+    stf<TO>(o + 2, grad);
+    for (int c = 3; c < Cd; ++c) stf<TO>(o + c, 0.f);
+  }
+}
+
 // ---- cell-binned form of the same gather ----------------------------------------------------------------------
 // What bounds the kernel above is the 4x read amplification of bilinear sampling on the L2 -> SM path: every point pulls its
 // four corner rows (4 x D floats = 12 KB at D = 768) through the L1 for 3 KB of output - 9.4 GB of gathers per cfg4 clip, of
@@ -389,6 +419,12 @@ static int lift_sample_impl(const float* tracks_2d, const float* depth, const fl
         lift_sample_binned_kernel<TO, 1><<<grid, 256, 0, st>>>(tracks_2d, depth, dino, rec, starts, xyz, (TO*)dino_out, (TO*)depth_out, N, T, H, W, Hp, Wp, D, Cd, scale_w, scale_h, fx, fy, cx, cy);
     });
     return check_launch("lift_sample_binned");
+  }
+  if (depth != nullptr && (dino == nullptr || dino_out == nullptr) && (depth_out == nullptr || Cd <= 8)) {   // geometry only
+    SPA3D_DISPATCH(out_dtype, TO, {
+      lift_points_kernel<TO><<<(unsigned)((pts + 255) / 256), 256, 0, st>>>(tracks_2d, depth, xyz, (TO*)depth_out, N, T, H, W, Cd, fx, fy, cx, cy);
+    });
+    return check_launch("lift_points");
   }
   unsigned blocks = (unsigned)((pts + 7) / 8);
   SPA3D_DISPATCH(out_dtype, TO, {

@@ -108,6 +108,11 @@ def test_lift_sample_binned_equals_per_point_kernel_and_oracle(spa, D, Cd, out_d
         np.testing.assert_array_equal(xyz.cpu().numpy(), olift.lift_2d_to_3d(tr, depth))
         if Cd == 256:
             np.testing.assert_array_equal(zf.float().cpu().numpy(), olift.sample_depth_features_for_tracks(depth, tr))
+        # geometry only (the maps path: no per-point patch features, 4-wide depth feature): one thread per point, same bits
+        xyz3, none3, zf3 = spa.ops.lift_sample(t_tr, t_depth, None, (H, W), None, torch.float32, 4, True, False, True)
+        assert none3 is None and torch.equal(xyz3, xyz)
+        want3 = olift.sample_depth_features_for_tracks(depth, tr)[..., :4]
+        np.testing.assert_array_equal(zf3.cpu().numpy(), want3)
     else:
         assert xyz is None and zf is None
 
