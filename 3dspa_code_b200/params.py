@@ -290,21 +290,33 @@ def unpack(pk, meta):
 
 
 # ---- checkpoints (inference.py:464-508) ----------------------------------------------------------
+def _unbox(entry):
+    """A Python object stored through ``np.savez`` comes back as a 0-d object array (a pickled dict) or as a mapping."""
+    return entry.item() if getattr(entry, "ndim", None) == 0 else dict(entry)
+
+
+def _from_optimizer(state):
+    # a saved optimiser state carries the parameters under "target" (flax.optim); a bare tree is taken as it is
+    return state.get("target", state) if isinstance(state, dict) else state
+
+
+# The three ``.npz`` layouts the reference's loader accepts (inference.py:464-508), tried in this order: the archive member that
+# identifies the layout -> how the parameter tree is read from the archive.  Anything else is the flat ``a/b/c`` key layout.
+_NPZ_LAYOUTS = (
+    ("params", lambda z: _unbox(z["params"])),
+    ("optimizer", lambda z: _from_optimizer(_unbox(z["optimizer"]))),
+)
+
+
 def load_checkpoint(path):
     """Read a ``.npz`` checkpoint in any of the three layouts the reference accepts."""
-    if not path.endswith(".npz"):
+    if not str(path).endswith(".npz"):
         raise ValueError("only .npz checkpoints are supported (the Flax msgpack branch needs flax)")
-    data = np.load(path, allow_pickle=True)
-    if "params" in data:
-        p = data["params"]
-        params = p.item() if hasattr(p, "item") and p.ndim == 0 else dict(p)
-    elif "optimizer" in data:
-        opt = data["optimizer"]
-        opt = opt.item() if hasattr(opt, "item") and opt.ndim == 0 else dict(opt)
-        params = opt.get("target", opt) if isinstance(opt, dict) else opt
-    else:
-        params = unflatten({k: np.array(data[k]) for k in data.files})
-    return params
+    with np.load(path, allow_pickle=True) as z:
+        for member, read in _NPZ_LAYOUTS:
+            if member in z.files:
+                return read(z)
+        return unflatten({k: np.array(z[k]) for k in z.files})
 
 
 def save_checkpoint(path, tree):
